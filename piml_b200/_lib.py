@@ -1,0 +1,112 @@
+"""ctypes binding of libpiml_b200.so (the C ABI declared in include/piml_b200.h).
+
+The product path has NO CPU fallback: if the library is missing, or an entry point is called without a CUDA device,
+this module raises -- it never routes to the oracle or to eager PyTorch.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpiml_b200.so")
+
+_lib = None
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class MlapmParams(C.Structure):
+    """piml_mlapm_params"""
+    _fields_ = [("version", i32), ("tau", f32), ("A", f32), ("B", f32), ("C", f32), ("D", f32),
+                ("theta_deg", f32), ("exact_math", i32)]
+
+
+class NetDesc(C.Structure):
+    """piml_net_desc"""
+    _fields_ = [("n_enc", i32), ("enc_dims", i32 * 9), ("proc_mode", i32), ("n_dec", i32), ("dec_dims", i32 * 9),
+                ("n_coll", i32), ("coll_dims", i32 * 5), ("kind", i32)]
+
+
+# name -> (restype, argtypes); must list every symbol include/piml_b200.h declares (tests check this).
+SIGNATURES = {
+    "piml_version": (i32, []),
+    "piml_last_error": (C.c_char_p, []),
+    "piml_launch_count": (i64, []),
+    "piml_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
+    "piml_heading_f32": (i32, [vp, i32, i32, i32, vp, vp]),
+    "piml_select_neighbors_f32": (i32, [vp, vp, i64, vp, i32, i32, i32, i32, f32, vp, vp, vp]),
+    "piml_relative_features_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32,
+                                         f32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "piml_collision_label_f32": (i32, [vp, i64, vp, vp]),
+    "piml_mlapm_workspace_bytes": (i64, [i64]),
+    "piml_mlapm_step_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, vp, vp, vp]),
+    "piml_mlapm_advance_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, vp, vp,
+                                     vp, vp, vp]),
+    "piml_calc_acceleration_f32": (i32, [vp, i64, i32, i32, f32, f32, f32, f32, f32, f32, vp, vp]),
+    "piml_pinnsf_forward_f32": (i32, [C.POINTER(NetDesc), vp, i32, f32, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp,
+                                      vp, vp, vp, vp]),
+    "piml_integrate_step_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp,
+                                      vp, vp, vp, vp, vp, vp, vp]),
+}
+
+
+def load():
+    """Load the shared library (no GPU needed for loading / symbol lookup)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m piml_b200.build` (nvcc, sm_100a). "
+                "piml_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().piml_last_error().decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def launch_count():
+    return int(load().piml_launch_count())
+
+
+def require_cuda(*tensors):
+    """Every tensor argument of a compute entry point must live on one CUDA device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("piml_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("piml_b200: expected CUDA tensors (move inputs with .cuda() first)")
+        dev = dev or t.device
+        if t.device != dev:
+            raise RuntimeError("piml_b200: tensors on different devices")
+    return dev
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def f32c(t):
+    """fp32 + contiguous view/copy of t (no copy when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()

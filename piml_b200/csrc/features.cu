@@ -1,0 +1,441 @@
+// features.cu -- neighbour selection + relative features for sm_100a.
+//
+// Replaces Pedestrians.get_heading_direction / get_relative_quantity / get_nearby_obj_in_sight /
+// get_filtered_features / get_relative_features (reference src/data/data.py:351-512).  The reference materialises
+// (T,N,N,2)x3 + (T,N,N,6) tensors and fully sorts every row; here one kernel streams candidate tiles through
+// shared memory (TMA bulk copies, double buffered), keeps a running top-k per row in registers, merges the lanes
+// that share a row with warp shuffles, and writes the k gathered 6-d features directly.
+//
+// Bit-exactness: the field-of-view predicate and the distances use the exact fp32 operation order of the
+// reference's CPU kernels through explicit _rn intrinsics; ordering is (distance, index)
+// ascending, which is what torch.sort produces for distinct finite distances (ties/inf are unspecified there).
+#include <math.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace piml {
+
+constexpr int FEAT_THREADS = 128;
+constexpr int FEAT_TILE = 1024;              // candidates per shared-memory tile (8 KB as float2)
+constexpr uint64_t EMPTY_KEY = ~0ull;
+
+// Ascending list of the KMAX smallest 64-bit keys seen so far, held in registers (fully unrolled).
+template <int KMAX>
+struct TopK {
+    uint64_t key[KMAX];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) key[i] = EMPTY_KEY;
+    }
+    __device__ __forceinline__ void insert(uint64_t c) {
+        if (c >= key[KMAX - 1]) return;
+#pragma unroll
+        for (int i = KMAX - 1; i > 0; --i) {
+            const uint64_t lo = key[i - 1];
+            key[i] = (c < lo) ? lo : ((c < key[i]) ? c : key[i]);
+        }
+        key[0] = (c < key[0]) ? c : key[0];
+    }
+    __device__ __forceinline__ void pop_front() {
+#pragma unroll
+        for (int i = 0; i < KMAX - 1; ++i) key[i] = key[i + 1];
+        key[KMAX - 1] = EMPTY_KEY;
+    }
+};
+
+__device__ __forceinline__ uint64_t make_key(float dist, int idx) {
+    return (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | static_cast<uint32_t>(idx);
+}
+__device__ __forceinline__ float key_dist(uint64_t k) { return __uint_as_float(static_cast<uint32_t>(k >> 32)); }
+__device__ __forceinline__ int key_idx(uint64_t k) { return static_cast<int>(static_cast<uint32_t>(k)); }
+
+template <int G>
+__device__ __forceinline__ uint64_t group_min(uint64_t v) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = (o < v) ? o : v;
+    }
+    return v;
+}
+
+// Distance from (px,py) to (ox,oy) with the field-of-view gate applied: data.py:432-443.
+// (hx,hy) is the heading already divided by max(||heading||, 1e-8) (cosine_similarity normalises each operand).
+__device__ __forceinline__ float gated_distance(float rx, float ry, float hx, float hy, float cos_thr) {
+    if (rx != rx) rx = CUDART_INF_F;                             // relative_pos[isnan] = inf   (:433)
+    if (ry != ry) ry = CUDART_INF_F;
+    float d = norm2_rn(rx, ry);                                  // torch.norm                  (:434)
+    const float nr = fmaxf(d, 1e-8f);
+    float c = __fadd_rn(__fmul_rn(__fdiv_rn(rx, nr), hx), __fmul_rn(__fdiv_rn(ry, nr), hy));   // (:439-440)
+    if (c != c) c = -1.0f;                                       // view_field[isnan] = -1      (:441)
+    if (c < cos_thr) d = CUDART_INF_F;                           // (:442-443)
+    return d;
+}
+
+// Scan `M` candidates (float2 array `cand`, one frame) for the rows owned by this CTA and build, per row, the
+// ascending list of the best keys.  RADIUS: only candidates with distance <= thr are kept and a cheap squared
+// distance prefilter skips the exact arithmetic for everything else.  All threads of the CTA must call this.
+template <int KMAX, int G, bool RADIUS>
+__device__ __forceinline__ void scan_candidates(TopK<KMAX> &best, const float2 *__restrict__ cand, int M, float px,
+                                                float py, float hx, float hy, float cos_thr, float thr, float pre2,
+                                                int g, float2 (*tile)[FEAT_TILE], uint64_t *bars,
+                                                uint32_t &phase_bits) {
+    best.init();
+    const int ntiles = (M + FEAT_TILE - 1) / FEAT_TILE;
+    if (ntiles == 0) return;
+    bool waits[2];
+    waits[0] = stage_float2(tile[0], cand, min(M, FEAT_TILE), &bars[0]);
+    __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) {
+            const int m1 = (t + 1) * FEAT_TILE;
+            waits[buf ^ 1] = stage_float2(tile[buf ^ 1], cand + m1, min(M - m1, FEAT_TILE), &bars[buf ^ 1]);
+        }
+        if (waits[buf]) {
+            mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= (1u << buf);
+        }
+        const int m0 = t * FEAT_TILE;
+        const int tn = min(M - m0, FEAT_TILE);
+        const float2 *tl = tile[buf];
+#pragma unroll 4
+        for (int j = g; j < tn; j += G) {
+            const float2 o = tl[j];
+            const float rx = __fsub_rn(o.x, px);                 // relative = B - A            (:412)
+            const float ry = __fsub_rn(o.y, py);
+            bool cand_ok = true;
+            if (RADIUS) cand_ok = __fmaf_rn(ry, ry, __fmul_rn(rx, rx)) <= pre2;
+            if (cand_ok) {
+                const float d = gated_distance(rx, ry, hx, hy, cos_thr);
+                if (!RADIUS || d <= thr) best.insert(make_key(d, m0 + j));
+            }
+        }
+        __syncthreads();        // tile[buf] is free for the copy issued at the top of iteration t+1
+    }
+}
+
+struct FeatArgs {
+    const float *pos; float *vel; float *acc; const float *dest; const float *head; const float *obs;
+    int64_t obs_frame_stride;    // floats between consecutive frames' obstacle arrays (0: shared)
+    int obs_channel_T;           // if > 0: obstacle array index = frame / obs_channel_T (per-channel obstacles)
+    int B, N, M, kp, ko;         // kp, ko already clamped to min(k, N|M)
+    float cos_p, thr_p, pre2_p, cos_o, thr_o, pre2_o;
+    float *ped_f; float *obs_f; float *dest_f;
+    int64_t *ped_idx; float *ped_dist; int64_t *obs_idx; float *obs_dist;
+};
+
+// grid = (ceil(N / (FEAT_THREADS/G)), B).  G lanes cooperate on one row.
+template <int KP, int KO, int G>
+__global__ void __launch_bounds__(FEAT_THREADS) relative_features_kernel(FeatArgs a) {
+    __shared__ __align__(16) float2 tile[2][FEAT_TILE];
+    __shared__ __align__(8) uint64_t bars[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase_bits = 0;
+
+    constexpr int ROWS = FEAT_THREADS / G;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G;
+    const int n = blockIdx.x * ROWS + threadIdx.x / G;
+    const bool live = n < a.N;
+    const int nn = live ? n : a.N - 1;                          // dead lanes shadow the last row, never write
+    const int64_t row = static_cast<int64_t>(b) * a.N + nn;
+
+    const float2 p = reinterpret_cast<const float2 *>(a.pos)[row];
+    float2 v = reinterpret_cast<const float2 *>(a.vel)[row];
+    float2 ac = reinterpret_cast<const float2 *>(a.acc)[row];
+    // acceleration[isnan] = 0 ; velocity[isnan] = 0, in place on the caller's tensors (data.py:483-484)
+    if (live && g == 0) {
+        if (v.x != v.x || v.y != v.y)
+            reinterpret_cast<float2 *>(a.vel)[row] = make_float2(nan_to_zero(v.x), nan_to_zero(v.y));
+        if (ac.x != ac.x || ac.y != ac.y)
+            reinterpret_cast<float2 *>(a.acc)[row] = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+    }
+    v = make_float2(nan_to_zero(v.x), nan_to_zero(v.y));
+    ac = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+
+    float2 h;
+    if (a.head) {
+        h = reinterpret_cast<const float2 *>(a.head)[row];
+    } else {                                                     // T == 1: heading = v / ||v||, 0 -> /0.1 (:391-394)
+        float nv = norm2_rn(v.x, v.y);
+        if (nv == 0.0f) nv = 0.1f;
+        h = make_float2(__fdiv_rn(v.x, nv), __fdiv_rn(v.y, nv));
+    }
+    {                                                            // cosine_similarity's own normalisation of x2
+        const float nh = fmaxf(norm2_rn(h.x, h.y), 1e-8f);
+        h = make_float2(__fdiv_rn(h.x, nh), __fdiv_rn(h.y, nh));
+    }
+
+    // ---- pedestrian - pedestrian (data.py:489-494) ----
+    {
+        TopK<KP> best;
+        const float2 *cand = reinterpret_cast<const float2 *>(a.pos) + static_cast<int64_t>(b) * a.N;
+        scan_candidates<KP, G, true>(best, cand, a.N, p.x, p.y, h.x, h.y, a.cos_p, a.thr_p, a.pre2_p, g, tile,
+                                     bars, phase_bits);
+        const float2 *fv = reinterpret_cast<const float2 *>(a.vel) + static_cast<int64_t>(b) * a.N;
+        const float2 *fa = reinterpret_cast<const float2 *>(a.acc) + static_cast<int64_t>(b) * a.N;
+        for (int j = 0; j < a.kp; ++j) {
+            const uint64_t w = group_min<G>(best.key[0]);
+            if (w != EMPTY_KEY && best.key[0] == w) best.pop_front();
+            if (live && g == (j % G)) {
+                float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0;
+                if (w != EMPTY_KEY) {
+                    const int m = key_idx(w);
+                    const float2 pm = cand[m];
+                    const float2 vm = fv[m];
+                    const float2 am = fa[m];
+                    f0 = make_float2(__fsub_rn(pm.x, p.x), __fsub_rn(pm.y, p.y));
+                    f1 = make_float2(__fsub_rn(nan_to_zero(vm.x), v.x), __fsub_rn(nan_to_zero(vm.y), v.y));
+                    f2 = make_float2(__fsub_rn(nan_to_zero(am.x), ac.x), __fsub_rn(nan_to_zero(am.y), ac.y));
+                }
+                float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + j) * 3;
+                out[0] = f0; out[1] = f1; out[2] = f2;
+                if (a.ped_idx) a.ped_idx[row * a.kp + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+                if (a.ped_dist) a.ped_dist[row * a.kp + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+            }
+        }
+    }
+
+    // ---- destination (data.py:496-497) ----
+    if (live && g == 0) {
+        const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
+        reinterpret_cast<float2 *>(a.dest_f)[row] =
+            make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+    }
+
+    // ---- pedestrian - obstacle (data.py:499-510): obs = (o, 0, 0) ----
+    if (a.M > 0) {
+        TopK<KO> best;
+        const int oframe = a.obs_channel_T > 0 ? b / a.obs_channel_T : b;
+        const float2 *cand = reinterpret_cast<const float2 *>(a.obs + static_cast<int64_t>(oframe) * a.obs_frame_stride);
+        scan_candidates<KO, G, true>(best, cand, a.M, p.x, p.y, h.x, h.y, a.cos_o, a.thr_o, a.pre2_o, g, tile, bars,
+                                     phase_bits);
+        for (int j = 0; j < a.ko; ++j) {
+            const uint64_t w = group_min<G>(best.key[0]);
+            if (w != EMPTY_KEY && best.key[0] == w) best.pop_front();
+            if (live && g == (j % G)) {
+                float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0;
+                if (w != EMPTY_KEY) {
+                    const float2 om = cand[key_idx(w)];
+                    f0 = make_float2(__fsub_rn(om.x, p.x), __fsub_rn(om.y, p.y));
+                    f1 = make_float2(__fsub_rn(0.f, v.x), __fsub_rn(0.f, v.y));
+                    f2 = make_float2(__fsub_rn(0.f, ac.x), __fsub_rn(0.f, ac.y));
+                }
+                float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + j) * 3;
+                out[0] = f0; out[1] = f1; out[2] = f2;
+                if (a.obs_idx) a.obs_idx[row * a.ko + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+                if (a.obs_dist) a.obs_dist[row * a.ko + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+            }
+        }
+    }
+}
+
+// get_nearby_obj_in_sight proper: no radius, every object competes (inf-distance ones ordered by index).
+struct SelArgs {
+    const float *pos; const float *obj; int64_t obj_frame_stride; const float *head;
+    int B, N, M, kk; float cos_thr; float *out_dist; int64_t *out_idx;
+};
+
+template <int KMAX, int G>
+__global__ void __launch_bounds__(FEAT_THREADS) select_kernel(SelArgs a) {
+    __shared__ __align__(16) float2 tile[2][FEAT_TILE];
+    __shared__ __align__(8) uint64_t bars[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase_bits = 0;
+    constexpr int ROWS = FEAT_THREADS / G;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G;
+    const int n = blockIdx.x * ROWS + threadIdx.x / G;
+    const bool live = n < a.N;
+    const int64_t row = static_cast<int64_t>(b) * a.N + (live ? n : a.N - 1);
+    const float2 p = reinterpret_cast<const float2 *>(a.pos)[row];
+    float2 h = reinterpret_cast<const float2 *>(a.head)[row];
+    const float nh = fmaxf(norm2_rn(h.x, h.y), 1e-8f);
+    h = make_float2(__fdiv_rn(h.x, nh), __fdiv_rn(h.y, nh));
+    TopK<KMAX> best;
+    const float2 *cand = reinterpret_cast<const float2 *>(a.obj + static_cast<int64_t>(b) * a.obj_frame_stride);
+    scan_candidates<KMAX, G, false>(best, cand, a.M, p.x, p.y, h.x, h.y, a.cos_thr, 0.f, 0.f, g, tile, bars,
+                                    phase_bits);
+    for (int j = 0; j < a.kk; ++j) {
+        const uint64_t w = group_min<G>(best.key[0]);
+        if (best.key[0] == w) best.pop_front();
+        if (live && g == (j % G)) {
+            a.out_dist[row * a.kk + j] = key_dist(w);
+            a.out_idx[row * a.kk + j] = key_idx(w);
+        }
+    }
+}
+
+// get_heading_direction for T > 1 (data.py:362-395): one thread per (channel, pedestrian) walks the time axis.
+__global__ void heading_kernel(const float2 *__restrict__ vel, int C, int T, int N, float2 *__restrict__ head) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * N) return;
+    const int c = i / N, n = i % N;
+    const float2 *v = vel + static_cast<int64_t>(c) * T * N + n;
+    float2 *h = head + static_cast<int64_t>(c) * T * N + n;
+    float2 tmp = make_float2(0.f, 0.f);
+    for (int t = T - 1; t >= 0; --t) {                           // nearest LATER non-zero velocity (:366-370)
+        float2 x = v[static_cast<int64_t>(t) * N];
+        x = make_float2(nan_to_zero(x.x), nan_to_zero(x.y));
+        if (norm2_rn(x.x, x.y) == 0.0f) x = tmp; else tmp = x;
+        h[static_cast<int64_t>(t) * N] = x;
+    }
+    for (int t = 0; t < T; ++t) {                                // else nearest EARLIER one (:371-375), normalise
+        float2 x = h[static_cast<int64_t>(t) * N];
+        if (norm2_rn(x.x, x.y) == 0.0f) x = tmp; else tmp = x;
+        float nv = norm2_rn(x.x, x.y);
+        if (nv == 0.0f) nv = 0.1f;
+        h[static_cast<int64_t>(t) * N] = make_float2(__fdiv_rn(x.x, nv), __fdiv_rn(x.y, nv));
+    }
+}
+
+// calculate_collision_label (data.py:515-535)
+__global__ void collision_label_kernel(const float *__restrict__ ped_f, int64_t S, float *__restrict__ out) {
+    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const float2 rp = reinterpret_cast<const float2 *>(ped_f)[s * 3];
+    const float2 rv = reinterpret_cast<const float2 *>(ped_f)[s * 3 + 1];
+    float hit = 0.f;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+        const float tq = __fmul_rn(static_cast<float>(q), 0.1f);
+        const float d = norm2_rn(__fadd_rn(rp.x, __fmul_rn(rv.x, tq)), __fadd_rn(rp.y, __fmul_rn(rv.y, tq)));
+        if (d < 0.5f && d != 0.f) hit = 1.f;
+    }
+    out[s] = hit;
+}
+
+static int pick_group(int64_t B, int N) {
+    // enough CTAs to fill 148 SMs several times over with one thread per row?  otherwise spread a row over lanes
+    const int64_t target = 4LL * sm_count();
+    if (B * ((N + FEAT_THREADS - 1) / FEAT_THREADS) >= target) return 1;
+    if (B * ((N + FEAT_THREADS / 8 - 1) / (FEAT_THREADS / 8)) >= target) return 8;
+    return 32;
+}
+
+// slack so that sqrtf(d2) <= thr  =>  d2 <= pre2 for every fp32 d2 (prefilter must be a superset)
+static float prefilter_sq(float thr) {
+    if (!(thr < 1e18f)) return INFINITY;
+    const double t = static_cast<double>(thr);
+    return static_cast<float>(t * t * (1.0 + 1e-6)) + 1e-30f;
+}
+
+template <int KP, int KO>
+static void launch_features(const FeatArgs &a, int G, cudaStream_t st) {
+    if (G == 1) {
+        dim3 grid((a.N + FEAT_THREADS - 1) / FEAT_THREADS, a.B);
+        relative_features_kernel<KP, KO, 1><<<grid, FEAT_THREADS, 0, st>>>(a);
+    } else if (G == 8) {
+        dim3 grid((a.N + FEAT_THREADS / 8 - 1) / (FEAT_THREADS / 8), a.B);
+        relative_features_kernel<KP, KO, 8><<<grid, FEAT_THREADS, 0, st>>>(a);
+    } else {
+        dim3 grid((a.N + FEAT_THREADS / 32 - 1) / (FEAT_THREADS / 32), a.B);
+        relative_features_kernel<KP, KO, 32><<<grid, FEAT_THREADS, 0, st>>>(a);
+    }
+}
+
+template <int KMAX>
+static void launch_select(const SelArgs &a, int G, cudaStream_t st) {
+    if (G == 1) {
+        dim3 grid((a.N + FEAT_THREADS - 1) / FEAT_THREADS, a.B);
+        select_kernel<KMAX, 1><<<grid, FEAT_THREADS, 0, st>>>(a);
+    } else if (G == 8) {
+        dim3 grid((a.N + FEAT_THREADS / 8 - 1) / (FEAT_THREADS / 8), a.B);
+        select_kernel<KMAX, 8><<<grid, FEAT_THREADS, 0, st>>>(a);
+    } else {
+        dim3 grid((a.N + FEAT_THREADS / 32 - 1) / (FEAT_THREADS / 32), a.B);
+        select_kernel<KMAX, 32><<<grid, FEAT_THREADS, 0, st>>>(a);
+    }
+}
+
+}  // namespace piml
+
+using namespace piml;
+
+extern "C" int piml_heading_f32(const float *vel, int C, int T, int N, float *head, void *stream) {
+    PIML_REQUIRE(vel && head, "piml_heading_f32: null pointer");
+    PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0, "piml_heading_f32: negative dimension");
+    if (static_cast<int64_t>(C) * T * N == 0) return PIML_OK;
+    const int threads = 128;
+    heading_kernel<<<(C * N + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(vel), C, T, N, reinterpret_cast<float2 *>(head));
+    count_launch();
+    return check_launch("heading_kernel");
+}
+
+extern "C" int piml_select_neighbors_f32(const float *pos, const float *obj, int64_t obj_frame_stride,
+                                         const float *head, int B, int N, int M, int k, float cos_thr,
+                                         float *out_dist, int64_t *out_idx, void *stream) {
+    PIML_REQUIRE(pos && obj && head && out_dist && out_idx, "piml_select_neighbors_f32: null pointer");
+    PIML_REQUIRE(B >= 0 && N >= 0 && M >= 0 && k >= 0, "piml_select_neighbors_f32: negative dimension");
+    const int kk = k < M ? k : M;
+    PIML_REQUIRE(kk <= 32, "piml_select_neighbors_f32: k=%d > 32 is not supported", k);
+    PIML_REQUIRE(B <= 65535, "piml_select_neighbors_f32: more than 65535 frames per call");
+    if (static_cast<int64_t>(B) * N == 0 || kk == 0) return PIML_OK;
+    SelArgs a{pos, obj, obj_frame_stride, head, B, N, M, kk, cos_thr, out_dist, out_idx};
+    const int G = pick_group(B, N);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kk <= 8) launch_select<8>(a, G, st);
+    else if (kk <= 16) launch_select<16>(a, G, st);
+    else launch_select<32>(a, G, st);
+    count_launch();
+    return check_launch("select_kernel");
+}
+
+extern "C" int piml_relative_features_f32(const float *pos, float *vel, float *acc, const float *dest,
+                                          const float *head, const float *obs, int obs_per_channel, int C, int T,
+                                          int N, int M, int kp, float cos_thr_ped, float dist_thr_ped, int ko,
+                                          float cos_thr_obs, float dist_thr_obs, float *ped_f, float *obs_f,
+                                          float *dest_f, int64_t *ped_idx, float *ped_dist, int64_t *obs_idx,
+                                          float *obs_dist, void *stream) {
+    PIML_REQUIRE(pos && vel && acc && dest && ped_f && dest_f, "piml_relative_features_f32: null pointer");
+    PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0 && M >= 0 && kp >= 0 && ko >= 0,
+                 "piml_relative_features_f32: negative dimension");
+    PIML_REQUIRE(M == 0 || (obs && obs_f), "piml_relative_features_f32: obstacles given but obs/obs_f is null");
+    PIML_REQUIRE(head || T == 1, "piml_relative_features_f32: head may only be NULL when T == 1 (got T=%d)", T);
+    const int kpp = kp < N ? kp : N;
+    const int kop = ko < M ? ko : M;
+    PIML_REQUIRE(kpp <= 32 && kop <= 32, "piml_relative_features_f32: topk (%d,%d) > 32 is not supported", kp, ko);
+    const int64_t B = static_cast<int64_t>(C) * T;
+    PIML_REQUIRE(B <= 65535, "piml_relative_features_f32: more than 65535 frames per call (split the batch)");
+    if (B * N == 0) return PIML_OK;
+    FeatArgs a;
+    a.pos = pos; a.vel = vel; a.acc = acc; a.dest = dest; a.head = head; a.obs = obs;
+    a.obs_frame_stride = obs_per_channel ? static_cast<int64_t>(M) * 2 : 0;
+    a.obs_channel_T = obs_per_channel ? T : 0;
+    a.B = static_cast<int>(B); a.N = N; a.M = M; a.kp = kpp; a.ko = kop;
+    a.cos_p = cos_thr_ped; a.thr_p = dist_thr_ped; a.pre2_p = prefilter_sq(dist_thr_ped);
+    a.cos_o = cos_thr_obs; a.thr_o = dist_thr_obs; a.pre2_o = prefilter_sq(dist_thr_obs);
+    a.ped_f = ped_f; a.obs_f = obs_f; a.dest_f = dest_f;
+    a.ped_idx = ped_idx; a.ped_dist = ped_dist; a.obs_idx = obs_idx; a.obs_dist = obs_dist;
+    const int G = pick_group(B, N);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kpp <= 8 && kop <= 16) launch_features<8, 16>(a, G, st);
+    else if (kpp <= 16 && kop <= 16) launch_features<16, 16>(a, G, st);
+    else launch_features<32, 32>(a, G, st);
+    count_launch();
+    return check_launch("relative_features_kernel");
+}
+
+extern "C" int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream) {
+    PIML_REQUIRE(ped_f && out, "piml_collision_label_f32: null pointer");
+    PIML_REQUIRE(S >= 0, "piml_collision_label_f32: negative size");
+    if (S == 0) return PIML_OK;
+    const int threads = 256;
+    collision_label_kernel<<<static_cast<unsigned>((S + threads - 1) / threads), threads, 0,
+                             static_cast<cudaStream_t>(stream)>>>(ped_f, S, out);
+    count_launch();
+    return check_launch("collision_label_kernel");
+}

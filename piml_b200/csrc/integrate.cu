@@ -1,0 +1,84 @@
+// integrate.cu -- fused rollout state update for sm_100a.
+//
+// Replaces the elementwise / gather / masked-write chain of BaseSimulator.get_multiple_rollouts
+// (reference src/models/simulators.py:596-639, ~25 eager launches and 5 host syncs per step) by one kernel: record
+// the state at t, lagged explicit Euler, arrival / waypoint switch, removal on arrival, teacher-forced entry and the
+// history-velocity update.  One thread per (scene, slot); state is read and written once.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace piml {
+
+struct IntArgs {
+    float2 *p, *v, *a; const float2 *a_next; float2 *dest; int64_t *dest_idx; const int64_t *dest_num;
+    const float2 *waypoints; int S, D, N; float dt; int remove_on_arrival;
+    const int64_t *entry; const float2 *p_gt, *v_gt, *a_gt, *dest_gt; const int64_t *dest_idx_gt;
+    float2 *hist_v; float2 *rec_p, *rec_v, *rec_a; float *rec_mask;
+};
+
+__global__ void integrate_kernel(IntArgs g) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<int64_t>(g.S) * g.N) return;
+    const int s = static_cast<int>(i / g.N), n = static_cast<int>(i % g.N);
+    const float2 p = g.p[i], v = g.v[i], a = g.a[i];
+    // p_res[t] = p_cur ... mask_p_new[t][~isnan(p.x)] = 1          (simulators.py:596-600)
+    if (g.rec_p) g.rec_p[i] = p;
+    if (g.rec_v) g.rec_v[i] = v;
+    if (g.rec_a) g.rec_a[i] = a;
+    if (g.rec_mask && !(p.x != p.x)) g.rec_mask[i] = 1.0f;
+    // v_next = v + a*dt ; p_next = p + v*dt  with the OLD a and v   (simulators.py:603-604)
+    float2 vn = make_float2(__fadd_rn(v.x, __fmul_rn(a.x, g.dt)), __fadd_rn(v.y, __fmul_rn(a.y, g.dt)));
+    float2 pn = make_float2(__fadd_rn(p.x, __fmul_rn(v.x, g.dt)), __fadd_rn(p.y, __fmul_rn(v.y, g.dt)));
+    float2 an = g.a_next[i];
+    float2 d = g.dest[i];
+    int64_t di = g.dest_idx[i];
+    const float dis = norm2_rn(__fsub_rn(p.x, d.x), __fsub_rn(p.y, d.y));      // :608
+    if (dis < 0.5f) di += 1;                                                   // :609
+    if (di > g.dest_num[i] - 1) {
+        if (g.remove_on_arrival) pn = make_float2(CUDART_NAN_F, CUDART_NAN_F); // :611
+        di -= 1;                                                               // :613
+    }
+    d = g.waypoints[(static_cast<int64_t>(s) * g.D + di) * g.N + n];           // :614-616
+    float2 hv = vn;                                                            // :624-626
+    if (g.entry && g.entry[i] == 1) {                                          // :629-639
+        pn = g.p_gt[i]; vn = g.v_gt[i]; an = g.a_gt[i]; d = g.dest_gt[i]; di = g.dest_idx_gt[i];
+        hv = vn;
+    }
+    g.p[i] = pn; g.v[i] = vn; g.a[i] = an; g.dest[i] = d; g.dest_idx[i] = di;
+    if (g.hist_v) g.hist_v[i] = hv;
+}
+
+}  // namespace piml
+
+using namespace piml;
+
+extern "C" int piml_integrate_step_f32(float *p, float *v, float *a, const float *a_next, float *dest,
+                                       int64_t *dest_idx, const int64_t *dest_num, const float *waypoints, int S,
+                                       int D, int N, float dt, int remove_on_arrival, const int64_t *entry,
+                                       const float *p_gt, const float *v_gt, const float *a_gt, const float *dest_gt,
+                                       const int64_t *dest_idx_gt, float *hist_v, float *rec_p, float *rec_v,
+                                       float *rec_a, float *rec_mask, void *stream) {
+    PIML_REQUIRE(p && v && a && a_next && dest && dest_idx && dest_num && waypoints,
+                 "piml_integrate_step_f32: null pointer");
+    PIML_REQUIRE(S >= 0 && D >= 1 && N >= 0, "piml_integrate_step_f32: bad dimensions S=%d D=%d N=%d", S, D, N);
+    PIML_REQUIRE(!entry || (p_gt && v_gt && a_gt && dest_gt && dest_idx_gt),
+                 "piml_integrate_step_f32: entry mask given without ground-truth arrays");
+    const int64_t tot = static_cast<int64_t>(S) * N;
+    if (tot == 0) return PIML_OK;
+    IntArgs g;
+    g.p = reinterpret_cast<float2 *>(p); g.v = reinterpret_cast<float2 *>(v); g.a = reinterpret_cast<float2 *>(a);
+    g.a_next = reinterpret_cast<const float2 *>(a_next); g.dest = reinterpret_cast<float2 *>(dest);
+    g.dest_idx = dest_idx; g.dest_num = dest_num; g.waypoints = reinterpret_cast<const float2 *>(waypoints);
+    g.S = S; g.D = D; g.N = N; g.dt = dt; g.remove_on_arrival = remove_on_arrival; g.entry = entry;
+    g.p_gt = reinterpret_cast<const float2 *>(p_gt); g.v_gt = reinterpret_cast<const float2 *>(v_gt);
+    g.a_gt = reinterpret_cast<const float2 *>(a_gt); g.dest_gt = reinterpret_cast<const float2 *>(dest_gt);
+    g.dest_idx_gt = dest_idx_gt; g.hist_v = reinterpret_cast<float2 *>(hist_v);
+    g.rec_p = reinterpret_cast<float2 *>(rec_p); g.rec_v = reinterpret_cast<float2 *>(rec_v);
+    g.rec_a = reinterpret_cast<float2 *>(rec_a); g.rec_mask = rec_mask;
+    const int threads = 128;
+    integrate_kernel<<<static_cast<unsigned>((tot + threads - 1) / threads), threads, 0,
+                       static_cast<cudaStream_t>(stream)>>>(g);
+    count_launch();
+    return check_launch("integrate_kernel");
+}

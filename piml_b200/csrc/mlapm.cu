@@ -1,0 +1,340 @@
+// mlapm.cu -- dense all-pairs MLAPM force for sm_100a.
+//
+// Replaces MLAPM.step (reference src/models/mlapm.py:10-58) and the loop body of src/main_mlapm.py:19-34.
+// The reference materialises (N,N,2)x4 + (N,N,2,2) + (N,N)x6 temporaries (~100 B per ordered pair); here each thread
+// keeps R rows in registers and streams the columns through shared memory (TMA bulk copies of position / velocity
+// tiles, double buffered), so DRAM traffic is O(N) and the kernel is bound by the FP32 and MUFU pipes.
+//
+// Grid: (row blocks of 128*R rows) x (column splits).  Each CTA writes its partial row sums to workspace[split][row];
+// a finalize kernel adds the splits in a fixed order (deterministic), applies the destination term and the Euler
+// update.  The field-of-view gate `v_n . (p_m - p_n) > 0` uses the reference's exact fp32 form
+// fmaf(v1, r1, v0*r0) (einsum -> bmm); the force magnitude only has to hold 1e-5 relative, which
+// both math variants below do:
+//   EXACT: IEEE div / sqrt / expf in the reference's operation order (validation variant)
+//   fast : rsqrt.approx + ex2.approx, shared 1/r, constant-angle rotation folded into two FMAs (production)
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace piml {
+
+constexpr int ML_THREADS = 128;
+constexpr int ML_TILE = 512;          // columns per shared-memory stage: 4 KB positions + 4 KB velocities
+
+struct MlConst {
+    int version;
+    float A, B, C, D;                  // reference constants
+    float Bl, Cl, Dl;                  // pre-multiplied by log2(e) for ex2
+    float cos_t, sin_t;                // cos/sin of theta (fp32 angle as the reference builds it)
+    float inv_tau, tau;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {            // one MUFU.EX2
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {          // one MUFU.RSQ
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Stage one tile of positions and velocities (n float2 each) on ONE mbarrier phase.  All threads call it.
+__device__ __forceinline__ bool stage_tile_pv(float2 *dp, float2 *dv, const float2 *gp, const float2 *gv, int n,
+                                              uint64_t *bar) {
+    const bool tma = ((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(gv)) & 15u) == 0 && n >= 2;
+    if (tma) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(n & ~1) * 8u;
+            mbar_expect_tx(bar, 2u * bytes);
+            tma_bulk_g2s(dp, gp, bytes, bar);
+            tma_bulk_g2s(dv, gv, bytes, bar);
+            if (n & 1) { dp[n - 1] = gp[n - 1]; dv[n - 1] = gv[n - 1]; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { dp[i] = gp[i]; dv[i] = gv[i]; }
+    }
+    return tma;
+}
+
+// One ordered pair, production math.  ~37 issue slots for version GC.
+template <int VERSION>
+__device__ __forceinline__ void pair_fast(float px, float py, float vx, float vy, float ex, float ey, float2 pm,
+                                          float2 vm, const MlConst &k, float &fx, float &fy) {
+    const float rx = __fsub_rn(pm.x, px);
+    const float ry = __fsub_rn(pm.y, py);
+    const float gate = (__fmaf_rn(vy, ry, __fmul_rn(vx, rx)) > 0.f) ? k.A : 0.f;     // exact FoV gate (mlapm.py:27)
+    const float r2 = fmaf(ry, ry, rx * rx);
+    const float inv_r = rsqrt_approx(fmaxf(r2, 1e-30f));
+    const float r = r2 * inv_r;
+    if (VERSION == 0) {
+        const float w = gate * ex2_approx(k.Bl * r) * inv_r;          // view*A*exp(B r) * vr/|vr|   (mlapm.py:29)
+        fx = fmaf(w, rx, fx);
+        fy = fmaf(w, ry, fy);
+    } else {
+        const float ux = vm.x - vx, uy = vm.y - vy;
+        const float u2 = fmaf(uy, uy, ux * ux);
+        const float dot = fmaf(ry, uy, rx * ux);
+        const float cosv = dot * inv_r * rsqrt_approx(fmaxf(u2, 1e-30f));   // cosine_similarity(vr, vv)  (mlapm.py:32)
+        const float cross = fmaf(rx, ey, -(ry * ex));                 // sign picks +-theta           (mlapm.py:33-34)
+        const float s = (cross > 0.f) ? -k.sin_t : k.sin_t;
+        const float dx = fmaf(k.cos_t, rx, -(s * ry));                // R(theta) * vr                (mlapm.py:35-38)
+        const float dy = fmaf(s, rx, k.cos_t * ry);
+        const float arg = fmaf(fmaf(k.Dl, r, k.Cl), cosv, k.Bl * r);  // (B r + C cos + D r cos) * log2 e
+        const float w = gate * ex2_approx(arg) * inv_r;
+        fx = fmaf(w, dx, fx);
+        fy = fmaf(w, dy, fy);
+    }
+}
+
+// One ordered pair in the reference's own operation order with IEEE arithmetic (validation variant).
+template <int VERSION>
+__device__ __forceinline__ void pair_exact(float px, float py, float vx, float vy, float ex, float ey, float2 pm,
+                                           float2 vm, const MlConst &k, float &fx, float &fy) {
+    const float rx = __fsub_rn(pm.x, px);
+    const float ry = __fsub_rn(pm.y, py);
+    const float r = norm2_rn(rx, ry);
+    const float gate = (__fmaf_rn(vy, ry, __fmul_rn(vx, rx)) > 0.f) ? 1.f : 0.f;
+    const float nr = fmaxf(r, 1e-12f);
+    const float nx = __fdiv_rn(rx, nr), ny = __fdiv_rn(ry, nr);
+    const float ga = __fmul_rn(gate, k.A);
+    if (VERSION == 0) {
+        const float e = expf(__fmul_rn(k.B, r));
+        fx = __fadd_rn(fx, __fmul_rn(__fmul_rn(ga, e), nx));
+        fy = __fadd_rn(fy, __fmul_rn(__fmul_rn(ga, e), ny));
+    } else {
+        const float ux = __fsub_rn(vm.x, vx), uy = __fsub_rn(vm.y, vy);
+        const float cr = fmaxf(r, 1e-8f), cu = fmaxf(norm2_rn(ux, uy), 1e-8f);
+        const float cosv = __fadd_rn(__fmul_rn(__fdiv_rn(rx, cr), __fdiv_rn(ux, cu)),
+                                     __fmul_rn(__fdiv_rn(ry, cr), __fdiv_rn(uy, cu)));
+        const float cross = __fsub_rn(__fmul_rn(rx, ey), __fmul_rn(ry, ex));
+        const float s = (cross > 0.f) ? -k.sin_t : k.sin_t;
+        const float dx = __fadd_rn(__fmul_rn(k.cos_t, nx), __fmul_rn(-s, ny));
+        const float dy = __fadd_rn(__fmul_rn(s, nx), __fmul_rn(k.cos_t, ny));
+        const float arg = __fadd_rn(__fadd_rn(__fmul_rn(k.B, r), __fmul_rn(k.C, cosv)),
+                                    __fmul_rn(__fmul_rn(k.D, r), cosv));
+        const float e = expf(arg);
+        fx = __fadd_rn(fx, __fmul_rn(__fmul_rn(ga, e), dx));
+        fy = __fadd_rn(fy, __fmul_rn(__fmul_rn(ga, e), dy));
+    }
+}
+
+// partial[split][row - row0] = sum over this split's columns of  view*A*exp(..)*direc
+template <int VERSION, int R, bool EXACT>
+__global__ void __launch_bounds__(ML_THREADS) mlapm_pairs_kernel(const float2 *__restrict__ pos,
+                                                                 const float2 *__restrict__ vel,
+                                                                 const float2 *__restrict__ dest, int N, int row0,
+                                                                 int row1, int cols_per_split, MlConst k,
+                                                                 float2 *__restrict__ partial) {
+    __shared__ __align__(16) float2 sp[2][ML_TILE];
+    __shared__ __align__(16) float2 sv[2][ML_TILE];
+    __shared__ __align__(8) uint64_t bars[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nrows = row1 - row0;
+    const int rbase = blockIdx.x * (ML_THREADS * R);
+    float px[R], py[R], vx[R], vy[R], ex[R], ey[R], fx[R], fy[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        int rl = rbase + i * ML_THREADS + threadIdx.x;
+        rl = rl < nrows ? rl : nrows - 1;
+        const int n = row0 + rl;
+        const float2 p = pos[n], v = vel[n], d = dest[n];
+        px[i] = p.x; py[i] = p.y; vx[i] = v.x; vy[i] = v.y;
+        // ed = F.normalize(destination - position)   (mlapm.py:21)
+        const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
+        const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
+        ex[i] = __fdiv_rn(dx, dn); ey[i] = __fdiv_rn(dy, dn);
+        fx[i] = 0.f; fy[i] = 0.f;
+    }
+
+    const int c0 = blockIdx.y * cols_per_split;
+    const int c1 = min(N, c0 + cols_per_split);
+    const int ncols = c1 - c0;
+    const int ntiles = (ncols + ML_TILE - 1) / ML_TILE;
+    uint32_t phase_bits = 0;
+    bool waits[2] = {false, false};
+    if (ntiles > 0) {
+        const int tn = min(ncols, ML_TILE);
+        waits[0] = stage_tile_pv(sp[0], sv[0], pos + c0, vel + c0, tn, &bars[0]);
+    }
+    __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) {
+            const int m1 = c0 + (t + 1) * ML_TILE;
+            const int tn1 = min(c1 - m1, ML_TILE);
+            waits[buf ^ 1] = stage_tile_pv(sp[buf ^ 1], sv[buf ^ 1], pos + m1, vel + m1, tn1, &bars[buf ^ 1]);
+        }
+        if (waits[buf]) {
+            mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= (1u << buf);
+        }
+        const int tn = min(c1 - (c0 + t * ML_TILE), ML_TILE);
+        const float2 *tp = sp[buf];
+        const float2 *tv = sv[buf];
+#pragma unroll 2
+        for (int j = 0; j < tn; ++j) {
+            const float2 pm = tp[j];
+            const float2 vm = tv[j];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if (EXACT) pair_exact<VERSION>(px[i], py[i], vx[i], vy[i], ex[i], ey[i], pm, vm, k, fx[i], fy[i]);
+                else pair_fast<VERSION>(px[i], py[i], vx[i], vy[i], ex[i], ey[i], pm, vm, k, fx[i], fy[i]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int rl = rbase + i * ML_THREADS + threadIdx.x;
+        if (rl < nrows) partial[static_cast<int64_t>(blockIdx.y) * nrows + rl] = make_float2(fx[i], fy[i]);
+    }
+}
+
+// force = (v0*ed - v)/tau - sum_splits partial ; action = v + force*dt ; optional p' = p + action*dt and arrival.
+__global__ void mlapm_finalize_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+                                      const float *__restrict__ ds, int ds_dim, const float2 *__restrict__ dest,
+                                      int row0, int row1, int nsplit, const float2 *__restrict__ partial, float tau,
+                                      float dt, float radius, float2 *__restrict__ action,
+                                      float2 *__restrict__ pos_new, uint8_t *__restrict__ arrived) {
+    const int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = row1 - row0;
+    if (rl >= nrows) return;
+    const int n = row0 + rl;
+    const float2 p = pos[n], v = vel[n], d = dest[n];
+    const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
+    const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
+    const float ex = __fdiv_rn(dx, dn), ey = __fdiv_rn(dy, dn);
+    const float dsx = ds[static_cast<int64_t>(n) * ds_dim];
+    const float dsy = ds[static_cast<int64_t>(n) * ds_dim + (ds_dim > 1 ? 1 : 0)];
+    // force += (desired_speed * ed - velocity) / tau      (mlapm.py:22)
+    float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
+    float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
+    float sx = 0.f, sy = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float2 q = partial[static_cast<int64_t>(s) * nrows + rl];
+        sx = __fadd_rn(sx, q.x); sy = __fadd_rn(sy, q.y);
+    }
+    fx = __fsub_rn(fx, sx); fy = __fsub_rn(fy, sy);               // force -= (...).sum(dim=1)   (mlapm.py:29/39)
+    const float ax = __fadd_rn(v.x, __fmul_rn(fx, dt));           // action = velocity + force*dt (mlapm.py:57)
+    const float ay = __fadd_rn(v.y, __fmul_rn(fy, dt));
+    action[rl] = make_float2(ax, ay);
+    if (pos_new || arrived) {
+        const float qx = __fadd_rn(p.x, __fmul_rn(ax, dt));       // p = position + v*dt          (main_mlapm.py:26)
+        const float qy = __fadd_rn(p.y, __fmul_rn(ay, dt));
+        if (pos_new) pos_new[rl] = make_float2(qx, qy);
+        if (arrived)                                              // ||p - destination|| < radius (main_mlapm.py:34)
+            arrived[rl] = norm2_rn(__fsub_rn(qx, d.x), __fsub_rn(qy, d.y)) < radius ? 1 : 0;
+    }
+}
+
+constexpr int ML_MAX_SPLIT = 64;
+
+static int pick_rows_per_thread(int64_t nrows) { return nrows >= 4096 ? 4 : (nrows >= 1024 ? 2 : 1); }
+
+// Column splits: enough CTAs for ~8 waves over the SMs, each split a multiple of ML_TILE columns.
+static void pick_split(int64_t nrows, int64_t N, int R, int *nsplit, int *cols_per_split) {
+    const int64_t row_blocks = (nrows + ML_THREADS * R - 1) / (ML_THREADS * R);
+    const int64_t want_ctas = 8LL * 6 * sm_count();
+    int64_t s = (want_ctas + row_blocks - 1) / row_blocks;
+    const int64_t max_by_cols = (N + ML_TILE - 1) / ML_TILE;
+    if (s > max_by_cols) s = max_by_cols;
+    if (s > ML_MAX_SPLIT) s = ML_MAX_SPLIT;
+    if (s < 1) s = 1;
+    int64_t cps = (N + s - 1) / s;
+    cps = (cps + ML_TILE - 1) / ML_TILE * ML_TILE;
+    *cols_per_split = static_cast<int>(cps);
+    *nsplit = static_cast<int>((N + cps - 1) / cps);
+}
+
+template <int VERSION, bool EXACT>
+static void launch_pairs(int R, dim3 grid, cudaStream_t st, const float2 *pos, const float2 *vel, const float2 *dest,
+                         int N, int row0, int row1, int cps, const MlConst &k, float2 *partial) {
+    if (R == 4)
+        mlapm_pairs_kernel<VERSION, 4, EXACT><<<grid, ML_THREADS, 0, st>>>(pos, vel, dest, N, row0, row1, cps, k, partial);
+    else if (R == 2)
+        mlapm_pairs_kernel<VERSION, 2, EXACT><<<grid, ML_THREADS, 0, st>>>(pos, vel, dest, N, row0, row1, cps, k, partial);
+    else
+        mlapm_pairs_kernel<VERSION, 1, EXACT><<<grid, ML_THREADS, 0, st>>>(pos, vel, dest, N, row0, row1, cps, k, partial);
+}
+
+}  // namespace piml
+
+using namespace piml;
+
+extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
+    if (N < 0) return 0;
+    return static_cast<int64_t>(ML_MAX_SPLIT) * N * 2 * sizeof(float) + 256;
+}
+
+extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                      const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                      const piml_mlapm_params *prm, float dt, float radius, float *action,
+                                      float *pos_new, uint8_t *arrived, void *workspace, void *stream) {
+    PIML_REQUIRE(pos && vel && desired_speed && dest && prm && action && workspace, "piml_mlapm: null pointer");
+    PIML_REQUIRE(ds_dim == 1 || ds_dim == 2, "piml_mlapm: desired_speed must be (N,1) or (N,2), got ds_dim=%d", ds_dim);
+    PIML_REQUIRE(N >= 0 && N < (1LL << 31), "piml_mlapm: N=%lld out of range", static_cast<long long>(N));
+    PIML_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= N, "piml_mlapm: bad row range [%lld,%lld) for N=%lld",
+                 static_cast<long long>(row0), static_cast<long long>(row1), static_cast<long long>(N));
+    PIML_REQUIRE(prm->version == 0 || prm->version == 1,
+                 "piml_mlapm: version %d unsupported (0='raw', 1='GC'; 'UCY' is not runnable in the reference)",
+                 prm->version);
+    PIML_REQUIRE((reinterpret_cast<uintptr_t>(pos) & 7u) == 0 && (reinterpret_cast<uintptr_t>(vel) & 7u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dest) & 7u) == 0 && (reinterpret_cast<uintptr_t>(action) & 7u) == 0,
+                 "piml_mlapm: pointers must be 8-byte aligned");
+    const int64_t nrows = row1 - row0;
+    if (nrows == 0) return PIML_OK;
+
+    MlConst k;
+    k.version = prm->version;
+    k.A = prm->A; k.B = prm->B; k.C = prm->C; k.D = prm->D;
+    const double log2e = 1.4426950408889634;
+    k.Bl = static_cast<float>(prm->B * log2e); k.Cl = static_cast<float>(prm->C * log2e);
+    k.Dl = static_cast<float>(prm->D * log2e);
+    // theta tensor as the reference builds it in fp32: ((+-1 * theta) / 180) * pi   (mlapm.py:33)
+    const float th = (prm->theta_deg / 180.0f) * 3.14159274101257324f;
+    k.cos_t = static_cast<float>(cos(static_cast<double>(th)));
+    k.sin_t = static_cast<float>(sin(static_cast<double>(th)));
+    k.tau = prm->tau; k.inv_tau = 1.0f / prm->tau;
+
+    const int R = pick_rows_per_thread(nrows);
+    int nsplit, cps;
+    pick_split(nrows, N, R, &nsplit, &cps);
+    dim3 grid(static_cast<unsigned>((nrows + ML_THREADS * R - 1) / (ML_THREADS * R)), static_cast<unsigned>(nsplit));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float2 *p2 = reinterpret_cast<const float2 *>(pos), *v2 = reinterpret_cast<const float2 *>(vel);
+    const float2 *d2 = reinterpret_cast<const float2 *>(dest);
+    float2 *partial = reinterpret_cast<float2 *>(workspace);
+    const int iN = static_cast<int>(N), r0 = static_cast<int>(row0), r1 = static_cast<int>(row1);
+    if (prm->version == 0) {
+        if (prm->exact_math) launch_pairs<0, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+        else launch_pairs<0, false>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+    } else {
+        if (prm->exact_math) launch_pairs<1, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+        else launch_pairs<1, false>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+    }
+    count_launch();
+    int rc = check_launch("mlapm_pairs_kernel");
+    if (rc) return rc;
+    const int threads = 256;
+    mlapm_finalize_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+        p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial, prm->tau, dt, radius,
+        reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived);
+    count_launch();
+    return check_launch("mlapm_finalize_kernel");
+}
+
+extern "C" int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                   const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                   const piml_mlapm_params *prm, float dt, float *action, void *workspace,
+                                   void *stream) {
+    return piml_mlapm_advance_f32(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, 0.f, action,
+                                  nullptr, nullptr, workspace, stream);
+}

@@ -1,0 +1,295 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the build container only:   python tests/golden/make_golden.py [group ...]
+Groups: features models mlapm sfm rollout training.   Output: tests/golden/*.npz (small, compressed).
+
+The reference ships no tests and no golden vectors, so these files ARE the pin: they
+hold the reference's own outputs on its own data files (GC / UCY / toy clips) and on seeded synthetic crowds.
+Nothing here is imported at test time; tests only np.load the .npz files.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _refharness as H  # noqa: E402
+
+DATA, MODEL, MLAPM, SIM, UTILS = H.import_reference()
+torch.set_num_threads(1)        # reproducible fp32 reductions
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def synthetic_crowd(N, M, seed=666, rho=0.5):
+    """SURVEY.md 8d config 4 recipe (scenarios.py:363-366 flavoured). Returns fp32 tensors."""
+    g = torch.Generator().manual_seed(seed)
+    L = float(np.sqrt(N / rho))
+    p = torch.rand(N, 2, generator=g) * L
+    dest = torch.rand(N, 2, generator=g) * L
+    e = dest - p
+    e = e / e.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+    v = 1.34 * e * (0.5 + 0.5 * torch.rand(N, 1, generator=g)) + 0.1 * torch.randn(N, 2, generator=g)
+    a = torch.zeros(N, 2)
+    ds = (1.34 + np.sqrt(0.26) * torch.randn(N, 1, generator=g)).clamp_min(0.7)
+    rings = max(M // 200, 1)
+    per = M // rings
+    ang = torch.arange(per) * (2 * np.pi / per)
+    obs = []
+    for r in range(rings):
+        cx, cy = (r % 5 + 0.5) * L / 5, (r // 5 + 0.5) * L / 2
+        obs.append(torch.stack([cx + 2.75 * ang.cos(), cy + 2.75 * ang.sin()], -1))
+    obs = torch.cat(obs, 0).float()[:M]
+    return p, v, a, dest, ds, obs
+
+
+def feature_case(name, p, v, a, d, obs, kp=6, ap=90, tp=4, ko=10, ao=90, to=4):
+    """Runs get_relative_features + the two get_nearby_obj_in_sight calls it makes (data.py:466-512)."""
+    ped = DATA.Pedestrians()
+    v_in, a_in = v.clone(), a.clone()
+    v_w, a_w = v.clone(), a.clone()
+    pf, of, df = ped.get_relative_features(p.clone(), v_w, a_w, d.clone(), obs.clone(), kp, ap, tp, ko, ao, to)
+    head = ped.get_heading_direction(v_w)
+    pd_, pi_ = ped.get_nearby_obj_in_sight(p.clone(), p.clone(), head, kp, ap)
+    dim = obs.dim()
+    T = p.shape[-3]
+    obs_t = obs.unsqueeze(-3).repeat(*([1] * (dim - 2) + [T] + [1, 1]))
+    od_, oi_ = ped.get_nearby_obj_in_sight(p.clone(), obs_t, head, ko, ao)
+    pre = name + "/"
+    return {pre + "position": p, pre + "velocity": v_in, pre + "acceleration": a_in, pre + "destination": d,
+            pre + "obstacles": obs, pre + "params": np.array([kp, ap, tp, ko, ao, to], np.int64),
+            pre + "velocity_after": v_w, pre + "acceleration_after": a_w, pre + "heading": head,
+            pre + "ped_features": pf, pre + "obs_features": of, pre + "dest_features": df,
+            pre + "ped_dist": pd_, pre + "ped_idx": pi_.to(torch.int32), pre + "obs_dist": od_,
+            pre + "obs_idx": oi_.to(torch.int32)}
+
+
+def gen_features():
+    out = {}
+    raw = H.load_raw(H.GC_CLIP)
+    ts = [25, 100, 180, 260, 333, 410, 555, 700]
+    out.update(feature_case("gc", raw.position[ts], raw.velocity[ts], raw.acceleration[ts], raw.destination[ts],
+                            raw.obstacles))
+    # a contiguous window: exercises the heading forward/backward fill over time (last frame of a ped has v=0)
+    sl = slice(300, 340)
+    out.update(feature_case("gc_window", raw.position[sl], raw.velocity[sl], raw.acceleration[sl],
+                            raw.destination[sl], raw.obstacles))
+    ucy = H.load_raw(H.UCY_CLIP)
+    ts = [0, 50, 200, 400, 600, 675]
+    out.update(feature_case("ucy", ucy.position[ts], ucy.velocity[ts], ucy.acceleration[ts], ucy.destination[ts],
+                            ucy.obstacles))
+    toy = H.load_raw(H.TOY_CLIP)
+    sl = slice(20, 60)
+    out.update(feature_case("toy", toy.position[sl], toy.velocity[sl], toy.acceleration[sl], toy.destination[sl],
+                            toy.obstacles))
+    p, v, a, d, ds, obs = synthetic_crowd(512, 2000)
+    out.update(feature_case("syn512", p[None], v[None], a[None], d[None], obs))
+    # wide field of view (self is selected at distance 0, SURVEY B-6), odd k / thresholds, NaN agents, NaN v/a
+    p, v, a, d, ds, obs = synthetic_crowd(300, 400, seed=7)
+    p[::17] = float('nan'); d[::17] = float('nan'); v[::17] = 0; v[5] = float('nan'); a[9] = float('nan')
+    v[40:60] = 0
+    out.update(feature_case("syn300_wide", p[None], v[None], a[None], d[None], obs, 4, 100, 3, 7, 120, 5))
+    # channelled (C,T,N,2) with per-channel obstacles and stationary stretches
+    g = torch.Generator().manual_seed(11)
+    Cc, T, N, M = 3, 5, 40, 12
+    p = torch.rand(Cc, T, N, 2, generator=g) * 9
+    v = torch.randn(Cc, T, N, 2, generator=g)
+    v[:, 1:3, ::3] = 0
+    v[1, :, 7] = 0
+    v[2, 4, :] = 0
+    a = torch.randn(Cc, T, N, 2, generator=g)
+    d = torch.rand(Cc, T, N, 2, generator=g) * 9
+    p[0, :, 3] = float('nan'); d[0, :, 3] = float('nan')
+    obs = torch.rand(Cc, M, 2, generator=g) * 9
+    out.update(feature_case("channelled", p, v, a, d, obs))
+    save("features", **out)
+
+
+def model_args(kind, small=False, obs=True, dataset_name='ucy'):
+    a = H.default_args(model=kind, dataset_name=dataset_name, obs_feature_dim=6 if obs else 0)
+    if small:
+        a.encoder_hidden_size = 32; a.processor_hidden_size = 32; a.decoder_hidden_size = 16
+        a.encoder_hidden_layers = 2; a.processor_hidden_layers = 1; a.decoder_hidden_layers = 1
+    return a
+
+
+MODEL_CLASSES = {'pinnsf': 'PINNSF', 'pinnsf_bottleneck': 'PINNSF_bottleneck',
+                 'pinnsf_bm': 'PINNSF_bottleneck_multitask', 'pinnsf_m': 'PINNSF_multitask'}
+
+
+def build_model(kind, args, seed=666):
+    torch.manual_seed(seed)
+    m = getattr(MODEL, MODEL_CLASSES[kind])(args)
+    m.eval()
+    return m
+
+
+def gen_models():
+    raw = H.load_raw(H.GC_CLIP)
+    args0 = H.default_args()
+    d = H.make_time_indexed(args0, raw)
+    t = 333
+    ped, obs, slf = d.ped_features[t].clone(), d.obs_features[t].clone(), d.self_features[t].clone()
+    chan = slice(330, 334)
+    pedc, obsc, slfc = d.ped_features[chan].clone(), d.obs_features[chan].clone(), d.self_features[chan].clone()
+    out = {"ped": ped, "obs": obs, "self": slf, "ped_c": pedc, "obs_c": obsc, "self_c": slfc}
+    cases = [("pinnsf_bm", False, True, 'gc1560'), ("pinnsf_m", False, True, 'ucy'),
+             ("pinnsf_bottleneck", True, True, 'ucy'), ("pinnsf", True, False, 'ucy')]
+    for kind, small, has_obs, dsn in cases:
+        args = model_args(kind, small, has_obs, dsn)
+        m = build_model(kind, args)
+        pre = kind + "/"
+        for k, v in m.state_dict().items():
+            out[pre + "sd/" + k] = v
+        out[pre + "cfg"] = np.array([args.encoder_hidden_size, args.processor_hidden_size, args.decoder_hidden_size,
+                                     args.encoder_hidden_layers, args.processor_hidden_layers,
+                                     args.decoder_hidden_layers, 1 if has_obs else 0], np.int64)
+        out[pre + "dataset_name"] = np.array(dsn)
+        out[pre + "tau"] = np.float64(m.tau)
+        with torch.no_grad():
+            res = m(ped, obs, slf)
+            resc = m(pedc, obsc, slfc)
+        for i, r in enumerate(res):
+            out[pre + f"out{i}"] = r
+        for i, r in enumerate(resc):
+            out[pre + f"outc{i}"] = r
+    save("models", **out)
+
+
+def gen_mlapm():
+    out = {}
+    # main_mlapm.py:6-36 scene, seeded
+    torch.manual_seed(0)
+    N, dt, radius = 7, 0.08, 0.3
+    theta = torch.linspace(0, 2 * torch.pi * (1 - 1. / N), N)
+    position = torch.stack([10 * theta.cos(), 10 * theta.sin()], dim=-1).view(-1, 1, 2)
+    velocity = torch.rand(N, 1, 2)
+    mask = torch.full([N, 1, 1], True)
+    desired_speed = torch.full([N, 2], 1.5)
+    destination = -position.view(-1, 2)
+    model = MLAPM.MLAPM(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
+    for i in range(200):
+        v = model.step(position[mask[:, -1, 0], -1, :], velocity[mask[:, -1, 0], -1, :],
+                       desired_speed[mask[:, -1, 0], :], destination[mask[:, -1, 0], :], dt=dt, radius=radius)
+        p = position[mask[:, -1, 0], -1, :] + v * dt
+        position = torch.concat([position, torch.full([N, 1, 2], float('nan'))], dim=1)
+        velocity = torch.concat([velocity, torch.full([N, 1, 2], float('nan'))], dim=1)
+        mask = torch.concat([mask, mask[:, (-1,), :]], dim=1)
+        position[mask[:, -1, 0], -1, :] = p
+        velocity[mask[:, -1, 0], -1, :] = v
+        mask[:, -1, :] &= ~((position[:, -1, :] - destination).norm(dim=-1, keepdim=True) < radius)
+        if not mask.any():
+            break
+    out.update({"circle/position": position, "circle/velocity": velocity, "circle/mask": mask[:, :, 0],
+                "circle/desired_speed": desired_speed, "circle/destination": destination})
+    kw = dict(tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
+    for N in (257, 1000):
+        p, v, a, d, ds, obs = synthetic_crowd(N, 200, seed=N)
+        for ver in ("raw", "GC"):
+            m = MLAPM.MLAPM(version=ver, **kw)
+            act = m.step(p, v, ds, d, dt=0.08)
+            out[f"syn{N}/{ver}/action"] = act
+        vr = p.view(1, -1, 2) - p.view(-1, 1, 2)
+        view = torch.einsum('nk,nmk->nm', v, vr) > 0.          # mlapm.py:27
+        out[f"syn{N}/view_bits"] = np.packbits(view.numpy())
+        out.update({f"syn{N}/position": p, f"syn{N}/velocity": v, f"syn{N}/desired_speed": ds,
+                    f"syn{N}/destination": d})
+    # (N,2) desired speed as main_mlapm passes it, non-default parameters
+    p, v, a, d, ds, obs = synthetic_crowd(300, 200, seed=3)
+    ds2 = torch.cat([ds, ds * 1.1], -1)
+    m = MLAPM.MLAPM(version='GC', tau=0.7, A=5.0, B=-2.0, C=0.1, D=-0.2, theta=30)
+    out.update({"syn300b/position": p, "syn300b/velocity": v, "syn300b/desired_speed": ds2,
+                "syn300b/destination": d, "syn300b/GC/action": m.step(p, v, ds2, d, dt=0.05),
+                "syn300b/params": np.array([0.7, 5.0, -2.0, 0.1, -0.2, 30, 0.05])})
+    save("mlapm", **out)
+
+
+def gen_sfm():
+    raw = H.load_raw(H.GC_CLIP)
+    d = H.make_time_indexed(H.default_args(), raw)
+    ped = d.ped_features[333].clone()                    # (N,6,6)
+    out = {"ped": ped}
+    for ver, dsn in (("v0", "gc1560"), ("v0", "ucy"), ("v1", "gc2344"), ("v1", "ucy"), ("v2", "gc2344")):
+        out[f"{ver}/{dsn}"] = UTILS.calc_acceleration(ped.clone(), ver, dsn)
+    pc = d.ped_features[330:334].clone()                 # (4,N,6,6) -> the 'bnmj' einsum branch
+    out["ped_c"] = pc
+    out["v2c/gc2344"] = UTILS.calc_acceleration(pc.clone(), "v2", "gc2344")
+    out["v0c/gc1560"] = UTILS.calc_acceleration(pc.clone(), "v0", "gc1560")
+    save("sfm", **out)
+
+
+def rollout_case(clip, kind, dataset_name, t_start=25, seed=666, max_frames=None):
+    """BaseSimulator.get_multiple_rollouts (simulators.py:556-657) on a deepcopy of the clip, recording the state
+    handed to get_relative_features each step (= the reference's own p/v/a/dest after update + entry)."""
+    raw = H.load_raw(clip)
+    args = H.default_args(model=kind, dataset_name=dataset_name)
+    data = H.make_time_indexed(args, raw)
+    if max_frames is not None and max_frames < data.num_frames:
+        data.num_frames = max_frames
+    args.ped_feature_dim, args.obs_feature_dim, args.self_feature_dim = 6, 6, 7
+    torch.manual_seed(seed)
+    with H.quiet():
+        sim = SIM.BaseSimulator(args)
+    sim.model.eval()
+    inp = {}
+    for k in ("position", "velocity", "acceleration", "destination", "waypoints", "obstacles", "mask_p",
+              "mask_p_pred", "dest_num"):
+        inp[k] = getattr(data, k).clone()
+    inp["dest_idx"] = data.dest_idx.clone().to(torch.int32)
+    inp["desired_speed"] = data.self_features[t_start, :, -1].clone()
+    inp["ped_features0"] = data.ped_features[t_start].clone()
+    inp["obs_features0"] = data.obs_features[t_start].clone()
+    inp["self_features0"] = data.self_features[t_start].clone()
+    rec_dest, rec_idx = [], []
+    orig = sim.get_relative_features
+
+    def spy(p, v, a, dst, *rest):
+        rec_dest.append(dst.squeeze(-3).clone())
+        return orig(p, v, a, dst, *rest)
+    sim.get_relative_features = spy
+    work = copy.deepcopy(data)
+    with H.quiet(), torch.no_grad():
+        res = sim.get_multiple_rollouts(work, t_start=t_start, load_model=False)
+    T = data.num_frames
+    out = {"in/" + k: v for k, v in inp.items()}
+    out["in/t_start"] = np.int64(t_start)
+    out["in/num_frames"] = np.int64(T)
+    out["in/time_unit"] = np.float64(data.time_unit)
+    out["in/model"] = np.array(kind)
+    out["in/dataset_name"] = np.array(dataset_name)
+    out["in/tau"] = np.float64(sim.model.tau)
+    for k, v in sim.model.state_dict().items():
+        out["sd/" + k] = v
+    out["out/position"] = res.position[:T]
+    out["out/velocity"] = res.velocity[:T]
+    out["out/acceleration"] = res.acceleration[:T]
+    out["out/mask_p"] = res.mask_p[:T]
+    out["out/dest_after_step"] = torch.stack(rec_dest, 0)     # (T - t_start, N, 2): dest_cur after step t
+    return out
+
+
+def gen_rollout():
+    save("rollout_gc_bm", **rollout_case(H.GC_CLIP, "pinnsf_bm", "gc1560"))
+    save("rollout_toy5_m", **rollout_case(H.TOY_CLIP, "pinnsf_m", "ucy", t_start=25))
+    save("rollout_ucy_bm", **rollout_case(H.UCY_CLIP, "pinnsf_bm", "ucy", t_start=25, max_frames=200))
+
+
+GROUPS = {"features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
+          "rollout": gen_rollout}
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or list(GROUPS)
+    for gname in which:
+        GROUPS[gname]()
