@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the PIML crowd-rollout hot path on B200 (contract in the task statement, tier (4)).
+
+Headline workload (BASELINE.json configs[3], the one the north-star target is quoted on): the discovered MLAPM
+model's rollout loop (reference src/main_mlapm.py:18-36 -> src/models/mlapm.py:10-58) on a synthetic crowd of
+N = 100 000 agents (SURVEY.md 8d recipe, rho = 0.5 ped/m^2).  A "step" is one iteration of that loop: dense all-pairs
+force (N^2 ordered pairs), destination term, v' = v + F dt, p' = p + v' dt, arrival test.
+
+  value     device-resident agent-steps/s over all ranks (N agents * K steps / max-over-ranks device time)
+  e2e       the same step through the public host-buffer API (piml_b200.MLAPM.advance with pinned CPU tensors),
+            H2D + kernels + D2H inside the timed region
+  roofline  the all-pairs kernel against the FP32 FMA peak measured live by an FMA-chain probe (the kernel is
+            FP32/MUFU-pipe bound, DRAM traffic is O(N)); algorithmic work = 51 FLOP per ordered pair
+  cpu_baseline  the oracle's C port of MLAPM.step timed on the host cores on a bounded row sample (rank 0, N=1 only)
+
+Multi-GPU (--gpus N under torchrun): the crowd is agent-sharded -- rank g owns rows [g N/G, (g+1) N/G), computes them
+against all N columns, and the new positions/velocities are exchanged with ONE NCCL all-gather per step (strong
+scaling at fixed N).   --impl reference times the reference's CPU algorithm (oracle port, all host threads).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "agent_steps_per_sec"
+UNIT = "agent-steps/s"
+FLOP_PER_PAIR = 51.0          # SURVEY.md 8d, MLAPM-GC per ordered pair
+MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)     # main_mlapm.py:16
+DT, RADIUS = 0.08, 0.3
+
+
+def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
+    """p ~ U[0,L)^2, L = sqrt(N/rho); v = 1.34 e_dest U(0.5,1) + N(0,0.1^2);
+    desired_speed ~ max(0.7, 1.34 + sqrt(0.26) N(0,1)); destination ~ U[0,L)^2; M obstacle points on rings."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    L = math.sqrt(N / rho)
+    p = torch.rand(N, 2, generator=g) * L
+    dest = torch.rand(N, 2, generator=g) * L
+    e = dest - p
+    e = e / e.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+    v = 1.34 * e * (0.5 + 0.5 * torch.rand(N, 1, generator=g)) + 0.1 * torch.randn(N, 2, generator=g)
+    ds = (1.34 + math.sqrt(0.26) * torch.randn(N, 1, generator=g)).clamp_min(0.7)
+    rings = max(M // 200, 1)
+    per = max(M // rings, 1)
+    ang = torch.arange(per) * (2 * math.pi / per)
+    obs = torch.cat([torch.stack([(r % 5 + 0.5) * L / 5 + 2.75 * ang.cos(),
+                                  (r // 5 + 0.5) * L / 2 + 2.75 * ang.sin()], -1) for r in range(rings)], 0)[:M]
+    return p.float(), v.float(), ds.float(), dest.float(), obs.float()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(N, seconds=12.0, threads=None):
+    """Oracle C port of MLAPM.step (mlapm.py:10-58) on the host cores, rows [0,R) against all N columns."""
+    from oracle import oracle as O
+    import numpy as np
+    if threads:
+        O.set_num_threads(threads)
+    cores = O.num_threads()
+    p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
+    probe = max(8, cores * 2)
+    t0 = time.perf_counter()
+    O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))
+    rate = probe / max(time.perf_counter() - t0, 1e-6)            # rows/s
+    R = int(min(N, max(probe, rate * seconds)))
+    t0 = time.perf_counter()
+    out = O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, R))
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out).all()
+    return {"value": R / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle C port (OpenMP, {cores} threads) of MLAPM.step: rows [0,{R}) x all {N} columns, "
+                      f"{R * N / dt / 1e6:.1f} Mpairs/s, {dt:.1f} s"}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU algorithm for this path (oracle port; the Python reference itself
+    cannot run N = 100k -- one (N,N,2) fp32 temporary is 80 GB -- and does not travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    import numpy as np
+    N = a.agents
+    cores = O.num_threads()
+    p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
+    probe = max(8, cores * 2)
+    t0 = time.perf_counter()
+    O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    budget = 90.0 / max(a.steps + a.warmup, 1)                     # whole run within a few minutes
+    R = int(min(N, max(probe, rate * min(budget, 10.0))))
+    for _ in range(a.warmup):
+        O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, R))
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        r0 = (s * R) % max(N - R, 1)
+        O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(r0, r0 + R))
+    dt = time.perf_counter() - t0
+    val = R * a.steps / dt
+    sample = (f"each step = rows [r0,r0+{R}) x all {N} columns of one MLAPM.step (oracle C port, OpenMP {cores} "
+              f"threads); {R * N * a.steps / dt / 1e6:.1f} Mpairs/s")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "sample_rows_per_step": R},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def probe_peaks(L, torch, dev):
+    """FP32 FMA and MUFU pipe peaks, measured live with the library's probe kernels (best of 5)."""
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    ctas, iters = sms * 8, 4096
+    out = torch.empty(ctas * 256, device=dev)
+    res = {}
+    for which, name, per in ((0, "fp32_tflops", 2.0), (1, "mufu_tops", 1.0)):
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.load().piml_pipe_probe(which, ctas, iters, L.ptr(out), L.stream_ptr(dev)), "piml_pipe_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = max(best, ctas * 256 * iters * 32 * per / (ms * 1e-3) / 1e12)
+        res[name] = best
+    return res
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import piml_b200 as P
+    from piml_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the piml_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = a.agents
+    if N % world:
+        raise SystemExit(f"--agents {N} must be divisible by the number of ranks {world}")
+    shard = N // world
+    r0, r1 = rank * shard, (rank + 1) * shard
+
+    p_h, v_h, ds_h, dest_h, obs_h = [x.pin_memory() for x in synthetic_crowd(N)]
+    pos, vel, ds, dest = p_h.to(dev), v_h.to(dev), ds_h.to(dev), dest_h.to(dev)
+    model = P.MLAPM(**MLAPM_KW)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    pos_next, vel_next = torch.empty_like(pos), torch.empty_like(vel)
+
+    def step():
+        nonlocal pos, vel, pos_next, vel_next
+        flush.zero_()                                                   # L2 flush between steps
+        act, pnew, arrived = model.advance(pos, vel, ds, dest, DT, RADIUS, rows=(r0, r1))
+        if world > 1:                                                   # the path's one exchange step
+            dist.all_gather_into_tensor(pos_next, pnew)
+            dist.all_gather_into_tensor(vel_next, act)
+            pos, pos_next = pos_next, pos
+            vel, vel_next = vel_next, vel
+        else:
+            pos, vel = pnew, act
+        return arrived
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    peaks = probe_peaks(L, torch, dev) if rank == 0 else {}
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    # ---- device-resident timed region: EXACTLY K steps --------------------------------------------------------
+    sync_all()
+    launches0 = L.launch_count()
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps):
+        flush.zero_()
+        k_ev[s][0].record()
+        act, pnew, arrived = model.advance(pos, vel, ds, dest, DT, RADIUS, rows=(r0, r1))
+        k_ev[s][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(pos_next, pnew)
+            dist.all_gather_into_tensor(vel_next, act)
+            pos, pos_next = pos_next, pos
+            vel, vel_next = vel_next, vel
+        else:
+            pos, vel = pnew, act
+    e1.record()
+    sync_all()
+    launches = L.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    kernel_ms = torch.tensor([sum(x.elapsed_time(y) for x, y in k_ev) / a.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+    ms, kernel_ms = float(ms), float(kernel_ms)
+    assert torch.isfinite(pos).all(), "non-finite positions after the timed rollout"
+
+    # ---- end-to-end through the public host-buffer API ------------------------------------------------------------
+    act_h = torch.empty(shard, 2).pin_memory()
+    pnew_h = torch.empty(shard, 2).pin_memory()
+    arr_h = torch.empty(shard, dtype=torch.bool).pin_memory()
+
+    def e2e_step():
+        act, pnew, arrived = model.advance(p_h, v_h, ds_h, dest_h, DT, RADIUS, rows=(r0, r1))   # host in, host out
+        act_h.copy_(act); pnew_h.copy_(pnew); arr_h.copy_(arrived)
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    g1.record()
+    sync_all()
+    wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = torch.tensor([max(g0.elapsed_time(g1), wall)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+    if sampler:
+        sampler.stop()
+    h2d = (p_h.numel() + v_h.numel() + ds_h.numel() + dest_h.numel()) * 4
+    d2h = (act_h.numel() + pnew_h.numel()) * 4 + arr_h.numel()
+
+    if rank == 0:
+        pairs = float(shard) * N                       # ordered pairs one launch of the pairs kernel evaluates
+        achieved = FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12
+        peak = peaks.get("fp32_tflops") or None
+        line = {
+            "metric": METRIC, "value": N * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "obstacle_points": int(obs_h.shape[0]),
+                       "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
+                       "parallelism": f"agent-sharded rows x{world}" + (" + NCCL all-gather/step" if world > 1 else ""),
+                       "l2": "256 MB memset between steps, inside the timed region"},
+            "roofline": {"bound": "fp32", "kernel": "mlapm_pairs_kernel<GC,R=4,fast> (+finalize)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if peak else None, "traffic": None,
+                         "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
+                                        "MEASURED_PEAKS.json",
+                         "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
+                         "pairs_per_sec": pairs / (kernel_ms * 1e-3), "mufu_peak_tops": peaks.get("mufu_tops")},
+            "e2e": {"value": N * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
+                    "api": "piml_b200.MLAPM.advance(pinned host tensors) -> host tensors"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if world == 1 and not a.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(N)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=100000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

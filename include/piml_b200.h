@@ -24,29 +24,41 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define PIML_API __attribute__((visibility("default")))
+#else
+#define PIML_API
+#endif
+
 #define PIML_OK 0
 #define PIML_ERR_INVALID 1   /* bad argument (shape, k too large, misaligned pointer, ...) */
 #define PIML_ERR_CUDA 2      /* a CUDA runtime call or kernel launch failed */
 #define PIML_ERR_UNSUPPORTED 3
 
-int piml_version(void);
-const char *piml_last_error(void);
+PIML_API int piml_version(void);
+PIML_API const char *piml_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches counter). */
-int64_t piml_launch_count(void);
+PIML_API int64_t piml_launch_count(void);
 /* compute capability major*10+minor of the current device, SM count; <0 on error */
-int piml_device_info(int *sm_count, int *cc);
+PIML_API int piml_device_info(int *sm_count, int *cc);
+
+/* Pipe-throughput probe used by bench.py for the roofline denominators (no reference counterpart):
+ * which = 0: `ctas` CTAs x 256 threads each run iters*32 dependent-chain FFMAs on 8 independent chains
+ *            (FLOPs = ctas*256*iters*32*2);  which = 1: the same with MUFU.EX2 (ops = ctas*256*iters*32).
+ * out: ctas*256 floats. */
+PIML_API int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream);
 
 /* ---- features: src/data/data.py:351-512 ------------------------------------------------------------------ */
 
 /* Pedestrians.get_heading_direction (data.py:351-395).  vel (C,T,N,2) -> head (C,T,N,2): zero-speed frames take
  * the nearest later, else nearest earlier, non-zero velocity of the same pedestrian; then v/||v|| (0 stays 0). */
-int piml_heading_f32(const float *vel, int C, int T, int N, float *head, void *stream);
+PIML_API int piml_heading_f32(const float *vel, int C, int T, int N, float *head, void *stream);
 
 /* Pedestrians.get_nearby_obj_in_sight (data.py:416-447).  pos (B,N,2), obj (B,M,2) [obj_frame_stride = M*2] or
  * (M,2) shared by all frames [obj_frame_stride = 0], head (B,N,2).  k <= 32.
  * out_dist (B,N,kk) fp32 / out_idx (B,N,kk) int64, kk = min(k,M): the kk nearest objects inside the field of view
  * (cos(rel,head) >= cos_thr), ascending by (distance, index); out-of-view / NaN objects carry distance +inf. */
-int piml_select_neighbors_f32(const float *pos, const float *obj, int64_t obj_frame_stride, const float *head,
+PIML_API int piml_select_neighbors_f32(const float *pos, const float *obj, int64_t obj_frame_stride, const float *head,
                               int B, int N, int M, int k, float cos_thr, float *out_dist, int64_t *out_idx,
                               void *stream);
 
@@ -58,14 +70,24 @@ int piml_select_neighbors_f32(const float *pos, const float *obj, int64_t obj_fr
  * Outputs ped_f (C,T,N,kp',6), obs_f (C,T,N,ko',6), dest_f (C,T,N,2); kp'=min(kp,N), ko'=min(ko,M); kp,ko <= 32.
  * Optional (NULL to skip) selection outputs: *_idx int64 (-1 = empty slot) and *_dist (+inf = empty slot),
  * holding only neighbours with distance <= threshold. */
-int piml_relative_features_f32(const float *pos, float *vel, float *acc, const float *dest, const float *head,
+PIML_API int piml_relative_features_f32(const float *pos, float *vel, float *acc, const float *dest, const float *head,
                                const float *obs, int obs_per_channel, int C, int T, int N, int M, int kp,
                                float cos_thr_ped, float dist_thr_ped, int ko, float cos_thr_obs,
                                float dist_thr_obs, float *ped_f, float *obs_f, float *dest_f, int64_t *ped_idx,
                                float *ped_dist, int64_t *obs_idx, float *obs_dist, void *stream);
 
+/* The per-step feature rebuild of the rollout loops (simulators.py:642-652 / :772-778) for S scenes of N slots
+ * (one frame each): get_relative_features as above (heading = v/||v||) plus
+ * self_f (S,N,7) = cat(dest_features, hist_v, acceleration, desired_speed) written by the same kernel.
+ * obs (M,2) [obs_per_scene=0] or (S,M,2).  hist_v (S,N,2), desired_speed (S,N). */
+PIML_API int piml_state_features_f32(const float *pos, float *vel, float *acc, const float *dest, const float *obs,
+                            int obs_per_scene, int S, int N, int M, int kp, float cos_thr_ped, float dist_thr_ped,
+                            int ko, float cos_thr_obs, float dist_thr_obs, const float *hist_v,
+                            const float *desired_speed, float *ped_f, float *obs_f, float *self_f, float *dest_f,
+                            void *stream);
+
 /* Pedestrians.calculate_collision_label (data.py:515-535). ped_f (S,6) -> out (S) in {0,1}. */
-int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream);
+PIML_API int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream);
 
 /* ---- MLAPM: src/models/mlapm.py:10-58, loop src/main_mlapm.py:18-36 ----------------------------------------- */
 
@@ -77,13 +99,13 @@ typedef struct {
 } piml_mlapm_params;
 
 /* Bytes of workspace piml_mlapm_step_f32 needs for N agents (column-split partial sums). */
-int64_t piml_mlapm_workspace_bytes(int64_t N);
+PIML_API int64_t piml_mlapm_workspace_bytes(int64_t N);
 
 /* MLAPM.step for rows [row0,row1) against all N columns: action (row1-row0,2) = velocity + force*dt.
  * pos, vel, dest (N,2); desired_speed (N,ds_dim), ds_dim 1 or 2.  workspace >= piml_mlapm_workspace_bytes(N).
  * Dense all-pairs O(N^2), no cut-off, like the reference.  (row0,row1) lets an agent-sharded rank compute its
  * own rows after an all-gather of (pos,vel). */
-int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+PIML_API int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
                         const float *dest, int64_t N, int64_t row0, int64_t row1, const piml_mlapm_params *prm,
                         float dt, float *action, void *workspace, void *stream);
 
@@ -91,7 +113,7 @@ int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired
  *   action = MLAPM.step(..) ; pos_new = pos + action*dt ; arrived = ||pos_new - dest|| < radius  (uint8 0/1).
  * The caller compacts away inactive agents first, exactly as the reference's boolean-mask indexing does
  * (main_mlapm.py:20-23).  pos_new / arrived may be NULL. */
-int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+PIML_API int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
                            const float *dest, int64_t N, int64_t row0, int64_t row1,
                            const piml_mlapm_params *prm, float dt, float radius, float *action, float *pos_new,
                            uint8_t *arrived, void *workspace, void *stream);
@@ -100,7 +122,7 @@ int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desi
 
 /* UTILS.calc_acceleration.  rel (S, stride) with stride >= 4 floats per slot -> out (S,2).
  * version 0/1/2 = 'v0'/'v1'/'v2'; constants as the reference selects them per dataset. */
-int piml_calc_acceleration_f32(const float *rel, int64_t S, int stride, int version, float A, float B, float C,
+PIML_API int piml_calc_acceleration_f32(const float *rel, int64_t S, int stride, int version, float A, float B, float C,
                                float D, float theta, float eps, float *out, void *stream);
 
 /* ---- interaction networks: src/models/model.py:40-119, :720-792, :1062-1305 -------------------------------- */
@@ -120,7 +142,7 @@ typedef struct {
  * (the (N,7) call); = N: reduce over the agent axis per component ((C,N,7) call, model.py:1206 dim=1 quirk).
  * drop_ped / drop_obs: NULL, or (R,k,pw) multipliers applied to the processor output (Dropout in train()).
  * Outputs acc (R,2), ped_msgs (R,kp,msgw), obs_msgs (R,ko,msgw), coll (R,kp); any of the last three may be NULL. */
-int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *params, int has_obs, float tau,
+PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *params, int has_obs, float tau,
                             const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
                             int norm_group, const float *drop_ped, const float *drop_obs, float *acc,
                             float *ped_msgs, float *obs_msgs, float *coll, void *stream);
@@ -132,7 +154,7 @@ int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *params, int 
  *   p,v,a,dest (S,N,2) in/out; dest_idx (S,N) int64 in/out; a_next (S,N,2); dest_num (S,N) int64;
  *   waypoints (S,D,N,2); hist_v (S,N,2) out; entry (S,N) int64 or NULL; *_gt = ground truth at t+1, (S,N,..).
  *   rec_p/rec_v/rec_a (S,N,2) and rec_mask (S,N) fp32: where to record the state at t (NULL to skip). */
-int piml_integrate_step_f32(float *p, float *v, float *a, const float *a_next, float *dest, int64_t *dest_idx,
+PIML_API int piml_integrate_step_f32(float *p, float *v, float *a, const float *a_next, float *dest, int64_t *dest_idx,
                             const int64_t *dest_num, const float *waypoints, int S, int D, int N, float dt,
                             int remove_on_arrival, const int64_t *entry, const float *p_gt, const float *v_gt,
                             const float *a_gt, const float *dest_gt, const int64_t *dest_idx_gt, float *hist_v,

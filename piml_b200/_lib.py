@@ -34,10 +34,13 @@ SIGNATURES = {
     "piml_last_error": (C.c_char_p, []),
     "piml_launch_count": (i64, []),
     "piml_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
+    "piml_pipe_probe": (i32, [i32, i32, i32, vp, vp]),
     "piml_heading_f32": (i32, [vp, i32, i32, i32, vp, vp]),
     "piml_select_neighbors_f32": (i32, [vp, vp, i64, vp, i32, i32, i32, i32, f32, vp, vp, vp]),
     "piml_relative_features_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32,
                                          f32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "piml_state_features_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp,
+                                      vp, vp, vp, vp, vp]),
     "piml_collision_label_f32": (i32, [vp, i64, vp, vp]),
     "piml_mlapm_workspace_bytes": (i64, [i64]),
     "piml_mlapm_step_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, vp, vp, vp]),
@@ -81,10 +84,15 @@ def launch_count():
     return int(load().piml_launch_count())
 
 
-def require_cuda(*tensors):
-    """Every tensor argument of a compute entry point must live on one CUDA device."""
+def cuda_device():
     if not torch.cuda.is_available():
         raise RuntimeError("piml_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def require_cuda(*tensors):
+    """Every tensor argument of a compute entry point must live on one CUDA device."""
+    cuda_device()
     dev = None
     for t in tensors:
         if t is None:
@@ -95,6 +103,18 @@ def require_cuda(*tensors):
         if t.device != dev:
             raise RuntimeError("piml_b200: tensors on different devices")
     return dev
+
+
+def stage(*tensors):
+    """Host-buffer entry: returns (device, origin_device, [tensors on the device]).  CUDA tensors pass through;
+    host tensors are copied to the current CUDA device (the reference's scripts hand over CPU tensors).  The compute
+    itself always runs in libpiml_b200.so on the GPU."""
+    first = next(t for t in tensors if t is not None)
+    origin = first.device
+    dev = first.device if first.is_cuda else cuda_device()
+    out = [None if t is None else (t if t.is_cuda else t.to(dev, non_blocking=True)) for t in tensors]
+    require_cuda(*out)
+    return dev, origin, out
 
 
 def ptr(t):

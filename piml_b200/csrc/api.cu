@@ -39,7 +39,52 @@ int sm_count() {
     return cached;
 }
 
+// ---- pipe-throughput probes: measured denominators for the FP32 / MUFU roofline of the all-pairs kernels ----------
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = static_cast<float>(threadIdx.x + q) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = fmaf(x[q], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += x[q];
+    out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) mufu_probe_kernel(float *out, int iters) {
+    float x[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] = static_cast<float>(threadIdx.x + q) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x[q]) : "f"(-x[q]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += x[q];
+    out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace piml
+
+extern "C" int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream) {
+    PIML_REQUIRE(out && ctas > 0 && iters > 0, "piml_pipe_probe: bad arguments");
+    PIML_REQUIRE(which == 0 || which == 1, "piml_pipe_probe: which must be 0 (FP32 FMA) or 1 (MUFU ex2)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (which == 0) piml::fp32_probe_kernel<<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f);
+    else piml::mufu_probe_kernel<<<ctas, 256, 0, st>>>(out, iters);
+    piml::count_launch();
+    return piml::check_launch("pipe_probe_kernel");
+}
 
 extern "C" int piml_version(void) { return 100; }
 

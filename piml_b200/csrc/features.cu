@@ -124,6 +124,8 @@ struct FeatArgs {
     float cos_p, thr_p, pre2_p, cos_o, thr_o, pre2_o;
     float *ped_f; float *obs_f; float *dest_f;
     int64_t *ped_idx; float *ped_dist; int64_t *obs_idx; float *obs_dist;
+    // optional rollout extras: self_f (B,N,7) = [dest_f, hist_v, acceleration, desired_speed]  (simulators.py:651)
+    const float *hist_v; const float *desired_speed; float *self_f;
 };
 
 // grid = (ceil(N / (FEAT_THREADS/G)), B).  G lanes cooperate on one row.
@@ -206,8 +208,14 @@ __global__ void __launch_bounds__(FEAT_THREADS) relative_features_kernel(FeatArg
     // ---- destination (data.py:496-497) ----
     if (live && g == 0) {
         const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
-        reinterpret_cast<float2 *>(a.dest_f)[row] =
-            make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+        const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+        reinterpret_cast<float2 *>(a.dest_f)[row] = df;
+        if (a.self_f) {
+            const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
+            float *sf = a.self_f + row * 7;
+            sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
+            sf[6] = a.desired_speed[row];
+        }
     }
 
     // ---- pedestrian - obstacle (data.py:499-510): obs = (o, 0, 0) ----
@@ -394,12 +402,13 @@ extern "C" int piml_select_neighbors_f32(const float *pos, const float *obj, int
     return check_launch("select_kernel");
 }
 
-extern "C" int piml_relative_features_f32(const float *pos, float *vel, float *acc, const float *dest,
+static int relative_features_impl(const float *pos, float *vel, float *acc, const float *dest,
                                           const float *head, const float *obs, int obs_per_channel, int C, int T,
                                           int N, int M, int kp, float cos_thr_ped, float dist_thr_ped, int ko,
                                           float cos_thr_obs, float dist_thr_obs, float *ped_f, float *obs_f,
                                           float *dest_f, int64_t *ped_idx, float *ped_dist, int64_t *obs_idx,
-                                          float *obs_dist, void *stream) {
+                                          float *obs_dist, const float *hist_v, const float *desired_speed,
+                                          float *self_f, void *stream) {
     PIML_REQUIRE(pos && vel && acc && dest && ped_f && dest_f, "piml_relative_features_f32: null pointer");
     PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0 && M >= 0 && kp >= 0 && ko >= 0,
                  "piml_relative_features_f32: negative dimension");
@@ -420,6 +429,7 @@ extern "C" int piml_relative_features_f32(const float *pos, float *vel, float *a
     a.cos_o = cos_thr_obs; a.thr_o = dist_thr_obs; a.pre2_o = prefilter_sq(dist_thr_obs);
     a.ped_f = ped_f; a.obs_f = obs_f; a.dest_f = dest_f;
     a.ped_idx = ped_idx; a.ped_dist = ped_dist; a.obs_idx = obs_idx; a.obs_dist = obs_dist;
+    a.hist_v = hist_v; a.desired_speed = desired_speed; a.self_f = self_f;
     const int G = pick_group(B, N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kpp <= 8 && kop <= 16) launch_features<8, 16>(a, G, st);
@@ -427,6 +437,28 @@ extern "C" int piml_relative_features_f32(const float *pos, float *vel, float *a
     else launch_features<32, 32>(a, G, st);
     count_launch();
     return check_launch("relative_features_kernel");
+}
+
+extern "C" int piml_relative_features_f32(const float *pos, float *vel, float *acc, const float *dest,
+                                          const float *head, const float *obs, int obs_per_channel, int C, int T,
+                                          int N, int M, int kp, float cos_thr_ped, float dist_thr_ped, int ko,
+                                          float cos_thr_obs, float dist_thr_obs, float *ped_f, float *obs_f,
+                                          float *dest_f, int64_t *ped_idx, float *ped_dist, int64_t *obs_idx,
+                                          float *obs_dist, void *stream) {
+    return relative_features_impl(pos, vel, acc, dest, head, obs, obs_per_channel, C, T, N, M, kp, cos_thr_ped,
+                                  dist_thr_ped, ko, cos_thr_obs, dist_thr_obs, ped_f, obs_f, dest_f, ped_idx,
+                                  ped_dist, obs_idx, obs_dist, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int piml_state_features_f32(const float *pos, float *vel, float *acc, const float *dest, const float *obs,
+                                       int obs_per_scene, int S, int N, int M, int kp, float cos_thr_ped,
+                                       float dist_thr_ped, int ko, float cos_thr_obs, float dist_thr_obs,
+                                       const float *hist_v, const float *desired_speed, float *ped_f, float *obs_f,
+                                       float *self_f, float *dest_f, void *stream) {
+    PIML_REQUIRE(hist_v && desired_speed && self_f, "piml_state_features_f32: null pointer");
+    return relative_features_impl(pos, vel, acc, dest, nullptr, obs, obs_per_scene, S, 1, N, M, kp, cos_thr_ped,
+                                  dist_thr_ped, ko, cos_thr_obs, dist_thr_obs, ped_f, obs_f, dest_f, nullptr,
+                                  nullptr, nullptr, nullptr, hist_v, desired_speed, self_f, stream);
 }
 
 extern "C" int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream) {

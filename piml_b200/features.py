@@ -25,16 +25,16 @@ class Pedestrians(object):
     @staticmethod
     def get_heading_direction(velocity):
         """velocity (*c, t, N, 2) -> heading_direction, same shape (zero-speed frames filled, then normalised)."""
-        L.require_cuda(velocity)
         if velocity.dim() not in (3, 4):
             raise ValueError("get_heading_direction expects (t,N,2) or (c,t,N,2)")
+        _, origin, (velocity,) = L.stage(velocity)
         v = L.f32c(velocity)
         Cc = v.shape[0] if v.dim() == 4 else 1
         T, N = v.shape[-3], v.shape[-2]
         out = torch.empty_like(v)
         L.check(L.load().piml_heading_f32(L.ptr(v), Cc, T, N, L.ptr(out), L.stream_ptr(v.device)),
                 "piml_heading_f32")
-        return out
+        return out.to(origin)
 
     # ---- data.py:398-414 -------------------------------------------------------------------------------------
     @staticmethod
@@ -46,7 +46,7 @@ class Pedestrians(object):
     # ---- data.py:416-447 -------------------------------------------------------------------------------------
     def get_nearby_obj_in_sight(self, position, objects, heading_direction, k, angle_threshold):
         """Returns (sorted_dist[..., :k], indices[..., :k]); objects outside the field of view carry inf."""
-        L.require_cuda(position, objects, heading_direction)
+        _, origin, (position, objects, heading_direction) = L.stage(position, objects, heading_direction)
         pos, obj, head = L.f32c(position), L.f32c(objects), L.f32c(heading_direction)
         lead = pos.shape[:-2]
         N, M = pos.shape[-2], obj.shape[-2]
@@ -68,7 +68,7 @@ class Pedestrians(object):
                 L.C.c_void_p(dist.data_ptr() + done * N * kk * 4), L.C.c_void_p(idx.data_ptr() + done * N * kk * 8),
                 L.stream_ptr(pos.device)), "piml_select_neighbors_f32")
             done += nb
-        return dist, idx
+        return dist.to(origin), idx.to(origin)
 
     # ---- data.py:449-464 -------------------------------------------------------------------------------------
     def get_filtered_features(self, features, nearby_idx, nearby_dist, dist_threshold):
@@ -85,12 +85,12 @@ class Pedestrians(object):
         """position/velocity/acceleration/destination (*c, t, N, 2); obstacles (M, 2) or (c, M, 2).
         Returns ped_features (*c,t,N,k1,6), obs_features (*c,t,N,k2,6), dest_features (*c,t,N,2).
         Like the reference it zeroes NaNs IN PLACE in the caller's velocity and acceleration tensors."""
-        L.require_cuda(position, velocity, acceleration, destination, obstacles)
         if position.dim() not in (3, 4):
             raise ValueError("get_relative_features expects (t,N,2) or (c,t,N,2) inputs")
-        pos, dest = L.f32c(position), L.f32c(destination)
-        vel, acc = L.f32c(velocity), L.f32c(acceleration)
-        obs = L.f32c(obstacles)
+        _, origin, (pos, vel, acc, dest, obs) = L.stage(position, velocity, acceleration, destination, obstacles)
+        pos, dest = L.f32c(pos), L.f32c(dest)
+        vel, acc = L.f32c(vel), L.f32c(acc)
+        obs = L.f32c(obs)
         lead = pos.shape[:-2]
         Cc = pos.shape[0] if pos.dim() == 4 else 1
         T, N = pos.shape[-3], pos.shape[-2]
@@ -129,6 +129,9 @@ class Pedestrians(object):
             velocity.copy_(vel)
         if acc.data_ptr() != acceleration.data_ptr():
             acceleration.copy_(acc)
+        if origin != dev:
+            ped_f, obs_f, dest_f = ped_f.to(origin), obs_f.to(origin), dest_f.to(origin)
+            sel = tuple(s_.to(origin) for s_ in sel) if sel else None
         if return_selection:
             return ped_f, obs_f, dest_f, sel
         return ped_f, obs_f, dest_f
@@ -137,9 +140,9 @@ class Pedestrians(object):
     @staticmethod
     def calculate_collision_label(ped_features):
         """ped_features (..., k, 6) -> collisions (..., k) in {0, 1}."""
-        L.require_cuda(ped_features)
+        _, origin, (ped_features,) = L.stage(ped_features)
         f = L.f32c(ped_features)
         out = torch.empty(f.shape[:-1], dtype=torch.float32, device=f.device)
         L.check(L.load().piml_collision_label_f32(L.ptr(f), out.numel(), L.ptr(out), L.stream_ptr(f.device)),
                 "piml_collision_label_f32")
-        return out
+        return out.to(origin)

@@ -33,7 +33,8 @@ class MLAPM:
 
     @staticmethod
     def _prep(position, velocity, desired_speed, destination):
-        dev = L.require_cuda(position, velocity, desired_speed, destination)
+        dev, origin, (position, velocity, desired_speed, destination) = L.stage(position, velocity, desired_speed,
+                                                                                 destination)
         pos, vel, dest = L.f32c(position), L.f32c(velocity), L.f32c(destination)
         ds = L.f32c(desired_speed)
         if ds.dim() == 1:
@@ -42,12 +43,12 @@ class MLAPM:
             raise ValueError("MLAPM.step expects position, velocity, destination of shape [N, 2]")
         if ds.shape[0] != pos.shape[0] or ds.shape[1] not in (1, 2):
             raise ValueError("MLAPM.step expects desired_speed of shape [N, 1] or [N, 2]")
-        return dev, pos, vel, ds, dest
+        return dev, origin, pos, vel, ds, dest
 
     def step(self, position, velocity, desired_speed, destination, dt, radius=0.3, rows=None):
         """position, velocity, destination [N,2]; desired_speed [N,1] or [N,2].  Returns velocity + force*dt.
         rows=(r0, r1): only those rows (agent-sharded ranks), output shape [r1-r0, 2]."""
-        dev, pos, vel, ds, dest = self._prep(position, velocity, desired_speed, destination)
+        dev, origin, pos, vel, ds, dest = self._prep(position, velocity, desired_speed, destination)
         N = pos.shape[0]
         r0, r1 = rows if rows is not None else (0, N)
         action = torch.empty(r1 - r0, 2, dtype=torch.float32, device=dev)
@@ -56,11 +57,11 @@ class MLAPM:
                                              L.C.byref(prm), float(dt), L.ptr(action),
                                              L.ptr(self._workspace(N, dev)), L.stream_ptr(dev)),
                 "piml_mlapm_step_f32")
-        return action
+        return action if origin == dev else action.to(origin)
 
     def advance(self, position, velocity, desired_speed, destination, dt, radius=0.3, rows=None):
         """Fused main_mlapm.py:19-34 body: returns (action, new_position, arrived[bool])."""
-        dev, pos, vel, ds, dest = self._prep(position, velocity, desired_speed, destination)
+        dev, origin, pos, vel, ds, dest = self._prep(position, velocity, desired_speed, destination)
         N = pos.shape[0]
         r0, r1 = rows if rows is not None else (0, N)
         action = torch.empty(r1 - r0, 2, dtype=torch.float32, device=dev)
@@ -71,13 +72,16 @@ class MLAPM:
                                                 r1, L.C.byref(prm), float(dt), float(radius), L.ptr(action),
                                                 L.ptr(pnew), L.ptr(arrived), L.ptr(self._workspace(N, dev)),
                                                 L.stream_ptr(dev)), "piml_mlapm_advance_f32")
+        if origin != dev:
+            return action.to(origin), pnew.to(origin), arrived.bool().to(origin)
         return action, pnew, arrived.bool()
 
 
 def rollout(model, position, velocity, desired_speed, destination, steps=200, dt=0.08, radius=0.3):
     """The loop of reference src/main_mlapm.py:18-36 (without the plot).  position/velocity [N,2] initial state.
     Returns (position [N,steps'+1,2], velocity [N,steps'+1,2], mask [N,steps'+1]) with NaN after arrival."""
-    dev = L.require_cuda(position, velocity, desired_speed, destination)
+    dev, origin, (position, velocity, desired_speed, destination) = L.stage(position, velocity, desired_speed,
+                                                                             destination)
     N = position.shape[0]
     pos = torch.full((N, steps + 1, 2), float('nan'), device=dev)
     vel = torch.full((N, steps + 1, 2), float('nan'), device=dev)
@@ -93,4 +97,4 @@ def rollout(model, position, velocity, desired_speed, destination, steps=200, dt
         done = i + 1
         if not bool(mask[:, i + 1].any()):                     # main_mlapm.py:36
             break
-    return pos[:, :done + 1], vel[:, :done + 1], mask[:, :done + 1]
+    return pos[:, :done + 1].to(origin), vel[:, :done + 1].to(origin), mask[:, :done + 1].to(origin)

@@ -1,0 +1,347 @@
+"""Parity of the CUDA path (through the C ABI, via the piml_b200 host adapters) against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded synthetic inputs.  Run on the B200 box: pytest -m gpu.
+
+Gates: neighbour sets / distances / features bit-exact; forces, MLP outputs within 1e-5 relative
+(per-vector 2-norm); positions and velocities of a re-synchronised rollout step bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.util import golden, group, rel_vec_err, untied_finite, valid_sets
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def cu(x, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(x), dtype=dtype).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+FEATURE_CASES = ["gc", "gc_window", "ucy", "toy", "syn512", "syn300_wide", "channelled"]
+
+
+@pytest.mark.parametrize("case", FEATURE_CASES)
+def test_relative_features_golden(case):
+    import piml_b200 as P
+    g = group(golden("features"), case)
+    kp, ap, tp, ko, ao, to = [int(v) for v in g["params"]]
+    vel, acc = cu(g["velocity"]), cu(g["acceleration"])
+    ped = P.Pedestrians()
+    pf, of, df, (pi, pd, oi, od) = ped.get_relative_features(
+        cu(g["position"]), vel, acc, cu(g["destination"]), cu(g["obstacles"]), kp, ap, tp, ko, ao, to,
+        return_selection=True)
+    assert np.array_equal(npy(df), g["dest_features"])
+    # slot order inside the radius is (distance, index) like the reference; compare slot by slot
+    assert np.array_equal(npy(pf), g["ped_features"])
+    assert np.array_equal(npy(of), g["obs_features"])
+    assert np.array_equal(npy(vel), g["velocity_after"]) and np.array_equal(npy(acc), g["acceleration_after"])
+    assert valid_sets(npy(pi), npy(pd), tp) == valid_sets(g["ped_idx"], g["ped_dist"], tp)
+    assert valid_sets(npy(oi), npy(od), to) == valid_sets(g["obs_idx"], g["obs_dist"], to)
+
+
+@pytest.mark.parametrize("case", FEATURE_CASES)
+def test_heading_and_selection_helpers_golden(case):
+    import piml_b200 as P
+    g = group(golden("features"), case)
+    kp, ap, tp, ko, ao, to = [int(v) for v in g["params"]]
+    ped = P.Pedestrians()
+    head = ped.get_heading_direction(cu(g["velocity_after"]))
+    assert np.array_equal(npy(head), g["heading"])
+    pos = cu(g["position"])
+    dist, idx = ped.get_nearby_obj_in_sight(pos, pos, head, kp, ap)
+    assert np.array_equal(npy(dist), g["ped_dist"])
+    fin = untied_finite(g["ped_dist"])
+    assert np.array_equal(npy(idx)[fin], g["ped_idx"][fin].astype(np.int64))
+    obs = cu(g["obstacles"])
+    T = pos.shape[-3]
+    obs_t = obs.unsqueeze(-3).repeat(*([1] * (obs.dim() - 2) + [T] + [1, 1]))      # data.py:502-503
+    dist, idx = ped.get_nearby_obj_in_sight(pos, obs_t, head, ko, ao)
+    assert np.array_equal(npy(dist), g["obs_dist"])
+    fin = untied_finite(g["obs_dist"])
+    assert np.array_equal(npy(idx)[fin], g["obs_idx"][fin].astype(np.int64))
+
+
+def _crowd(B, N, M, seed, rho=0.5, nan_frac=0.05):
+    rng = np.random.default_rng(seed)
+    L = np.sqrt(N / rho)
+    p = (rng.random((B, N, 2)) * L).astype(np.float32)
+    d = (rng.random((B, N, 2)) * L).astype(np.float32)
+    v = rng.normal(0, 1, (B, N, 2)).astype(np.float32)
+    a = rng.normal(0, 1, (B, N, 2)).astype(np.float32)
+    gone = rng.random((B, N)) < nan_frac
+    p[gone] = np.nan
+    d[gone] = np.nan
+    v[gone] = 0
+    v[rng.random((B, N)) < 0.03] = 0                      # stationary agents see nobody at 90 degrees
+    obs = (rng.random((M, 2)) * L).astype(np.float32)
+    return p, v, a, d, obs
+
+
+# (B, N, M) chosen to hit the three lane-group variants of the kernel: G=32, G=8, G=1 (see pick_group)
+@pytest.mark.parametrize("B,N,M", [(1, 3001, 2000), (8, 1500, 700), (40, 2000, 2000), (3, 7, 3), (2, 129, 0)])
+def test_relative_features_vs_oracle(B, N, M):
+    import piml_b200 as P
+    p, v, a, d, obs = _crowd(B, N, M, seed=B * 1000 + N)
+    want = O.relative_features(p, v.copy(), a.copy(), d, obs, 6, 90, 4, 10, 90, 4, return_selection=True)
+    ped = P.Pedestrians()
+    got = ped.get_relative_features(cu(p), cu(v), cu(a), cu(d), cu(obs).reshape(M, 2), 6, 90, 4, 10, 90, 4,
+                                    return_selection=True)
+    assert np.array_equal(npy(got[0]), want[0])
+    assert np.array_equal(npy(got[2]), want[2])
+    if M:
+        assert np.array_equal(npy(got[1]), want[1])
+    wpi, wpd, woi, wod = want[3]
+    gpi, gpd, goi, god = [npy(x) for x in got[3]]
+    assert valid_sets(gpi, gpd, 4) == valid_sets(wpi, wpd, 4)
+    if M:
+        assert valid_sets(goi, god, 4) == valid_sets(woi, wod, 4)
+
+
+def test_relative_features_large_k_and_angles():
+    import piml_b200 as P
+    p, v, a, d, obs = _crowd(2, 400, 300, seed=5)
+    for kp, ko, ang, thr in ((12, 20, 60, 6), (32, 32, 150, 3), (1, 1, 90, 4)):
+        want = O.relative_features(p, v.copy(), a.copy(), d, obs, kp, ang, thr, ko, ang, thr)
+        got = P.Pedestrians().get_relative_features(cu(p), cu(v), cu(a), cu(d), cu(obs), kp, ang, thr, ko, ang, thr)
+        for w, g_ in zip(want, got):
+            assert np.array_equal(npy(g_), w)
+
+
+def test_collision_label():
+    import piml_b200 as P
+    g = group(golden("features"), "gc")
+    want = O.collision_label(g["ped_features"])
+    got = P.Pedestrians.calculate_collision_label(cu(g["ped_features"]))
+    assert np.array_equal(npy(got), want)
+
+
+# ---- MLAPM -------------------------------------------------------------------------------------------------------
+GC_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("case,ver", [("syn257", "raw"), ("syn257", "GC"), ("syn1000", "raw"), ("syn1000", "GC")])
+def test_mlapm_step_golden(case, ver, exact):
+    import piml_b200 as P
+    g = group(golden("mlapm"), case)
+    kw = dict(GC_KW, version=ver, exact_math=exact)
+    act = P.MLAPM(**kw).step(cu(g["position"]), cu(g["velocity"]), cu(g["desired_speed"]), cu(g["destination"]),
+                             dt=0.08)
+    assert rel_vec_err(npy(act), g[ver + "/action"]) < TOL
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_mlapm_params_golden(exact):
+    import piml_b200 as P
+    g = group(golden("mlapm"), "syn300b")
+    tau, A, B, C_, D, th, dt = [float(v) for v in g["params"]]
+    m = P.MLAPM(version='GC', tau=tau, A=A, B=B, C=C_, D=D, theta=th, exact_math=exact)
+    act = m.step(cu(g["position"]), cu(g["velocity"]), cu(g["desired_speed"]), cu(g["destination"]), dt=dt)
+    assert rel_vec_err(npy(act), g["GC/action"]) < TOL
+
+
+def test_mlapm_circle_rollout_golden():
+    """main_mlapm.py scene: re-synchronised steps within 1e-5; free-running drift over 200 steps reported."""
+    import piml_b200 as P
+    from piml_b200.mlapm import rollout
+    g = group(golden("mlapm"), "circle")
+    pos, vel, mask = g["position"], g["velocity"], g["mask"]
+    model = P.MLAPM(**GC_KW)
+    worst = 0.0
+    for t in range(pos.shape[1] - 1):
+        m = mask[:, t]
+        if not m.any():
+            break
+        act, pnew, arrived = model.advance(cu(pos[m, t]), cu(vel[m, t]), cu(g["desired_speed"][m]),
+                                           cu(g["destination"][m]), 0.08, 0.3)
+        worst = max(worst, rel_vec_err(npy(act), vel[m, t + 1]))
+        assert np.array_equal(npy(arrived), ~mask[m, t + 1])
+    assert worst < TOL, worst
+    p, v, mk = rollout(model, cu(pos[:, 0]), cu(vel[:, 0]), cu(g["desired_speed"]), cu(g["destination"]), 200)
+    assert p.shape[1] == pos.shape[1] and np.array_equal(npy(mk), mask)
+    drift = np.nanmax(np.linalg.norm(npy(p) - pos, axis=-1))
+    print(f"free-running drift over {p.shape[1] - 1} steps: {drift:.3e} m")
+    assert drift < 1e-3
+
+
+@pytest.mark.parametrize("N", [4099, 8192])
+def test_mlapm_vs_oracle_and_row_ranges(N):
+    import piml_b200 as P
+    rng = np.random.default_rng(N)
+    L = np.sqrt(N / 0.5)
+    p = (rng.random((N, 2)) * L).astype(np.float32)
+    d = (rng.random((N, 2)) * L).astype(np.float32)
+    v = rng.normal(0, 1, (N, 2)).astype(np.float32)
+    ds = (1.34 + 0.3 * rng.normal(0, 1, (N, 1))).astype(np.float32)
+    want = O.mlapm_step(p, v, ds, d, 0.08, "GC")
+    model = P.MLAPM(**GC_KW)
+    full = npy(model.step(cu(p), cu(v), cu(ds), cu(d), 0.08))
+    assert rel_vec_err(full, want) < TOL
+    exact = npy(P.MLAPM(**dict(GC_KW, exact_math=True)).step(cu(p), cu(v), cu(ds), cu(d), 0.08))
+    assert rel_vec_err(exact, want) < TOL
+    # agent-sharded row ranges reproduce the full result bit-for-bit (SURVEY A.2b multi-GPU row)
+    r0, r1 = N // 3 + 1, 2 * N // 3
+    part = npy(model.step(cu(p), cu(v), cu(ds), cu(d), 0.08, rows=(r0, r1)))
+    assert rel_vec_err(part, want[r0:r1]) < TOL
+
+
+def test_mlapm_nan_poisons_like_reference():
+    """mlapm.py: view*A*exp(..)*direc is a product, so one NaN position makes every force NaN."""
+    import piml_b200 as P
+    g = group(golden("mlapm"), "syn257")
+    p = g["position"].copy()
+    p[17] = np.nan
+    act = npy(P.MLAPM(**GC_KW).step(cu(p), cu(g["velocity"]), cu(g["desired_speed"]), cu(g["destination"]), 0.08))
+    want = O.mlapm_step(p, g["velocity"], g["desired_speed"], g["destination"], 0.08, "GC")
+    assert np.isnan(want).all() and np.isnan(act).all()
+
+
+# ---- SFM -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["v0/gc1560", "v0/ucy", "v1/gc2344", "v1/ucy", "v2/gc2344"])
+def test_calc_acceleration_golden(key):
+    import piml_b200 as P
+    z = golden("sfm")
+    ver, ds = key.split("/")
+    out = npy(P.calc_acceleration(cu(z["ped"]), ver, ds))
+    assert rel_vec_err(out, z[key]) < TOL
+    assert np.array_equal(out == 0, z[key] == 0)
+    outc = npy(P.calc_acceleration(cu(z["ped_c"]), "v2", "gc2344"))
+    assert rel_vec_err(outc, z["v2c/gc2344"]) < TOL
+
+
+# ---- interaction networks ------------------------------------------------------------------------------------------
+def _mirror_model(z, kind):
+    from tests.golden_args import model_args
+    from piml_b200 import models as M
+    g = group(z, kind)
+    args = model_args(kind, g["cfg"], str(g["dataset_name"]))
+    m = M.CLASSES[kind](args)
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")})
+    return g, m.cuda().eval()
+
+
+@pytest.mark.parametrize("kind", ["pinnsf_bm", "pinnsf_m", "pinnsf_bottleneck", "pinnsf"])
+def test_pinnsf_forward_golden(kind):
+    z = golden("models")
+    g, m = _mirror_model(z, kind)
+    for suffix in ("", "c"):
+        tag = "_c" if suffix else ""
+        out = m(cu(z["ped" + tag]), cu(z["obs" + tag]), cu(z["self" + tag]))
+        refs = [g[f"out{suffix}{i}"] for i in range(len(out))]
+        assert len(out) == len([k for k in g if k.startswith("out" + suffix) and k[len("out" + suffix):].isdigit()])
+        for i, (o, ref) in enumerate(zip(out, refs)):
+            o = npy(o)
+            assert o.shape == ref.shape, (kind, suffix, i, o.shape, ref.shape)
+            if o.ndim >= 2 and o.shape[-1] in (2, 128, 32):
+                err = rel_vec_err(o, ref, floor=1e-3)
+            else:
+                err = float(np.abs(o - ref).max())
+            assert err < TOL, (kind, suffix, i, err)
+
+
+# ---- integrator ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
+def test_integrate_step_golden(name):
+    """Re-synchronised steps over the whole reference rollout: p, v, dest bit-exact."""
+    from piml_b200.rollout import integrate_step
+    z = golden(name)
+    i, o = group(z, "in"), group(z, "out")
+    T, t0, dt = int(i["num_frames"]), int(i["t_start"]), float(i["time_unit"])
+    flag = cu((i["mask_p"] - i["mask_p_pred"]), torch.int64)
+    P_, V_, A_ = cu(o["position"]), cu(o["velocity"]), cu(o["acceleration"])
+    gt = {k: cu(i[k]) for k in ("position", "velocity", "acceleration", "destination")}
+    gt_idx = cu(i["dest_idx"], torch.int64)
+    dest = cu(i["destination"][t0]).clone()
+    didx = cu(i["dest_idx"][t0], torch.int64).clone()
+    dnum = cu(i["dest_num"], torch.int64)
+    wp = cu(i["waypoints"])
+    for t in range(t0, T - 1):
+        p, v, a = P_[t].clone(), V_[t].clone(), A_[t].clone()
+        hist = torch.empty_like(v)
+        integrate_step(p, v, a, A_[t + 1], dest, didx, dnum, wp, dt, True, flag[t + 1], gt["position"][t + 1],
+                       gt["velocity"][t + 1], gt["acceleration"][t + 1], gt["destination"][t + 1], gt_idx[t + 1],
+                       hist)
+        assert torch.equal(torch.nan_to_num(p, nan=-7.0), torch.nan_to_num(P_[t + 1], nan=-7.0)), (name, t)
+        assert torch.equal(v, V_[t + 1]), (name, t)
+        assert np.array_equal(npy(dest), o["dest_after_step"][t - t0], equal_nan=True), (name, t)
+
+
+# ---- whole rollout ---------------------------------------------------------------------------------------------------
+def _rollout_inputs(name):
+    from tests.golden_args import base_args
+    from piml_b200 import models as M
+    z = golden(name)
+    i, o = group(z, "in"), group(z, "out")
+    kind, dsn = str(i["model"]), str(i["dataset_name"])
+    args = base_args(model=kind, dataset_name=dsn, time_unit=float(i["time_unit"]))
+    m = M.CLASSES[kind](args)
+    zm = golden("models")                       # the rollout fixtures use the seed-666 weights stored in models.npz
+    sd = {k[3:]: torch.from_numpy(v) for k, v in group(zm, kind).items() if k.startswith("sd/")}
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    return z, i, o, args, m
+
+
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
+def test_rollout_resynchronised_steps(name):
+    """From the reference's own state at step t: rebuild features, run the network, integrate.  The new acceleration
+    must be within 1e-5 (vector norm, relative to the typical |a| of the frame) of the reference's a[t+1]."""
+    from piml_b200.rollout import state_features
+    from piml_b200 import models as M
+    z, i, o, args, m = _rollout_inputs(name)
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    P_, V_, A_ = cu(o["position"]), cu(o["velocity"]), cu(o["acceleration"])
+    flag = i["mask_p"] - i["mask_p_pred"]
+    ds = cu(i["desired_speed"])[None]
+    obs = cu(i["obstacles"])
+    spec = m.spec
+    packed = M.pack_state_dict(m.state_dict(), spec).cuda()
+    worst = 0.0
+    for t in range(t0 + 1, T - 1, max(1, (T - t0) // 60)):
+        p, v, a = P_[t][None].clone(), V_[t][None].clone(), A_[t][None].clone()
+        dest = cu(o["dest_after_step"][t - t0 - 1])[None]
+        hist = v.clone()                                    # hist_v == v_cur after the update (h = 1)
+        ped_f, obs_f, self_f = state_features(p, v, a, dest, obs, hist, ds, 6, 90, 4, 10, 90, 4)
+        acc = M.pinnsf_forward(spec, packed, ped_f[0], obs_f[0], self_f[0], need_msgs=False)[0]
+        sim = flag[t + 1] == 0                              # entering pedestrians are overwritten from the data
+        ref = o["acceleration"][t + 1][sim]
+        got = npy(acc)[sim]
+        scale = max(float(np.linalg.norm(ref, axis=-1).mean()), 1e-3)
+        err = float(np.linalg.norm(got - ref, axis=-1).max()) / scale
+        worst = max(worst, err)
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
+def test_rollout_free_running(name):
+    """Whole get_multiple_rollouts drop-in: NaN pattern and mask_p identical, drift reported (chaotic dynamics:
+    the reference drifts 3e-4..6e-3 m from itself after 725 steps under a 1-ulp perturbation)."""
+    from piml_b200.rollout import rollout_scenes
+    from piml_b200 import models as M
+    z, i, o, args, m = _rollout_inputs(name)
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    scene = {k: cu(i[k])[None] for k in ("position", "velocity", "acceleration", "destination", "waypoints",
+                                          "mask_p", "mask_p_pred", "desired_speed")}
+    scene["dest_idx"] = cu(i["dest_idx"], torch.int64)[None]
+    scene["dest_num"] = cu(i["dest_num"], torch.int64)[None]
+    scene["obstacles"] = cu(i["obstacles"])
+    for k in ("ped_features0", "obs_features0", "self_features0"):
+        scene[k] = cu(i[k])[None]
+    packed = M.pack_state_dict(m.state_dict(), m.spec).cuda()
+    p_res, v_res, a_res, mask = rollout_scenes(m.spec, packed, args, scene, t0, T)
+    p_res, mask = npy(p_res[0]), npy(mask[0])
+    assert np.array_equal(mask, o["mask_p"])
+    drift = np.linalg.norm(p_res - o["position"], axis=-1)
+    same_nan = np.array_equal(np.isnan(p_res), np.isnan(o["position"]))
+    print(f"{name}: max drift {np.nanmax(drift):.3e} m over {T - t0} steps; NaN pattern identical: {same_nan}")
+    first = min(T, t0 + 26)
+    assert np.array_equal(np.isnan(p_res[:first]), np.isnan(o["position"][:first]))
+    assert np.nanmax(drift[:first]) < 1e-4
+    assert np.nanmax(drift) < 0.5

@@ -1,0 +1,59 @@
+"""CPU tests of the host-side logic: parameter packing, the module mirrors' state_dict/initialisation parity with
+the reference, spec derivation and the cos-threshold constant."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_args import base_args, model_args
+from tests.util import golden, group
+
+
+def test_cos_threshold_matches_reference_constant():
+    from piml_b200 import cos_threshold
+    assert np.float32(cos_threshold(90)) == np.float32(7.9632673e-4)
+    assert cos_threshold(100) < 0 < cos_threshold(60)
+
+
+@pytest.mark.parametrize("kind", ["pinnsf_bm", "pinnsf_m", "pinnsf_bottleneck", "pinnsf"])
+def test_mirror_modules_share_keys_and_seeded_init_with_reference(kind):
+    """Same state_dict keys/shapes as the reference classes, and torch.manual_seed(666) reproduces the reference's
+    initial weights bit-for-bit (sub-modules are created in the reference's order)."""
+    from piml_b200 import models as M
+    g = group(golden("models"), kind)
+    args = model_args(kind, g["cfg"], str(g["dataset_name"]))
+    torch.manual_seed(666)
+    m = M.CLASSES[kind](args)
+    sd = m.state_dict()
+    ref = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    assert sorted(sd) == sorted(ref)
+    for k in sd:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k
+    assert m.tau == pytest.approx(float(g["tau"]))
+
+
+def test_pack_layouts():
+    from piml_b200 import models as M
+    g = group(golden("models"), "pinnsf_bm")
+    args = model_args("pinnsf_bm", g["cfg"], "gc1560")
+    spec = M.spec_from_args("pinnsf_bm", args)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
+    a = M.pack_state_dict(sd, spec, transposed=True)
+    b = M.pack_state_dict(sd, spec, transposed=False)
+    n_branch = 6 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 64 + 64 + 64 * 64 + 64 + 64 * 2 + 2
+    assert a.numel() == b.numel() == 2 * n_branch + 64 * 64 + 64 + 64 + 1
+    w0 = sd["ped_encoder.mlp.0.weight"]
+    assert torch.equal(b[:768].view(128, 6), w0) and torch.equal(a[:768].view(6, 128), w0.t())
+    # dead weights (ResDNN block-0 Linear when processor_hidden_layers > 1) are not packed
+    assert spec.proc_mode == 0 and not any("processor" in k for k in M.linear_keys(spec))
+
+
+def test_spec_from_module_matches_spec_from_args():
+    from piml_b200 import models as M
+    for kind, over in (("pinnsf_bm", {}), ("pinnsf_m", {}), ("pinnsf", dict(processor_hidden_layers=1,
+                                                                              encoder_hidden_size=32,
+                                                                              processor_hidden_size=32))):
+        args = base_args(model=kind, **over)
+        m = M.CLASSES[kind](args)
+        s1, s2 = M.spec_from_args(kind, args), M.spec_from_module(m)
+        for f in ("enc_dims", "proc_mode", "dec_dims", "coll_dims", "kind", "has_obs", "tau"):
+            assert getattr(s1, f) == getattr(s2, f), (kind, f)
