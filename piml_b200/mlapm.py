@@ -79,7 +79,9 @@ class MLAPM:
 
 def rollout(model, position, velocity, desired_speed, destination, steps=200, dt=0.08, radius=0.3):
     """The loop of reference src/main_mlapm.py:18-36 (without the plot).  position/velocity [N,2] initial state.
-    Returns (position [N,steps'+1,2], velocity [N,steps'+1,2], mask [N,steps'+1]) with NaN after arrival."""
+    Returns (position [N,steps+1,2], velocity [N,steps+1,2], mask [N,steps+1]) with NaN after arrival.  Like the
+    reference (whose `mask.any()` looks at ALL time steps and therefore never breaks early) the arrays always span
+    the full `steps`; once nobody is active the remaining columns stay NaN / False."""
     dev, origin, (position, velocity, desired_speed, destination) = L.stage(position, velocity, desired_speed,
                                                                              destination)
     N = position.shape[0]
@@ -87,14 +89,12 @@ def rollout(model, position, velocity, desired_speed, destination, steps=200, dt
     vel = torch.full((N, steps + 1, 2), float('nan'), device=dev)
     mask = torch.zeros(N, steps + 1, dtype=torch.bool, device=dev)
     pos[:, 0], vel[:, 0], mask[:, 0] = position, velocity, True
-    done = 0
     for i in range(steps):
         idx = mask[:, i].nonzero(as_tuple=True)[0]             # boolean-mask compaction, main_mlapm.py:20-23
         v, p, arrived = model.advance(pos[idx, i], vel[idx, i], desired_speed[idx], destination[idx], dt, radius)
         pos[idx, i + 1] = p
         vel[idx, i + 1] = v
         mask[idx, i + 1] = ~arrived                            # main_mlapm.py:34
-        done = i + 1
-        if not bool(mask[:, i + 1].any()):                     # main_mlapm.py:36
+        if not bool(mask[:, i + 1].any()):                     # nothing left to simulate
             break
-    return pos[:, :done + 1].to(origin), vel[:, :done + 1].to(origin), mask[:, :done + 1].to(origin)
+    return pos.to(origin), vel.to(origin), mask.to(origin)

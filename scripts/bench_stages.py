@@ -1,0 +1,108 @@
+"""Per-stage device timings of the hot path at the BASELINE shapes (not the headline bench; evidence for DESIGN.md).
+
+    python scripts/bench_stages.py [--agents 100000] [--scenes 4096]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import piml_b200 as P  # noqa: E402
+from piml_b200 import models as M  # noqa: E402
+from piml_b200.rollout import integrate_step, state_features  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bm_args():
+    return argparse.Namespace(model='pinnsf_bm', dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128,
+                              processor_hidden_size=128, decoder_hidden_size=64, encoder_hidden_layers=3,
+                              processor_hidden_layers=16, decoder_hidden_layers=2, ped_feature_dim=6,
+                              obs_feature_dim=6, self_feature_dim=7)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--agents", type=int, default=100000)
+    ap.add_argument("--scenes", type=int, default=4096)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    out = {}
+    N = a.agents
+    p, v, ds, dest, obs = [x.to(dev) for x in bench.synthetic_crowd(N)]
+    acc = torch.zeros_like(v)
+    ped = P.Pedestrians()
+    fargs = (6, 90, 4, 10, 90, 4)
+    feats = ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs)
+    ms = timeit(lambda: ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs))
+    out["features_N%d_M%d" % (N, obs.shape[0])] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
+                                                  "pairs_per_s": N * (N + obs.shape[0]) / ms * 1e3}
+    torch.manual_seed(666)
+    net = M.PINNSF_bottleneck_multitask(bm_args()).to(dev).eval()
+    packed = M.pack_state_dict(net.state_dict(), net.spec).to(dev)
+    slf = torch.cat([feats[2][0], v, acc, ds], -1)
+    ms = timeit(lambda: M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False))
+    out["pinnsf_bm_forward_N%d" % N] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
+                                        "tflops": 1.52e6 * N / ms * 1e3 / 1e12}
+    # GC-shaped scenes, one NN rollout step (forward + integrate + features) for S scenes of 122 slots
+    S, Ns, Mo = a.scenes, 122, 100
+    g = torch.Generator().manual_seed(1)
+    pos = (torch.rand(S, Ns, 2, generator=g) * 20).to(dev)
+    pos[:, 30:] = float('nan')                                  # ~25% of the slots active, like the GC clips
+    vel = torch.randn(S, Ns, 2, generator=g).to(dev)
+    ac = torch.zeros(S, Ns, 2, device=dev)
+    dst = (torch.rand(S, Ns, 2, generator=g) * 20).to(dev)
+    ob = (torch.rand(Mo, 2, generator=g) * 20).to(dev)
+    dsp = torch.full((S, Ns), 1.3, device=dev)
+    hist = vel.clone()
+    didx = torch.zeros(S, Ns, dtype=torch.int64, device=dev)
+    dnum = torch.ones(S, Ns, dtype=torch.int64, device=dev)
+    wp = dst[:, None].contiguous()
+    pf, of, sf = state_features(pos, vel, ac, dst, ob, hist, dsp, *fargs)
+    bufs = (pf, of, sf, torch.empty(S, Ns, 2, device=dev))
+
+    def fwd():
+        return M.pinnsf_forward(net.spec, packed, pf.view(S * Ns, 6, 6), of.view(S * Ns, 10, 6), sf.view(S * Ns, 7),
+                                need_msgs=False)[0].view(S, Ns, 2)
+
+    def nn_step():
+        a_next = fwd()
+        integrate_step(pos, vel, ac, a_next, dst, didx, dnum, wp, 0.0, False, hist_v=hist)   # dt=0: state stays put
+        state_features(pos, vel, ac, dst, ob, hist, dsp, *fargs, out=bufs)
+    key = "nn_rollout_step_S%d_N%d" % (S, Ns)
+    ms = timeit(nn_step)
+    out[key] = {"ms": ms, "agent_steps_per_s": S * Ns / ms * 1e3}
+    out[key]["forward_ms"] = timeit(fwd)
+    out[key]["features_ms"] = timeit(lambda: state_features(pos, vel, ac, dst, ob, hist, dsp, *fargs, out=bufs))
+    # single GC scene: latency of one step (launch-bound regime)
+    S1 = 1
+    one = [x[:S1].contiguous() for x in (pos, vel, ac, dst, hist, dsp, didx, dnum, wp)]
+    pf1, of1, sf1 = state_features(one[0], one[1], one[2], one[3], ob, one[4], one[5], *fargs)
+
+    def one_step():
+        a_next = M.pinnsf_forward(net.spec, packed, pf1[0], of1[0], sf1[0], need_msgs=False)[0][None]
+        integrate_step(one[0], one[1], one[2], a_next, one[3], one[6], one[7], one[8], 0.0, False, hist_v=one[4])
+        state_features(one[0], one[1], one[2], one[3], ob, one[4], one[5], *fargs)
+    ms = timeit(one_step, iters=50)
+    out["nn_rollout_step_S1_N122"] = {"ms": ms, "agent_steps_per_s": Ns / ms * 1e3}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

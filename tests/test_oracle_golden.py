@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.util import golden, group, rel_vec_err, untied_finite, valid_sets
+from tests.util import accel_err, golden, group, rel_vec_err, untied_finite, valid_sets
 
 FEATURE_CASES = ["gc", "gc_window", "ucy", "toy", "syn512", "syn300_wide", "channelled"]
 
@@ -152,3 +152,30 @@ def test_integrate_step_matches_reference_rollout():
             assert np.array_equal(p, P[t + 1], equal_nan=True), (name, t)
             assert np.array_equal(v, V[t + 1]), (name, t)
             assert np.array_equal(dest, o["dest_after_step"][t - t0], equal_nan=True), (name, t)
+
+
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
+def test_rollout_resynchronised_network_output(name):
+    """Oracle features + oracle network on the reference's recorded state at t reproduce the reference's a[t+1]."""
+    import torch
+    from piml_b200 import models as M
+    from tests.golden_args import base_args
+    z = golden(name)
+    i, o = group(z, "in"), group(z, "out")
+    kind, dsn = str(i["model"]), str(i["dataset_name"])
+    spec = M.spec_from_args(kind, base_args(model=kind, dataset_name=dsn))
+    sd = {k[3:]: torch.from_numpy(v) for k, v in group(golden("models"), kind).items() if k.startswith("sd/")}
+    packed = M.pack_state_dict(sd, spec, transposed=False).numpy()
+    desc = O.net_desc(spec.enc_dims, spec.proc_mode, spec.dec_dims, spec.coll_dims, spec.kind)
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    flag = i["mask_p"] - i["mask_p_pred"]
+    worst = 0.0
+    for t in range(t0 + 1, T - 1, max(1, (T - t0) // 40)):
+        p, v, a = o["position"][t][None], o["velocity"][t][None].copy(), o["acceleration"][t][None].copy()
+        dest = o["dest_after_step"][t - t0 - 1][None]
+        pf, of, df = O.relative_features(p, v, a, dest, i["obstacles"])
+        slf = np.concatenate([df[0], v[0], a[0], i["desired_speed"][:, None]], -1)
+        acc = O.pinnsf_forward(desc, packed, spec.tau, pf[0], of[0], slf)[0]
+        sim = flag[t + 1] == 0
+        worst = max(worst, accel_err(acc[sim], o["acceleration"][t + 1][sim], slf[sim], spec.tau))
+    assert worst < 1e-5, worst

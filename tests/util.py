@@ -48,3 +48,16 @@ def untied_finite(dist):
     ok[..., 1:] &= d[..., 1:] != d[..., :-1]
     ok[..., :-1] &= d[..., :-1] != d[..., 1:]
     return ok
+
+
+def accel_err(got, ref, self_f, tau):
+    """Error of a predicted acceleration relative to the magnitude of what is being summed: the network output is
+    sum(messages) + (v0*e - v)/tau (model.py:1205-1212); when those cancel, fp32 rounding (in the reference's own
+    MKL GEMMs as much as anywhere) is relative to the operands, not to the small result.  Per agent:
+    ||got - ref|| / max(||ref||, ||dest term||, 1e-3); returns the max."""
+    got, ref, self_f = np.asarray(got, np.float64), np.asarray(ref, np.float64), np.asarray(self_f, np.float64)
+    n = np.linalg.norm(self_f[:, :2], axis=-1, keepdims=True)
+    n = np.where(n == 0, 0.1, n)
+    dterm = (self_f[:, 6:7] * self_f[:, :2] / n - self_f[:, 2:4]) / tau
+    scale = np.maximum(np.maximum(np.linalg.norm(ref, axis=-1), np.linalg.norm(dterm, axis=-1)), 1e-3)
+    return float((np.linalg.norm(got - ref, axis=-1) / scale).max())
