@@ -42,10 +42,12 @@ PIML_API int64_t piml_launch_count(void);
 /* compute capability major*10+minor of the current device, SM count; <0 on error */
 PIML_API int piml_device_info(int *sm_count, int *cc);
 
-/* Pipe-throughput probe used by bench.py for the roofline denominators (no reference counterpart):
- * which = 0: `ctas` CTAs x 256 threads each run iters*32 dependent-chain FFMAs on 8 independent chains
- *            (FLOPs = ctas*256*iters*32*2);  which = 1: the same with MUFU.EX2 (ops = ctas*256*iters*32).
- * out: ctas*256 floats. */
+/* Pipe-throughput probes used by bench.py for the roofline denominators (no reference counterpart).  `ctas` CTAs x
+ * 256 threads each run iters*4 "units" on independent dependent chains; out: ctas*256 floats.
+ *   which = 0: unit = 8 FFMA                         (FLOPs = ctas*256*iters*32*2)
+ *   which = 1: unit = 8 MUFU.EX2                     (ops   = ctas*256*iters*32)
+ *   which = 2: unit = 8 FFMA2 (fma.rn.f32x2, packed) (FLOPs = ctas*256*iters*32*4)
+ *   which = 3..6: unit = 8 FFMA2 + {2,4,0,4} MUFU.EX2 + {0,0,4,4} FSETP/FSEL pairs (co-issue test) */
 PIML_API int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream);
 
 /* ---- features: src/data/data.py:351-512 ------------------------------------------------------------------ */

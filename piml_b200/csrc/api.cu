@@ -74,14 +74,88 @@ __global__ void __launch_bounds__(256) mufu_probe_kernel(float *out, int iters) 
     out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Packed FP32 (Blackwell fma.rn.f32x2 -> SASS FFMA2): 8 independent 64-bit chains, 2 FMAs per instruction.
+__global__ void __launch_bounds__(256) fp32x2_probe_kernel(float *out, int iters, float a, float b) {
+    unsigned long long x[8], av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float f = static_cast<float>(threadIdx.x + q) * 1e-3f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(x[q]) : "f"(f));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[q]) : "l"(av), "l"(bv));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[q]));
+        s += lo + hi;
+    }
+    out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
+// Co-issue probe: per unit 8 FFMA2 (16 FMAs) + NM MUFU.EX2 + NA FSEL-class ALU ops on independent chains.  Tells
+// whether MUFU / ALU-pipe work hides behind packed FP32 work (time == max of the pipes) or adds to it.
+template <int NM, int NA>
+__global__ void __launch_bounds__(256) mix_probe_kernel(float *out, int iters, float a, float b) {
+    unsigned long long x[8], av, bv;
+    float m[4], c[4];
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float f = static_cast<float>(threadIdx.x + q) * 1e-3f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(x[q]) : "f"(f));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { m[q] = static_cast<float>(threadIdx.x + q) * 1e-3f; c[q] = m[q] + 1.f; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[q]) : "l"(av), "l"(bv));
+#pragma unroll
+            for (int q = 0; q < NM; ++q) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(m[q & 3]) : "f"(-m[q & 3]));
+#pragma unroll
+            for (int q = 0; q < NA; ++q)
+                asm volatile("{.reg .pred p; setp.gt.f32 p, %0, %1; selp.f32 %0, %1, %0, p;}" : "+f"(c[q & 3]) : "f"(a));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[q]));
+        s += lo + hi;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += m[q] + c[q];
+    out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace piml
 
 extern "C" int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream) {
     PIML_REQUIRE(out && ctas > 0 && iters > 0, "piml_pipe_probe: bad arguments");
-    PIML_REQUIRE(which == 0 || which == 1, "piml_pipe_probe: which must be 0 (FP32 FMA) or 1 (MUFU ex2)");
+    PIML_REQUIRE(which >= 0 && which <= 6, "piml_pipe_probe: which must be 0..6");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (which == 0) piml::fp32_probe_kernel<<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f);
-    else piml::mufu_probe_kernel<<<ctas, 256, 0, st>>>(out, iters);
+    switch (which) {
+        case 0: piml::fp32_probe_kernel<<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 1: piml::mufu_probe_kernel<<<ctas, 256, 0, st>>>(out, iters); break;
+        case 2: piml::fp32x2_probe_kernel<<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 3: piml::mix_probe_kernel<2, 0><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 4: piml::mix_probe_kernel<4, 0><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 5: piml::mix_probe_kernel<0, 4><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        default: piml::mix_probe_kernel<4, 4><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+    }
     piml::count_launch();
     return piml::check_launch("pipe_probe_kernel");
 }

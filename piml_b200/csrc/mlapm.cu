@@ -13,6 +13,9 @@
 //   EXACT: IEEE div / sqrt / expf in the reference's operation order (validation variant)
 //   fast : rsqrt.approx + ex2.approx, shared 1/r, constant-angle rotation folded into two FMAs (production)
 #include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -235,23 +238,278 @@ __global__ void mlapm_finalize_kernel(const float2 *__restrict__ pos, const floa
     }
 }
 
+
+// =====================================================================================================================
+// Production pair kernel (v2): packed FP32 (Blackwell FFMA2/FMUL2/FADD2, two rows per instruction), SoA-duplicated
+// column tiles staged by ONE TMA bulk copy per stage, rotation and amplitude hoisted out of the pair loop.
+//
+//   sum_m view*A*exp(..)*R(theta_nm) r^  =  A * [ cos_t*Sx - sin_t*Ty' ,  sin_t*Tx' + cos_t*Sy ]
+//     Sx = sum w rx,  Sy = sum w ry,  Ty' = sum (w sigma) ry,  Tx' = sum (w sigma) rx,
+//     w = view * exp(..)/r,  sigma = -1 if (vr x e) > 0 else +1                        (mlapm.py:33-39)
+//
+// Per ordered pair: 26 packed-FP32 instructions per TWO pairs + 3 MUFU + 2 ALU-pipe selects per pair, i.e. 19 issue
+// slots per pair (v1: 37), FP32 pipe 26 and MUFU pipe 24 cycles per 32 pairs per SM sub-partition.
+// The two discontinuous gates use the reference's exact fp32 arithmetic: view = fmaf(vy,ry,vx*rx) > 0 (einsum/bmm),
+// cross = fl(fl(rx*ey) - fl(ry*ex)) un-fused, whose sign is the order of the two rounded products (equal products ->
+// sigma = +1, the reference's masked_fill_(theta == 0, +theta)).
+// =====================================================================================================================
+constexpr int M2_THREADS = 128;
+constexpr int M2_TILE = 512;                      // columns per stage: 512 * 32 B = 16 KB
+constexpr int M2_COLF = 8;                        // floats per column record {cx,cx,cy,cy,cvx,cvx,cvy,cvy}
+
+__device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
+
+// col8[j] = {px,px,py,py,vx,vx,vy,vy} for j < N, padded up to Npad with copies of the last agent (never evaluated:
+// the pair loop stops at N; the padding only keeps the fixed-size TMA bulk copies in bounds).
+__global__ void mlapm_prep_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel, int N, int Npad,
+                                  float4 *__restrict__ col8) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    const int s = j < N ? j : N - 1;
+    const float2 p = pos[s], v = vel[s];
+    col8[2 * j] = make_float4(p.x, p.x, p.y, p.y);
+    col8[2 * j + 1] = make_float4(v.x, v.x, v.y, v.y);
+}
+
+struct M2Const {
+    float Bl, Cl, Dl;                  // B, C, D times log2(e)
+};
+
+// DBG != 0 (timing experiments only): the MUFU ops are replaced by moves, to expose the FP32-pipe-only time.
+template <int DBG> __device__ __forceinline__ float mufu_rsq(float x) { return DBG ? x : rsqrt_approx(x); }
+template <int DBG> __device__ __forceinline__ float mufu_ex2(float x) { return DBG ? x : ex2_approx(x); }
+
+// Two rows (packed lanes) against one column.
+template <int VERSION, int DBG>
+__device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const float2 vx, const float2 vy,
+                                      const float2 nvx, const float2 nvy, const float2 ex, const float2 ey,
+                                      const float4 cp, const float4 cv, const float2 Bl, const float2 Cl,
+                                      const float2 Dl, float2 &Sx, float2 &Sy, float2 &Tx, float2 &Ty) {
+    const float2 eps = splat(1e-30f);
+    const float2 rx = __fadd2_rn(make_float2(cp.x, cp.y), npx);            // vr = p_m - p_n          (mlapm.py:25)
+    const float2 ry = __fadd2_rn(make_float2(cp.z, cp.w), npy);
+    const float2 g = __ffma2_rn(vy, ry, __fmul2_rn(vx, rx));               // einsum('nk,nmk->nm')    (mlapm.py:27)
+    const float2 r2 = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, eps));
+    const float2 ir = make_float2(mufu_rsq<DBG>(r2.x), mufu_rsq<DBG>(r2.y));
+    const float2 r = __fmul2_rn(r2, ir);
+    float2 w;
+    if (VERSION == 0) {
+        const float2 arg = __fmul2_rn(Bl, r);
+        w = __fmul2_rn(make_float2(mufu_ex2<DBG>(arg.x), mufu_ex2<DBG>(arg.y)), ir);
+        w.x = g.x > 0.f ? w.x : 0.f;
+        w.y = g.y > 0.f ? w.y : 0.f;
+        Sx = __ffma2_rn(w, rx, Sx);
+        Sy = __ffma2_rn(w, ry, Sy);
+    } else {
+        const float2 ux = __fadd2_rn(make_float2(cv.x, cv.y), nvx);        // vv = v_m - v_n          (mlapm.py:31)
+        const float2 uy = __fadd2_rn(make_float2(cv.z, cv.w), nvy);
+        const float2 u2 = __ffma2_rn(uy, uy, __ffma2_rn(ux, ux, eps));
+        const float2 iu = make_float2(mufu_rsq<DBG>(u2.x), mufu_rsq<DBG>(u2.y));
+        const float2 dot = __ffma2_rn(ry, uy, __fmul2_rn(rx, ux));
+        const float2 cs = __fmul2_rn(__fmul2_rn(dot, ir), iu);             // cosine_similarity        (mlapm.py:32)
+        // vr x e = fl(rx*ey) - fl(ry*ex) un-fused: its sign is the order of the two rounded products    (mlapm.py:33)
+        const float2 m1 = __fmul2_rn(rx, ey), m2 = __fmul2_rn(ry, ex);
+        const float2 arg = __ffma2_rn(__ffma2_rn(Dl, r, Cl), cs, __fmul2_rn(Bl, r));
+        w = __fmul2_rn(make_float2(mufu_ex2<DBG>(arg.x), mufu_ex2<DBG>(arg.y)), ir);
+        w.x = g.x > 0.f ? w.x : 0.f;                                       // view gate
+        w.y = g.y > 0.f ? w.y : 0.f;
+        float2 ws;                                                         // w * sigma; cross == 0 -> +theta  (:34)
+        ws.x = m1.x > m2.x ? -w.x : w.x;
+        ws.y = m1.y > m2.y ? -w.y : w.y;
+        Sx = __ffma2_rn(w, rx, Sx);
+        Sy = __ffma2_rn(w, ry, Sy);
+        Tx = __ffma2_rn(ws, rx, Tx);
+        Ty = __ffma2_rn(ws, ry, Ty);
+    }
+}
+
+// partial[split][row - row0] = (Sx, Sy, Tx', Ty') over this split's columns.  Each thread owns 2*RP rows.
+template <int VERSION, int RP, int UNROLL, int DBG>
+__global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *__restrict__ pos,
+                                                                  const float2 *__restrict__ vel,
+                                                                  const float2 *__restrict__ dest,
+                                                                  const float4 *__restrict__ col8, int N, int row0,
+                                                                  int row1, int cols_per_split, M2Const k,
+                                                                  float4 *__restrict__ partial) {
+    __shared__ __align__(128) float4 tile[2][M2_TILE * 2];
+    __shared__ __align__(8) uint64_t bars[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nrows = row1 - row0;
+    const int rbase = blockIdx.x * (M2_THREADS * 2 * RP);
+    float2 npx[RP], npy[RP], vx[RP], vy[RP], nvx[RP], nvy[RP], ex[RP], ey[RP], Sx[RP], Sy[RP], Tx[RP], Ty[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+        float t[2][6];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int rl = rbase + (2 * i + h) * M2_THREADS + threadIdx.x;
+            rl = rl < nrows ? rl : nrows - 1;
+            const int n = row0 + rl;
+            const float2 p = pos[n], v = vel[n], d = dest[n];
+            // ed = F.normalize(destination - position)   (mlapm.py:21)
+            const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
+            const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
+            t[h][0] = p.x; t[h][1] = p.y; t[h][2] = v.x; t[h][3] = v.y;
+            t[h][4] = __fdiv_rn(dx, dn); t[h][5] = __fdiv_rn(dy, dn);
+        }
+        npx[i] = make_float2(-t[0][0], -t[1][0]); npy[i] = make_float2(-t[0][1], -t[1][1]);
+        vx[i] = make_float2(t[0][2], t[1][2]); vy[i] = make_float2(t[0][3], t[1][3]);
+        nvx[i] = make_float2(-t[0][2], -t[1][2]); nvy[i] = make_float2(-t[0][3], -t[1][3]);
+        ex[i] = make_float2(t[0][4], t[1][4]); ey[i] = make_float2(t[0][5], t[1][5]);
+        Sx[i] = Sy[i] = Tx[i] = Ty[i] = make_float2(0.f, 0.f);
+    }
+    const float2 Bl = splat(k.Bl), Cl = splat(k.Cl), Dl = splat(k.Dl);
+
+    const int c0 = blockIdx.y * cols_per_split;                 // multiple of M2_TILE
+    const int c1 = min(N, c0 + cols_per_split);
+    const int ntiles = (c1 - c0 + M2_TILE - 1) / M2_TILE;
+    constexpr uint32_t TILE_BYTES = M2_TILE * M2_COLF * sizeof(float);
+    if (threadIdx.x == 0 && ntiles > 0) {
+        mbar_expect_tx(&bars[0], TILE_BYTES);
+        tma_bulk_g2s(tile[0], col8 + static_cast<int64_t>(c0) * 2, TILE_BYTES, &bars[0]);
+    }
+    uint32_t phase_bits = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (threadIdx.x == 0 && t + 1 < ntiles) {               // tile[buf^1] was released by the barrier below
+            mbar_expect_tx(&bars[buf ^ 1], TILE_BYTES);
+            tma_bulk_g2s(tile[buf ^ 1], col8 + static_cast<int64_t>(c0 + (t + 1) * M2_TILE) * 2, TILE_BYTES,
+                         &bars[buf ^ 1]);
+        }
+        mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
+        phase_bits ^= (1u << buf);
+        const int tn = min(c1 - (c0 + t * M2_TILE), M2_TILE);
+        const float4 *tl = tile[buf];
+#pragma unroll(UNROLL)
+        for (int j = 0; j < tn; ++j) {
+            const float4 cp = tl[2 * j];
+            const float4 cv = tl[2 * j + 1];
+#pragma unroll
+            for (int i = 0; i < RP; ++i)
+                pair2<VERSION, DBG>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, cv, Bl, Cl, Dl, Sx[i],
+                               Sy[i], Tx[i], Ty[i]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+        const int ra = rbase + (2 * i) * M2_THREADS + threadIdx.x;
+        const int rb = ra + M2_THREADS;
+        float4 *out = partial + static_cast<int64_t>(blockIdx.y) * nrows;
+        if (ra < nrows) out[ra] = make_float4(Sx[i].x, Sy[i].x, Tx[i].x, Ty[i].x);
+        if (rb < nrows) out[rb] = make_float4(Sx[i].y, Sy[i].y, Tx[i].y, Ty[i].y);
+    }
+}
+
+// force = (v0*ed - v)/tau - A*R(sum partial) ; action = v + force*dt ; optional p' = p + action*dt and arrival.
+__global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+                                       const float *__restrict__ ds, int ds_dim, const float2 *__restrict__ dest,
+                                       int row0, int row1, int nsplit, const float4 *__restrict__ partial, float A,
+                                       float cos_t, float sin_t, int version, float tau, float dt, float radius,
+                                       float2 *__restrict__ action, float2 *__restrict__ pos_new,
+                                       uint8_t *__restrict__ arrived) {
+    const int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = row1 - row0;
+    if (rl >= nrows) return;
+    const int n = row0 + rl;
+    const float2 p = pos[n], v = vel[n], d = dest[n];
+    const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
+    const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
+    const float ex = __fdiv_rn(dx, dn), ey = __fdiv_rn(dy, dn);
+    const float dsx = ds[static_cast<int64_t>(n) * ds_dim];
+    const float dsy = ds[static_cast<int64_t>(n) * ds_dim + (ds_dim > 1 ? 1 : 0)];
+    // force += (desired_speed * ed - velocity) / tau      (mlapm.py:22)
+    float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
+    float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < nsplit; ++q) {                            // fixed order: deterministic
+        const float4 t = partial[static_cast<int64_t>(q) * nrows + rl];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    float sx, sy;
+    if (version == 0) { sx = s.x; sy = s.y; }
+    else {                                                        // R(sigma theta) r^ summed    (mlapm.py:35-38)
+        sx = fmaf(cos_t, s.x, -(sin_t * s.w));
+        sy = fmaf(sin_t, s.z, cos_t * s.y);
+    }
+    fx = __fsub_rn(fx, __fmul_rn(A, sx));                         // force -= (...).sum(dim=1)   (mlapm.py:29/39)
+    fy = __fsub_rn(fy, __fmul_rn(A, sy));
+    const float ax = __fadd_rn(v.x, __fmul_rn(fx, dt));           // action = velocity + force*dt (mlapm.py:57)
+    const float ay = __fadd_rn(v.y, __fmul_rn(fy, dt));
+    action[rl] = make_float2(ax, ay);
+    if (pos_new || arrived) {
+        const float qx = __fadd_rn(p.x, __fmul_rn(ax, dt));       // p = position + v*dt          (main_mlapm.py:26)
+        const float qy = __fadd_rn(p.y, __fmul_rn(ay, dt));
+        if (pos_new) pos_new[rl] = make_float2(qx, qy);
+        if (arrived)                                              // ||p - destination|| < radius (main_mlapm.py:34)
+            arrived[rl] = norm2_rn(__fsub_rn(qx, d.x), __fsub_rn(qy, d.y)) < radius ? 1 : 0;
+    }
+}
+
 constexpr int ML_MAX_SPLIT = 64;
 
 static int pick_rows_per_thread(int64_t nrows) { return nrows >= 4096 ? 4 : (nrows >= 1024 ? 2 : 1); }
 
-// Column splits: enough CTAs for ~8 waves over the SMs, each split a multiple of ML_TILE columns.
-static void pick_split(int64_t nrows, int64_t N, int R, int *nsplit, int *cols_per_split) {
-    const int64_t row_blocks = (nrows + ML_THREADS * R - 1) / (ML_THREADS * R);
+// Row pairs per thread of the packed kernel (2*RP rows per thread).  PIML_MLAPM_RP overrides (tuning).
+static int pick_row_pairs(int64_t nrows) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("PIML_MLAPM_RP");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    return nrows >= 8192 ? 2 : 1;
+}
+
+// Column splits: enough CTAs for ~8 waves over the SMs, each split a multiple of `tile` columns.
+static void pick_split(int64_t nrows, int64_t N, int rows_per_cta, int tile, int *nsplit, int *cols_per_split) {
+    const int64_t row_blocks = (nrows + rows_per_cta - 1) / rows_per_cta;
     const int64_t want_ctas = 8LL * 6 * sm_count();
     int64_t s = (want_ctas + row_blocks - 1) / row_blocks;
-    const int64_t max_by_cols = (N + ML_TILE - 1) / ML_TILE;
+    const int64_t max_by_cols = (N + tile - 1) / tile;
     if (s > max_by_cols) s = max_by_cols;
     if (s > ML_MAX_SPLIT) s = ML_MAX_SPLIT;
     if (s < 1) s = 1;
     int64_t cps = (N + s - 1) / s;
-    cps = (cps + ML_TILE - 1) / ML_TILE * ML_TILE;
+    cps = (cps + tile - 1) / tile * tile;
     *cols_per_split = static_cast<int>(cps);
     *nsplit = static_cast<int>((N + cps - 1) / cps);
+}
+
+// Column splits for the packed kernel, chosen against wave quantisation: with `slots` CTAs resident on the GPU
+// (occupancy x SMs), B row blocks and S splits run in ceil(B*S/slots) waves of ceil(tiles/S) tile-iterations each;
+// take the S that minimises the product (ties -> larger S, finer dynamic balancing).  PIML_MLAPM_SPLIT overrides.
+static int pick_split2(const void *kernel, int64_t nrows, int64_t N, int rows_per_cta, int *nsplit,
+                       int *cols_per_split) {
+    int occ = 0;
+    PIML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, M2_THREADS, 0));
+    if (occ < 1) occ = 1;
+    const int64_t slots = static_cast<int64_t>(occ) * sm_count();
+    const int64_t B = (nrows + rows_per_cta - 1) / rows_per_cta;
+    const int64_t tiles = (N + M2_TILE - 1) / M2_TILE;
+    int64_t best_s = 1, best_cost = INT64_MAX;
+    const int64_t smax = tiles < ML_MAX_SPLIT ? tiles : ML_MAX_SPLIT;
+    for (int64_t s = 1; s <= smax; ++s) {
+        const int64_t per = (tiles + s - 1) / s;
+        const int64_t s_eff = (tiles + per - 1) / per;                  // splits that actually have columns
+        const int64_t waves = (B * s_eff + slots - 1) / slots;
+        const int64_t cost = waves * per;
+        if (cost <= best_cost) { best_cost = cost; best_s = s_eff; }
+    }
+    if (const char *e = getenv("PIML_MLAPM_SPLIT")) {
+        const int64_t f = atoll(e);
+        if (f >= 1 && f <= smax) best_s = f;
+    }
+    const int64_t per = (tiles + best_s - 1) / best_s;
+    *cols_per_split = static_cast<int>(per * M2_TILE);
+    *nsplit = static_cast<int>((tiles + per - 1) / per);
+    return PIML_OK;
 }
 
 template <int VERSION, bool EXACT>
@@ -271,7 +529,9 @@ using namespace piml;
 
 extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
     if (N < 0) return 0;
-    return static_cast<int64_t>(ML_MAX_SPLIT) * N * 2 * sizeof(float) + 256;
+    // column records (32 B per agent, padded to a tile) + per-split partial sums (16 B per row and split)
+    const int64_t npad = (N + M2_TILE - 1) / M2_TILE * M2_TILE;
+    return npad * M2_COLF * sizeof(float) + static_cast<int64_t>(ML_MAX_SPLIT) * N * 4 * sizeof(float) + 256;
 }
 
 extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
@@ -304,31 +564,82 @@ extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const 
     k.sin_t = static_cast<float>(sin(static_cast<double>(th)));
     k.tau = prm->tau; k.inv_tau = 1.0f / prm->tau;
 
-    const int R = pick_rows_per_thread(nrows);
-    int nsplit, cps;
-    pick_split(nrows, N, R, &nsplit, &cps);
-    dim3 grid(static_cast<unsigned>((nrows + ML_THREADS * R - 1) / (ML_THREADS * R)), static_cast<unsigned>(nsplit));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2 *p2 = reinterpret_cast<const float2 *>(pos), *v2 = reinterpret_cast<const float2 *>(vel);
     const float2 *d2 = reinterpret_cast<const float2 *>(dest);
-    float2 *partial = reinterpret_cast<float2 *>(workspace);
     const int iN = static_cast<int>(N), r0 = static_cast<int>(row0), r1 = static_cast<int>(row1);
-    if (prm->version == 0) {
-        if (prm->exact_math) launch_pairs<0, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
-        else launch_pairs<0, false>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
-    } else {
-        if (prm->exact_math) launch_pairs<1, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
-        else launch_pairs<1, false>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+    int rc;
+    if (prm->exact_math) {
+        // validation variant: IEEE arithmetic in the reference's operation order
+        const int R = pick_rows_per_thread(nrows);
+        int nsplit, cps;
+        pick_split(nrows, N, ML_THREADS * R, ML_TILE, &nsplit, &cps);
+        dim3 grid(static_cast<unsigned>((nrows + ML_THREADS * R - 1) / (ML_THREADS * R)),
+                  static_cast<unsigned>(nsplit));
+        float2 *partial = reinterpret_cast<float2 *>(workspace);
+        if (prm->version == 0) launch_pairs<0, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+        else launch_pairs<1, true>(R, grid, st, p2, v2, d2, iN, r0, r1, cps, k, partial);
+        count_launch();
+        rc = check_launch("mlapm_pairs_kernel");
+        if (rc) return rc;
+        const int threads = 256;
+        mlapm_finalize_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+            p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial, prm->tau, dt, radius,
+            reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived);
+        count_launch();
+        return check_launch("mlapm_finalize_kernel");
     }
+    // production: packed-FP32 kernel on SoA-duplicated column records
+    const int64_t npad = (N + M2_TILE - 1) / M2_TILE * M2_TILE;
+    float4 *col8 = reinterpret_cast<float4 *>(workspace);
+    float4 *partial4 = col8 + npad * 2;
+    {
+        const int threads = 256;
+        mlapm_prep_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
+            p2, v2, iN, static_cast<int>(npad), col8);
+        count_launch();
+        rc = check_launch("mlapm_prep_kernel");
+        if (rc) return rc;
+    }
+    int RP = pick_row_pairs(nrows), unroll = 2, dbg = 0;
+    if (const char *e = getenv("PIML_MLAPM_EXP")) sscanf(e, "%d,%d,%d", &RP, &unroll, &dbg);   // tuning experiments
+    M2Const k2{k.Bl, k.Cl, k.Dl};
+    dim3 grid;
+    int nsplit = 1, cps = 0, rc2 = PIML_OK;
+#define PIML_LAUNCH_PAIRS2(V, RPV, UN, DB)                                                                         \
+    do {                                                                                                           \
+        rc2 = pick_split2(reinterpret_cast<const void *>(&mlapm_pairs2_kernel<V, RPV, UN, DB>), nrows, N,          \
+                          M2_THREADS * 2 * RPV, &nsplit, &cps);                                                    \
+        grid = dim3(static_cast<unsigned>((nrows + M2_THREADS * 2 * RPV - 1) / (M2_THREADS * 2 * RPV)),            \
+                    static_cast<unsigned>(nsplit));                                                                \
+        if (rc2 == PIML_OK)                                                                                        \
+            mlapm_pairs2_kernel<V, RPV, UN, DB><<<grid, M2_THREADS, 0, st>>>(p2, v2, d2, col8, iN, r0, r1, cps, k2, \
+                                                                             partial4);                            \
+    } while (0)
+    if (prm->version == 0) {
+        if (RP == 4) PIML_LAUNCH_PAIRS2(0, 4, 2, 0); else if (RP == 2) PIML_LAUNCH_PAIRS2(0, 2, 2, 0);
+        else PIML_LAUNCH_PAIRS2(0, 1, 2, 0);
+    } else if (dbg) {
+        PIML_LAUNCH_PAIRS2(1, 2, 2, 1);
+    } else if (RP == 4) {
+        if (unroll == 1) PIML_LAUNCH_PAIRS2(1, 4, 1, 0); else PIML_LAUNCH_PAIRS2(1, 4, 2, 0);
+    } else if (RP == 2) {
+        if (unroll == 1) PIML_LAUNCH_PAIRS2(1, 2, 1, 0); else if (unroll == 4) PIML_LAUNCH_PAIRS2(1, 2, 4, 0);
+        else PIML_LAUNCH_PAIRS2(1, 2, 2, 0);
+    } else {
+        if (unroll == 4) PIML_LAUNCH_PAIRS2(1, 1, 4, 0); else PIML_LAUNCH_PAIRS2(1, 1, 2, 0);
+    }
+    if (rc2) return rc2;
+#undef PIML_LAUNCH_PAIRS2
     count_launch();
-    int rc = check_launch("mlapm_pairs_kernel");
+    rc = check_launch("mlapm_pairs2_kernel");
     if (rc) return rc;
     const int threads = 256;
-    mlapm_finalize_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
-        p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial, prm->tau, dt, radius,
-        reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived);
+    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+        p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial4, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
+        dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived);
     count_launch();
-    return check_launch("mlapm_finalize_kernel");
+    return check_launch("mlapm_finalize2_kernel");
 }
 
 extern "C" int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
