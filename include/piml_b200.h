@@ -47,7 +47,9 @@ PIML_API int piml_device_info(int *sm_count, int *cc);
  *   which = 0: unit = 8 FFMA                         (FLOPs = ctas*256*iters*32*2)
  *   which = 1: unit = 8 MUFU.EX2                     (ops   = ctas*256*iters*32)
  *   which = 2: unit = 8 FFMA2 (fma.rn.f32x2, packed) (FLOPs = ctas*256*iters*32*4)
- *   which = 3..6: unit = 8 FFMA2 + {2,4,0,4} MUFU.EX2 + {0,0,4,4} FSETP/FSEL pairs (co-issue test) */
+ *   which = 3..6: unit = 8 FFMA2 + {2,4,0,4} MUFU.EX2 + {0,0,4,4} FSETP/FSEL pairs (co-issue test)
+ *   which = 7..12: unit = 8 ops with all-distinct register operands: fma2(x,y,z), mul2, add2, fma2(y,y,x),
+ *                  scalar fma(x,y,z), fma2(y,z',x)  (register-read-bandwidth test) */
 PIML_API int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream);
 
 /* ---- features: src/data/data.py:351-512 ------------------------------------------------------------------ */

@@ -141,11 +141,50 @@ __global__ void __launch_bounds__(256) mix_probe_kernel(float *out, int iters, f
     out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
 }
 
+// Operand-pattern probes for the packed FP32 pipe: 8 chains whose source operands are all distinct registers (no
+// loop-invariant operand for the reuse cache).  MODE 0: x=fma2(x,y,z)  1: x=mul2(x,y)  2: x=add2(x,y)
+// 3: x=fma2(y,y,x)  4: scalar x=fma(x,y,z)  5: x=fma2(y_q, z_{q+1}, x)  (accumulate form)
+template <int MODE>
+__global__ void __launch_bounds__(256) operand_probe_kernel(float *out, int iters) {
+    unsigned long long x[8], y[8], z[8];
+    float xs[8], ys[8], zs[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float f = static_cast<float>(threadIdx.x + q) * 1e-3f;
+        xs[q] = f; ys[q] = 0.999f + f * 1e-6f; zs[q] = 1e-3f + f * 1e-6f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[q]) : "f"(xs[q]), "f"(xs[q] + 0.5f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(y[q]) : "f"(ys[q]), "f"(ys[q] - 1e-4f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(z[q]) : "f"(zs[q]), "f"(zs[q] + 1e-4f));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (MODE == 0) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[q]) : "l"(y[q]), "l"(z[q]));
+                if (MODE == 1) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(x[q]) : "l"(y[q]));
+                if (MODE == 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x[q]) : "l"(z[q]));
+                if (MODE == 3) asm volatile("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(x[q]) : "l"(z[q]));
+                if (MODE == 4) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(xs[q]) : "f"(ys[q]), "f"(zs[q]));
+                if (MODE == 5) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x[q]) : "l"(y[q]), "l"(z[(q + 1) & 7]));
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[q]));
+        s += lo + hi + xs[q];
+    }
+    out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace piml
 
 extern "C" int piml_pipe_probe(int which, int ctas, int iters, float *out, void *stream) {
     PIML_REQUIRE(out && ctas > 0 && iters > 0, "piml_pipe_probe: bad arguments");
-    PIML_REQUIRE(which >= 0 && which <= 6, "piml_pipe_probe: which must be 0..6");
+    PIML_REQUIRE(which >= 0 && which <= 12, "piml_pipe_probe: which must be 0..12");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (which) {
         case 0: piml::fp32_probe_kernel<<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
@@ -154,7 +193,13 @@ extern "C" int piml_pipe_probe(int which, int ctas, int iters, float *out, void 
         case 3: piml::mix_probe_kernel<2, 0><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
         case 4: piml::mix_probe_kernel<4, 0><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
         case 5: piml::mix_probe_kernel<0, 4><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
-        default: piml::mix_probe_kernel<4, 4><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 6: piml::mix_probe_kernel<4, 4><<<ctas, 256, 0, st>>>(out, iters, 0.999f, 1e-3f); break;
+        case 7: piml::operand_probe_kernel<0><<<ctas, 256, 0, st>>>(out, iters); break;
+        case 8: piml::operand_probe_kernel<1><<<ctas, 256, 0, st>>>(out, iters); break;
+        case 9: piml::operand_probe_kernel<2><<<ctas, 256, 0, st>>>(out, iters); break;
+        case 10: piml::operand_probe_kernel<3><<<ctas, 256, 0, st>>>(out, iters); break;
+        case 11: piml::operand_probe_kernel<4><<<ctas, 256, 0, st>>>(out, iters); break;
+        default: piml::operand_probe_kernel<5><<<ctas, 256, 0, st>>>(out, iters); break;
     }
     piml::count_launch();
     return piml::check_launch("pipe_probe_kernel");

@@ -275,12 +275,8 @@ struct M2Const {
     float Bl, Cl, Dl;                  // B, C, D times log2(e)
 };
 
-// DBG != 0 (timing experiments only): the MUFU ops are replaced by moves, to expose the FP32-pipe-only time.
-template <int DBG> __device__ __forceinline__ float mufu_rsq(float x) { return DBG ? x : rsqrt_approx(x); }
-template <int DBG> __device__ __forceinline__ float mufu_ex2(float x) { return DBG ? x : ex2_approx(x); }
-
 // Two rows (packed lanes) against one column.
-template <int VERSION, int DBG>
+template <int VERSION>
 __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const float2 vx, const float2 vy,
                                       const float2 nvx, const float2 nvy, const float2 ex, const float2 ey,
                                       const float4 cp, const float4 cv, const float2 Bl, const float2 Cl,
@@ -290,12 +286,12 @@ __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const 
     const float2 ry = __fadd2_rn(make_float2(cp.z, cp.w), npy);
     const float2 g = __ffma2_rn(vy, ry, __fmul2_rn(vx, rx));               // einsum('nk,nmk->nm')    (mlapm.py:27)
     const float2 r2 = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, eps));
-    const float2 ir = make_float2(mufu_rsq<DBG>(r2.x), mufu_rsq<DBG>(r2.y));
+    const float2 ir = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
     const float2 r = __fmul2_rn(r2, ir);
     float2 w;
     if (VERSION == 0) {
         const float2 arg = __fmul2_rn(Bl, r);
-        w = __fmul2_rn(make_float2(mufu_ex2<DBG>(arg.x), mufu_ex2<DBG>(arg.y)), ir);
+        w = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ir);
         w.x = g.x > 0.f ? w.x : 0.f;
         w.y = g.y > 0.f ? w.y : 0.f;
         Sx = __ffma2_rn(w, rx, Sx);
@@ -304,13 +300,13 @@ __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const 
         const float2 ux = __fadd2_rn(make_float2(cv.x, cv.y), nvx);        // vv = v_m - v_n          (mlapm.py:31)
         const float2 uy = __fadd2_rn(make_float2(cv.z, cv.w), nvy);
         const float2 u2 = __ffma2_rn(uy, uy, __ffma2_rn(ux, ux, eps));
-        const float2 iu = make_float2(mufu_rsq<DBG>(u2.x), mufu_rsq<DBG>(u2.y));
+        const float2 iu = make_float2(rsqrt_approx(u2.x), rsqrt_approx(u2.y));
         const float2 dot = __ffma2_rn(ry, uy, __fmul2_rn(rx, ux));
         const float2 cs = __fmul2_rn(__fmul2_rn(dot, ir), iu);             // cosine_similarity        (mlapm.py:32)
         // vr x e = fl(rx*ey) - fl(ry*ex) un-fused: its sign is the order of the two rounded products    (mlapm.py:33)
         const float2 m1 = __fmul2_rn(rx, ey), m2 = __fmul2_rn(ry, ex);
         const float2 arg = __ffma2_rn(__ffma2_rn(Dl, r, Cl), cs, __fmul2_rn(Bl, r));
-        w = __fmul2_rn(make_float2(mufu_ex2<DBG>(arg.x), mufu_ex2<DBG>(arg.y)), ir);
+        w = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ir);
         w.x = g.x > 0.f ? w.x : 0.f;                                       // view gate
         w.y = g.y > 0.f ? w.y : 0.f;
         float2 ws;                                                         // w * sigma; cross == 0 -> +theta  (:34)
@@ -324,7 +320,7 @@ __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const 
 }
 
 // partial[split][row - row0] = (Sx, Sy, Tx', Ty') over this split's columns.  Each thread owns 2*RP rows.
-template <int VERSION, int RP, int UNROLL, int DBG>
+template <int VERSION, int RP, int UNROLL>
 __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *__restrict__ pos,
                                                                   const float2 *__restrict__ vel,
                                                                   const float2 *__restrict__ dest,
@@ -392,7 +388,7 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
             const float4 cv = tl[2 * j + 1];
 #pragma unroll
             for (int i = 0; i < RP; ++i)
-                pair2<VERSION, DBG>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, cv, Bl, Cl, Dl, Sx[i],
+                pair2<VERSION>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, cv, Bl, Cl, Dl, Sx[i],
                                Sy[i], Tx[i], Ty[i]);
         }
         __syncthreads();
@@ -456,16 +452,8 @@ constexpr int ML_MAX_SPLIT = 64;
 
 static int pick_rows_per_thread(int64_t nrows) { return nrows >= 4096 ? 4 : (nrows >= 1024 ? 2 : 1); }
 
-// Row pairs per thread of the packed kernel (2*RP rows per thread).  PIML_MLAPM_RP overrides (tuning).
-static int pick_row_pairs(int64_t nrows) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char *e = getenv("PIML_MLAPM_RP");
-        forced = e ? atoi(e) : 0;
-    }
-    if (forced == 1 || forced == 2 || forced == 4) return forced;
-    return nrows >= 8192 ? 2 : 1;
-}
+// Row pairs per thread of the packed kernel (2*RP rows per thread).
+static int pick_row_pairs(int64_t nrows) { return nrows >= 8192 ? 2 : 1; }
 
 // Column splits: enough CTAs for ~8 waves over the SMs, each split a multiple of `tile` columns.
 static void pick_split(int64_t nrows, int64_t N, int rows_per_cta, int tile, int *nsplit, int *cols_per_split) {
@@ -482,31 +470,31 @@ static void pick_split(int64_t nrows, int64_t N, int rows_per_cta, int tile, int
     *nsplit = static_cast<int>((N + cps - 1) / cps);
 }
 
-// Column splits for the packed kernel, chosen against wave quantisation: with `slots` CTAs resident on the GPU
-// (occupancy x SMs), B row blocks and S splits run in ceil(B*S/slots) waves of ceil(tiles/S) tile-iterations each;
-// take the S that minimises the product (ties -> larger S, finer dynamic balancing).  PIML_MLAPM_SPLIT overrides.
+// Column splits for the packed kernel: enough CTAs for >= 8 waves over the resident slots (occupancy x SMs), each
+// split a whole number of tiles.  Measured at N = 100k (profiles/r01_mlapm_experiments.md): 27-36 splits (6-8 waves)
+// are ~2% faster than the exact 2- or 4-wave fits (9, 18), 4 splits (1 wave) 18% slower.  PIML_MLAPM_SPLIT overrides.
 static int pick_split2(const void *kernel, int64_t nrows, int64_t N, int rows_per_cta, int *nsplit,
                        int *cols_per_split) {
-    int occ = 0;
-    PIML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, M2_THREADS, 0));
-    if (occ < 1) occ = 1;
-    const int64_t slots = static_cast<int64_t>(occ) * sm_count();
+    static const void *cached_kernel = nullptr;
+    static int cached_occ = 0;
+    if (kernel != cached_kernel) {
+        int occ = 0;
+        PIML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, M2_THREADS, 0));
+        cached_occ = occ < 1 ? 1 : occ;
+        cached_kernel = kernel;
+    }
+    const int64_t slots = static_cast<int64_t>(cached_occ) * sm_count();
     const int64_t B = (nrows + rows_per_cta - 1) / rows_per_cta;
     const int64_t tiles = (N + M2_TILE - 1) / M2_TILE;
-    int64_t best_s = 1, best_cost = INT64_MAX;
-    const int64_t smax = tiles < ML_MAX_SPLIT ? tiles : ML_MAX_SPLIT;
-    for (int64_t s = 1; s <= smax; ++s) {
-        const int64_t per = (tiles + s - 1) / s;
-        const int64_t s_eff = (tiles + per - 1) / per;                  // splits that actually have columns
-        const int64_t waves = (B * s_eff + slots - 1) / slots;
-        const int64_t cost = waves * per;
-        if (cost <= best_cost) { best_cost = cost; best_s = s_eff; }
-    }
+    int64_t s = (8 * slots + B - 1) / B;
+    if (s > tiles) s = tiles;
+    if (s > ML_MAX_SPLIT) s = ML_MAX_SPLIT;
+    if (s < 1) s = 1;
     if (const char *e = getenv("PIML_MLAPM_SPLIT")) {
         const int64_t f = atoll(e);
-        if (f >= 1 && f <= smax) best_s = f;
+        if (f >= 1 && f <= ML_MAX_SPLIT && f <= tiles) s = f;
     }
-    const int64_t per = (tiles + best_s - 1) / best_s;
+    const int64_t per = (tiles + s - 1) / s;
     *cols_per_split = static_cast<int>(per * M2_TILE);
     *nsplit = static_cast<int>((tiles + per - 1) / per);
     return PIML_OK;
@@ -601,33 +589,29 @@ extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const 
         rc = check_launch("mlapm_prep_kernel");
         if (rc) return rc;
     }
-    int RP = pick_row_pairs(nrows), unroll = 2, dbg = 0;
-    if (const char *e = getenv("PIML_MLAPM_EXP")) sscanf(e, "%d,%d,%d", &RP, &unroll, &dbg);   // tuning experiments
+    int RP = pick_row_pairs(nrows), unroll = 4;
+    if (const char *e = getenv("PIML_MLAPM_EXP")) sscanf(e, "%d,%d", &RP, &unroll);            // tuning experiments
     M2Const k2{k.Bl, k.Cl, k.Dl};
     dim3 grid;
     int nsplit = 1, cps = 0, rc2 = PIML_OK;
-#define PIML_LAUNCH_PAIRS2(V, RPV, UN, DB)                                                                         \
+#define PIML_LAUNCH_PAIRS2(V, RPV, UN)                                                                             \
     do {                                                                                                           \
-        rc2 = pick_split2(reinterpret_cast<const void *>(&mlapm_pairs2_kernel<V, RPV, UN, DB>), nrows, N,          \
+        rc2 = pick_split2(reinterpret_cast<const void *>(&mlapm_pairs2_kernel<V, RPV, UN>), nrows, N,              \
                           M2_THREADS * 2 * RPV, &nsplit, &cps);                                                    \
         grid = dim3(static_cast<unsigned>((nrows + M2_THREADS * 2 * RPV - 1) / (M2_THREADS * 2 * RPV)),            \
                     static_cast<unsigned>(nsplit));                                                                \
         if (rc2 == PIML_OK)                                                                                        \
-            mlapm_pairs2_kernel<V, RPV, UN, DB><<<grid, M2_THREADS, 0, st>>>(p2, v2, d2, col8, iN, r0, r1, cps, k2, \
-                                                                             partial4);                            \
+            mlapm_pairs2_kernel<V, RPV, UN><<<grid, M2_THREADS, 0, st>>>(p2, v2, d2, col8, iN, r0, r1, cps, k2,    \
+                                                                         partial4);                                \
     } while (0)
     if (prm->version == 0) {
-        if (RP == 4) PIML_LAUNCH_PAIRS2(0, 4, 2, 0); else if (RP == 2) PIML_LAUNCH_PAIRS2(0, 2, 2, 0);
-        else PIML_LAUNCH_PAIRS2(0, 1, 2, 0);
-    } else if (dbg) {
-        PIML_LAUNCH_PAIRS2(1, 2, 2, 1);
+        if (RP == 2) PIML_LAUNCH_PAIRS2(0, 2, 4); else PIML_LAUNCH_PAIRS2(0, 1, 4);
     } else if (RP == 4) {
-        if (unroll == 1) PIML_LAUNCH_PAIRS2(1, 4, 1, 0); else PIML_LAUNCH_PAIRS2(1, 4, 2, 0);
+        PIML_LAUNCH_PAIRS2(1, 4, 2);
     } else if (RP == 2) {
-        if (unroll == 1) PIML_LAUNCH_PAIRS2(1, 2, 1, 0); else if (unroll == 4) PIML_LAUNCH_PAIRS2(1, 2, 4, 0);
-        else PIML_LAUNCH_PAIRS2(1, 2, 2, 0);
+        if (unroll == 2) PIML_LAUNCH_PAIRS2(1, 2, 2); else PIML_LAUNCH_PAIRS2(1, 2, 4);
     } else {
-        if (unroll == 4) PIML_LAUNCH_PAIRS2(1, 1, 4, 0); else PIML_LAUNCH_PAIRS2(1, 1, 2, 0);
+        if (unroll == 2) PIML_LAUNCH_PAIRS2(1, 1, 2); else PIML_LAUNCH_PAIRS2(1, 1, 4);
     }
     if (rc2) return rc2;
 #undef PIML_LAUNCH_PAIRS2

@@ -14,7 +14,8 @@ sms = torch.cuda.get_device_properties(dev).multi_processor_count
 ctas, iters = sms * 8, 4096
 out = torch.empty(ctas * 256, device=dev)
 names = {0: "ffma", 1: "mufu_ex2", 2: "ffma2", 3: "ffma2x8+mufu2", 4: "ffma2x8+mufu4", 5: "ffma2x8+alu4x2",
-         6: "ffma2x8+mufu4+alu4x2"}
+         6: "ffma2x8+mufu4+alu4x2", 7: "fma2(x,y,z) distinct", 8: "mul2(x,y) distinct", 9: "add2(x,z) distinct",
+         10: "fma2(z,z,x)", 11: "scalar fma(x,y,z) distinct", 12: "fma2(y,z',x) accumulate"}
 res = {"sms": sms}
 for which, name in names.items():
     best = 1e9
