@@ -1,0 +1,81 @@
+"""The opt-in switch: piml_b200.patch swaps the five reference signatures and restores them (CPU, no compute)."""
+import sys
+import types
+
+import pytest
+
+
+def _fake_reference():
+    DATA = types.ModuleType("data.data")
+
+    class Pedestrians(object):
+        @staticmethod
+        def get_heading_direction(velocity):
+            return "ref"
+
+        def get_nearby_obj_in_sight(self, position, objects, heading_direction, k, angle_threshold):
+            return "ref"
+
+        def get_relative_features(self, *a):
+            return "ref"
+
+        @staticmethod
+        def calculate_collision_label(ped_features):
+            return "ref"
+
+    class RawData(object):
+        pass
+    DATA.Pedestrians, DATA.RawData = Pedestrians, RawData
+    MODEL = types.ModuleType("models.model")
+    for c in ("PINNSF", "PINNSF_bottleneck", "PINNSF_bottleneck_multitask", "PINNSF_multitask"):
+        setattr(MODEL, c, type(c, (), {"forward": lambda self, p, o, s: "ref"}))
+    ML = types.ModuleType("models.mlapm")
+    ML.MLAPM = type("MLAPM", (), {"__init__": lambda self, **a: setattr(self, "args", a),
+                                  "step": lambda self, *a, **k: "ref"})
+    UT = types.ModuleType("utils.utils")
+    UT.calc_acceleration = lambda *a, **k: "ref"
+    SIM = types.ModuleType("models.simulators")
+    SIM.DATA = DATA
+    SIM.BaseSimulator = type("BaseSimulator", (Pedestrians,), {"get_multiple_rollouts": lambda self, d, t_start=0,
+                                                               load_model=True: "ref"})
+    return DATA, ML, MODEL, SIM, UT
+
+
+def test_install_swaps_and_uninstall_restores(monkeypatch):
+    import piml_b200.patch as patch
+    DATA, ML, MODEL, SIM, UT = _fake_reference()
+    monkeypatch.delenv("PIML_B200", raising=False)
+    assert patch.install_from_env(DATA=DATA, MLAPM_MOD=ML, MODEL=MODEL, SIM=SIM, UTILS=UT) == []
+    assert UT.calc_acceleration() == "ref"
+    monkeypatch.setenv("PIML_B200", "1")
+    names = patch.install_from_env(DATA=DATA, MLAPM_MOD=ML, MODEL=MODEL, SIM=SIM, UTILS=UT)
+    assert len(names) == 4 + 4 + 1 + 1 + 1
+    import piml_b200 as P
+    assert UT.calc_acceleration is P.calc_acceleration
+    assert DATA.Pedestrians.__dict__["get_relative_features"] is P.Pedestrians.__dict__["get_relative_features"]
+    # BaseSimulator inherits Pedestrians in the reference (simulators.py:25): the patched method is what it sees
+    assert SIM.BaseSimulator.get_relative_features is DATA.Pedestrians.get_relative_features
+    assert ML.MLAPM(version="GC").step.__func__.__name__ == "step"
+    patch.uninstall()
+    assert UT.calc_acceleration() == "ref"
+    assert DATA.Pedestrians().get_relative_features() == "ref"
+    assert MODEL.PINNSF().forward(0, 0, 0) == "ref"
+    assert ML.MLAPM().step() == "ref" and SIM.BaseSimulator().get_multiple_rollouts(None) == "ref"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_install_on_the_real_reference_modules():
+    """In the build container: the real reference modules expose exactly the attributes the patch replaces."""
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import _refharness as H
+    DATA, MODEL, MLAPM, SIM, UTILS = H.import_reference()
+    import piml_b200.patch as patch
+    orig = DATA.Pedestrians.get_relative_features
+    names = patch.install(DATA=DATA, MLAPM_MOD=MLAPM, MODEL=MODEL, SIM=SIM, UTILS=UTILS)
+    try:
+        assert len(names) == 11
+        assert SIM.BaseSimulator.get_relative_features is not orig
+    finally:
+        patch.uninstall()
+    assert DATA.Pedestrians.get_relative_features is orig
