@@ -140,12 +140,24 @@ typedef struct {
                                      1: sum embeddings over slots, then decode (pinnsf, pinnsf_m) */
 } piml_net_desc;
 
+/* Number of floats of the device parameter layout of `desc` (both branches + collision head); <0 on a bad desc. */
+PIML_API int64_t piml_pinnsf_packed_floats(const piml_net_desc *desc);
+
+/* Re-layout the parameters for the fused forward.  params_torch (device): the Linears' parameters concatenated in
+ * torch's own layout and forward order -- pedestrian branch (encoder, [processor block 0 if proc_mode==1], decoder,
+ * predictor), obstacle branch (same), collision head; per Linear `weight` (out,in) row-major then `bias` (out) --
+ * i.e. the reference module's state_dict tensors, untouched.  packed (device, 16-byte aligned,
+ * piml_pinnsf_packed_floats floats): per Linear W^T padded to 16*NJ columns in the tile kernel's column order, then the
+ * bias.  Call once per weight update. */
+PIML_API int piml_pinnsf_pack_f32(const piml_net_desc *desc, const float *params_torch, float *packed, void *stream);
+
 /* Forward of a PINNSF-family model (eval mode, or train mode with caller-supplied dropout multipliers).
- * params: packed fp32 vector (ped branch, obs branch, collision head; per Linear W(out,in) then b).
+ * params: the vector written by piml_pinnsf_pack_f32.  Layer widths <= 128.
  * ped (R,kp,6), obs (R,ko,6) (ignored if has_obs==0), self (R,7).  norm_group = 0: destination norm per row
  * (the (N,7) call); = N: reduce over the agent axis per component ((C,N,7) call, model.py:1206 dim=1 quirk).
  * drop_ped / drop_obs: NULL, or (R,k,pw) multipliers applied to the processor output (Dropout in train()).
- * Outputs acc (R,2), ped_msgs (R,kp,msgw), obs_msgs (R,ko,msgw), coll (R,kp); any of the last three may be NULL. */
+ * Outputs acc (R,2), ped_msgs (R,kp,msgw), obs_msgs (R,ko,msgw), coll (R,kp); any of the last three may be NULL.
+ * Uses a small stream-keyed scratch buffer owned by the library (per-agent message sums). */
 PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *params, int has_obs, float tau,
                             const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
                             int norm_group, const float *drop_ped, const float *drop_obs, float *acc,

@@ -100,17 +100,29 @@ def linear_keys(spec):
     return keys
 
 
-def pack_state_dict(sd, spec, transposed=True):
-    """Flatten the weights the forward pass uses into ONE fp32 vector: ped branch, obs branch, collision head; per
-    Linear the weight then the bias.  transposed=True stores W^T (in,out) -- the layout libpiml_b200 reads
-    coalesced; transposed=False keeps torch's (out,in) (the oracle's layout)."""
+def pack_state_dict(sd, spec):
+    """Concatenate the parameters the forward pass uses into ONE fp32 vector in torch's own layout: ped branch, obs
+    branch, collision head; per Linear `weight` (out,in) then `bias`.  This is what piml_pinnsf_pack_f32 (and the
+    oracle) take; dead weights (ResDNN block 0 when processor_hidden_layers > 1) are not included."""
     parts = []
     for k in linear_keys(spec):
-        w = sd[k + ".weight"].detach().to(torch.float32)
-        b = sd[k + ".bias"].detach().to(torch.float32)
-        parts.append((w.t() if transposed else w).contiguous().reshape(-1))
-        parts.append(b.reshape(-1))
+        parts.append(sd[k + ".weight"].detach().to(torch.float32).contiguous().reshape(-1))
+        parts.append(sd[k + ".bias"].detach().to(torch.float32).reshape(-1))
     return torch.cat(parts)
+
+
+def pack_device(sd, spec, device=None):
+    """Device parameter layout of the fused forward kernel (piml_pinnsf_pack_f32); call once per weight update."""
+    dev = device if device is not None else L.cuda_device()
+    src = pack_state_dict(sd, spec).to(dev)
+    desc = spec.desc()
+    n = int(L.load().piml_pinnsf_packed_floats(L.C.byref(desc)))
+    if n < 0:
+        raise RuntimeError(f"piml_pinnsf_packed_floats failed: {L.last_error()}")
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    L.check(L.load().piml_pinnsf_pack_f32(L.C.byref(desc), L.ptr(src), L.ptr(out), L.stream_ptr(dev)),
+            "piml_pinnsf_pack_f32")
+    return out
 
 
 def pinnsf_forward(spec, packed, ped_features, obs_features, self_features, drop_ped=None, drop_obs=None,
@@ -163,7 +175,7 @@ class _PackCache(object):
         params = [p for _, p in sorted(module.state_dict(keep_vars=True).items())]
         key = tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
-            self.packed = pack_state_dict(module.state_dict(), spec).to(params[0].device)
+            self.packed = pack_device(module.state_dict(), spec, params[0].device)
             self.key = key
         return self.packed
 

@@ -158,7 +158,7 @@ def get_multiple_rollouts(simulator, data, t_start=0, load_model=True, result_cl
     dev = torch.device("cuda", torch.cuda.current_device())
     module = simulator.model.module if isinstance(simulator.model, torch.nn.DataParallel) else simulator.model
     spec = M.spec_from_module(module)
-    packed = M.pack_state_dict(module.state_dict(), spec).to(dev)
+    packed = M.pack_device(module.state_dict(), spec, dev)
     if not hasattr(args, "time_unit"):
         args.time_unit = data.time_unit
     scene = scene_from_data(data, t_start, dev)

@@ -55,7 +55,7 @@ def main():
                                                   "pairs_per_s": N * (N + obs.shape[0]) / ms * 1e3}
     torch.manual_seed(666)
     net = M.PINNSF_bottleneck_multitask(bm_args()).to(dev).eval()
-    packed = M.pack_state_dict(net.state_dict(), net.spec).to(dev)
+    packed = M.pack_device(net.state_dict(), net.spec, dev)
     slf = torch.cat([feats[2][0], v, acc, ds], -1)
     ms = timeit(lambda: M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False))
     out["pinnsf_bm_forward_N%d" % N] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,

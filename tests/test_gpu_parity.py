@@ -302,7 +302,7 @@ def test_rollout_resynchronised_steps(name):
     ds = cu(i["desired_speed"])[None]
     obs = cu(i["obstacles"])
     spec = m.spec
-    packed = M.pack_state_dict(m.state_dict(), spec).cuda()
+    packed = M.pack_device(m.state_dict(), spec)
     worst = 0.0
     for t in range(t0 + 1, T - 1, max(1, (T - t0) // 60)):
         p, v, a = P_[t][None].clone(), V_[t][None].clone(), A_[t][None].clone()
@@ -330,7 +330,7 @@ def test_rollout_free_running(name):
     scene["obstacles"] = cu(i["obstacles"])
     for k in ("ped_features0", "obs_features0", "self_features0"):
         scene[k] = cu(i[k])[None]
-    packed = M.pack_state_dict(m.state_dict(), m.spec).cuda()
+    packed = M.pack_device(m.state_dict(), m.spec)
     p_res, v_res, a_res, mask = rollout_scenes(m.spec, packed, args, scene, t0, T)
     p_res, mask = npy(p_res[0]), npy(mask[0])
     assert np.array_equal(mask, o["mask_p"])

@@ -37,12 +37,18 @@ def test_pack_layouts():
     args = model_args("pinnsf_bm", g["cfg"], "gc1560")
     spec = M.spec_from_args("pinnsf_bm", args)
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
-    a = M.pack_state_dict(sd, spec, transposed=True)
-    b = M.pack_state_dict(sd, spec, transposed=False)
+    b = M.pack_state_dict(sd, spec)
     n_branch = 6 * 128 + 128 + 2 * (128 * 128 + 128) + 128 * 64 + 64 + 64 * 64 + 64 + 64 * 2 + 2
-    assert a.numel() == b.numel() == 2 * n_branch + 64 * 64 + 64 + 64 + 1
+    assert b.numel() == 2 * n_branch + 64 * 64 + 64 + 64 + 1
     w0 = sd["ped_encoder.mlp.0.weight"]
-    assert torch.equal(b[:768].view(128, 6), w0) and torch.equal(a[:768].view(6, 128), w0.t())
+    assert torch.equal(b[:768].view(128, 6), w0)
+    # the device layout pads every Linear to 16*NJ columns (+ a padded bias); size comes from the library (no GPU)
+    from piml_b200 import _lib
+    desc = spec.desc()
+    n_dev = _lib.load().piml_pinnsf_packed_floats(_lib.C.byref(desc))
+    pad = lambda k, o: (k + 1) * (16 * (8 if o > 64 else 4 if o > 32 else 2 if o > 16 else 1))   # noqa: E731
+    n_branch_dev = pad(6, 128) + 2 * pad(128, 128) + pad(128, 64) + pad(64, 64) + pad(64, 2)
+    assert n_dev == 2 * n_branch_dev + pad(64, 64) + pad(64, 1)
     # dead weights (ResDNN block-0 Linear when processor_hidden_layers > 1) are not packed
     assert spec.proc_mode == 0 and not any("processor" in k for k in M.linear_keys(spec))
 

@@ -108,7 +108,7 @@ def _oracle_model(z, kind):
     coll_dims = [dec[-1], dec[-1], 1] if coll == 'dec' else ([hs_p, dec[-1], 1] if coll == 'proc' else [])
     spec = M.NetSpec(enc, 0 if nl_p > 1 else 1, dec, coll_dims, kind_id, bool(has_obs), float(g["tau"]))
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
-    packed = M.pack_state_dict(sd, spec, transposed=False).numpy()
+    packed = M.pack_state_dict(sd, spec).numpy()
     desc = O.net_desc(spec.enc_dims, spec.proc_mode, spec.dec_dims, spec.coll_dims, spec.kind)
     return g, spec, desc, packed
 
@@ -165,7 +165,7 @@ def test_rollout_resynchronised_network_output(name):
     kind, dsn = str(i["model"]), str(i["dataset_name"])
     spec = M.spec_from_args(kind, base_args(model=kind, dataset_name=dsn))
     sd = {k[3:]: torch.from_numpy(v) for k, v in group(golden("models"), kind).items() if k.startswith("sd/")}
-    packed = M.pack_state_dict(sd, spec, transposed=False).numpy()
+    packed = M.pack_state_dict(sd, spec).numpy()
     desc = O.net_desc(spec.enc_dims, spec.proc_mode, spec.dec_dims, spec.coll_dims, spec.kind)
     T, t0 = int(i["num_frames"]), int(i["t_start"])
     flag = i["mask_p"] - i["mask_p_pred"]
