@@ -93,6 +93,25 @@ PIML_API int piml_state_features_f32(const float *pos, float *vel, float *acc, c
 /* Pedestrians.calculate_collision_label (data.py:515-535). ped_f (S,6) -> out (S) in {0,1}. */
 PIML_API int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream);
 
+/* Backward of piml_relative_features_f32 / the feature rebuild inside the differentiable rollout
+ * (simulators.py:772-778 -> data.py:466-512; autograd through the subtractions of get_relative_quantity and the
+ * gather of get_filtered_features; the sort indices carry no gradient).  B frames of N agents.
+ * ped_idx (B,N,kp), obs_idx (B,N,ko): the selection the forward reported (-1 = zero-padded slot).
+ * g_ped_f (B,N,kp,6), g_obs_f (B,N,ko,6) [NULL if ko == 0], g_dest_f (B,N,2) [may be NULL].
+ * Outputs g_pos, g_vel, g_acc, g_dest (B,N,2); neighbour contributions are scattered with fp32 atomics. */
+PIML_API int piml_relative_features_backward_f32(const float *pos, const float *dest, const int64_t *ped_idx,
+                                        const int64_t *obs_idx, int B, int N, int kp, int ko, const float *g_ped_f,
+                                        const float *g_obs_f, const float *g_dest_f, float *g_pos, float *g_vel,
+                                        float *g_acc, float *g_dest, void *stream);
+
+/* Pedestrians.collision_detection (data.py:538-601).  mode 3: position (T,N,2) [pass C = 1]; pairs that are closer
+ * than `threshold` in more than 25 frames of position (or of real_position (T,N,2) when given) are friends and do not
+ * count.  mode 4: position (C,T,N,2); pairs that touch in any of the first 4 frames of a channel are friends.
+ * out_full (C,T,N,N) 0/1 and/or out_rowsum (C,T,N) = sum over the last axis (the only use the training rollout makes
+ * of it, simulators.py:707-724); either may be NULL. */
+PIML_API int piml_collision_detection_f32(const float *position, const float *real_position, int C, int T, int N,
+                                 float threshold, int mode, float *out_full, float *out_rowsum, void *stream);
+
 /* ---- MLAPM: src/models/mlapm.py:10-58, loop src/main_mlapm.py:18-36 ----------------------------------------- */
 
 typedef struct {
@@ -163,6 +182,36 @@ PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *par
                             int norm_group, const float *drop_ped, const float *drop_obs, float *acc,
                             float *ped_msgs, float *obs_msgs, float *coll, void *stream);
 
+/* ---- training: forward with activation stash + backward (loss.backward(), simulators.py:359, through the models) -- */
+
+/* Floats of the activation stash of the training-mode forward for R agents (every Linear's post-activation output,
+ * row-major per layer) and of the backward's workspace (per-layer pre-activation gradients + dW split partials). */
+PIML_API int64_t piml_pinnsf_stash_floats(const piml_net_desc *desc, int has_obs, int64_t R, int kp, int ko);
+PIML_API int64_t piml_pinnsf_backward_workspace_floats(const piml_net_desc *desc, int has_obs, int64_t R, int kp, int ko);
+
+/* piml_pinnsf_forward_f32 that also fills `stash` (piml_pinnsf_stash_floats floats) for piml_pinnsf_backward_f32.
+ * coll must be non-NULL when the model has a collision head.  processor_hidden_layers == 1 -> PIML_ERR_UNSUPPORTED. */
+PIML_API int piml_pinnsf_forward_train_f32(const piml_net_desc *desc, const float *params, int has_obs, float tau,
+                                  const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
+                                  int norm_group, const float *drop_ped, const float *drop_obs, float *acc,
+                                  float *ped_msgs, float *obs_msgs, float *coll, float *stash, void *stream);
+
+/* Backward-pass parameter layout: per Linear torch's own (out,in) matrix with tile-permuted columns (dX = dY W). */
+PIML_API int64_t piml_pinnsf_packed_bwd_floats(const piml_net_desc *desc);
+PIML_API int piml_pinnsf_pack_bwd_f32(const piml_net_desc *desc, const float *params_torch, float *packed_bwd, void *stream);
+
+/* Backward of the forward above.  Inputs: the forward's inputs and stash, and the gradients of its outputs
+ * g_acc (R,2) [required], g_ped_msgs (R,kp,msgw), g_obs_msgs (R,ko,msgw), g_coll (R,kp) [each may be NULL = zero].
+ * Outputs: g_params = gradient in the layout of params_torch (piml_pinnsf_pack_f32's input; ped branch, obs branch,
+ * collision head; per Linear weight (out,in) then bias); g_ped (R,kp,6), g_obs (R,ko,6), g_self (R,7) [may be NULL].
+ * workspace: piml_pinnsf_backward_workspace_floats floats, 16-byte aligned.  Deterministic (no atomics). */
+PIML_API int piml_pinnsf_backward_f32(const piml_net_desc *desc, const float *packed_bwd, int has_obs, float tau,
+                             const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
+                             int norm_group, const float *drop_ped, const float *drop_obs, const float *stash,
+                             const float *g_acc, const float *g_ped_msgs, const float *g_obs_msgs,
+                             const float *g_coll, float *g_params, float *g_ped, float *g_obs, float *g_self,
+                             float *workspace, void *stream);
+
 /* ---- integrator: src/models/simulators.py:603-639 ---------------------------------------------------------- */
 
 /* One state update of get_multiple_rollouts for S scenes of N slots: lagged explicit
@@ -175,6 +224,13 @@ PIML_API int piml_integrate_step_f32(float *p, float *v, float *a, const float *
                             int remove_on_arrival, const int64_t *entry, const float *p_gt, const float *v_gt,
                             const float *a_gt, const float *dest_gt, const int64_t *dest_idx_gt, float *hist_v,
                             float *rec_p, float *rec_v, float *rec_a, float *rec_mask, void *stream);
+
+/* Backward of the differentiable rollout's state update (simulators.py:741-769: v' = v + a dt, p' = p + v dt,
+ * a' = model output; agents overwritten by teacher-forced entry get no gradient).  n = S*N agents.
+ * entry (n) int64 or NULL; g_p2,g_v2,g_a2 (n,2) = gradients of the updated state -> g_p,g_v,g_a,g_a_next (n,2). */
+PIML_API int piml_integrate_step_backward_f32(const int64_t *entry, int64_t n, float dt, const float *g_p2,
+                                     const float *g_v2, const float *g_a2, float *g_p, float *g_v, float *g_a,
+                                     float *g_a_next, void *stream);
 
 #ifdef __cplusplus
 }

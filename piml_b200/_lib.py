@@ -51,6 +51,17 @@ SIGNATURES = {
     "piml_pinnsf_pack_f32": (i32, [C.POINTER(NetDesc), vp, vp, vp]),
     "piml_pinnsf_forward_f32": (i32, [C.POINTER(NetDesc), vp, i32, f32, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp,
                                       vp, vp, vp, vp]),
+    "piml_pinnsf_stash_floats": (i64, [C.POINTER(NetDesc), i32, i64, i32, i32]),
+    "piml_pinnsf_backward_workspace_floats": (i64, [C.POINTER(NetDesc), i32, i64, i32, i32]),
+    "piml_pinnsf_forward_train_f32": (i32, [C.POINTER(NetDesc), vp, i32, f32, vp, vp, vp, i64, i32, i32, i32, vp, vp,
+                                            vp, vp, vp, vp, vp, vp]),
+    "piml_pinnsf_packed_bwd_floats": (i64, [C.POINTER(NetDesc)]),
+    "piml_pinnsf_pack_bwd_f32": (i32, [C.POINTER(NetDesc), vp, vp, vp]),
+    "piml_pinnsf_backward_f32": (i32, [C.POINTER(NetDesc), vp, i32, f32, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp,
+                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "piml_relative_features_backward_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "piml_collision_detection_f32": (i32, [vp, vp, i32, i32, i32, f32, i32, vp, vp, vp]),
+    "piml_integrate_step_backward_f32": (i32, [vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_integrate_step_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp,
                                       vp, vp, vp, vp, vp, vp, vp]),
 }

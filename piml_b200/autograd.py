@@ -1,0 +1,173 @@
+"""torch.autograd bindings of the CUDA forward/backward kernels used by the training paths.
+
+The reference trains through eager autograd: `loss.backward()` (src/models/simulators.py:359) walks the graph built
+by `model(*state_features)` (:330, :701), the Euler chain (:741-743), the entry overwrite (:762-769) and
+`get_relative_features` (:772-776 -> src/data/data.py:466-512).  Here each of those stages is one
+`torch.autograd.Function` whose forward AND backward are kernels of libpiml_b200.so; torch only routes the gradients.
+"""
+import torch
+
+from . import _lib as L
+
+
+def _floats(fn_name, desc, has_obs, R, kp, ko):
+    n = int(getattr(L.load(), fn_name)(L.C.byref(desc), 1 if has_obs else 0, R, kp, ko))
+    if n < 0:
+        raise RuntimeError(f"{fn_name} failed: {L.last_error()}")
+    return n
+
+
+class PinnsfFunction(torch.autograd.Function):
+    """PINNSF-family forward with activation stash (piml_pinnsf_forward_train_f32) and its backward
+    (piml_pinnsf_backward_f32).  `params` are the module's Linear weights/biases in `models.linear_keys` order; they
+    only route gradients -- the kernels read the packed copies `packed_fwd` / `packed_bwd`."""
+
+    @staticmethod
+    def forward(ctx, spec, packed_fwd, packed_bwd, ped, obs, slf, drop_ped, drop_obs, *params):
+        dev = L.require_cuda(packed_fwd, ped, slf)
+        ped, slf = L.f32c(ped), L.f32c(slf)
+        lead = slf.shape[:-1]
+        R = 1
+        for s in lead:
+            R *= s
+        kp = ped.shape[-2]
+        if slf.dim() == 2:
+            group = 0
+        elif slf.dim() == 3:
+            group = slf.shape[1]          # torch.norm(..., dim=1) reduces over the agents of a channel (model.py:1206)
+        else:
+            raise NotImplementedError("self_features must be (N,7) or (C,N,7)")
+        ko = 0
+        if spec.has_obs:
+            obs = L.f32c(obs)
+            ko = obs.shape[-2]
+        else:
+            obs = None
+        desc = spec.desc()
+        mw = spec.msg_width
+        acc = torch.empty(*lead, 2, device=dev)
+        pm = torch.empty(*lead, kp, mw, device=dev)
+        om = torch.empty(*lead, ko, mw, device=dev) if spec.has_obs else None
+        coll = torch.empty(*lead, kp, 1, device=dev) if spec.coll_dims else None
+        stash = torch.empty(_floats("piml_pinnsf_stash_floats", desc, spec.has_obs, R, kp, ko), device=dev)
+        dp = L.f32c(drop_ped) if drop_ped is not None else None
+        do = L.f32c(drop_obs) if (drop_obs is not None and spec.has_obs) else None
+        L.check(L.load().piml_pinnsf_forward_train_f32(
+            L.C.byref(desc), L.ptr(packed_fwd), 1 if spec.has_obs else 0, spec.tau, L.ptr(ped), L.ptr(obs),
+            L.ptr(slf), R, kp, ko, group, L.ptr(dp), L.ptr(do), L.ptr(acc), L.ptr(pm), L.ptr(om), L.ptr(coll),
+            L.ptr(stash), L.stream_ptr(dev)), "piml_pinnsf_forward_train_f32")
+        ctx.spec, ctx.dims = spec, (R, kp, ko, group)
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(packed_bwd, ped, obs, slf, dp, do, stash)
+        outs = [acc, pm]
+        if spec.has_obs:
+            outs.append(om)
+        if spec.coll_dims:
+            outs.append(coll)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        packed_bwd, ped, obs, slf, dp, do, stash = ctx.saved_tensors
+        spec = ctx.spec
+        R, kp, ko, group = ctx.dims
+        dev = ped.device
+        grads = list(grads)
+        g_acc = grads.pop(0)
+        g_pm = grads.pop(0)
+        g_om = grads.pop(0) if spec.has_obs else None
+        g_coll = grads.pop(0) if spec.coll_dims else None
+        g_acc = L.f32c(g_acc) if g_acc is not None else torch.zeros(R, 2, device=dev)
+        g_pm = L.f32c(g_pm) if g_pm is not None else None
+        g_om = L.f32c(g_om) if g_om is not None else None
+        g_coll = L.f32c(g_coll) if g_coll is not None else None
+        desc = spec.desc()
+        n_par = sum(int(torch.Size(s).numel()) for s in ctx.param_shapes)
+        g_params = torch.empty(n_par, device=dev)
+        g_ped = torch.empty_like(ped) if ctx.needs_input_grad[3] else None
+        g_obs = torch.empty_like(obs) if (obs is not None and ctx.needs_input_grad[4]) else None
+        g_self = torch.empty_like(slf) if ctx.needs_input_grad[5] else None
+        ws = torch.empty(_floats("piml_pinnsf_backward_workspace_floats", desc, spec.has_obs, R, kp, ko), device=dev)
+        L.check(L.load().piml_pinnsf_backward_f32(
+            L.C.byref(desc), L.ptr(packed_bwd), 1 if spec.has_obs else 0, spec.tau, L.ptr(ped), L.ptr(obs),
+            L.ptr(slf), R, kp, ko, group, L.ptr(dp), L.ptr(do), L.ptr(stash), L.ptr(g_acc), L.ptr(g_pm), L.ptr(g_om),
+            L.ptr(g_coll), L.ptr(g_params), L.ptr(g_ped), L.ptr(g_obs), L.ptr(g_self), L.ptr(ws), L.stream_ptr(dev)),
+            "piml_pinnsf_backward_f32")
+        pg, off = [], 0
+        for shp in ctx.param_shapes:
+            n = int(torch.Size(shp).numel())
+            pg.append(g_params[off:off + n].view(shp))
+            off += n
+        return (None, None, None, g_ped, g_obs, g_self, None, None, *pg)
+
+
+class RelativeFeaturesFunction(torch.autograd.Function):
+    """`Pedestrians.get_relative_features` (data.py:466-512) with a CUDA backward: the forward kernel reports which
+    agent / obstacle filled every slot; the backward scatters the feature gradients back to p, v, a and dest."""
+
+    @staticmethod
+    def forward(ctx, peds, position, velocity, acceleration, destination, obstacles, topk_ped, sight_angle_ped,
+                dist_threshold_ped, topk_obs, sight_angle_obs, dist_threshold_obs):
+        ped_f, obs_f, dest_f, sel = peds._relative_features_raw(
+            position, velocity, acceleration, destination, obstacles, topk_ped, sight_angle_ped, dist_threshold_ped,
+            topk_obs, sight_angle_obs, dist_threshold_obs, return_selection=True)
+        ctx.save_for_backward(L.f32c(position), L.f32c(destination), sel[0], sel[2])
+        return ped_f, obs_f, dest_f
+
+    @staticmethod
+    def backward(ctx, g_ped, g_obs, g_dest):
+        pos, dest, pidx, oidx = ctx.saved_tensors
+        dev = pos.device
+        N = pos.shape[-2]
+        B = pos.numel() // (2 * N)
+        kp, ko = pidx.shape[-1], oidx.shape[-1]
+        g_ped = L.f32c(g_ped) if g_ped is not None else torch.zeros(*pidx.shape, 6, device=dev)
+        if ko:
+            g_obs = L.f32c(g_obs) if g_obs is not None else torch.zeros(*oidx.shape, 6, device=dev)
+        else:
+            g_obs = None
+        g_dest = L.f32c(g_dest) if g_dest is not None else None
+        outs = [torch.empty_like(pos) for _ in range(4)]
+        L.check(L.load().piml_relative_features_backward_f32(
+            L.ptr(pos), L.ptr(dest), L.ptr(pidx), L.ptr(oidx) if ko else None, B, N, kp, ko, L.ptr(g_ped),
+            L.ptr(g_obs), L.ptr(g_dest), *[L.ptr(o) for o in outs], L.stream_ptr(dev)),
+            "piml_relative_features_backward_f32")
+        g_pos, g_vel, g_acc, g_dst = outs
+        return (None, g_pos, g_vel, g_acc, g_dst, None, None, None, None, None, None, None)
+
+
+class IntegrateTrainFunction(torch.autograd.Function):
+    """State update of the differentiable rollout (simulators.py:741-769): lagged explicit Euler, waypoint switch
+    WITHOUT removal on arrival, teacher-forced entry.  Returns new tensors (p, v, a, dest, dest_idx); the last two
+    carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, p, v, a, a_next, dest, dest_idx, dest_num, waypoints, dt, entry, p_gt, v_gt, a_gt, dest_gt,
+                dest_idx_gt):
+        from .rollout import integrate_step
+        p2, v2, a2 = L.f32c(p).clone(), L.f32c(v).clone(), L.f32c(a).clone()
+        dest2, didx2 = L.f32c(dest).clone(), dest_idx.contiguous().clone()
+        integrate_step(p2, v2, a2, a_next, dest2, didx2, dest_num, waypoints, dt, False, entry, p_gt, v_gt, a_gt,
+                       dest_gt, dest_idx_gt)
+        ctx.dt = float(dt)
+        ctx.save_for_backward(entry.contiguous() if entry is not None else None)
+        ctx.mark_non_differentiable(dest2, didx2)
+        return p2, v2, a2, dest2, didx2
+
+    @staticmethod
+    def backward(ctx, g_p2, g_v2, g_a2, _gd, _gi):
+        (entry,) = ctx.saved_tensors
+        ref = next(g for g in (g_p2, g_v2, g_a2) if g is not None)
+        dev = ref.device
+        z = None
+        gs = []
+        for g in (g_p2, g_v2, g_a2):
+            if g is None:
+                z = z if z is not None else torch.zeros_like(ref)
+                g = z
+            gs.append(L.f32c(g))
+        outs = [torch.empty_like(gs[0]) for _ in range(4)]
+        L.check(L.load().piml_integrate_step_backward_f32(
+            L.ptr(entry), gs[0].numel() // 2, ctx.dt, *[L.ptr(g) for g in gs], *[L.ptr(o) for o in outs],
+            L.stream_ptr(dev)), "piml_integrate_step_backward_f32")
+        return (outs[0], outs[1], outs[2], outs[3]) + (None,) * 11

@@ -325,6 +325,95 @@ __global__ void collision_label_kernel(const float *__restrict__ ped_f, int64_t 
     out[s] = hit;
 }
 
+
+// ---- backward of the relative features (differentiable rollout, simulators.py:772-778) -----------------------------
+struct FeatBwdArgs {
+    const float2 *pos; const float2 *dest; const int64_t *ped_idx; const int64_t *obs_idx; int64_t rows; int N, kp, ko;
+    const float2 *g_ped_f; const float2 *g_obs_f; const float2 *g_dest_f;
+    float *g_pos; float *g_vel; float *g_acc; float2 *g_dest;
+};
+
+__device__ __forceinline__ void atomic_add2(float *base, int64_t i, float2 g) {
+    atomicAdd(base + 2 * i, g.x);
+    atomicAdd(base + 2 * i + 1, g.y);
+}
+
+// one thread per (frame, agent): its own (negative) share is summed in registers, the neighbours' (positive) shares
+// are scattered.  ped_f = (p_m - p_n, v_m - v_n, a_m - a_n), obs_f = (o - p_n, -v_n, -a_n), dest_f = dest - p_n.
+__global__ void relative_features_bwd_kernel(FeatBwdArgs a) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= a.rows) return;
+    const int64_t frame0 = (row / a.N) * a.N;
+    float2 gp = make_float2(0.f, 0.f), gv = gp, ga = gp;
+    for (int j = 0; j < a.kp; ++j) {
+        const int64_t m = a.ped_idx[row * a.kp + j];
+        if (m < 0) continue;                                      // zero-padded slot: constant (data.py:459-462)
+        const float2 *g = a.g_ped_f + (row * a.kp + j) * 3;
+        const float2 g0 = g[0], g1 = g[1], g2 = g[2];
+        gp.x -= g0.x; gp.y -= g0.y; gv.x -= g1.x; gv.y -= g1.y; ga.x -= g2.x; ga.y -= g2.y;
+        atomic_add2(a.g_pos, frame0 + m, g0);
+        atomic_add2(a.g_vel, frame0 + m, g1);
+        atomic_add2(a.g_acc, frame0 + m, g2);
+    }
+    for (int j = 0; j < a.ko; ++j) {
+        if (a.obs_idx[row * a.ko + j] < 0) continue;
+        const float2 *g = a.g_obs_f + (row * a.ko + j) * 3;
+        const float2 g0 = g[0], g1 = g[1], g2 = g[2];
+        gp.x -= g0.x; gp.y -= g0.y; gv.x -= g1.x; gv.y -= g1.y; ga.x -= g2.x; ga.y -= g2.y;
+    }
+    float2 gd = make_float2(0.f, 0.f);
+    if (a.g_dest_f) {                                             // dest_features[isnan] = 0 cuts the gradient (:497)
+        const float2 p = a.pos[row], d = a.dest[row], g = a.g_dest_f[row];
+        const float dx = d.x - p.x, dy = d.y - p.y;
+        if (!(dx != dx)) { gd.x = g.x; gp.x -= g.x; }
+        if (!(dy != dy)) { gd.y = g.y; gp.y -= g.y; }
+    }
+    a.g_dest[row] = gd;
+    atomic_add2(a.g_pos, row, gp);
+    atomic_add2(a.g_vel, row, gv);
+    atomic_add2(a.g_acc, row, ga);
+}
+
+// ---- Pedestrians.collision_detection (data.py:538-601) ---------------------------------------------------------
+struct CollArgs {
+    const float2 *pos; const float2 *real; int C, T, N; float thr; int mode; float *full; float *rowsum;
+};
+
+__device__ __forceinline__ bool touching(const float2 *frame, int n, int m, float thr) {
+    const float2 pn = frame[n], pm = frame[m];
+    const float d = norm2_rn(__fsub_rn(pm.x, pn.x), __fsub_rn(pm.y, pn.y));      // NaN compares false -> 0 (:550)
+    return d < thr;
+}
+
+// one thread per (channel, n, m); walks the time axis twice (friends, then output).
+__global__ void collision_detection_kernel(CollArgs a) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t NN = static_cast<int64_t>(a.N) * a.N;
+    if (i >= NN * a.C) return;
+    const int c = static_cast<int>(i / NN);
+    const int n = static_cast<int>((i % NN) / a.N), m = static_cast<int>(i % a.N);
+    const float2 *base = a.pos + static_cast<int64_t>(c) * a.T * a.N;
+    bool friends;
+    if (a.mode == 3) {
+        // friends: more than 25 touching frames in real_position (diagonal included there, :571-579) or in position
+        int cnt = 0;
+        if (a.real) { for (int t = 0; t < a.T; ++t) cnt += touching(a.real + static_cast<int64_t>(t) * a.N, n, m, a.thr); }
+        else if (n != m) { for (int t = 0; t < a.T; ++t) cnt += touching(base + static_cast<int64_t>(t) * a.N, n, m, a.thr); }
+        friends = cnt > 25;
+    } else {
+        // training: pairs touching in any of the first 4 frames are friends (:588-593)
+        friends = false;
+        if (n != m)
+            for (int t = 0; t < min(4, a.T); ++t) friends |= touching(base + static_cast<int64_t>(t) * a.N, n, m, a.thr);
+    }
+    for (int t = 0; t < a.T; ++t) {
+        const bool hit = n != m && !friends && touching(base + static_cast<int64_t>(t) * a.N, n, m, a.thr);
+        const int64_t fr = static_cast<int64_t>(c) * a.T + t;
+        if (a.full) a.full[(fr * a.N + n) * a.N + m] = hit ? 1.f : 0.f;
+        if (a.rowsum && hit) atomicAdd(a.rowsum + fr * a.N + n, 1.f);       // integer-valued: order independent
+    }
+}
+
 static int pick_group(int64_t B, int N) {
     // enough CTAs to fill 148 SMs several times over with one thread per row?  otherwise spread a row over lanes
     const int64_t target = 4LL * sm_count();
@@ -470,4 +559,51 @@ extern "C" int piml_collision_label_f32(const float *ped_f, int64_t S, float *ou
                              static_cast<cudaStream_t>(stream)>>>(ped_f, S, out);
     count_launch();
     return check_launch("collision_label_kernel");
+}
+
+extern "C" int piml_relative_features_backward_f32(const float *pos, const float *dest, const int64_t *ped_idx,
+                                                   const int64_t *obs_idx, int B, int N, int kp, int ko,
+                                                   const float *g_ped_f, const float *g_obs_f, const float *g_dest_f,
+                                                   float *g_pos, float *g_vel, float *g_acc, float *g_dest,
+                                                   void *stream) {
+    PIML_REQUIRE(pos && dest && g_pos && g_vel && g_acc && g_dest, "piml_relative_features_backward_f32: null pointer");
+    PIML_REQUIRE(B >= 0 && N >= 0 && kp >= 0 && ko >= 0, "piml_relative_features_backward_f32: negative dimension");
+    PIML_REQUIRE(kp == 0 || (ped_idx && g_ped_f), "piml_relative_features_backward_f32: ped_idx / g_ped_f is null");
+    PIML_REQUIRE(ko == 0 || (obs_idx && g_obs_f), "piml_relative_features_backward_f32: obs_idx / g_obs_f is null");
+    const int64_t rows = static_cast<int64_t>(B) * N;
+    if (rows == 0) return PIML_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PIML_CUDA(cudaMemsetAsync(g_pos, 0, sizeof(float) * 2 * rows, st));
+    PIML_CUDA(cudaMemsetAsync(g_vel, 0, sizeof(float) * 2 * rows, st));
+    PIML_CUDA(cudaMemsetAsync(g_acc, 0, sizeof(float) * 2 * rows, st));
+    FeatBwdArgs a;
+    a.pos = reinterpret_cast<const float2 *>(pos); a.dest = reinterpret_cast<const float2 *>(dest);
+    a.ped_idx = ped_idx; a.obs_idx = obs_idx; a.rows = rows; a.N = N; a.kp = kp; a.ko = ko;
+    a.g_ped_f = reinterpret_cast<const float2 *>(g_ped_f); a.g_obs_f = reinterpret_cast<const float2 *>(g_obs_f);
+    a.g_dest_f = reinterpret_cast<const float2 *>(g_dest_f);
+    a.g_pos = g_pos; a.g_vel = g_vel; a.g_acc = g_acc; a.g_dest = reinterpret_cast<float2 *>(g_dest);
+    const int threads = 128;
+    relative_features_bwd_kernel<<<static_cast<unsigned>((rows + threads - 1) / threads), threads, 0, st>>>(a);
+    count_launch();
+    return check_launch("relative_features_bwd_kernel");
+}
+
+extern "C" int piml_collision_detection_f32(const float *position, const float *real_position, int C, int T, int N,
+                                            float threshold, int mode, float *out_full, float *out_rowsum,
+                                            void *stream) {
+    PIML_REQUIRE(position && (out_full || out_rowsum), "piml_collision_detection_f32: null pointer");
+    PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0, "piml_collision_detection_f32: negative dimension");
+    PIML_REQUIRE(mode == 3 || mode == 4, "piml_collision_detection_f32: mode must be 3 or 4 (input rank)");
+    PIML_REQUIRE(mode == 4 || C == 1, "piml_collision_detection_f32: mode 3 takes one (T,N,2) clip (C = 1)");
+    PIML_REQUIRE(!real_position || mode == 3, "piml_collision_detection_f32: real_position only with mode 3");
+    const int64_t tot = static_cast<int64_t>(C) * N * N;
+    if (tot == 0 || T == 0) return PIML_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out_rowsum) PIML_CUDA(cudaMemsetAsync(out_rowsum, 0, sizeof(float) * C * T * N, st));
+    CollArgs a{reinterpret_cast<const float2 *>(position), reinterpret_cast<const float2 *>(real_position), C, T, N,
+               threshold, mode, out_full, out_rowsum};
+    const int threads = 256;
+    collision_detection_kernel<<<static_cast<unsigned>((tot + threads - 1) / threads), threads, 0, st>>>(a);
+    count_launch();
+    return check_launch("collision_detection_kernel");
 }

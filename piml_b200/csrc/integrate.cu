@@ -49,6 +49,21 @@ __global__ void integrate_kernel(IntArgs g) {
     if (g.hist_v) g.hist_v[i] = hv;
 }
 
+// backward of v' = v + a dt, p' = p + v dt, a' = a_next with teacher-forced entry (simulators.py:741-769)
+__global__ void integrate_bwd_kernel(const int64_t *__restrict__ entry, int64_t n, float dt,
+                                     const float2 *__restrict__ g_p2, const float2 *__restrict__ g_v2,
+                                     const float2 *__restrict__ g_a2, float2 *__restrict__ g_p,
+                                     float2 *__restrict__ g_v, float2 *__restrict__ g_a, float2 *__restrict__ g_an) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 gp = g_p2[i], gv = g_v2[i], ga = g_a2[i];
+    if (entry && entry[i] == 1) gp = gv = ga = make_float2(0.f, 0.f);           // overwritten from the data
+    g_p[i] = gp;
+    g_v[i] = make_float2(fmaf(gp.x, dt, gv.x), fmaf(gp.y, dt, gv.y));
+    g_a[i] = make_float2(gv.x * dt, gv.y * dt);
+    g_an[i] = ga;
+}
+
 }  // namespace piml
 
 using namespace piml;
@@ -81,4 +96,20 @@ extern "C" int piml_integrate_step_f32(float *p, float *v, float *a, const float
                        static_cast<cudaStream_t>(stream)>>>(g);
     count_launch();
     return check_launch("integrate_kernel");
+}
+
+extern "C" int piml_integrate_step_backward_f32(const int64_t *entry, int64_t n, float dt, const float *g_p2,
+                                                const float *g_v2, const float *g_a2, float *g_p, float *g_v,
+                                                float *g_a, float *g_a_next, void *stream) {
+    PIML_REQUIRE(g_p2 && g_v2 && g_a2 && g_p && g_v && g_a && g_a_next, "piml_integrate_step_backward_f32: null pointer");
+    PIML_REQUIRE(n >= 0, "piml_integrate_step_backward_f32: negative size");
+    if (n == 0) return PIML_OK;
+    const int threads = 128;
+    integrate_bwd_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0,
+                           static_cast<cudaStream_t>(stream)>>>(
+        entry, n, dt, reinterpret_cast<const float2 *>(g_p2), reinterpret_cast<const float2 *>(g_v2),
+        reinterpret_cast<const float2 *>(g_a2), reinterpret_cast<float2 *>(g_p), reinterpret_cast<float2 *>(g_v),
+        reinterpret_cast<float2 *>(g_a), reinterpret_cast<float2 *>(g_a_next));
+    count_launch();
+    return check_launch("integrate_bwd_kernel");
 }

@@ -84,7 +84,25 @@ class Pedestrians(object):
                               return_selection=False):
         """position/velocity/acceleration/destination (*c, t, N, 2); obstacles (M, 2) or (c, M, 2).
         Returns ped_features (*c,t,N,k1,6), obs_features (*c,t,N,k2,6), dest_features (*c,t,N,2).
-        Like the reference it zeroes NaNs IN PLACE in the caller's velocity and acceleration tensors."""
+        Like the reference it zeroes NaNs IN PLACE in the caller's velocity and acceleration tensors.
+        When gradients are being recorded for position / velocity / acceleration / destination (the differentiable
+        rollout, simulators.py:772-776) the call goes through autograd.RelativeFeaturesFunction, whose backward is
+        the CUDA scatter kernel; velocity / acceleration must then be NaN-free (they are: simulators.py:745)."""
+        if torch.is_grad_enabled() and not return_selection and any(
+                t.requires_grad for t in (position, velocity, acceleration, destination)):
+            from .autograd import RelativeFeaturesFunction
+            if not position.is_cuda:
+                raise RuntimeError("piml_b200: the differentiable feature path needs CUDA tensors; no CPU fallback")
+            return RelativeFeaturesFunction.apply(self, position, velocity, acceleration, destination, obstacles,
+                                                  topk_ped, sight_angle_ped, dist_threshold_ped, topk_obs,
+                                                  sight_angle_obs, dist_threshold_obs)
+        return self._relative_features_raw(position, velocity, acceleration, destination, obstacles, topk_ped,
+                                           sight_angle_ped, dist_threshold_ped, topk_obs, sight_angle_obs,
+                                           dist_threshold_obs, return_selection)
+
+    def _relative_features_raw(self, position, velocity, acceleration, destination, obstacles, topk_ped,
+                               sight_angle_ped, dist_threshold_ped, topk_obs, sight_angle_obs, dist_threshold_obs,
+                               return_selection=False):
         if position.dim() not in (3, 4):
             raise ValueError("get_relative_features expects (t,N,2) or (c,t,N,2) inputs")
         _, origin, (pos, vel, acc, dest, obs) = L.stage(position, velocity, acceleration, destination, obstacles)
@@ -126,9 +144,9 @@ class Pedestrians(object):
             L.ptr(dest_f), *selp, L.stream_ptr(dev)), "piml_relative_features_f32")
         # in-place NaN->0 side effect on the caller's tensors (data.py:483-484) when we had to copy them
         if vel.data_ptr() != velocity.data_ptr():
-            velocity.copy_(vel)
+            velocity.detach().copy_(vel)
         if acc.data_ptr() != acceleration.data_ptr():
-            acceleration.copy_(acc)
+            acceleration.detach().copy_(acc)
         if origin != dev:
             ped_f, obs_f, dest_f = ped_f.to(origin), obs_f.to(origin), dest_f.to(origin)
             sel = tuple(s_.to(origin) for s_ in sel) if sel else None
@@ -146,3 +164,33 @@ class Pedestrians(object):
         L.check(L.load().piml_collision_label_f32(L.ptr(f), out.numel(), L.ptr(out), L.stream_ptr(f.device)),
                 "piml_collision_label_f32")
         return out.to(origin)
+
+    # ---- data.py:538-601 -------------------------------------------------------------------------------------
+    @staticmethod
+    def collision_detection(position, threshold, real_position=None, rowsum_only=False):
+        """position (t,N,2) or (c,t,N,2) with NaN for absent pedestrians -> collisions (...,N,N) in {0,1}: pairs
+        closer than `threshold`, self pairs and "friends" removed (3-d input: pairs touching in more than 25 frames of
+        position / real_position; 4-d input: pairs touching within the first 4 frames of a channel).
+        rowsum_only=True returns collisions.sum(-1) without materialising the N x N tensor -- the only use the
+        training rollout makes of it (simulators.py:707-724)."""
+        if position.dim() not in (3, 4):
+            raise ValueError("collision_detection expects (t,N,2) or (c,t,N,2)")
+        if real_position is not None and (real_position.dim() != 3 or position.dim() != 3):
+            raise AssertionError('Value Error: real_position only supports 3 dimensional inputs (t,N,2)')
+        _, origin, (position, real_position) = L.stage(position, real_position)
+        pos = L.f32c(position.detach())
+        real = L.f32c(real_position.detach()) if real_position is not None else None
+        if real is not None and real.shape[-2] != pos.shape[-2]:
+            raise ValueError("real_position must have the same number of pedestrians as position")
+        mode = pos.dim()
+        Cc = pos.shape[0] if mode == 4 else 1
+        T, N = pos.shape[-3], pos.shape[-2]
+        if real is not None and real.shape[0] != T:
+            raise NotImplementedError("real_position with a different number of frames")
+        dev = pos.device
+        full = None if rowsum_only else torch.empty(*pos.shape[:-1], N, device=dev)
+        rows = torch.empty(*pos.shape[:-1], device=dev) if rowsum_only else None
+        L.check(L.load().piml_collision_detection_f32(L.ptr(pos), L.ptr(real), Cc, T, N, float(threshold), mode,
+                                                      L.ptr(full), L.ptr(rows), L.stream_ptr(dev)),
+                "piml_collision_detection_f32")
+        return (rows if rowsum_only else full).to(origin)

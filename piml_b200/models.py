@@ -180,6 +180,60 @@ class _PackCache(object):
         return self.packed
 
 
+def pack_device_bwd(sd, spec, device=None):
+    """Backward-pass parameter layout (piml_pinnsf_pack_bwd_f32): torch's (out,in) matrices, tile-permuted columns."""
+    dev = device if device is not None else L.cuda_device()
+    src = pack_state_dict(sd, spec).to(dev)
+    desc = spec.desc()
+    n = int(L.load().piml_pinnsf_packed_bwd_floats(L.C.byref(desc)))
+    if n < 0:
+        raise RuntimeError(f"piml_pinnsf_packed_bwd_floats failed: {L.last_error()}")
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    L.check(L.load().piml_pinnsf_pack_bwd_f32(L.C.byref(desc), L.ptr(src), L.ptr(out), L.stream_ptr(dev)),
+            "piml_pinnsf_pack_bwd_f32")
+    return out
+
+
+class _TrainPackCache(object):
+    """Forward and backward packed parameter vectors for the autograd path, rebuilt when a parameter changed."""
+
+    def __init__(self):
+        self.key, self.fwd, self.bwd = None, None, None
+
+    def get(self, module, spec):
+        named = dict(module.named_parameters())
+        params = []
+        for k in linear_keys(spec):
+            params += [named[k + ".weight"], named[k + ".bias"]]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            sd = module.state_dict()
+            dev = params[0].device
+            self.fwd, self.bwd, self.key = pack_device(sd, spec, dev), pack_device_bwd(sd, spec, dev), key
+        return params, self.fwd, self.bwd
+
+
+def pinnsf_forward_autograd(module, spec, cache, ped_features, obs_features, self_features, drop_ped, drop_obs):
+    """Differentiable forward: the reference's list [acc, ped_msgs, (obs_msgs), (pred_collision)] with gradients to
+    the module's parameters and to the three feature tensors, through autograd.PinnsfFunction (CUDA both ways)."""
+    from .autograd import PinnsfFunction
+    if self_features.shape[-1] != 7:
+        raise AssertionError('Error: PINN model do not accept inputs of historical velocity')   # model.py:763
+    params, pf, pb = cache.get(module, spec)
+    outs = list(PinnsfFunction.apply(spec, pf, pb, ped_features, obs_features if spec.has_obs else None,
+                                     self_features, drop_ped, drop_obs, *params))
+    if spec.coll_dims:
+        outs[-1] = outs[-1].squeeze()                                                          # model.py:1215
+    return outs
+
+
+def _wants_grad(module, *tensors):
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in module.parameters()) or any(
+        t is not None and t.requires_grad for t in tensors)
+
+
 def _dropout_multipliers(spec, training, ped, obs):
     """Dropout(p) on the processor output in train() (model.py:108,118): multipliers drawn with torch's RNG in the
     reference's order (ped first, then obs) and with the reference's shapes."""
@@ -258,10 +312,14 @@ class _PINNSFBase(nn.Module):
         elif coll == 'proc':
             self.ped_collision_predictor = MLP(pro[-1][-1], [dec[-1], 1])
         self._cache = _PackCache()
+        self._train_cache = _TrainPackCache()
 
     def forward(self, ped_features, obs_features, self_features):
-        packed = self._cache.get(self, self.spec)
         dp, do = _dropout_multipliers(self.spec, self.training, ped_features, obs_features)
+        if _wants_grad(self, ped_features, obs_features, self_features):
+            return pinnsf_forward_autograd(self, self.spec, self._train_cache, ped_features, obs_features,
+                                           self_features, dp, do)
+        packed = self._cache.get(self, self.spec)
         return pinnsf_forward(self.spec, packed, ped_features, obs_features, self_features, dp, do)
 
 
@@ -319,9 +377,11 @@ def forward_from_module(module, ped_features, obs_features, self_features):
     """CUDA forward using the weights held by `module` (a reference model or one of the mirrors above)."""
     ent = _MODULE_CACHES.get(id(module))
     if ent is None or ent[0] is not module:
-        ent = (module, spec_from_module(module), _PackCache())
+        ent = (module, spec_from_module(module), _PackCache(), _TrainPackCache())
         _MODULE_CACHES[id(module)] = ent
-    _, spec, cache = ent
-    packed = cache.get(module, spec)
+    _, spec, cache, train_cache = ent
     dp, do = _dropout_multipliers(spec, module.training, ped_features, obs_features)
+    if _wants_grad(module, ped_features, obs_features, self_features):
+        return pinnsf_forward_autograd(module, spec, train_cache, ped_features, obs_features, self_features, dp, do)
+    packed = cache.get(module, spec)
     return pinnsf_forward(spec, packed, ped_features, obs_features, self_features, dp, do)

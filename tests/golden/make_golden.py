@@ -286,8 +286,143 @@ def gen_rollout():
     save("rollout_ucy_bm", **rollout_case(H.UCY_CLIP, "pinnsf_bm", "ucy", t_start=25, max_frames=200))
 
 
+def _linear_keys(sd):
+    """Linear layers the forward actually uses, in the order piml_b200.models.linear_keys produces them."""
+    keys = []
+    for br in ("ped", "obs"):
+        l = 0
+        while f"{br}_encoder.mlp.{2 * l}.weight" in sd:
+            keys.append(f"{br}_encoder.mlp.{2 * l}"); l += 1
+        l = 0
+        while f"{br}_decoder.mlp.{2 * l}.weight" in sd:
+            keys.append(f"{br}_decoder.mlp.{2 * l}"); l += 1
+        keys.append(f"{br}_predictor.mlp.0")
+    l = 0
+    while f"ped_collision_predictor.mlp.{2 * l}.weight" in sd:
+        keys.append(f"ped_collision_predictor.mlp.{2 * l}"); l += 1
+    return keys
+
+
+def single_step_case(kind, dsn, train_mode, ped, obs, slf, seed=666):
+    """One forward + backward of the reference module (simulators.py:330-359 shape of work): a fixed random linear
+    functional of every output, gradients w.r.t. every parameter and the three inputs.  In train() mode the
+    Dropout multipliers the reference drew are recorded so the CUDA path can be fed the same ones."""
+    args = model_args(kind, False, True, dsn)
+    torch.manual_seed(seed)
+    m = getattr(MODEL, MODEL_CLASSES[kind])(args)
+    m.train(train_mode)
+    masks = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            x = inp[0]
+            masks[name] = torch.where(x != 0, out / x, torch.ones_like(x) * float('nan')).detach()
+        return f
+    hs = [m.ped_processor.dropout.register_forward_hook(hook("ped")),
+          m.obs_processor.dropout.register_forward_hook(hook("obs"))]
+    ped, obs, slf = [x.clone().requires_grad_(True) for x in (ped, obs, slf)]
+    torch.manual_seed(seed + 1)
+    outs = m(ped, obs, slf)
+    g = torch.Generator().manual_seed(seed + 2)
+    ws = [torch.randn(o.shape, generator=g) for o in outs]
+    loss = sum((o * w).sum() for o, w in zip(outs, ws))
+    loss.backward()
+    for h in hs:
+        h.remove()
+    pre = f"{kind}_{'train' if train_mode else 'eval'}/"
+    out = {pre + "loss": loss.detach(), pre + "g_ped": ped.grad, pre + "g_obs": obs.grad, pre + "g_self": slf.grad,
+           pre + "dataset_name": np.array(dsn)}
+    for i, (o, w) in enumerate(zip(outs, ws)):
+        out[pre + f"out{i}"] = o.detach()
+        out[pre + f"w{i}"] = w
+    named = dict(m.named_parameters())
+    for k in _linear_keys(m.state_dict()):
+        out[pre + "grad/" + k + ".weight"] = named[k + ".weight"].grad
+        out[pre + "grad/" + k + ".bias"] = named[k + ".bias"].grad
+    dead = [k for k, p_ in named.items() if p_.grad is None]
+    out[pre + "dead"] = np.array(dead)
+    if train_mode:
+        # multiplier = 0 or 1/(1-p); where the input was exactly 0 the ratio is unknown -> any value gives 0
+        for name in ("ped", "obs"):
+            mk = masks[name]
+            out[pre + "dropbits_" + name] = np.packbits((torch.nan_to_num(mk, nan=0.0) > 0).numpy())
+            out[pre + "dropshape_" + name] = np.array(mk.shape)
+    return out
+
+
+def training_rollout_case(name, clip, kind, dsn, chans, valid_steps, **over):
+    """BaseSimulator.test_multiple_rollouts_for_training (simulators.py:659-832) + loss.backward() (:359) on a
+    channelled batch, eval() mode (no dropout)."""
+    raw = H.load_raw(clip)
+    args = H.default_args(model=kind, dataset_name=dsn, valid_steps=valid_steps, **over)
+    data = H.make_time_indexed(args, raw)
+    ch = DATA.ChanneledTimeIndexedPedData()
+    with H.quiet():
+        ch.load_from_time_indexed_peddata(data, stride=valid_steps, mode='slice')
+    batch = DATA.ChanneledTimeIndexedPedData.slice(ch, chans)
+    fields = ("ped_features", "obs_features", "self_features", "labels", "mask_p", "mask_p_pred", "position",
+              "velocity", "acceleration", "destination", "dest_idx", "waypoints")
+    for f in fields:
+        setattr(batch, f, getattr(batch, f).clone())
+    pre = name + "/"
+    out = {pre + "in/" + f: getattr(batch, f).clone() for f in fields}
+    out[pre + "in/obstacles"] = batch.obstacles.clone()
+    out[pre + "in/dest_num"] = batch.dest_num.clone()
+    out[pre + "in/abnormal_mask"] = batch.abnormal_mask.clone()
+    out[pre + "in/time_unit"] = np.float64(batch.time_unit)
+    out[pre + "in/num_frames"] = np.int64(batch.num_frames)
+    out[pre + "in/model"] = np.array(kind)
+    out[pre + "in/dataset_name"] = np.array(dsn)
+    out[pre + "in/args"] = np.array([args.reg_weight, args.collision_threshold, args.collision_loss_weight,
+                                     args.hard_collision_penalty, args.teacher_weight, args.collision_pred_weight,
+                                     args.collision_focus_weight, args.new_collision_loss_flag, args.time_decay],
+                                    np.float64)
+    out[pre + "in/collision_loss_version"] = np.array(args.collision_loss_version)
+    torch.manual_seed(666)
+    with H.quiet():
+        sim = SIM.BaseSimulator(args)
+    sim.model.eval()
+    sim.collision_count, sim.hard_collision_count, sim.epoch, sim.batch_idx = 0, 0, 0, 0
+    with H.quiet():
+        res = sim.test_multiple_rollouts_for_training(batch)
+    res[0].backward()
+    for i, r in enumerate(res):
+        out[pre + f"out{i}"] = r.detach()
+    out[pre + "collision_count"] = np.float64(sim.collision_count)
+    out[pre + "hard_collision_count"] = np.float64(sim.hard_collision_count)
+    out[pre + "dest_idx_after"] = batch.dest_idx.clone()
+    named = dict(sim.model.named_parameters())
+    for k in _linear_keys(sim.model.state_dict()):
+        out[pre + "grad/" + k + ".weight"] = named[k + ".weight"].grad
+        out[pre + "grad/" + k + ".bias"] = named[k + ".bias"].grad
+    return out
+
+
+def gen_training():
+    raw = H.load_raw(H.GC_CLIP)
+    d = H.make_time_indexed(H.default_args(), raw)
+    t = 333
+    ped, obs, slf = d.ped_features[t].clone(), d.obs_features[t].clone(), d.self_features[t].clone()
+    out = {"ped": ped, "obs": obs, "self": slf}
+    for kind, dsn in (("pinnsf_bm", "gc1560"), ("pinnsf_m", "ucy")):
+        for train_mode in (False, True):
+            out.update(single_step_case(kind, dsn, train_mode, ped, obs, slf))
+    # channelled (C,N,.) inputs: the dim=1 destination-norm quirk in the backward
+    chan = slice(330, 333)
+    pedc, obsc, slfc = d.ped_features[chan].clone(), d.obs_features[chan].clone(), d.self_features[chan].clone()
+    outc = single_step_case("pinnsf_bm", "ucy", False, pedc, obsc, slfc)
+    out.update({k.replace("pinnsf_bm_eval/", "pinnsf_bm_chan/"): v for k, v in outc.items()})
+    out.update({"ped_c": pedc, "obs_c": obsc, "self_c": slfc})
+    save("training_step", **out)
+    out = {}
+    out.update(training_rollout_case("ucy_bm", H.UCY_CLIP, "pinnsf_bm", "ucy", slice(200, 206), 5))
+    out.update(training_rollout_case("gc_bm_full", H.GC_CLIP, "pinnsf_bm", "gc1560", slice(300, 304), 6,
+                                     reg_weight=1e-3, teacher_weight=0.5, new_collision_loss_flag=1, time_decay=0.9))
+    save("training_rollout", **out)
+
+
 GROUPS = {"features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
-          "rollout": gen_rollout}
+          "rollout": gen_rollout, "training": gen_training}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GROUPS)
