@@ -93,6 +93,14 @@ PIML_API int piml_state_features_f32(const float *pos, float *vel, float *acc, c
 /* Pedestrians.calculate_collision_label (data.py:515-535). ped_f (S,6) -> out (S) in {0,1}. */
 PIML_API int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream);
 
+/* piml_relative_features_f32 / piml_state_features_f32 pick between two evaluations that return the identical result:
+ * all pairs (every agent scans all N + M candidates, like the reference) and a uniform-grid cell list (cells as wide
+ * as the larger distance threshold; only the 3 x 3 cells around an agent are scanned) used from 4096 agents per frame.
+ * algo: 0 = automatic (default), 1 = always all pairs, 2 = always cell list.  Process-wide setting. */
+PIML_API int piml_set_feature_algorithm(int algo);
+/* Frees the stream-keyed device scratch the cell-list path caches between calls (grid arrays). */
+PIML_API int piml_free_workspace(void);
+
 /* Backward of piml_relative_features_f32 / the feature rebuild inside the differentiable rollout
  * (simulators.py:772-778 -> data.py:466-512; autograd through the subtractions of get_relative_quantity and the
  * gather of get_filtered_features; the sort indices carry no gradient).  B frames of N agents.

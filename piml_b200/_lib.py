@@ -42,6 +42,8 @@ SIGNATURES = {
     "piml_state_features_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp,
                                       vp, vp, vp, vp, vp]),
     "piml_collision_label_f32": (i32, [vp, i64, vp, vp]),
+    "piml_set_feature_algorithm": (i32, [i32]),
+    "piml_free_workspace": (i32, []),
     "piml_mlapm_workspace_bytes": (i64, [i64]),
     "piml_mlapm_step_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, vp, vp, vp]),
     "piml_mlapm_advance_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, vp, vp,

@@ -12,66 +12,11 @@
 #include <math.h>
 #include <math_constants.h>
 
-#include "common.cuh"
+#include <atomic>
+
+#include "features_common.cuh"
 
 namespace piml {
-
-constexpr int FEAT_THREADS = 128;
-constexpr int FEAT_TILE = 1024;              // candidates per shared-memory tile (8 KB as float2)
-constexpr uint64_t EMPTY_KEY = ~0ull;
-
-// Ascending list of the KMAX smallest 64-bit keys seen so far, held in registers (fully unrolled).
-template <int KMAX>
-struct TopK {
-    uint64_t key[KMAX];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < KMAX; ++i) key[i] = EMPTY_KEY;
-    }
-    __device__ __forceinline__ void insert(uint64_t c) {
-        if (c >= key[KMAX - 1]) return;
-#pragma unroll
-        for (int i = KMAX - 1; i > 0; --i) {
-            const uint64_t lo = key[i - 1];
-            key[i] = (c < lo) ? lo : ((c < key[i]) ? c : key[i]);
-        }
-        key[0] = (c < key[0]) ? c : key[0];
-    }
-    __device__ __forceinline__ void pop_front() {
-#pragma unroll
-        for (int i = 0; i < KMAX - 1; ++i) key[i] = key[i + 1];
-        key[KMAX - 1] = EMPTY_KEY;
-    }
-};
-
-__device__ __forceinline__ uint64_t make_key(float dist, int idx) {
-    return (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | static_cast<uint32_t>(idx);
-}
-__device__ __forceinline__ float key_dist(uint64_t k) { return __uint_as_float(static_cast<uint32_t>(k >> 32)); }
-__device__ __forceinline__ int key_idx(uint64_t k) { return static_cast<int>(static_cast<uint32_t>(k)); }
-
-template <int G>
-__device__ __forceinline__ uint64_t group_min(uint64_t v) {
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, off);
-        v = (o < v) ? o : v;
-    }
-    return v;
-}
-
-// Distance from (px,py) to (ox,oy) with the field-of-view gate applied: data.py:432-443.
-// (hx,hy) is the heading already divided by max(||heading||, 1e-8) (cosine_similarity normalises each operand).
-__device__ __forceinline__ float gated_distance(float rx, float ry, float hx, float hy, float cos_thr) {
-    if (rx != rx) rx = CUDART_INF_F;                             // relative_pos[isnan] = inf   (:433)
-    if (ry != ry) ry = CUDART_INF_F;
-    float d = norm2_rn(rx, ry);                                  // torch.norm                  (:434)
-    const float nr = fmaxf(d, 1e-8f);
-    float c = __fadd_rn(__fmul_rn(__fdiv_rn(rx, nr), hx), __fmul_rn(__fdiv_rn(ry, nr), hy));   // (:439-440)
-    if (c != c) c = -1.0f;                                       // view_field[isnan] = -1      (:441)
-    if (c < cos_thr) d = CUDART_INF_F;                           // (:442-443)
-    return d;
-}
 
 // Scan `M` candidates (float2 array `cand`, one frame) for the rows owned by this CTA and build, per row, the
 // ascending list of the best keys.  RADIUS: only candidates with distance <= thr are kept and a cheap squared
@@ -116,17 +61,6 @@ __device__ __forceinline__ void scan_candidates(TopK<KMAX> &best, const float2 *
     }
 }
 
-struct FeatArgs {
-    const float *pos; float *vel; float *acc; const float *dest; const float *head; const float *obs;
-    int64_t obs_frame_stride;    // floats between consecutive frames' obstacle arrays (0: shared)
-    int obs_channel_T;           // if > 0: obstacle array index = frame / obs_channel_T (per-channel obstacles)
-    int B, N, M, kp, ko;         // kp, ko already clamped to min(k, N|M)
-    float cos_p, thr_p, pre2_p, cos_o, thr_o, pre2_o;
-    float *ped_f; float *obs_f; float *dest_f;
-    int64_t *ped_idx; float *ped_dist; int64_t *obs_idx; float *obs_dist;
-    // optional rollout extras: self_f (B,N,7) = [dest_f, hist_v, acceleration, desired_speed]  (simulators.py:651)
-    const float *hist_v; const float *desired_speed; float *self_f;
-};
 
 // grid = (ceil(N / (FEAT_THREADS/G)), B).  G lanes cooperate on one row.
 template <int KP, int KO, int G>
@@ -414,6 +348,9 @@ __global__ void collision_detection_kernel(CollArgs a) {
     }
 }
 
+static std::atomic<int> g_feature_algo{0};     // 0: automatic, 1: all pairs, 2: cell list
+constexpr int CELLS_MIN_AGENTS = 4096;
+
 static int pick_group(int64_t B, int N) {
     // enough CTAs to fill 148 SMs several times over with one thread per row?  otherwise spread a row over lanes
     const int64_t target = 4LL * sm_count();
@@ -422,12 +359,6 @@ static int pick_group(int64_t B, int N) {
     return 32;
 }
 
-// slack so that sqrtf(d2) <= thr  =>  d2 <= pre2 for every fp32 d2 (prefilter must be a superset)
-static float prefilter_sq(float thr) {
-    if (!(thr < 1e18f)) return INFINITY;
-    const double t = static_cast<double>(thr);
-    return static_cast<float>(t * t * (1.0 + 1e-6)) + 1e-30f;
-}
 
 template <int KP, int KO>
 static void launch_features(const FeatArgs &a, int G, cudaStream_t st) {
@@ -519,8 +450,14 @@ static int relative_features_impl(const float *pos, float *vel, float *acc, cons
     a.ped_f = ped_f; a.obs_f = obs_f; a.dest_f = dest_f;
     a.ped_idx = ped_idx; a.ped_dist = ped_dist; a.obs_idx = obs_idx; a.obs_dist = obs_dist;
     a.hist_v = hist_v; a.desired_speed = desired_speed; a.self_f = self_f;
-    const int G = pick_group(B, N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // large crowds: uniform-grid cell list (identical neighbour set, see features_cells.cu); small scenes: all pairs
+    const int algo = g_feature_algo.load(std::memory_order_relaxed);
+    const float thr_max = fmaxf(dist_thr_ped, M > 0 ? dist_thr_obs : 0.f);
+    const bool cells_ok = thr_max > 0.f && thr_max < 1e18f;
+    if (cells_ok && (algo == 2 || (algo == 0 && N >= CELLS_MIN_AGENTS)))
+        return relative_features_cells(a, obs_per_channel ? C : 1, st);
+    const int G = pick_group(B, N);
     if (kpp <= 8 && kop <= 16) launch_features<8, 16>(a, G, st);
     else if (kpp <= 16 && kop <= 16) launch_features<16, 16>(a, G, st);
     else launch_features<32, 32>(a, G, st);
@@ -606,4 +543,15 @@ extern "C" int piml_collision_detection_f32(const float *position, const float *
     collision_detection_kernel<<<static_cast<unsigned>((tot + threads - 1) / threads), threads, 0, st>>>(a);
     count_launch();
     return check_launch("collision_detection_kernel");
+}
+
+extern "C" int piml_set_feature_algorithm(int algo) {
+    PIML_REQUIRE(algo >= 0 && algo <= 2, "piml_set_feature_algorithm: 0 = automatic, 1 = all pairs, 2 = cell list");
+    g_feature_algo.store(algo, std::memory_order_relaxed);
+    return PIML_OK;
+}
+
+extern "C" int piml_free_workspace(void) {
+    cell_scratch_free();
+    return PIML_OK;
 }

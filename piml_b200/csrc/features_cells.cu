@@ -1,0 +1,373 @@
+// features_cells.cu -- uniform-grid (cell list) variant of the neighbour-selection + relative-feature kernel for large
+// crowds (sm_100a).  Same outputs, bit for bit, as relative_features_kernel in features.cu, which scans all N (+M)
+// candidates per agent like the reference does (src/data/data.py:416-447 sorts every row of the N x N distance matrix).
+//
+// Why the neighbour set is identical: get_filtered_features zeroes every slot farther than dist_threshold
+// (data.py:459-462), so only candidates within the radius can ever appear in the output; a grid of cells at least as
+// wide as the radius guarantees that all of them lie in the 3 x 3 block of cells around the agent, and both variants
+// evaluate the same exact-arithmetic predicate (gated_distance) and keep the k smallest (distance, index) keys.
+//
+// Pipeline per call (no host synchronisation, all on the caller's stream):
+//   1. cell_count_kernel   : cell of every point -> spatial-hash bucket; atomic count per bucket, rank of the point
+//   2. scan (3 tiny kernels): exclusive prefix sum of the bucket counts
+//   3. cell_scatter_kernel : records {x, y, index, packed cell} sorted by bucket (counting sort)
+//   4. features_cells_kernel: one thread per agent walks the 9 buckets around its cell; hash collisions and repeated
+//      buckets are filtered by comparing the record's packed cell with the cell being visited.
+// Buckets are a hash of the integer cell coordinates (no bounding box needed => no device->host read of extents);
+// cell coordinates are computed in fp64 so that rounding can never move a candidate two cells away.
+#include "features_common.cuh"
+
+namespace piml {
+
+constexpr int CELL_THREADS = 128;
+constexpr int SCAN_PER_BLOCK = 2048;      // elements per block of the prefix sum (256 threads x 8)
+
+struct HashGrid {
+    int H;                 // buckets per frame (power of two)
+    int frames, n;         // frames x n points
+    const int *start;      // frames * H + 1 exclusive prefix sums
+    const float4 *rec;     // frames * n records sorted by bucket: {x, y, as_float(index), as_float(packed cell)}
+};
+
+__device__ __forceinline__ int cell_coord(float x, double inv_cs) {
+    double t = floor(static_cast<double>(x) * inv_cs);
+    t = fmin(fmax(t, -32768.0), 32767.0);                          // monotone clamp keeps "at most one cell apart"
+    return static_cast<int>(t);
+}
+__device__ __forceinline__ uint32_t pack_cell(int cx, int cy) {
+    return (static_cast<uint32_t>(cx) & 0xffffu) | (static_cast<uint32_t>(cy) << 16);
+}
+__device__ __forceinline__ uint32_t bucket_of(int cx, int cy, int H) {
+    const uint32_t h = static_cast<uint32_t>(cx) * 73856093u ^ static_cast<uint32_t>(cy) * 19349663u;
+    return (h ^ (h >> 15)) & static_cast<uint32_t>(H - 1);
+}
+
+__global__ void cell_count_kernel(const float2 *__restrict__ pts, int64_t total, int n, double inv_cs, int H,
+                                  int *__restrict__ counts, int *__restrict__ rank) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 p = pts[i];
+    if (p.x != p.x || p.y != p.y) { rank[i] = -1; return; }       // absent agents are never candidates (data.py:433)
+    const int64_t frame = i / n;
+    const uint32_t b = bucket_of(cell_coord(p.x, inv_cs), cell_coord(p.y, inv_cs), H);
+    rank[i] = atomicAdd(&counts[frame * H + b], 1);
+}
+
+// exclusive scan, phase 1: per-block totals
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const int *__restrict__ in, int64_t n,
+                                                              int *__restrict__ block_sums) {
+    __shared__ int red[256];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_PER_BLOCK;
+    int s = 0;
+    for (int e = threadIdx.x; e < SCAN_PER_BLOCK; e += 256)
+        if (base + e < n) s += in[base + e];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = red[0];
+}
+
+// phase 2: one block turns the block totals into exclusive offsets (sequential over chunks of 1024)
+__global__ void __launch_bounds__(1024) scan_offsets_kernel(int *__restrict__ block_sums, int nblocks) {
+    __shared__ int buf[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < nblocks; c0 += 1024) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < nblocks ? block_sums[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const int t = threadIdx.x >= off ? buf[threadIdx.x - off] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) block_sums[i] = carry + buf[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += buf[1023];
+        __syncthreads();
+    }
+}
+
+// phase 3: exclusive scan inside each block + block offset; out has n + 1 entries (out[n] = grand total)
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int *__restrict__ in, int64_t n,
+                                                         const int *__restrict__ block_offs, int *__restrict__ out) {
+    __shared__ int part[256];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_PER_BLOCK + threadIdx.x * 8;
+    int v[8], s = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = (base + q < n) ? in[base + q] : 0; s += v[q]; }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const int t = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = block_offs[blockIdx.x] + part[threadIdx.x] - s;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (base + q < n) out[base + q] = run;
+        run += v[q];
+    }
+    if (base <= n - 1 && n - 1 < base + 8) out[n] = run;           // the thread owning the last element
+}
+
+__global__ void cell_scatter_kernel(const float2 *__restrict__ pts, int64_t total, int n, double inv_cs, int H,
+                                    const int *__restrict__ start, const int *__restrict__ rank,
+                                    float4 *__restrict__ rec) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = rank[i];
+    if (r < 0) return;
+    const float2 p = pts[i];
+    const int64_t frame = i / n;
+    const int cx = cell_coord(p.x, inv_cs), cy = cell_coord(p.y, inv_cs);
+    const uint32_t b = bucket_of(cx, cy, H);
+    rec[start[frame * H + b] + r] = make_float4(p.x, p.y, __int_as_float(static_cast<int>(i - frame * n)),
+                                                __uint_as_float(pack_cell(cx, cy)));
+}
+
+// Keep the k best gated candidates of the 3 x 3 cell block around (cx, cy).
+template <int KMAX>
+__device__ __forceinline__ void scan_cells(TopK<KMAX> &best, const HashGrid &g, int64_t gframe, int cx, int cy, float px,
+                                           float py, float hx, float hy, float cos_thr, float thr, float pre2) {
+    best.init();
+    const int *st = g.start + gframe * g.H;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int ccx = cx + dx, ccy = cy + dy;
+            const uint32_t want = pack_cell(ccx, ccy);
+            const uint32_t b = bucket_of(ccx, ccy, g.H);
+            const int e1 = st[b + 1];
+            for (int e = st[b]; e < e1; ++e) {
+                const float4 r = g.rec[e];
+                if (__float_as_uint(r.w) != want) continue;       // hash collision or a wrapped neighbour cell
+                const float rx = __fsub_rn(r.x, px), ry = __fsub_rn(r.y, py);
+                if (!(__fmaf_rn(ry, ry, __fmul_rn(rx, rx)) <= pre2)) continue;
+                const float d = gated_distance(rx, ry, hx, hy, cos_thr);
+                if (d <= thr) best.insert(make_key(d, __float_as_int(r.z)));
+            }
+        }
+}
+
+template <int KP, int KO>
+__global__ void __launch_bounds__(CELL_THREADS) features_cells_kernel(FeatArgs a, HashGrid gp, HashGrid go,
+                                                                      double inv_cs) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= static_cast<int64_t>(a.B) * a.N) return;
+    const int b = static_cast<int>(row / a.N);
+    const float2 p = reinterpret_cast<const float2 *>(a.pos)[row];
+    float2 v = reinterpret_cast<const float2 *>(a.vel)[row];
+    float2 ac = reinterpret_cast<const float2 *>(a.acc)[row];
+    if (v.x != v.x || v.y != v.y)                                  // in-place NaN -> 0 (data.py:483-484)
+        reinterpret_cast<float2 *>(a.vel)[row] = make_float2(nan_to_zero(v.x), nan_to_zero(v.y));
+    if (ac.x != ac.x || ac.y != ac.y)
+        reinterpret_cast<float2 *>(a.acc)[row] = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+    v = make_float2(nan_to_zero(v.x), nan_to_zero(v.y));
+    ac = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+    float2 h;
+    if (a.head) {
+        h = reinterpret_cast<const float2 *>(a.head)[row];
+    } else {
+        float nv = norm2_rn(v.x, v.y);
+        if (nv == 0.0f) nv = 0.1f;
+        h = make_float2(__fdiv_rn(v.x, nv), __fdiv_rn(v.y, nv));
+    }
+    {
+        const float nh = fmaxf(norm2_rn(h.x, h.y), 1e-8f);
+        h = make_float2(__fdiv_rn(h.x, nh), __fdiv_rn(h.y, nh));
+    }
+    const bool present = !(p.x != p.x || p.y != p.y);
+    const int cx = present ? cell_coord(p.x, inv_cs) : 0, cy = present ? cell_coord(p.y, inv_cs) : 0;
+
+    // ---- pedestrian - pedestrian ----
+    {
+        TopK<KP> best;
+        best.init();
+        if (present) scan_cells<KP>(best, gp, b, cx, cy, p.x, p.y, h.x, h.y, a.cos_p, a.thr_p, a.pre2_p);
+        const float2 *fp = reinterpret_cast<const float2 *>(a.pos) + static_cast<int64_t>(b) * a.N;
+        const float2 *fv = reinterpret_cast<const float2 *>(a.vel) + static_cast<int64_t>(b) * a.N;
+        const float2 *fa = reinterpret_cast<const float2 *>(a.acc) + static_cast<int64_t>(b) * a.N;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            if (j >= a.kp) break;
+            const uint64_t w = best.key[j];
+            float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0;
+            if (w != EMPTY_KEY) {
+                const int m = key_idx(w);
+                const float2 pm = fp[m], vm = fv[m], am = fa[m];
+                f0 = make_float2(__fsub_rn(pm.x, p.x), __fsub_rn(pm.y, p.y));
+                f1 = make_float2(__fsub_rn(nan_to_zero(vm.x), v.x), __fsub_rn(nan_to_zero(vm.y), v.y));
+                f2 = make_float2(__fsub_rn(nan_to_zero(am.x), ac.x), __fsub_rn(nan_to_zero(am.y), ac.y));
+            }
+            float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + j) * 3;
+            out[0] = f0; out[1] = f1; out[2] = f2;
+            if (a.ped_idx) a.ped_idx[row * a.kp + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+            if (a.ped_dist) a.ped_dist[row * a.kp + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+        }
+    }
+    // ---- destination ----
+    {
+        const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
+        const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+        reinterpret_cast<float2 *>(a.dest_f)[row] = df;
+        if (a.self_f) {
+            const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
+            float *sf = a.self_f + row * 7;
+            sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
+            sf[6] = a.desired_speed[row];
+        }
+    }
+    // ---- pedestrian - obstacle ----
+    if (a.M > 0) {
+        TopK<KO> best;
+        best.init();
+        const int oframe = a.obs_frame_stride == 0 ? 0 : (a.obs_channel_T > 0 ? b / a.obs_channel_T : b);
+        if (present) scan_cells<KO>(best, go, oframe, cx, cy, p.x, p.y, h.x, h.y, a.cos_o, a.thr_o, a.pre2_o);
+        const float2 *cand = reinterpret_cast<const float2 *>(a.obs + static_cast<int64_t>(oframe) * a.obs_frame_stride);
+#pragma unroll
+        for (int j = 0; j < KO; ++j) {
+            if (j >= a.ko) break;
+            const uint64_t w = best.key[j];
+            float2 f0 = make_float2(0.f, 0.f), f1 = f0, f2 = f0;
+            if (w != EMPTY_KEY) {
+                const float2 om = cand[key_idx(w)];
+                f0 = make_float2(__fsub_rn(om.x, p.x), __fsub_rn(om.y, p.y));
+                f1 = make_float2(__fsub_rn(0.f, v.x), __fsub_rn(0.f, v.y));
+                f2 = make_float2(__fsub_rn(0.f, ac.x), __fsub_rn(0.f, ac.y));
+            }
+            float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + j) * 3;
+            out[0] = f0; out[1] = f1; out[2] = f2;
+            if (a.obs_idx) a.obs_idx[row * a.ko + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+            if (a.obs_dist) a.obs_dist[row * a.ko + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+struct ByteScratch { cudaStream_t st; int dev; char *buf; size_t cap; };
+static ByteScratch g_cell_scratch[8] = {};
+static int g_cell_used = 0;
+
+static int cell_scratch_get(cudaStream_t st, size_t bytes, char **out) {
+    int dev = 0;
+    PIML_CUDA(cudaGetDevice(&dev));
+    ByteScratch *s = nullptr;
+    for (int i = 0; i < g_cell_used; ++i)
+        if (g_cell_scratch[i].st == st && g_cell_scratch[i].dev == dev) s = &g_cell_scratch[i];
+    if (!s) {
+        s = &g_cell_scratch[g_cell_used < 8 ? g_cell_used++ : 7];
+        if (s->buf) { cudaSetDevice(s->dev); cudaFree(s->buf); cudaSetDevice(dev); }
+        s->st = st; s->dev = dev; s->buf = nullptr; s->cap = 0;
+    }
+    if (s->cap < bytes) {
+        if (s->buf) {
+            PIML_CUDA(cudaStreamSynchronize(st));                  // kernels of an earlier call may still read it
+            PIML_CUDA(cudaFree(s->buf));
+        }
+        s->buf = nullptr; s->cap = 0;
+        const size_t want = bytes + bytes / 4;
+        PIML_CUDA(cudaMalloc(&s->buf, want));
+        s->cap = want;
+    }
+    *out = s->buf;
+    return PIML_OK;
+}
+
+void cell_scratch_free() {
+    for (int i = 0; i < g_cell_used; ++i)
+        if (g_cell_scratch[i].buf) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaSetDevice(g_cell_scratch[i].dev);
+            cudaFree(g_cell_scratch[i].buf);
+            cudaSetDevice(dev);
+            g_cell_scratch[i].buf = nullptr; g_cell_scratch[i].cap = 0;
+        }
+    g_cell_used = 0;
+}
+
+static int pow2_at_least(int64_t x) {
+    int h = 256;
+    while (h < x && h < (1 << 28)) h <<= 1;
+    return h;
+}
+
+struct GridMem { int *counts, *start, *rank, *bsums; float4 *rec; int H; int64_t cells; int nblocks; };
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static size_t grid_bytes(int frames, int n, GridMem *g) {
+    g->H = pow2_at_least(2LL * n);
+    g->cells = static_cast<int64_t>(frames) * g->H;
+    g->nblocks = static_cast<int>((g->cells + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
+    return align256(sizeof(int) * g->cells) + align256(sizeof(int) * (g->cells + 1)) +
+           align256(sizeof(int) * static_cast<size_t>(frames) * n) + align256(sizeof(int) * (g->nblocks + 1)) +
+           align256(sizeof(float4) * static_cast<size_t>(frames) * n);
+}
+
+static char *grid_carve(char *base, int frames, int n, GridMem *g) {
+    g->counts = reinterpret_cast<int *>(base); base += align256(sizeof(int) * g->cells);
+    g->start = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (g->cells + 1));
+    g->rank = reinterpret_cast<int *>(base); base += align256(sizeof(int) * static_cast<size_t>(frames) * n);
+    g->bsums = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (g->nblocks + 1));
+    g->rec = reinterpret_cast<float4 *>(base); base += align256(sizeof(float4) * static_cast<size_t>(frames) * n);
+    return base;
+}
+
+static int build_grid(const float *pts, int frames, int n, double inv_cs, const GridMem &g, cudaStream_t st) {
+    const int64_t total = static_cast<int64_t>(frames) * n;
+    PIML_CUDA(cudaMemsetAsync(g.counts, 0, sizeof(int) * g.cells, st));
+    const unsigned blocks = static_cast<unsigned>((total + CELL_THREADS - 1) / CELL_THREADS);
+    cell_count_kernel<<<blocks, CELL_THREADS, 0, st>>>(reinterpret_cast<const float2 *>(pts), total, n, inv_cs, g.H,
+                                                       g.counts, g.rank);
+    scan_block_sums_kernel<<<g.nblocks, 256, 0, st>>>(g.counts, g.cells, g.bsums);
+    scan_offsets_kernel<<<1, 1024, 0, st>>>(g.bsums, g.nblocks);
+    scan_apply_kernel<<<g.nblocks, 256, 0, st>>>(g.counts, g.cells, g.bsums, g.start);
+    cell_scatter_kernel<<<blocks, CELL_THREADS, 0, st>>>(reinterpret_cast<const float2 *>(pts), total, n, inv_cs, g.H,
+                                                         g.start, g.rank, g.rec);
+    count_launch(5);
+    return check_launch("cell-list build");
+}
+
+// Cell-list evaluation of the features described by `a` (same contract as relative_features_kernel).
+// obs_frames: number of distinct obstacle arrays (1 when shared by all frames).
+int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st) {
+    const float thr = fmaxf(a.thr_p, a.M > 0 ? a.thr_o : 0.f);
+    PIML_REQUIRE(thr > 0.f && thr < 1e18f, "cell-list features need a finite positive distance threshold");
+    const double inv_cs = 1.0 / (static_cast<double>(thr) * (1.0 + 1e-5));
+    PIML_REQUIRE(static_cast<int64_t>(a.B) * a.N < (1LL << 31) && static_cast<int64_t>(obs_frames) * a.M < (1LL << 31),
+                 "cell-list features: too many points");
+    GridMem gp, go;
+    size_t bytes = grid_bytes(a.B, a.N, &gp);
+    if (a.M > 0) bytes += grid_bytes(obs_frames, a.M, &go);
+    char *base = nullptr;
+    int rc = cell_scratch_get(st, bytes, &base);
+    if (rc) return rc;
+    base = grid_carve(base, a.B, a.N, &gp);
+    rc = build_grid(a.pos, a.B, a.N, inv_cs, gp, st);
+    if (rc) return rc;
+    HashGrid hp{gp.H, a.B, a.N, gp.start, gp.rec}, ho{0, 0, 0, nullptr, nullptr};
+    if (a.M > 0) {
+        grid_carve(base, obs_frames, a.M, &go);
+        rc = build_grid(a.obs, obs_frames, a.M, inv_cs, go, st);
+        if (rc) return rc;
+        ho = HashGrid{go.H, obs_frames, a.M, go.start, go.rec};
+    }
+    const int64_t rows = static_cast<int64_t>(a.B) * a.N;
+    const unsigned blocks = static_cast<unsigned>((rows + CELL_THREADS - 1) / CELL_THREADS);
+    if (a.kp <= 8 && a.ko <= 16) features_cells_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);
+    else if (a.kp <= 16 && a.ko <= 16) features_cells_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);
+    else features_cells_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);
+    count_launch();
+    return check_launch("features_cells_kernel");
+}
+
+}  // namespace piml

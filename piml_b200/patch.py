@@ -16,6 +16,11 @@ switch off the reference is byte-for-byte itself.  Opt-in only: `install_from_en
     MLAPM.step                                                     (src/models/mlapm.py:10)
     UTILS.calc_acceleration                                        (src/utils/utils.py:31)
     BaseSimulator.get_multiple_rollouts                            (src/models/simulators.py:556)
+    BaseSimulator.test_multiple_rollouts_for_training              (src/models/simulators.py:659)
+    Pedestrians.collision_detection                                (src/data/data.py:538)
+
+Training: the patched model forwards record a CUDA backward (piml_b200.autograd), so the reference's own
+`loss.backward(); optimizer.step()` (simulators.py:359-360) runs the library's backward kernels unchanged.
 """
 import os
 
@@ -24,16 +29,24 @@ from . import mlapm as _mlapm
 from . import models as _models
 from . import rollout as _rollout
 from . import sfm as _sfm
+from . import train_rollout as _train_rollout
 
 _saved = []          # (owner, attribute name, original)
 
 PINNSF_CLASSES = ("PINNSF", "PINNSF_bottleneck", "PINNSF_bottleneck_multitask", "PINNSF_multitask")
 PEDESTRIAN_METHODS = ("get_heading_direction", "get_nearby_obj_in_sight", "get_relative_features",
-                      "calculate_collision_label")
+                      "_relative_features_raw", "calculate_collision_label", "collision_detection")
+
+
+_MISSING = object()
 
 
 def _swap(owner, name, new):
-    _saved.append((owner, name, owner.__dict__[name] if name in owner.__dict__ else getattr(owner, name)))
+    if name in owner.__dict__:
+        orig = owner.__dict__[name]
+    else:
+        orig = getattr(owner, name, _MISSING)       # helpers the reference class does not have are removed again
+    _saved.append((owner, name, orig))
     setattr(owner, name, new)
 
 
@@ -71,6 +84,11 @@ def install(DATA=None, MLAPM_MOD=None, MODEL=None, SIM=None, UTILS=None):
             return _rollout.get_multiple_rollouts(self, data, t_start, load_model, result_cls=raw_cls)
         _swap(SIM.BaseSimulator, "get_multiple_rollouts", get_multiple_rollouts)
         done.append("models.simulators.BaseSimulator.get_multiple_rollouts")
+
+        def test_multiple_rollouts_for_training(self, data, t_start=0):
+            return _train_rollout.test_multiple_rollouts_for_training(self, data, t_start)
+        _swap(SIM.BaseSimulator, "test_multiple_rollouts_for_training", test_multiple_rollouts_for_training)
+        done.append("models.simulators.BaseSimulator.test_multiple_rollouts_for_training")
     return done
 
 
@@ -84,4 +102,7 @@ def install_from_env(**modules):
 def uninstall():
     while _saved:
         owner, name, orig = _saved.pop()
-        setattr(owner, name, orig)
+        if orig is _MISSING:
+            delattr(owner, name)
+        else:
+            setattr(owner, name, orig)

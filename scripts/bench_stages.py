@@ -50,9 +50,13 @@ def main():
     ped = P.Pedestrians()
     fargs = (6, 90, 4, 10, 90, 4)
     feats = ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs)
-    ms = timeit(lambda: ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs))
-    out["features_N%d_M%d" % (N, obs.shape[0])] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
-                                                  "pairs_per_s": N * (N + obs.shape[0]) / ms * 1e3}
+    from piml_b200 import _lib as L
+    for algo, name in ((1, "allpairs"), (2, "cells")):
+        L.check(L.load().piml_set_feature_algorithm(algo), "piml_set_feature_algorithm")
+        ms = timeit(lambda: ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs))
+        out["features_%s_N%d_M%d" % (name, N, obs.shape[0])] = {
+            "ms": ms, "agent_steps_per_s": N / ms * 1e3, "pairs_per_s": N * (N + obs.shape[0]) / ms * 1e3}
+    L.check(L.load().piml_set_feature_algorithm(0), "piml_set_feature_algorithm")
     torch.manual_seed(666)
     net = M.PINNSF_bottleneck_multitask(bm_args()).to(dev).eval()
     packed = M.pack_device(net.state_dict(), net.spec, dev)

@@ -114,6 +114,83 @@ def test_relative_features_large_k_and_angles():
             assert np.array_equal(npy(g_), w)
 
 
+def _set_algo(algo):
+    from piml_b200 import _lib as L
+    L.check(L.load().piml_set_feature_algorithm(algo), "piml_set_feature_algorithm")
+
+
+def _features_both_ways(args, golden_check=None):
+    """Run get_relative_features with the all-pairs kernel and with the cell list; every output must be bit-identical."""
+    import piml_b200 as P
+    outs = []
+    try:
+        for algo in (1, 2):
+            _set_algo(algo)
+            ins = [cu(x) for x in args[:5]]
+            r = P.Pedestrians().get_relative_features(*ins, *args[5:], return_selection=True)
+            outs.append([npy(x) for x in r[:3]] + [npy(x) for x in r[3]] + [npy(ins[1]), npy(ins[2])])
+    finally:
+        _set_algo(0)
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y, equal_nan=True)
+    return outs[1]
+
+
+@pytest.mark.parametrize("B,N,M", [(1, 5003, 2000), (1, 20000, 2000), (3, 4500, 300), (5, 300, 40), (2, 129, 0)])
+def test_cell_list_identical_to_all_pairs(B, N, M):
+    """The uniform-grid variant (features_cells.cu) returns the same features, indices, distances and side effects as
+    the all-pairs kernel, and (where the C oracle finishes in seconds) the same as the oracle."""
+    p, v, a, d, obs = _crowd(B, N, M, seed=B * 77 + N)
+    v[0, 3] = np.nan; a[0, 4] = np.nan                    # in-place NaN -> 0 side effect on both paths
+    got = _features_both_ways((p, v, a, d, obs.reshape(M, 2), 6, 90, 4, 10, 90, 4))
+    if B * N * N <= 3e8:
+        want = O.relative_features(p, v.copy(), a.copy(), d, obs, 6, 90, 4, 10, 90, 4)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+        if M:
+            assert np.array_equal(got[1], want[1])
+
+
+def test_cell_list_awkward_geometry():
+    """Negative coordinates, far outliers (the (1e4,1e4) dummy obstacles of data.py:102-103), points beyond the int16
+    cell range, dense clumps (many agents per cell), wide angle (self selected), unequal thresholds, per-channel
+    obstacles, time axis with heading fill."""
+    rng = np.random.default_rng(3)
+    Cc, T, N, M = 2, 3, 700, 60
+    p = (rng.normal(0, 15, (Cc, T, N, 2))).astype(np.float32)
+    p[:, :, :200] = (rng.normal(0, 0.7, (Cc, T, 200, 2)) + 5).astype(np.float32)      # clump
+    p[:, :, 200:210] = 1e4
+    p[:, :, 210:215] = (rng.random((Cc, T, 5, 2)) * 3 + 2.5e5).astype(np.float32)     # clamped cells
+    p[:, :, 215:220] = (-2.5e5 - rng.random((Cc, T, 5, 2)) * 3).astype(np.float32)
+    p[0, :, 300] = np.nan
+    d = rng.normal(0, 15, (Cc, T, N, 2)).astype(np.float32)
+    v = rng.normal(0, 1, (Cc, T, N, 2)).astype(np.float32)
+    v[:, 1, ::5] = 0
+    a = rng.normal(0, 1, (Cc, T, N, 2)).astype(np.float32)
+    obs = rng.normal(0, 15, (Cc, M, 2)).astype(np.float32)
+    obs[:, :2] = 1e4
+    got = _features_both_ways((p, v, a, d, obs, 8, 100, 3, 12, 120, 5))
+    want = O.relative_features(p, v.copy(), a.copy(), d, obs, 8, 100, 3, 12, 120, 5)
+    for g_, w in zip(got[:3], want):
+        assert np.array_equal(g_, w)
+
+
+def test_cell_list_rollout_feature_rebuild():
+    """piml_state_features_f32 (the per-step rebuild incl. self_features) through the cell list == all pairs."""
+    from piml_b200.rollout import state_features
+    p, v, a, d, obs = _crowd(1, 6000, 500, seed=9)
+    hist = v.copy(); ds = np.full((1, 6000), 1.3, np.float32)
+    res = []
+    try:
+        for algo in (1, 2):
+            _set_algo(algo)
+            r = state_features(cu(p), cu(v), cu(a), cu(d), cu(obs), cu(hist), cu(ds), 6, 90, 4, 10, 90, 4)
+            res.append([npy(x) for x in r])
+    finally:
+        _set_algo(0)
+    for x, y in zip(*res):
+        assert np.array_equal(x, y)
+
+
 def test_collision_label():
     import piml_b200 as P
     g = group(golden("features"), "gc")

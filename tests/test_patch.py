@@ -23,6 +23,10 @@ def _fake_reference():
         def calculate_collision_label(ped_features):
             return "ref"
 
+        @staticmethod
+        def collision_detection(position, threshold, real_position=None):
+            return "ref"
+
     class RawData(object):
         pass
     DATA.Pedestrians, DATA.RawData = Pedestrians, RawData
@@ -37,7 +41,9 @@ def _fake_reference():
     SIM = types.ModuleType("models.simulators")
     SIM.DATA = DATA
     SIM.BaseSimulator = type("BaseSimulator", (Pedestrians,), {"get_multiple_rollouts": lambda self, d, t_start=0,
-                                                               load_model=True: "ref"})
+                                                               load_model=True: "ref",
+                                                               "test_multiple_rollouts_for_training":
+                                                               lambda self, d, t_start=0: "ref"})
     return DATA, ML, MODEL, SIM, UT
 
 
@@ -49,7 +55,7 @@ def test_install_swaps_and_uninstall_restores(monkeypatch):
     assert UT.calc_acceleration() == "ref"
     monkeypatch.setenv("PIML_B200", "1")
     names = patch.install_from_env(DATA=DATA, MLAPM_MOD=ML, MODEL=MODEL, SIM=SIM, UTILS=UT)
-    assert len(names) == 4 + 4 + 1 + 1 + 1
+    assert len(names) == 6 + 4 + 1 + 1 + 2
     import piml_b200 as P
     assert UT.calc_acceleration is P.calc_acceleration
     assert DATA.Pedestrians.__dict__["get_relative_features"] is P.Pedestrians.__dict__["get_relative_features"]
@@ -61,6 +67,9 @@ def test_install_swaps_and_uninstall_restores(monkeypatch):
     assert DATA.Pedestrians().get_relative_features() == "ref"
     assert MODEL.PINNSF().forward(0, 0, 0) == "ref"
     assert ML.MLAPM().step() == "ref" and SIM.BaseSimulator().get_multiple_rollouts(None) == "ref"
+    assert SIM.BaseSimulator().test_multiple_rollouts_for_training(None) == "ref"
+    assert DATA.Pedestrians.collision_detection(0, 0) == "ref"
+    assert not hasattr(DATA.Pedestrians, "_relative_features_raw")       # helper added by install is removed again
 
 
 @pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src"), reason="reference tree not present")
@@ -74,7 +83,7 @@ def test_install_on_the_real_reference_modules():
     orig = DATA.Pedestrians.get_relative_features
     names = patch.install(DATA=DATA, MLAPM_MOD=MLAPM, MODEL=MODEL, SIM=SIM, UTILS=UTILS)
     try:
-        assert len(names) == 11
+        assert len(names) == 14
         assert SIM.BaseSimulator.get_relative_features is not orig
     finally:
         patch.uninstall()
