@@ -35,6 +35,7 @@ UNIT = "agent-steps/s"
 FLOP_PER_PAIR = 51.0          # SURVEY.md 8d, MLAPM-GC per ordered pair
 MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)     # main_mlapm.py:16
 DT, RADIUS = 0.08, 0.3
+FLUSH_MB = 160                 # L2 is 126 MB
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -105,7 +106,8 @@ def cpu_baseline(N, seconds=12.0, threads=None):
         O.set_num_threads(threads)
     cores = O.num_threads()
     p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
-    probe = max(8, cores * 2)
+    probe = max(64, cores * 16)
+    O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))       # spin up the OpenMP team
     t0 = time.perf_counter()
     O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))
     rate = probe / max(time.perf_counter() - t0, 1e-6)            # rows/s
@@ -130,7 +132,8 @@ def run_reference(a):
     N = a.agents
     cores = O.num_threads()
     p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
-    probe = max(8, cores * 2)
+    probe = max(64, cores * 16)
+    O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))       # spin up the OpenMP team
     t0 = time.perf_counter()
     O.mlapm_step(p, v, ds, dest, DT, "GC", rows=(0, probe))
     rate = probe / max(time.perf_counter() - t0, 1e-6)
@@ -175,6 +178,56 @@ def probe_peaks(L, torch, dev):
     return res
 
 
+def nn_path_step(torch, dev, N, obs_h, iters=10):
+    """Secondary evidence (not the headline metric): one step of the NN-augmented rollout (simulators.py:602-652) on
+    the same crowd -- fused pinnsf_bm forward, fused integrate, cell-list feature rebuild -- device-resident."""
+    import argparse as ap
+    import piml_b200 as P
+    from piml_b200 import models as M
+    from piml_b200.rollout import integrate_step, state_features
+    args = ap.Namespace(model='pinnsf_bm', dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128,
+                        processor_hidden_size=128, decoder_hidden_size=64, encoder_hidden_layers=3,
+                        processor_hidden_layers=16, decoder_hidden_layers=2, ped_feature_dim=6, obs_feature_dim=6,
+                        self_feature_dim=7)
+    torch.manual_seed(666)
+    net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
+    packed = M.pack_device(net.state_dict(), net.spec, dev)
+    p, v, ds, dest, _ = [x.to(dev) for x in synthetic_crowd(N)]
+    p, v, dest = p[None].contiguous(), v[None].contiguous(), dest[None].contiguous()
+    acc, hist = torch.zeros_like(v), v.clone()
+    dsp = ds.reshape(1, N).contiguous()
+    obs = obs_h.to(dev)
+    didx = torch.zeros(1, N, dtype=torch.int64, device=dev)
+    dnum = torch.ones(1, N, dtype=torch.int64, device=dev)
+    wp = dest[:, None].contiguous()
+    fargs = (6, 90, 4, 10, 90, 4)
+    bufs = None
+
+    def step():
+        nonlocal bufs
+        pf, of, sf = bufs[:3] if bufs else state_features(p, v, acc, dest, obs, hist, dsp, *fargs)
+        a_next = M.pinnsf_forward(net.spec, packed, pf.view(N, 6, 6), of.view(N, -1, 6), sf.view(N, 7),
+                                  need_msgs=False)[0].view(1, N, 2)
+        integrate_step(p, v, acc, a_next, dest, didx, dnum, wp, DT, False, hist_v=hist)
+        if bufs is None:
+            bufs = (pf, of, sf, torch.empty(1, N, 2, device=dev))
+        state_features(p, v, acc, dest, obs, hist, dsp, *fargs, out=bufs)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    assert torch.isfinite(p).all()
+    return {"workload": f"pinnsf_bm NN rollout step, N={N}, M={int(obs.shape[0])}, k=6/10 (forward + integrate + "
+                        "cell-list feature rebuild)", "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
+            "forward_flop_per_agent": 1.52e6, "tflops_fp32": 1.52e6 * N / ms * 1e3 / 1e12}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -199,7 +252,7 @@ def run_ours(a):
     p_h, v_h, ds_h, dest_h, obs_h = [x.pin_memory() for x in synthetic_crowd(N)]
     pos, vel, ds, dest = p_h.to(dev), v_h.to(dev), ds_h.to(dev), dest_h.to(dev)
     model = P.MLAPM(**MLAPM_KW)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    flush = torch.empty(FLUSH_MB << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     pos_next, vel_next = torch.empty_like(pos), torch.empty_like(vel)
 
     def step():
@@ -295,7 +348,7 @@ def run_ours(a):
             "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "obstacle_points": int(obs_h.shape[0]),
                        "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
                        "parallelism": f"agent-sharded rows x{world}" + (" + NCCL all-gather/step" if world > 1 else ""),
-                       "l2": "256 MB memset between steps, inside the timed region"},
+                       "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
             "roofline": {"bound": "fp32", "kernel": "mlapm_pairs_kernel<GC,R=4,fast> (+finalize)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if peak else None, "traffic": None,
@@ -309,6 +362,8 @@ def run_ours(a):
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
         }
+        if world == 1:
+            line["nn_path"] = nn_path_step(torch, dev, N, obs_h)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(N)
         print(json.dumps(line))

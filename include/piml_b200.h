@@ -190,6 +190,10 @@ PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *par
                             int norm_group, const float *drop_ped, const float *drop_obs, float *acc,
                             float *ped_msgs, float *obs_msgs, float *coll, void *stream);
 
+/* Self test of the tensor-core path (tcgen05 kind::tf32, A in TMEM, accumulator in TMEM): y (128,N) = x (128,K) w^T
+ * with w (N,K) row-major; terms = 1: plain TF32, 3: 3xTF32 split (fp32-grade).  K % 8 == 0, N % 16 == 0, both <= 128. */
+PIML_API int piml_tc_selftest_f32(const float *x, const float *w, int K, int N, int terms, float *y, void *stream);
+
 /* ---- training: forward with activation stash + backward (loss.backward(), simulators.py:359, through the models) -- */
 
 /* Floats of the activation stash of the training-mode forward for R agents (every Linear's post-activation output,

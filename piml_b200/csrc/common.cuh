@@ -70,6 +70,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// Bounded variant for bring-up / self tests: gives up after ~`spins` polls and returns false instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity, uint32_t spins) {
+    for (uint32_t i = 0; i < spins; ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 // global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16B aligned), completion on `bar`
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
