@@ -194,6 +194,18 @@ PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *par
  * with w (N,K) row-major; terms = 1: plain TF32, 3: 3xTF32 split (fp32-grade).  K % 8 == 0, N % 16 == 0, both <= 128. */
 PIML_API int piml_tc_selftest_f32(const float *x, const float *w, int K, int N, int terms, float *y, void *stream);
 
+/* Tensor-core forward (tcgen05 kind::tf32 with the 3xTF32 split, accumulators and activations in TMEM): the inference
+ * path of the rollouts.  Same contract as piml_pinnsf_forward_f32 in eval mode without the collision head:
+ * acc (R,2) and, for kind 0 models, optional 2-d messages ped_msgs (R,kp,2) / obs_msgs (R,ko,2) (NULL to skip).
+ * Needs processor_hidden_layers > 1 and hidden widths that are multiples of 32 (<= 128);
+ * piml_pinnsf_packed_tc_floats returns -1 for networks it cannot run (callers then use piml_pinnsf_forward_f32).
+ * packed_tc: written by piml_pinnsf_pack_tc_f32 from the torch-layout vector (see piml_pinnsf_pack_f32). */
+PIML_API int64_t piml_pinnsf_packed_tc_floats(const piml_net_desc *desc);
+PIML_API int piml_pinnsf_pack_tc_f32(const piml_net_desc *desc, const float *params_torch, float *packed_tc, void *stream);
+PIML_API int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float *packed_tc, int has_obs, float tau,
+                               const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
+                               int norm_group, float *acc, float *ped_msgs, float *obs_msgs, void *stream);
+
 /* ---- training: forward with activation stash + backward (loss.backward(), simulators.py:359, through the models) -- */
 
 /* Floats of the activation stash of the training-mode forward for R agents (every Linear's post-activation output,

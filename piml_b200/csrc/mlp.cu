@@ -83,7 +83,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) pinnsf_tile_kernel(const __grid
         if (a.stash) { __syncthreads(); store_tile(cur, a.stash + S.enc[br][l], row0, nrows, P.enc[l].OUT); }
     }
     if (P.proc_mode == 1) {                  // single ResBlock: relu(Wx+b) + x, then dropout (model.py:68-79,118)
-        dense_any(wp, P.proc, pbase, cur, oth, nrows, true, 1.f, cur, drop, P.pw);
+        if (a.stash) {                       // training: keep relu(Wx+b) and the block output for the backward
+            dense_any(wp, P.proc, pbase, cur, oth, nrows, true, 1.f);
+            __syncthreads();
+            store_tile(oth, a.stash + S.proc_h[br], row0, nrows, P.pw);
+            const int pw = P.pw;
+            float *yout = a.stash + S.proc[br];
+            tile_pass(pw, nrows, [&](int i, int r) {
+                float y = oth[i * FT_TRP + r] + cur[i * FT_TRP + r];
+                if (drop) y *= drop[static_cast<int64_t>(r) * pw + i];
+                oth[i * FT_TRP + r] = y;
+                yout[(row0 + r) * pw + i] = y;
+            });
+        } else {
+            dense_any(wp, P.proc, pbase, cur, oth, nrows, true, 1.f, cur, drop, P.pw);
+        }
         float *t = cur; cur = oth; oth = t;
     }
     float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
@@ -285,8 +299,6 @@ static int pinnsf_forward_impl(const piml_net_desc *desc, const float *params, i
     if (rc) return rc;
     if (R == 0) return PIML_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (stash && P.proc_mode == 1)
-        return fail(PIML_ERR_UNSUPPORTED, "piml_pinnsf_forward_train_f32: processor_hidden_layers == 1 has no backward");
     const SPlan S = make_splan(P, has_obs != 0, R, kp, ko, coll != nullptr);
 
     FTab T;

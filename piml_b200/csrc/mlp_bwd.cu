@@ -135,8 +135,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) pinnsf_bwd_tile_kernel(const __
         if (coll) coll_backward(cur, oth);                         // (the dense calls synchronise before reading)
         __syncthreads();
     }
-    // ResDNN == 2x (+ dropout multipliers) folded into the last encoder layer (model.py:115-119)
-    {
+    if (P.proc_mode == 1) {
+        // single ResBlock y = (relu(W e + b) + e) * drop (model.py:68-79,118): g_e = g_y drop + (g_y drop . mask) W
+        const int pw = P.pw;
+        const float *dr = drop ? drop + row0 * pw : nullptr;
+        const float *hp = a.stash + S.proc_h[br];
+        float *gproc = a.G + Gp.proc[br];
+        tile_pass(pw, nrows, [&](int i, int r) {
+            float g = cur[i * FT_TRP + r];
+            if (dr) g *= dr[static_cast<int64_t>(r) * pw + i];
+            cur[i * FT_TRP + r] = g;
+            const float gm = hp[(row0 + r) * pw + i] > 0.f ? g : 0.f;
+            oth[i * FT_TRP + r] = gm;
+            gproc[(row0 + r) * pw + i] = gm;
+        });
+        dense_any(wp, P.proc, pbase, oth, cur, nrows, false, 1.f, cur);
+        __syncthreads();
+        store_tile(cur, a.G + Gp.enc[br][ne - 1], row0, nrows, pw);
+    } else {
+        // ResDNN == 2x (+ dropout multipliers) folded into the last encoder layer (model.py:115-119)
         const int pw = P.pw;
         float *gout = a.G + Gp.enc[br][ne - 1];
         const float *dr = drop ? drop + row0 * pw : nullptr;
@@ -185,6 +202,7 @@ static int build_chunks_bwd(const FPlan &P, int br, bool want_coll, FTab *T) {
     if (P.kind == 0 && coll) add_coll();
     for (int l = P.n_dec - 1; l >= 0; --l) bad |= add(P.dec[l], base);
     if (P.kind == 1 && coll) add_coll();
+    if (P.proc_mode == 1) bad |= add(P.proc, base);
     for (int l = P.n_enc - 1; l >= 0; --l) bad |= add(P.enc[l], base);
     T->n[br] = n;
     return bad;
@@ -399,8 +417,6 @@ extern "C" int piml_pinnsf_backward_f32(const piml_net_desc *desc, const float *
     if (rc) return rc;
     rc = build_plan(desc, &Pt, &PT, true);
     if (rc) return rc;
-    if (P.proc_mode == 1)
-        return fail(PIML_ERR_UNSUPPORTED, "piml_pinnsf_backward_f32: processor_hidden_layers == 1 has no backward");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t t_total = P.t_total, t_pad = (t_total + 3) / 4 * 4;
     if (R == 0) {
@@ -456,16 +472,18 @@ extern "C" int piml_pinnsf_backward_f32(const piml_net_desc *desc, const float *
         const int64_t tb = P.t_branch_off[br];
         for (int l = 0; l < P.n_enc; ++l)
             job(l == 0 ? feat : stash + S.enc[br][l - 1], Gp.enc[br][l], rows, P.enc[l], tb);
+        const float *proc_out = P.proc_mode == 1 ? stash + S.proc[br] : stash + S.enc[br][P.n_enc - 1];
+        if (P.proc_mode == 1) job(stash + S.enc[br][P.n_enc - 1], Gp.proc[br], rows, P.proc, tb);
         for (int l = 0; l < P.n_dec; ++l) {
-            const float *A = l > 0 ? stash + S.dec[br][l - 1]
-                                   : (P.kind == 0 ? stash + S.enc[br][P.n_enc - 1] : stash + S.sum[br]);
+            const float *A = l > 0 ? stash + S.dec[br][l - 1] : (P.kind == 0 ? proc_out : stash + S.sum[br]);
             job(A, Gp.dec[br][l], prow, P.dec[l], tb);
         }
         job(stash + S.dec[br][P.n_dec - 1], Gp.pred[br], prow, P.pred, tb);
     }
     if (coll) {
         const int64_t rows = R * kp;
-        const float *A0 = P.kind == 0 ? stash + S.dec[0][P.n_dec - 1] : stash + S.enc[0][P.n_enc - 1];
+        const float *A0 = P.kind == 0 ? stash + S.dec[0][P.n_dec - 1]
+                                      : (P.proc_mode == 1 ? stash + S.proc[0] : stash + S.enc[0][P.n_enc - 1]);
         if (P.n_coll == 2) {
             job(A0, Gp.collh, rows, P.coll[0], P.t_coll_off);
             job(stash + S.collh, Gp.prob, rows, P.coll[1], P.t_coll_off);

@@ -115,3 +115,498 @@ extern "C" int piml_tc_selftest_f32(const float *x, const float *w, int K, int N
     count_launch();
     return check_launch("tc_probe_kernel");
 }
+
+// =====================================================================================================================
+// Fused interaction-network forward on the tensor cores (inference: eval mode, acceleration output [+ 2-d messages]).
+//
+// Same mathematics as pinnsf_tile_kernel (mlp.cu) -- reference src/models/model.py:40-119, :762-792, :1104-1135,
+// :1185-1212, :1271-1296 -- but every wide Linear of a 128-row tile is a chain of tcgen05.mma (kind::tf32) with the
+// 3xTF32 split (x_lo w_hi + x_hi w_lo + x_hi w_hi, fp32 accumulation in TMEM): measured 1e-6 of fp64 per layer, i.e.
+// fp32-grade, which the 1e-5 parity gate needs and plain TF32 (3e-4) does not give.
+//
+// Per CTA (persistent, one per SM, 192 threads):
+//   warp 0  : TMA producer -- streams the layers' weight images (hi + lo, pre-split and pre-arranged as UMMA K-major
+//             core matrices by piml_pinnsf_pack_tc_f32) through a 5-stage shared-memory ring with cp.async.bulk;
+//   warp 1  : MMA issuer -- one thread issues the tcgen05.mma chain of a layer: A (activations, hi / lo) from TMEM,
+//             B from the ring, D into TMEM; tcgen05.commit frees ring stages and signals "D ready";
+//   warps 2-5: epilogue -- thread = tile row: tcgen05.ld D, + bias, ReLU / ResDNN 2x fold, split into tf32 hi / lo and
+//             tcgen05.st as the NEXT layer's A operand (activations never touch shared memory); the 2-wide predictor,
+//             the sum over an agent's slots and (kind 1) the per-agent embedding sum run on the CUDA cores in fp32.
+// TMEM columns: D [0,128), A_hi [128,256), A_lo [256,384).
+namespace piml {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_STAGES = 5;
+constexpr int TC_STAGE_BYTES = 32768;          // hi + lo image of a 32-deep K chunk of a 128-wide layer
+constexpr int TC_MAXL = 16;
+constexpr int TC_MAXCH = 64;
+constexpr int TC_COL_D = 0, TC_COL_AH = 128, TC_COL_AL = 256;
+
+struct TcLayer { int K, Kp, N, chunk0, nchunks, bias_off, relu; float scale; };   // bias_off: floats into the bias block
+struct TcChunk { int off, bytes, cells; };          // float offset from the branch's weight base; 16-byte K cells (even)
+struct TcPlan {
+    int kind, n_enc, n_dec, nl, pw, dw;
+    TcLayer L[TC_MAXL];
+    int nch; TcChunk C[TC_MAXCH];
+    int predw_off, predb_off, bias_floats;         // inside the bias block
+    int64_t w_off[2], b_off[2];                    // float offsets of a branch's chunk images / bias block
+    int64_t total;
+};
+
+struct TcArgs {
+    const float *params; const float *ped; const float *obs;
+    int64_t R; int kp, ko, ag_ped, ag_obs; int64_t n_ped_tiles, n_obs_tiles;
+    float *sums; float *ped_msgs; float *obs_msgs;
+};
+
+// mbarrier wait that can never hang the GPU: a protocol bug traps (launch error) after ~seconds instead of spinning.
+__device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
+    if (!mbar_wait_bounded(bar, parity, 1u << 28)) __trap();
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_constant__ TcPlan P,
+                                                                  const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    unsigned char *ring = tc_smem;                                                       // TC_STAGES x 32 KB
+    float *biasb = reinterpret_cast<float *>(ring + TC_STAGES * TC_STAGE_BYTES);         // [2][bias_floats]
+    float *small = biasb + 2 * P.bias_floats;                                            // [128][2]
+    float *stage = small + 256;                                                          // [128][33]  (kind 1)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 128 * 33 + 1);                 // full[S] empty[S] a_rdy d_rdy
+    bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bars) + 7) & ~static_cast<uintptr_t>(7));
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *a_ready = bars + 2 * TC_STAGES, *d_ready = a_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(a_ready, 128);
+        mbar_init(d_ready, 1);
+        mbar_fence_init();
+    }
+    for (int e = tid; e < 2 * P.bias_floats; e += TC_THREADS) {
+        const int br = e / P.bias_floats, i = e - br * P.bias_floats;
+        biasb[e] = (br == 0 || a.n_obs_tiles > 0) ? a.params[P.b_off[br] + i] : 0.f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const int64_t ntiles = a.n_ped_tiles + a.n_obs_tiles;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t pc = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int br = tile < a.n_ped_tiles ? 0 : 1;
+                const float *wbase = a.params + P.w_off[br];
+                for (int c = 0; c < P.nch; ++c, ++pc) {
+                    const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
+                    tc_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], static_cast<uint32_t>(P.C[c].bytes));
+                    tma_bulk_g2s(ring + s * TC_STAGE_BYTES, wbase + P.C[c].off, static_cast<uint32_t>(P.C[c].bytes),
+                                 &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t pc = 0, ev = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int li = 0; li < P.nl; ++li, ++ev) {
+                    const TcLayer &Ly = P.L[li];
+                    tc_wait(a_ready, ev & 1u);
+                    tc::fence_after_sync();
+                    const uint32_t idesc = tc::idesc_tf32(Ly.N);
+                    const uint32_t lbo = Ly.N * 16, sbo = 128, kstep = 2 * lbo;
+                    bool acc = false;
+                    for (int c = 0; c < Ly.nchunks; ++c, ++pc) {
+                        const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
+                        tc_wait(&full[s], ph);
+                        tc::fence_after_sync();
+                        const TcChunk &Ch = P.C[Ly.chunk0 + c];
+                        const uint32_t hi_addr = tc::smem_addr(ring + s * TC_STAGE_BYTES);
+                        const uint32_t lo_addr = hi_addr + Ch.cells * lbo;
+                        for (int ks = 0; ks < Ch.cells / 2; ++ks) {
+                            const uint32_t kcol = c * 32 + ks * 8;
+                            const uint64_t bh = tc::smem_desc(hi_addr + ks * kstep, lbo, sbo);
+                            const uint64_t bl = tc::smem_desc(lo_addr + ks * kstep, lbo, sbo);
+                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AL + kcol, bh, idesc, acc);   // x_lo w_hi
+                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AH + kcol, bl, idesc, true);  // x_hi w_lo
+                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AH + kcol, bh, idesc, true);  // x_hi w_hi
+                            acc = true;
+                        }
+                        tc::commit(&empty[s]);                     // ring stage free once these MMAs have read it
+                    }
+                    tc::commit(d_ready);                           // accumulator of this layer complete
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = tile row =====
+        const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int m = q4 * 32 + lane;                              // tile row == TMEM lane
+        const uint32_t tl = tbase + (static_cast<uint32_t>(q4 * 32) << 16);
+        uint32_t ev = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int br = tile < a.n_ped_tiles ? 0 : 1;
+            const int k = br == 0 ? a.kp : a.ko;
+            const int AG = br == 0 ? a.ag_ped : a.ag_obs;
+            const int64_t agent0 = (br == 0 ? tile : tile - a.n_ped_tiles) * AG;
+            const int na = static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
+            const int nrows = na * k;
+            const int64_t row0 = agent0 * k;
+            const float *bb = biasb + br * P.bias_floats;
+            {   // stage the 6-d features of this row as the first A operand (K padded to 8 with zeros)
+                uint32_t hi[8], lo[8];
+                const float *f = (br == 0 ? a.ped : a.obs) + (row0 + m) * 6;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float x = (q < 6 && m < nrows) ? f[q] : 0.f;
+                    tc::split_tf32(x, hi[q], lo[q]);
+                }
+                tc::st8(tl + TC_COL_AH, hi);
+                tc::st8(tl + TC_COL_AL, lo);
+                tc::wait_st();
+                tc::fence_before_sync();
+                tc::mbar_arrive(a_ready);
+            }
+            float m0 = 0.f, m1 = 0.f;
+            for (int li = 0; li < P.nl; ++li, ++ev) {
+                const TcLayer &Ly = P.L[li];
+                const bool last = li == P.nl - 1;
+                const bool to_sum = P.kind == 1 && li == P.n_enc - 1;        // kind 1: sum the slot embeddings per agent
+                tc_wait(d_ready, ev & 1u);
+                tc::fence_after_sync();
+                const float *bias = bb + Ly.bias_off;
+                for (int n0 = 0; n0 < Ly.N; n0 += 32) {
+                    uint32_t r[32];
+                    tc::ld32(tl + TC_COL_D + n0, r);
+                    tc::wait_ld();
+                    float y[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        float v = (__uint_as_float(r[q]) + bias[n0 + q]) * Ly.scale;
+                        if (Ly.relu) v = fmaxf(v, 0.f);
+                        y[q] = v;
+                    }
+                    if (last) {                                    // predictor Linear(dw, 2) on the CUDA cores
+                        const float *w0 = bb + P.predw_off + n0, *w1 = w0 + P.dw;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) { m0 = fmaf(y[q], w0[q], m0); m1 = fmaf(y[q], w1[q], m1); }
+                        continue;
+                    }
+                    if (to_sum) {                                  // torch.sum(dim=-2) over the k slots (model.py:1276)
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) stage[m * 33 + q] = y[q];
+                        epi_barrier();
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            float s = 0.f;
+                            if (m < na)
+                                for (int j = 0; j < k; ++j) s += stage[(m * k + j) * 33 + q];
+                            y[q] = s;
+                        }
+                        epi_barrier();
+                    }
+                    uint32_t lo[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) tc::split_tf32(y[q], r[q], lo[q]);
+                    tc::st32(tl + TC_COL_AH + n0, r);
+                    tc::st32(tl + TC_COL_AL + n0, lo);
+                }
+                if (!last) {
+                    tc::wait_st();
+                    tc::fence_before_sync();
+                    tc::mbar_arrive(a_ready);
+                }
+            }
+            m0 += bb[P.predb_off];
+            m1 += bb[P.predb_off + 1];
+            if (P.kind == 0) {
+                small[m * 2] = m0; small[m * 2 + 1] = m1;
+                float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
+                if (msgs_out && m < nrows) { msgs_out[(row0 + m) * 2] = m0; msgs_out[(row0 + m) * 2 + 1] = m1; }
+                epi_barrier();
+                if (m < 2 * na) {                                  // torch.sum(dim=-2) over the k slots (model.py:1194)
+                    const int ag = m >> 1, c = m & 1;
+                    float s = 0.f;
+                    for (int j = 0; j < k; ++j) s += small[(ag * k + j) * 2 + c];
+                    a.sums[(agent0 + ag) * 4 + br * 2 + c] = s;
+                }
+                epi_barrier();
+            } else if (m < na) {
+                a.sums[(agent0 + m) * 4 + br * 2] = m0;
+                a.sums[(agent0 + m) * 4 + br * 2 + 1] = m1;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// ---- plan + packing -------------------------------------------------------------------------------------------------
+struct TcPackRec { int K, Kp, N; int64_t src_w, src_b, dst_w, dst_b; };
+struct TcPackTab { int n; TcPackRec r[2 * TC_MAXL]; int dw; int64_t pred_src[2], predw_dst[2], predb_dst[2]; int64_t total; };
+
+static int tc_build_plan(const piml_net_desc *d, TcPlan *P, TcPackTab *T) {
+    PIML_REQUIRE(d->n_enc >= 1 && d->n_enc <= 8 && d->n_dec >= 1 && d->n_dec <= 8, "piml_pinnsf_tc: bad layer counts");
+    PIML_REQUIRE(d->proc_mode == 0, "piml_pinnsf_tc: processor_hidden_layers == 1 is not supported on the tensor-core path");
+    PIML_REQUIRE(d->enc_dims[0] == 6, "piml_pinnsf_tc: feature dim must be 6");
+    PIML_REQUIRE(d->dec_dims[0] == d->enc_dims[d->n_enc], "piml_pinnsf_tc: decoder input != processor width");
+    P->kind = d->kind; P->n_enc = d->n_enc; P->n_dec = d->n_dec; P->nl = d->n_enc + d->n_dec;
+    P->pw = d->enc_dims[d->n_enc]; P->dw = d->dec_dims[d->n_dec];
+    int nch = 0, woff = 0, boff = 0;
+    int64_t src = 0;
+    T->n = 0;
+    auto layer = [&](int li, int K, int N, int relu, float scale) -> int {
+        PIML_REQUIRE(N % 32 == 0 && N <= 128 && K <= 128 && (K % 8 == 0 || li == 0),
+                     "piml_pinnsf_tc: layer %d (%d -> %d) needs widths that are multiples of 32 (<= 128)", li, K, N);
+        TcLayer &L = P->L[li];
+        L.K = K; L.Kp = (K + 7) & ~7; L.N = N; L.relu = relu; L.scale = scale; L.bias_off = boff; L.chunk0 = nch;
+        L.nchunks = (L.Kp + 31) / 32;
+        TcPackRec &r = T->r[T->n++];
+        r.K = K; r.Kp = L.Kp; r.N = N; r.src_w = src; r.src_b = src + static_cast<int64_t>(K) * N; r.dst_w = woff; r.dst_b = boff;
+        for (int c = 0; c < L.nchunks; ++c) {
+            PIML_REQUIRE(nch < TC_MAXCH, "piml_pinnsf_tc: too many weight chunks");
+            const int cells = (L.Kp - c * 32 < 32 ? L.Kp - c * 32 : 32) / 4;
+            P->C[nch].off = woff; P->C[nch].cells = cells; P->C[nch].bytes = 2 * cells * N * 16;
+            woff += 2 * cells * N * 4;
+            ++nch;
+        }
+        boff += N;
+        src += static_cast<int64_t>(K) * N + N;
+        return PIML_OK;
+    };
+    int li = 0;
+    for (int l = 0; l < d->n_enc; ++l, ++li) {
+        const bool last = l == d->n_enc - 1;
+        int rc = layer(li, d->enc_dims[l], d->enc_dims[l + 1], last ? 0 : 1, last ? 2.f : 1.f);   // ResDNN == 2x fold
+        if (rc) return rc;
+    }
+    for (int l = 0; l < d->n_dec; ++l, ++li) {
+        int rc = layer(li, d->dec_dims[l], d->dec_dims[l + 1], l < d->n_dec - 1 ? 1 : 0, 1.f);
+        if (rc) return rc;
+    }
+    P->nch = nch;
+    P->predw_off = boff; boff += 2 * P->dw;
+    P->predb_off = boff; boff += 2;
+    P->bias_floats = (boff + 3) & ~3;
+    const int64_t branch_src = src + 2 * P->dw + 2;                // torch floats of one branch
+    const int64_t branch_dst = static_cast<int64_t>(woff) + P->bias_floats;
+    for (int br = 0; br < 2; ++br) {
+        P->w_off[br] = br * branch_dst;
+        P->b_off[br] = br * branch_dst + woff;
+        T->pred_src[br] = br * branch_src + src;
+        T->predw_dst[br] = P->b_off[br] + P->predw_off;
+        T->predb_dst[br] = P->b_off[br] + P->predb_off;
+    }
+    T->dw = P->dw;
+    // second branch: same records shifted
+    const int n1 = T->n;
+    for (int i = 0; i < n1; ++i) {
+        TcPackRec r = T->r[i];
+        r.src_w += branch_src; r.src_b += branch_src; r.dst_w += branch_dst; r.dst_b += P->b_off[1];
+        T->r[T->n++] = r;
+    }
+    for (int i = 0; i < n1; ++i) T->r[i].dst_b += P->b_off[0];
+    P->total = 2 * branch_dst;
+    T->total = P->total;
+    return PIML_OK;
+}
+
+// one thread per float of the packed vector
+__global__ void pinnsf_pack_tc_kernel(const __grid_constant__ TcPackTab T, const float *__restrict__ src,
+                                      float *__restrict__ dst, int nlayers_per_branch, int64_t branch_floats,
+                                      int64_t wfloats) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= T.total) return;
+    const int br = static_cast<int>(i / branch_floats);
+    const int64_t off = i - br * branch_floats;
+    float v = 0.f;
+    if (off < wfloats) {
+        // inside a weight image: find the layer, then (chunk, half, cell, n, kk)
+        int l = 0;
+        while (l + 1 < nlayers_per_branch && off >= T.r[l + 1].dst_w) ++l;
+        const TcPackRec &R = T.r[br * nlayers_per_branch + l];
+        int64_t e = off - T.r[l].dst_w;
+        int c = 0;
+        for (;;) {                                                 // chunks of this layer
+            const int cells = (R.Kp - c * 32 < 32 ? R.Kp - c * 32 : 32) / 4;
+            const int64_t cf = 2LL * cells * R.N * 4;
+            if (e < cf) {
+                const int half = static_cast<int>(e / (cells * R.N * 4));
+                const int64_t r = e - static_cast<int64_t>(half) * cells * R.N * 4;
+                const int cell = static_cast<int>(r / (R.N * 4)), n = static_cast<int>((r / 4) % R.N), kk = static_cast<int>(r & 3);
+                const int kx = c * 32 + cell * 4 + kk;
+                const float w = kx < R.K ? src[R.src_w + static_cast<int64_t>(n) * R.K + kx] : 0.f;
+                uint32_t hi, lo;
+                tc::split_tf32(w, hi, lo);
+                v = __uint_as_float(half == 0 ? hi : lo);
+                break;
+            }
+            e -= cf; ++c;
+        }
+    } else {
+        const int64_t b = off - wfloats;                           // inside the bias block
+        const int64_t predw = T.predw_dst[0] - wfloats, predb = T.predb_dst[0] - wfloats;
+        if (b >= predb) { if (b < predb + 2) v = src[T.pred_src[br] + 2LL * T.dw + (b - predb)]; }
+        else if (b >= predw) { v = src[T.pred_src[br] + (b - predw)]; }
+        else {
+            int l = 0;
+            while (l + 1 < nlayers_per_branch && b >= T.r[l + 1].dst_b - T.r[0].dst_b) ++l;
+            const TcPackRec &R = T.r[br * nlayers_per_branch + l];
+            const int64_t o = b - (T.r[l].dst_b - T.r[0].dst_b);
+            if (o < R.N) v = src[R.src_b + o];
+        }
+    }
+    dst[i] = v;
+}
+
+// per-agent sums scratch shared with mlp.cu's finish kernel
+__global__ void pinnsf_tc_finish_kernel(const float *__restrict__ sums, const float *__restrict__ self,
+                                        const float *__restrict__ dnorm, int64_t R, int has_obs, float tau,
+                                        float *__restrict__ acc) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= 2 * R) return;
+    const int64_t ag = i >> 1;
+    const int c = static_cast<int>(i & 1);
+    const float *s = self + ag * 7;
+    float nrm = dnorm ? dnorm[ag * 2 + c] : norm2_rn(s[0], s[1]);
+    if (nrm == 0.f) nrm = __fadd_rn(nrm, 0.1f);
+    const float dir = __fdiv_rn(s[c], nrm);
+    const float dterm = __fdiv_rn(__fsub_rn(__fmul_rn(s[6], dir), s[2 + c]), tau);
+    float mm = sums[ag * 4 + c];
+    if (has_obs) mm = __fadd_rn(mm, sums[ag * 4 + 2 + c]);
+    acc[i] = __fadd_rn(mm, dterm);
+}
+
+__global__ void tc_colnorm_kernel(const float *__restrict__ self, int group, float *__restrict__ dnorm) {
+    __shared__ float red[2][128];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * group;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = threadIdx.x; i < group; i += blockDim.x) {
+        const float x = self[(base + i) * 7], y = self[(base + i) * 7 + 1];
+        s0 = fmaf(x, x, s0); s1 = fmaf(y, y, s1);
+    }
+    red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { red[0][threadIdx.x] += red[0][threadIdx.x + off]; red[1][threadIdx.x] += red[1][threadIdx.x + off]; }
+        __syncthreads();
+    }
+    const float n0 = sqrtf(red[0][0]), n1 = sqrtf(red[1][0]);
+    for (int i = threadIdx.x; i < group; i += blockDim.x) { dnorm[(base + i) * 2] = n0; dnorm[(base + i) * 2 + 1] = n1; }
+}
+
+struct TcScratch { cudaStream_t st; int dev; float *buf; int64_t cap; };
+static int tc_scratch_get(cudaStream_t st, int64_t floats, float **out) {
+    static thread_local TcScratch slots[8] = {};
+    static thread_local int used = 0;
+    int dev = 0;
+    PIML_CUDA(cudaGetDevice(&dev));
+    TcScratch *s = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (slots[i].st == st && slots[i].dev == dev) s = &slots[i];
+    if (!s) {
+        s = &slots[used < 8 ? used++ : 7];
+        if (s->buf) { cudaSetDevice(s->dev); cudaFree(s->buf); cudaSetDevice(dev); }
+        s->st = st; s->dev = dev; s->buf = nullptr; s->cap = 0;
+    }
+    if (s->cap < floats) {
+        if (s->buf) { PIML_CUDA(cudaStreamSynchronize(st)); PIML_CUDA(cudaFree(s->buf)); }
+        s->buf = nullptr; s->cap = 0;
+        PIML_CUDA(cudaMalloc(&s->buf, sizeof(float) * floats));
+        s->cap = floats;
+    }
+    *out = s->buf;
+    return PIML_OK;
+}
+
+}  // namespace piml
+
+extern "C" int64_t piml_pinnsf_packed_tc_floats(const piml_net_desc *desc) {
+    if (!desc) return -1;
+    TcPlan P;
+    TcPackTab T;
+    if (tc_build_plan(desc, &P, &T)) return -1;
+    return P.total;
+}
+
+extern "C" int piml_pinnsf_pack_tc_f32(const piml_net_desc *desc, const float *params_torch, float *packed_tc,
+                                       void *stream) {
+    PIML_REQUIRE(desc && params_torch && packed_tc, "piml_pinnsf_pack_tc_f32: null pointer");
+    TcPlan P;
+    TcPackTab T;
+    int rc = tc_build_plan(desc, &P, &T);
+    if (rc) return rc;
+    PIML_REQUIRE(aligned16(packed_tc), "piml_pinnsf_pack_tc_f32: packed_tc must be 16-byte aligned");
+    const int threads = 256;
+    pinnsf_pack_tc_kernel<<<static_cast<unsigned>((P.total + threads - 1) / threads), threads, 0,
+                            static_cast<cudaStream_t>(stream)>>>(T, params_torch, packed_tc, P.nl, P.total / 2,
+                                                                 P.b_off[0]);
+    count_launch();
+    return check_launch("pinnsf_pack_tc_kernel");
+}
+
+extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float *packed_tc, int has_obs, float tau,
+                                          const float *ped, const float *obs, const float *self, int64_t R, int kp,
+                                          int ko, int norm_group, float *acc, float *ped_msgs, float *obs_msgs,
+                                          void *stream) {
+    PIML_REQUIRE(desc && packed_tc && ped && self && acc, "piml_pinnsf_forward_tc_f32: null pointer");
+    PIML_REQUIRE(!has_obs || obs, "piml_pinnsf_forward_tc_f32: has_obs set but obs is null");
+    PIML_REQUIRE(R >= 0 && kp >= 1 && ko >= 0 && kp <= 128 && ko <= 128, "piml_pinnsf_forward_tc_f32: bad dimensions");
+    PIML_REQUIRE(aligned16(packed_tc), "piml_pinnsf_forward_tc_f32: packed_tc must be 16-byte aligned");
+    if (!has_obs || ko == 0) { has_obs = 0; ko = 0; }
+    TcPlan P;
+    TcPackTab T;
+    int rc = tc_build_plan(desc, &P, &T);
+    if (rc) return rc;
+    PIML_REQUIRE(P.kind == 0 || (!ped_msgs && !obs_msgs),
+                 "piml_pinnsf_forward_tc_f32: per-slot embedding messages (kind 1) are only produced by the FP32 path");
+    if (R == 0) return PIML_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *scratch = nullptr;
+    rc = tc_scratch_get(st, R * 4 + (norm_group > 0 ? R * 2 : 0), &scratch);
+    if (rc) return rc;
+    const float *dnorm = nullptr;
+    if (norm_group > 0) {
+        PIML_REQUIRE(R % norm_group == 0, "piml_pinnsf_forward_tc_f32: R not a multiple of norm_group");
+        float *dn = scratch + R * 4;
+        tc_colnorm_kernel<<<static_cast<unsigned>(R / norm_group), 128, 0, st>>>(self, norm_group, dn);
+        count_launch();
+        rc = check_launch("tc_colnorm_kernel");
+        if (rc) return rc;
+        dnorm = dn;
+    }
+    TcArgs a;
+    a.params = packed_tc; a.ped = ped; a.obs = obs; a.R = R; a.kp = kp; a.ko = ko;
+    a.ag_ped = 128 / kp; a.ag_obs = ko ? 128 / ko : 1;
+    a.n_ped_tiles = (R + a.ag_ped - 1) / a.ag_ped;
+    a.n_obs_tiles = has_obs ? (R + a.ag_obs - 1) / a.ag_obs : 0;
+    a.sums = scratch; a.ped_msgs = ped_msgs; a.obs_msgs = has_obs ? obs_msgs : nullptr;
+    const size_t smem = static_cast<size_t>(TC_STAGES) * TC_STAGE_BYTES +
+                        sizeof(float) * (2 * P.bias_floats + 256 + 128 * 33 + 1) + 8 * (2 * TC_STAGES + 2) + 64;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    PIML_REQUIRE(smem <= 200 * 1024, "piml_pinnsf_forward_tc_f32: network too large for the shared-memory plan");
+    const int64_t tiles = a.n_ped_tiles + a.n_obs_tiles;
+    const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+    pinnsf_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, a);
+    count_launch();
+    rc = check_launch("pinnsf_tc_kernel");
+    if (rc) return rc;
+    const int threads = 256;
+    pinnsf_tc_finish_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
+        scratch, self, dnorm, R, has_obs, tau, acc);
+    count_launch();
+    return check_launch("pinnsf_tc_finish_kernel");
+}

@@ -177,6 +177,8 @@ __device__ __forceinline__ void store_tile(const float *tile, float *dst, int64_
 struct SPlan {
     int64_t enc[2][8];   // encoder layer l of branch br: (rows_br, width_l); the last one after the 2x / dropout fold
     int64_t dec[2][8];   // decoder layer l: kind 0 (rows_br, width_l), kind 1 (R, width_l)
+    int64_t proc_h[2];   // single-block processor only: relu(W e + b) (rows_br, pw)
+    int64_t proc[2];     // single-block processor only: its output (relu(..) + e) * dropout (rows_br, pw)
     int64_t sum[2];      // kind 1 only: per-agent sum of the slot embeddings (R, pw)
     int64_t pred[2];     // G only: predictor output gradient, kind 0 (rows_br, 2), kind 1 (R, 2)
     int64_t collh;       // collision head hidden layer (rows_ped, hidden)
@@ -194,6 +196,8 @@ static SPlan make_splan(const FPlan &P, bool has_obs, int64_t R, int kp, int ko,
             S.enc[br][l] = l < P.n_enc ? take(rows, P.enc[l].OUT) : 0;
             S.dec[br][l] = 0;
         }
+        S.proc_h[br] = P.proc_mode == 1 ? take(rows, P.pw) : 0;
+        S.proc[br] = P.proc_mode == 1 ? take(rows, P.pw) : 0;
         for (int l = 0; l < P.n_dec; ++l) S.dec[br][l] = take(P.kind == 0 ? rows : (rows ? R : 0), P.dec[l].OUT);
         S.sum[br] = P.kind == 1 ? take(rows ? R : 0, P.pw) : 0;
         S.pred[br] = take(P.kind == 0 ? rows : (rows ? R : 0), 2);

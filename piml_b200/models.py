@@ -9,6 +9,8 @@ the same `torch.manual_seed` gives the same initial weights), but `forward` runs
 `forward_from_module(module, ped, obs, self)` runs the same kernel on the weights of an UNMODIFIED reference
 module; piml_b200.patch uses it to drop the CUDA path in behind `model(*state_features)`.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -125,10 +127,33 @@ def pack_device(sd, spec, device=None):
     return out
 
 
+def tc_enabled():
+    """The tensor-core forward is on unless PIML_MLP_TC=0 (A/B switch for measurements)."""
+    return os.environ.get("PIML_MLP_TC", "1") != "0"
+
+
+def pack_device_tc(sd, spec, device=None):
+    """Parameter layout of the tensor-core forward (piml_pinnsf_pack_tc_f32): per Linear the tf32 hi / lo images of the
+    weight as UMMA K-major core matrices, fp32 biases and predictor.  Returns None when the network cannot run on the
+    tensor-core path (widths not multiples of 32, single-block processor); callers then use the FP32-pipe kernel."""
+    dev = device if device is not None else L.cuda_device()
+    desc = spec.desc()
+    n = int(L.load().piml_pinnsf_packed_tc_floats(L.C.byref(desc)))
+    if n < 0:
+        return None
+    src = pack_state_dict(sd, spec).to(dev)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    L.check(L.load().piml_pinnsf_pack_tc_f32(L.C.byref(desc), L.ptr(src), L.ptr(out), L.stream_ptr(dev)),
+            "piml_pinnsf_pack_tc_f32")
+    return out
+
+
 def pinnsf_forward(spec, packed, ped_features, obs_features, self_features, drop_ped=None, drop_obs=None,
-                   need_msgs=True):
-    """Run the fused forward.  Returns the reference's list [acc, ped_msgs, (obs_msgs), (pred_collision)]."""
-    dev = L.require_cuda(packed, ped_features, self_features)
+                   need_msgs=True, packed_tc=None):
+    """Run the fused forward.  Returns the reference's list [acc, ped_msgs, (obs_msgs), (pred_collision)].
+    With `packed_tc` (pack_device_tc) and a request the tensor-core kernel covers -- eval mode, no collision head
+    output, messages only for the per-slot-decoder models -- the tcgen05 path runs instead of the FP32-pipe kernel."""
+    dev = L.require_cuda(packed if packed is not None else packed_tc, ped_features, self_features)
     if self_features.shape[-1] != 7:
         raise AssertionError('Error: PINN model do not accept inputs of historical velocity')   # model.py:763
     ped, slf = L.f32c(ped_features), L.f32c(self_features)
@@ -149,6 +174,21 @@ def pinnsf_forward(spec, packed, ped_features, obs_features, self_features, drop
         ko = obs.shape[-2]
     acc = torch.empty(*lead, 2, dtype=torch.float32, device=dev)
     mw = spec.msg_width
+    use_tc = (packed_tc is not None and drop_ped is None and drop_obs is None and tc_enabled()
+              and (not need_msgs or (spec.kind == 0 and not spec.coll_dims)))
+    if use_tc:
+        pm = torch.empty(*lead, kp, 2, dtype=torch.float32, device=dev) if need_msgs else None
+        om = torch.empty(*lead, ko, 2, dtype=torch.float32, device=dev) if (need_msgs and spec.has_obs) else None
+        desc = spec.desc()
+        L.check(L.load().piml_pinnsf_forward_tc_f32(
+            L.C.byref(desc), L.ptr(packed_tc), 1 if spec.has_obs else 0, spec.tau, L.ptr(ped), L.ptr(obs), L.ptr(slf),
+            R, kp, ko, group, L.ptr(acc), L.ptr(pm), L.ptr(om), L.stream_ptr(dev)), "piml_pinnsf_forward_tc_f32")
+        out = [acc, pm]
+        if spec.has_obs:
+            out.append(om)
+        if spec.coll_dims:
+            out.append(None)
+        return out
     pm = torch.empty(*lead, kp, mw, dtype=torch.float32, device=dev) if need_msgs else None
     om = torch.empty(*lead, ko, mw, dtype=torch.float32, device=dev) if (need_msgs and spec.has_obs) else None
     coll = torch.empty(*lead, kp, 1, dtype=torch.float32, device=dev) if (spec.coll_dims and need_msgs) else None

@@ -72,7 +72,7 @@ class RolloutResult(object):
         self.num_steps, self.num_pedestrians = position.shape[-3], position.shape[-2]
 
 
-def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None):
+def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed_tc=None):
     """Roll S independent scenes forward together (one launch per stage per step, no host sync).
 
     scene: dict of CUDA tensors
@@ -111,7 +111,7 @@ def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None):
                 torch.empty(S, N, 7, device=dev), torch.empty(S, N, 2, device=dev))
     for t in range(t_start, T):
         a_next = M.pinnsf_forward(spec, packed, ped_f.view(S * N, kp, 6), obs_f.view(S * N, ko, 6),
-                                  self_f.view(S * N, 7), need_msgs=False)[0].view(S, N, 2)     # :602
+                                  self_f.view(S * N, 7), need_msgs=False, packed_tc=packed_tc)[0].view(S, N, 2)  # :602
         last = t >= T - 1
         integrate_step(p, v, a, a_next, dest, didx, dnum, wp, dt, True,
                        None if last else flag_tm[t + 1],
@@ -159,11 +159,12 @@ def get_multiple_rollouts(simulator, data, t_start=0, load_model=True, result_cl
     module = simulator.model.module if isinstance(simulator.model, torch.nn.DataParallel) else simulator.model
     spec = M.spec_from_module(module)
     packed = M.pack_device(module.state_dict(), spec, dev)
+    packed_tc = M.pack_device_tc(module.state_dict(), spec, dev)        # None if the net cannot use the tensor cores
     if not hasattr(args, "time_unit"):
         args.time_unit = data.time_unit
     scene = scene_from_data(data, t_start, dev)
     p_res, v_res, a_res, mask_new = rollout_scenes(spec, packed, _with_dt(args, data.time_unit), scene, t_start,
-                                                   data.num_frames)
+                                                   data.num_frames, packed_tc=packed_tc)
     out_dev = data.position.device
     res = (p_res[0].to(out_dev), v_res[0].to(out_dev), a_res[0].to(out_dev))
     if result_cls is None:

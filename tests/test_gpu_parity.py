@@ -323,6 +323,70 @@ def test_pinnsf_forward_golden(kind):
             assert err < TOL, (kind, suffix, i, err)
 
 
+@pytest.mark.parametrize("kind", ["pinnsf_bm", "pinnsf_m"])
+def test_pinnsf_forward_tensor_cores_golden(kind):
+    """The tcgen05 (3xTF32) forward against the reference's own outputs: acceleration within 1e-5 of the operand scale
+    (accel_err), for (N,.) and channelled (C,N,.) inputs."""
+    from piml_b200 import models as M
+    z = golden("models")
+    g, m = _mirror_model(z, kind)
+    ptc = M.pack_device_tc(m.state_dict(), m.spec)
+    assert ptc is not None
+    packed = M.pack_device(m.state_dict(), m.spec)
+    for suffix in ("", "c"):
+        tag = "_c" if suffix else ""
+        ped, obs, slf = cu(z["ped" + tag]), cu(z["obs" + tag]), cu(z["self" + tag])
+        out = M.pinnsf_forward(m.spec, packed, ped, obs, slf, need_msgs=False, packed_tc=ptc)
+        ref = g[f"out{suffix}0"]
+        if suffix:      # channelled: the destination norm is per channel and component (SURVEY.md B-3), compare directly
+            err = rel_vec_err(npy(out[0]), ref, floor=1e-1)
+        else:
+            err = accel_err(npy(out[0]), ref, z["self"], float(g["tau"]))
+        assert err < TOL, (kind, suffix, err)
+
+
+def test_tensor_core_path_declines_unsupported_nets():
+    """Widths that are not multiples of 32 cannot run on the tcgen05 path: pack_device_tc says so (-> FP32 kernel)."""
+    from piml_b200 import models as M
+    z = golden("models")
+    for kind in ("pinnsf_bottleneck", "pinnsf"):
+        g, m = _mirror_model(z, kind)
+        assert M.pack_device_tc(m.state_dict(), m.spec) is None
+
+
+@pytest.mark.parametrize("kind,R,kp,ko,chan,has_obs", [
+    ("pinnsf_bm", 21, 6, 10, 0, True), ("pinnsf_bm", 3001, 6, 10, 0, True), ("pinnsf_bottleneck", 999, 5, 3, 0, True),
+    ("pinnsf_m", 257, 6, 10, 0, True), ("pinnsf", 640, 6, 0, 0, False), ("pinnsf_bm", 640, 6, 2, 5, True),
+    ("pinnsf_m", 1200, 4, 7, 6, True)])
+def test_pinnsf_forward_tensor_cores_vs_fp32_kernel(kind, R, kp, ko, chan, has_obs):
+    """tcgen05 forward vs the FP32-pipe kernel on random inputs: tile tails, both decoder placements, no obstacle
+    branch, channelled destination norm, 2-d messages of the per-slot-decoder models."""
+    from piml_b200 import models as M
+    from .golden_args import base_args
+    args = base_args(model=kind, dataset_name="gc1560", obs_feature_dim=6 if has_obs else 0)
+    torch.manual_seed(R)
+    net = M.CLASSES[kind](args).cuda().eval()
+    g = torch.Generator().manual_seed(R + 1)
+    lead = (chan, R // chan) if chan else (R,)
+    ped = torch.randn(*lead, kp, 6, generator=g).cuda()
+    ped[..., -1, :] = 0
+    obs = torch.randn(*lead, max(ko, 1), 6, generator=g)[..., :ko, :].cuda()
+    slf = torch.randn(*lead, 7, generator=g).cuda()
+    packed = M.pack_device(net.state_dict(), net.spec)
+    ptc = M.pack_device_tc(net.state_dict(), net.spec)
+    need = net.spec.kind == 0 and not net.spec.coll_dims
+    ref = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True)
+    got = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=need, packed_tc=ptc)
+    # error relative to the scale of what is summed (messages + destination term), like the FP32 kernel's gate
+    err = accel_err(npy(got[0]).reshape(-1, 2), npy(ref[0]).reshape(-1, 2), npy(slf).reshape(-1, 7), net.spec.tau)
+    assert err < TOL, err
+    if need:
+        scale = float(ref[1].abs().max())
+        assert float((got[1] - ref[1]).abs().max()) < TOL * scale
+        if has_obs:
+            assert float((got[2] - ref[2]).abs().max()) < TOL * float(ref[2].abs().max())
+
+
 # ---- integrator ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
 def test_integrate_step_golden(name):

@@ -73,7 +73,8 @@ def test_pinnsf_backward_golden(case, kind, inp, train):
 @pytest.mark.parametrize("kind,R,kp,ko,small,has_obs,chan", [
     ("pinnsf_bm", 301, 6, 10, False, True, 0), ("pinnsf_m", 77, 6, 10, False, True, 0),
     ("pinnsf_bm", 64, 3, 2, True, True, 4), ("pinnsf_m", 45, 5, 0, True, False, 0),
-    ("pinnsf_bottleneck", 130, 6, 10, True, True, 0), ("pinnsf", 50, 4, 7, False, True, 5)])
+    ("pinnsf_bottleneck", 130, 6, 10, True, True, 0), ("pinnsf", 50, 4, 7, False, True, 5),
+    ("pinnsf_bm", 140, 6, 10, "single", True, 0), ("pinnsf_m", 90, 6, 4, "single", True, 0)])
 def test_pinnsf_backward_random(kind, R, kp, ko, small, has_obs, chan):
     """Random inputs / shapes vs torch autograd of the plain-torch restatement (tile tails, no obstacle branch,
     narrow nets, channelled destination norm, train-mode dropout multipliers)."""
@@ -81,6 +82,8 @@ def test_pinnsf_backward_random(kind, R, kp, ko, small, has_obs, chan):
     if small:
         over = dict(encoder_hidden_size=32, processor_hidden_size=32, decoder_hidden_size=16, encoder_hidden_layers=2,
                     processor_hidden_layers=4, decoder_hidden_layers=1)
+    if small == "single":                                   # one processor block: relu(W e + b) + e instead of 2e
+        over["processor_hidden_layers"] = 1
     if not has_obs:
         over["obs_feature_dim"] = 0
     from piml_b200 import models as M
@@ -96,7 +99,8 @@ def test_pinnsf_backward_random(kind, R, kp, ko, small, has_obs, chan):
     do = (torch.rand(*lead, ko, net.spec.pw, generator=g) > 0.5).float() * 2
     sd_cpu = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
     ins_cpu = [x.clone().requires_grad_(True) for x in (ped, obs, slf)]
-    ref = TR.pinnsf_forward_ref(sd_cpu, kind, net.spec.tau, *ins_cpu, has_obs, dp, do if has_obs else None)
+    ref = TR.pinnsf_forward_ref(sd_cpu, kind, net.spec.tau, *ins_cpu, has_obs, dp, do if has_obs else None,
+                                single_block=net.spec.proc_mode == 1)
     ws = [torch.randn(o.shape, generator=g) for o in ref]
     sum((o * w).sum() for o, w in zip(ref, ws)).backward()
     ins = [x.to(dev()).requires_grad_(True) for x in (ped, obs, slf)]

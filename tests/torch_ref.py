@@ -22,7 +22,7 @@ def _count(sd, prefix):
     return n
 
 
-def pinnsf_forward_ref(sd, kind, tau, ped, obs, slf, has_obs=True, drop_ped=None, drop_obs=None):
+def pinnsf_forward_ref(sd, kind, tau, ped, obs, slf, has_obs=True, drop_ped=None, drop_obs=None, single_block=False):
     """PINNSF_bottleneck_multitask.forward (model.py:1185-1221, kind='pinnsf_bm'), PINNSF_multitask.forward
     (:1271-1305, 'pinnsf_m'), PINNSF_bottleneck (:1104-1135), PINNSF (:762-792), with processor_hidden_layers > 1 so
     that ResDNN(x) = dropout(2x) (model.py:115-119).  sd: dict of parameter tensors."""
@@ -30,7 +30,11 @@ def pinnsf_forward_ref(sd, kind, tau, ped, obs, slf, has_obs=True, drop_ped=None
 
     def branch(name, x, drop):
         e = _mlp(sd, f"{name}_encoder", x, _count(sd, f"{name}_encoder"))
-        e = 2 * e
+        if single_block:      # ResDNN with one block: relu(W e + b) + e  (model.py:68-79, :115-119)
+            e = torch.relu(F.linear(e, sd[f"{name}_processor.resnet.0.lin.mlp.0.weight"],
+                                    sd[f"{name}_processor.resnet.0.lin.mlp.0.bias"])) + e
+        else:
+            e = 2 * e
         if drop is not None:
             e = e * drop
         if per_slot:
