@@ -192,6 +192,7 @@ def nn_path_step(torch, dev, N, obs_h, iters=10):
     torch.manual_seed(666)
     net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
     packed = M.pack_device(net.state_dict(), net.spec, dev)
+    packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)          # tcgen05 (3xTF32) forward
     p, v, ds, dest, _ = [x.to(dev) for x in synthetic_crowd(N)]
     p, v, dest = p[None].contiguous(), v[None].contiguous(), dest[None].contiguous()
     acc, hist = torch.zeros_like(v), v.clone()
@@ -207,7 +208,7 @@ def nn_path_step(torch, dev, N, obs_h, iters=10):
         nonlocal bufs
         pf, of, sf = bufs[:3] if bufs else state_features(p, v, acc, dest, obs, hist, dsp, *fargs)
         a_next = M.pinnsf_forward(net.spec, packed, pf.view(N, 6, 6), of.view(N, -1, 6), sf.view(N, 7),
-                                  need_msgs=False)[0].view(1, N, 2)
+                                  need_msgs=False, packed_tc=packed_tc)[0].view(1, N, 2)
         integrate_step(p, v, acc, a_next, dest, didx, dnum, wp, DT, False, hist_v=hist)
         if bufs is None:
             bufs = (pf, of, sf, torch.empty(1, N, 2, device=dev))
@@ -224,8 +225,8 @@ def nn_path_step(torch, dev, N, obs_h, iters=10):
     ms = e0.elapsed_time(e1) / iters
     assert torch.isfinite(p).all()
     return {"workload": f"pinnsf_bm NN rollout step, N={N}, M={int(obs.shape[0])}, k=6/10 (forward + integrate + "
-                        "cell-list feature rebuild)", "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
-            "forward_flop_per_agent": 1.52e6, "tflops_fp32": 1.52e6 * N / ms * 1e3 / 1e12}
+                        "cell-list feature rebuild); forward on tcgen05 tensor cores (3xTF32)", "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
+            "forward_flop_per_agent": 1.52e6, "tflops_algorithmic": 1.52e6 * N / ms * 1e3 / 1e12}
 
 
 def run_ours(a):

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float *__restric
     if (tid == 0) {
         tc::fence_after_sync();
         const uint32_t idesc = tc::idesc_tf32(N);
-        const uint32_t lbo = lbo_o ? lbo_o : N * 16, sbo = sbo_o ? sbo_o : 128;
+        const uint32_t lbo = lbo_o > 0 ? lbo_o : N * 16, sbo = (lbo_o >= 0 && sbo_o) ? sbo_o : 128;
         const uint32_t kstep = 2 * N * 16;
         bool acc = false;
         for (int j = 0; j < K / 8; ++j) {
@@ -60,6 +60,45 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float *__restric
             acc = true;
         }
         tc::commit(&bar);
+    }
+    if (lbo_o < 0) {
+        // micro-benchmark (bring-up only): -lbo_o repetitions of the whole MMA chain; variant = sbo_o
+        //   0: as is (one accumulator)   1: alternate two accumulators   2: only x_hi w_hi   3: 2 with two accumulators
+        const bool ok = mbar_wait_bounded(&bar, 0, 1u << 22);
+        long long cyc = 0;
+        if (tid == 0 && ok) {
+            tc::fence_after_sync();
+            const uint32_t idesc = tc::idesc_tf32(N);
+            const uint32_t lbo = N * 16, sbo = 128, kstep = 2 * N * 16;
+            const long long t0 = clock64();
+            int cnt = 0;
+            for (int rep = 0; rep < -lbo_o; ++rep)
+                for (int j = 0; j < K / 8; ++j) {
+                    const uint64_t bh = tc::smem_desc(tc::smem_addr(w_hi) + j * kstep, lbo, sbo);
+                    const uint64_t bl = tc::smem_desc(tc::smem_addr(w_lo) + j * kstep, lbo, sbo);
+                    const uint32_t d0 = tbase + COL_D, d1 = tbase + ((sbo_o & 1) ? 384u : COL_D);
+                    if (!(sbo_o & 2)) {
+                        tc::mma_tf32_ts(d0, tbase + COL_AL + j * 8, bh, idesc, true);
+                        tc::mma_tf32_ts(d1, tbase + COL_AH + j * 8, bl, idesc, true);
+                        cnt += 2;
+                    }
+                    tc::mma_tf32_ts((j & 1) ? d1 : d0, tbase + COL_AH + j * 8, bh, idesc, true);
+                    ++cnt;
+                }
+            tc::commit(&bar);
+            const long long t1 = clock64();
+            mbar_wait_bounded(&bar, 1, 1u << 24);
+            const long long t2 = clock64();
+            y[0] = static_cast<float>(t1 - t0) / cnt;       // issue cycles per MMA
+            y[1] = static_cast<float>(t2 - t0) / cnt;       // issue + drain cycles per MMA
+            y[2] = static_cast<float>(cnt);
+            cyc = t2 - t0;
+        }
+        (void)cyc;
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tbase, 512);
+        return;
     }
     const bool done = mbar_wait_bounded(&bar, 0, 1u << 22);
     tc::fence_after_sync();
@@ -124,23 +163,26 @@ extern "C" int piml_tc_selftest_f32(const float *x, const float *w, int K, int N
 // 3xTF32 split (x_lo w_hi + x_hi w_lo + x_hi w_hi, fp32 accumulation in TMEM): measured 1e-6 of fp64 per layer, i.e.
 // fp32-grade, which the 1e-5 parity gate needs and plain TF32 (3e-4) does not give.
 //
-// Per CTA (persistent, one per SM, 192 threads):
+// Per CTA (persistent, one per SM, 320 threads):
 //   warp 0  : TMA producer -- streams the layers' weight images (hi + lo, pre-split and pre-arranged as UMMA K-major
 //             core matrices by piml_pinnsf_pack_tc_f32) through a 5-stage shared-memory ring with cp.async.bulk;
 //   warp 1  : MMA issuer -- one thread issues the tcgen05.mma chain of a layer: A (activations, hi / lo) from TMEM,
 //             B from the ring, D into TMEM; tcgen05.commit frees ring stages and signals "D ready";
-//   warps 2-5: epilogue -- thread = tile row: tcgen05.ld D, + bias, ReLU / ResDNN 2x fold, split into tf32 hi / lo and
-//             tcgen05.st as the NEXT layer's A operand (activations never touch shared memory); the 2-wide predictor,
-//             the sum over an agent's slots and (kind 1) the per-agent embedding sum run on the CUDA cores in fp32.
-// TMEM columns: D [0,128), A_hi [128,256), A_lo [256,384).
+//   warps 2-9: epilogue -- thread = tile row (two warps per TMEM lane quarter, alternating 32-column groups):
+//             tcgen05.ld D, + bias, ReLU / ResDNN 2x fold, split into tf32 hi / lo and tcgen05.st as the NEXT layer's A
+//             operand (activations never touch shared memory); the 2-wide predictor, the sum over an agent's slots
+//             and (kind 1) the per-agent embedding sum run on the CUDA cores in fp32.
+// TMEM columns: D0 [0,128), D1 [128,256) (alternating per layer), A_hi [256,384), A_lo [384,512).
 namespace piml {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter: column halves
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_STAGES = 5;
 constexpr int TC_STAGE_BYTES = 32768;          // hi + lo image of a 32-deep K chunk of a 128-wide layer
 constexpr int TC_MAXL = 16;
 constexpr int TC_MAXCH = 64;
-constexpr int TC_COL_D = 0, TC_COL_AH = 128, TC_COL_AL = 256;
+constexpr int TC_COL_D0 = 0, TC_COL_D1 = 128, TC_COL_AH = 256, TC_COL_AL = 384;
+constexpr int TC_STAGE_LD = 17;
 
 struct TcLayer { int K, Kp, N, chunk0, nchunks, bias_off, relu; float scale; };   // bias_off: floats into the bias block
 struct TcChunk { int off, bytes, cells; };          // float offset from the branch's weight base; 16-byte K cells (even)
@@ -157,6 +199,8 @@ struct TcArgs {
     const float *params; const float *ped; const float *obs;
     int64_t R; int kp, ko, ag_ped, ag_obs; int64_t n_ped_tiles, n_obs_tiles;
     float *sums; float *ped_msgs; float *obs_msgs;
+    long long *prof;                               // optional cycle counters of CTA 0 (bring-up only)
+    int dbg;                                       // timing experiments only (PIML_TC_DEBUG): 1 = skip epilogue math, 2 = one MMA term
 };
 
 // mbarrier wait that can never hang the GPU: a protocol bug traps (launch error) after ~seconds instead of spinning.
@@ -164,26 +208,36 @@ __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
     if (!mbar_wait_bounded(bar, parity, 1u << 28)) __trap();
 }
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void half_barrier(int half) {           // the 128 epilogue threads of one column half
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+}
+__device__ __forceinline__ void epi_barrier_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
+// Pipeline inside a tile (layer l reads A, writes D[l & 1]):
+//   epilogue of layer l   : waits "D[l&1] ready", then per 32-column group g: tcgen05.ld -> bias/ReLU -> hi/lo ->
+//                           tcgen05.st into A columns [32g, 32g+32) -> arrives on a_ready[g]
+//   MMAs of layer l + 1   : K chunk g starts as soon as a_ready[g] fired, i.e. while the epilogue is still converting
+//                           groups g+1.. of layer l; they accumulate into the OTHER accumulator D[(l+1)&1].
+// So tensor-core work of layer l+1 overlaps the CUDA-core epilogue of layer l; activations never leave TMEM.
 __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_constant__ TcPlan P,
                                                                   const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char tc_smem[];
     unsigned char *ring = tc_smem;                                                       // TC_STAGES x 32 KB
     float *biasb = reinterpret_cast<float *>(ring + TC_STAGES * TC_STAGE_BYTES);         // [2][bias_floats]
-    float *small = biasb + 2 * P.bias_floats;                                            // [128][2]
-    float *stage = small + 256;                                                          // [128][33]  (kind 1)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 128 * 33 + 1);                 // full[S] empty[S] a_rdy d_rdy
-    bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bars) + 7) & ~static_cast<uintptr_t>(7));
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *a_ready = bars + 2 * TC_STAGES, *d_ready = a_ready + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
+    float *small = biasb + 2 * P.bias_floats;                                            // [2 halves][128][2]
+    float *stage = small + 512;                                                          // [2 halves][128][33] (kind 1)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(
+        (reinterpret_cast<uintptr_t>(stage + 2 * 128 * TC_STAGE_LD) + 15) & ~static_cast<uintptr_t>(15));
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *a_ready = bars + 2 * TC_STAGES, *d_ready = a_ready + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_ready, 128);
-        mbar_init(d_ready, 1);
+        for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], 256);
+        mbar_init(&d_ready[0], 1);
+        mbar_init(&d_ready[1], 1);
         mbar_fence_init();
     }
     for (int e = tid; e < 2 * P.bias_floats; e += TC_THREADS) {
@@ -205,53 +259,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                 const float *wbase = a.params + P.w_off[br];
                 for (int c = 0; c < P.nch; ++c, ++pc) {
                     const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
+                    const long long t0 = clock64();
                     tc_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&full[s], static_cast<uint32_t>(P.C[c].bytes));
-                    tma_bulk_g2s(ring + s * TC_STAGE_BYTES, wbase + P.C[c].off, static_cast<uint32_t>(P.C[c].bytes),
-                                 &full[s]);
+                    if (a.prof && blockIdx.x == 0) a.prof[0] += clock64() - t0;
+                    const uint32_t bytes = static_cast<uint32_t>(P.C[c].bytes);
+                    mbar_expect_tx(&full[s], bytes);
+                    // several smaller bulk copies per chunk: one cp.async.bulk keeps only a few lines in flight
+                    const uint32_t piece = TC_STAGE_BYTES >> ((a.dbg >> 4) & 7);
+                    for (uint32_t o = 0; o < bytes; o += piece)
+                        tma_bulk_g2s(ring + s * TC_STAGE_BYTES + o, reinterpret_cast<const unsigned char *>(wbase + P.C[c].off) + o,
+                                     min(piece, bytes - o), &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            uint32_t pc = 0, ev = 0;
+            uint32_t pc = 0, aph = 0;                              // aph: phase bit per a_ready barrier
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int li = 0; li < P.nl; ++li, ++ev) {
+                for (int li = 0; li < P.nl; ++li) {
                     const TcLayer &Ly = P.L[li];
-                    tc_wait(a_ready, ev & 1u);
-                    tc::fence_after_sync();
+                    const uint32_t dcol = tbase + ((li & 1) ? TC_COL_D1 : TC_COL_D0);
                     const uint32_t idesc = tc::idesc_tf32(Ly.N);
                     const uint32_t lbo = Ly.N * 16, sbo = 128, kstep = 2 * lbo;
                     bool acc = false;
                     for (int c = 0; c < Ly.nchunks; ++c, ++pc) {
+                        const long long t0 = clock64();
+                        tc_wait(&a_ready[c], (aph >> c) & 1u);     // A columns of this K chunk are in TMEM
+                        aph ^= (1u << c);
+                        const long long t1 = clock64();
                         const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
                         tc_wait(&full[s], ph);
                         tc::fence_after_sync();
+                        const long long t2 = clock64();
+                        if (a.prof && blockIdx.x == 0) { a.prof[1] += t1 - t0; a.prof[2] += t2 - t1; }
                         const TcChunk &Ch = P.C[Ly.chunk0 + c];
                         const uint32_t hi_addr = tc::smem_addr(ring + s * TC_STAGE_BYTES);
-                        const uint32_t lo_addr = hi_addr + Ch.cells * lbo;
-                        for (int ks = 0; ks < Ch.cells / 2; ++ks) {
-                            const uint32_t kcol = c * 32 + ks * 8;
-                            const uint64_t bh = tc::smem_desc(hi_addr + ks * kstep, lbo, sbo);
-                            const uint64_t bl = tc::smem_desc(lo_addr + ks * kstep, lbo, sbo);
-                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AL + kcol, bh, idesc, acc);   // x_lo w_hi
-                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AH + kcol, bl, idesc, true);  // x_hi w_lo
-                            tc::mma_tf32_ts(tbase + TC_COL_D, tbase + TC_COL_AH + kcol, bh, idesc, true);  // x_hi w_hi
-                            acc = true;
+                        uint64_t bh = tc::smem_desc(hi_addr, lbo, sbo);
+                        uint64_t bl = tc::smem_desc(hi_addr + Ch.cells * lbo, lbo, sbo);
+                        const uint64_t dstep = kstep >> 4;         // start-address field advances by one K = 8 step
+                        uint32_t ah = tbase + TC_COL_AH + c * 32, al = tbase + TC_COL_AL + c * 32;
+                        const int nks = Ch.cells / 2;
+                        if (a.dbg & 2) {
+                            for (int ks = 0; ks < nks; ++ks, bh += dstep, ah += 8) {
+                                tc::mma_tf32_ts(dcol, ah, bh, idesc, acc);
+                                acc = true;
+                            }
+                        } else {
+#pragma unroll 4
+                            for (int ks = 0; ks < nks; ++ks, bh += dstep, bl += dstep, ah += 8, al += 8) {
+                                tc::mma_tf32_ts(dcol, al, bh, idesc, acc);      // x_lo w_hi
+                                tc::mma_tf32_ts(dcol, ah, bl, idesc, true);     // x_hi w_lo
+                                tc::mma_tf32_ts(dcol, ah, bh, idesc, true);     // x_hi w_hi
+                                acc = true;
+                            }
                         }
                         tc::commit(&empty[s]);                     // ring stage free once these MMAs have read it
+                        if (a.prof && blockIdx.x == 0) a.prof[3] += clock64() - t2;
                     }
-                    tc::commit(d_ready);                           // accumulator of this layer complete
+                    tc::commit(&d_ready[li & 1]);                  // accumulator of this layer complete
                 }
             }
         }
     } else {
-        // ===== epilogue warps: thread = tile row =====
+        // ===== epilogue warps: thread = tile row; the two warps of a lane quarter split the column groups =====
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                          // 0: even 32-column groups, 1: odd groups
         const int m = q4 * 32 + lane;                              // tile row == TMEM lane
         const uint32_t tl = tbase + (static_cast<uint32_t>(q4 * 32) << 16);
-        uint32_t ev = 0;
+        float *stg = stage + half * 128 * TC_STAGE_LD;
+        uint32_t dph = 0;                                          // phase bit per d_ready barrier
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int br = tile < a.n_ped_tiles ? 0 : 1;
             const int k = br == 0 ? a.kp : a.ko;
@@ -261,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
             const int nrows = na * k;
             const int64_t row0 = agent0 * k;
             const float *bb = biasb + br * P.bias_floats;
-            {   // stage the 6-d features of this row as the first A operand (K padded to 8 with zeros)
+            if (half == 0) {   // stage the 6-d features of this row as the first A operand (K padded to 8 with zeros)
                 uint32_t hi[8], lo[8];
                 const float *f = (br == 0 ? a.ped : a.obs) + (row0 + m) * 6;
 #pragma unroll
@@ -273,76 +350,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                 tc::st8(tl + TC_COL_AL, lo);
                 tc::wait_st();
                 tc::fence_before_sync();
-                tc::mbar_arrive(a_ready);
             }
+            tc::mbar_arrive(&a_ready[0]);
             float m0 = 0.f, m1 = 0.f;
-            for (int li = 0; li < P.nl; ++li, ++ev) {
+            for (int li = 0; li < P.nl; ++li) {
                 const TcLayer &Ly = P.L[li];
                 const bool last = li == P.nl - 1;
                 const bool to_sum = P.kind == 1 && li == P.n_enc - 1;        // kind 1: sum the slot embeddings per agent
-                tc_wait(d_ready, ev & 1u);
+                const uint32_t dcol = tl + ((li & 1) ? TC_COL_D1 : TC_COL_D0);
+                const long long e0 = clock64();
+                tc_wait(&d_ready[li & 1], (dph >> (li & 1)) & 1u);
+                dph ^= (1u << (li & 1));
                 tc::fence_after_sync();
+                if (a.prof && blockIdx.x == 0 && tid == 64) a.prof[4 + li] += clock64() - e0;
                 const float *bias = bb + Ly.bias_off;
-                for (int n0 = 0; n0 < Ly.N; n0 += 32) {
-                    uint32_t r[32];
-                    tc::ld32(tl + TC_COL_D + n0, r);
+                // every 32-column group is converted by BOTH warps of the lane quarter (16 columns each), so that
+                // the first K chunk of the next layer is released after half the latency
+                for (int g = 0; g < Ly.N / 32; ++g) {
+                    const int n0 = g * 32 + half * 16;
+                    if (a.dbg & 1) {                               // timing experiment: no epilogue work at all
+                        if (!last) { tc::fence_before_sync(); tc::mbar_arrive(&a_ready[g]); }
+                        continue;
+                    }
+                    uint32_t r[16];
+                    tc::ld16(dcol + n0, r);
                     tc::wait_ld();
-                    float y[32];
+                    float y[16];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        float v = (__uint_as_float(r[q]) + bias[n0 + q]) * Ly.scale;
+                    for (int q = 0; q < 16; ++q) {
+                        float v = __uint_as_float(r[q]) + bias[n0 + q];      // (ResDNN's 2x is folded into W and b)
                         if (Ly.relu) v = fmaxf(v, 0.f);
                         y[q] = v;
                     }
                     if (last) {                                    // predictor Linear(dw, 2) on the CUDA cores
                         const float *w0 = bb + P.predw_off + n0, *w1 = w0 + P.dw;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) { m0 = fmaf(y[q], w0[q], m0); m1 = fmaf(y[q], w1[q], m1); }
+                        for (int q = 0; q < 16; ++q) { m0 = fmaf(y[q], w0[q], m0); m1 = fmaf(y[q], w1[q], m1); }
                         continue;
                     }
                     if (to_sum) {                                  // torch.sum(dim=-2) over the k slots (model.py:1276)
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) stage[m * 33 + q] = y[q];
-                        epi_barrier();
+                        for (int q = 0; q < 16; ++q) stg[m * TC_STAGE_LD + q] = y[q];
+                        half_barrier(half);
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) {
+                        for (int q = 0; q < 16; ++q) {
                             float s = 0.f;
                             if (m < na)
-                                for (int j = 0; j < k; ++j) s += stage[(m * k + j) * 33 + q];
+                                for (int j = 0; j < k; ++j) s += stg[(m * k + j) * TC_STAGE_LD + q];
                             y[q] = s;
                         }
-                        epi_barrier();
+                        half_barrier(half);
                     }
-                    uint32_t lo[32];
+                    uint32_t lo[16];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) tc::split_tf32(y[q], r[q], lo[q]);
-                    tc::st32(tl + TC_COL_AH + n0, r);
-                    tc::st32(tl + TC_COL_AL + n0, lo);
-                }
-                if (!last) {
+                    for (int q = 0; q < 16; ++q) tc::split_tf32(y[q], r[q], lo[q]);
+                    tc::st16(tl + TC_COL_AH + n0, r);
+                    tc::st16(tl + TC_COL_AL + n0, lo);
                     tc::wait_st();
                     tc::fence_before_sync();
-                    tc::mbar_arrive(a_ready);
+                    tc::mbar_arrive(&a_ready[g]);                  // K chunk g of the next layer may start
                 }
             }
-            m0 += bb[P.predb_off];
-            m1 += bb[P.predb_off + 1];
-            if (P.kind == 0) {
-                small[m * 2] = m0; small[m * 2 + 1] = m1;
-                float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
-                if (msgs_out && m < nrows) { msgs_out[(row0 + m) * 2] = m0; msgs_out[(row0 + m) * 2 + 1] = m1; }
-                epi_barrier();
-                if (m < 2 * na) {                                  // torch.sum(dim=-2) over the k slots (model.py:1194)
-                    const int ag = m >> 1, c = m & 1;
-                    float s = 0.f;
-                    for (int j = 0; j < k; ++j) s += small[(ag * k + j) * 2 + c];
-                    a.sums[(agent0 + ag) * 4 + br * 2 + c] = s;
+            if (a.prof && blockIdx.x == 0 && tid == 64) a.prof[15] += 1;
+            // combine the two column halves of the predictor, then sum over an agent's slots
+            small[(half * 128 + m) * 2] = m0;
+            small[(half * 128 + m) * 2 + 1] = m1;
+            epi_barrier_all();
+            if (half == 0) {
+                m0 = small[m * 2] + small[(128 + m) * 2] + bb[P.predb_off];
+                m1 = small[m * 2 + 1] + small[(128 + m) * 2 + 1] + bb[P.predb_off + 1];
+                if (P.kind == 0) {
+                    float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
+                    if (msgs_out && m < nrows) { msgs_out[(row0 + m) * 2] = m0; msgs_out[(row0 + m) * 2 + 1] = m1; }
+                    half_barrier(0);                               // every partial read before the totals overwrite
+                    small[m * 2] = m0; small[m * 2 + 1] = m1;
+                    half_barrier(0);
+                    if (m < 2 * na) {                              // torch.sum(dim=-2) over the k slots (model.py:1194)
+                        const int ag = m >> 1, c = m & 1;
+                        float s = 0.f;
+                        for (int j = 0; j < k; ++j) s += small[(ag * k + j) * 2 + c];
+                        a.sums[(agent0 + ag) * 4 + br * 2 + c] = s;
+                    }
+                } else if (m < na) {
+                    a.sums[(agent0 + m) * 4 + br * 2] = m0;
+                    a.sums[(agent0 + m) * 4 + br * 2 + 1] = m1;
                 }
-                epi_barrier();
-            } else if (m < na) {
-                a.sums[(agent0 + m) * 4 + br * 2] = m0;
-                a.sums[(agent0 + m) * 4 + br * 2 + 1] = m1;
             }
+            epi_barrier_all();                                     // small[] is free for the next tile
         }
     }
     tc::fence_before_sync();
@@ -351,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
 }
 
 // ---- plan + packing -------------------------------------------------------------------------------------------------
-struct TcPackRec { int K, Kp, N; int64_t src_w, src_b, dst_w, dst_b; };
+struct TcPackRec { int K, Kp, N; float scale; int64_t src_w, src_b, dst_w, dst_b; };
 struct TcPackTab { int n; TcPackRec r[2 * TC_MAXL]; int dw; int64_t pred_src[2], predw_dst[2], predb_dst[2]; int64_t total; };
 
 static int tc_build_plan(const piml_net_desc *d, TcPlan *P, TcPackTab *T) {
@@ -371,7 +465,7 @@ static int tc_build_plan(const piml_net_desc *d, TcPlan *P, TcPackTab *T) {
         L.K = K; L.Kp = (K + 7) & ~7; L.N = N; L.relu = relu; L.scale = scale; L.bias_off = boff; L.chunk0 = nch;
         L.nchunks = (L.Kp + 31) / 32;
         TcPackRec &r = T->r[T->n++];
-        r.K = K; r.Kp = L.Kp; r.N = N; r.src_w = src; r.src_b = src + static_cast<int64_t>(K) * N; r.dst_w = woff; r.dst_b = boff;
+        r.K = K; r.Kp = L.Kp; r.N = N; r.scale = scale; r.src_w = src; r.src_b = src + static_cast<int64_t>(K) * N; r.dst_w = woff; r.dst_b = boff;
         for (int c = 0; c < L.nchunks; ++c) {
             PIML_REQUIRE(nch < TC_MAXCH, "piml_pinnsf_tc: too many weight chunks");
             const int cells = (L.Kp - c * 32 < 32 ? L.Kp - c * 32 : 32) / 4;
@@ -444,7 +538,7 @@ __global__ void pinnsf_pack_tc_kernel(const __grid_constant__ TcPackTab T, const
                 const int64_t r = e - static_cast<int64_t>(half) * cells * R.N * 4;
                 const int cell = static_cast<int>(r / (R.N * 4)), n = static_cast<int>((r / 4) % R.N), kk = static_cast<int>(r & 3);
                 const int kx = c * 32 + cell * 4 + kk;
-                const float w = kx < R.K ? src[R.src_w + static_cast<int64_t>(n) * R.K + kx] : 0.f;
+                const float w = kx < R.K ? src[R.src_w + static_cast<int64_t>(n) * R.K + kx] * R.scale : 0.f;   // 2x: exact
                 uint32_t hi, lo;
                 tc::split_tf32(w, hi, lo);
                 v = __uint_as_float(half == 0 ? hi : lo);
@@ -462,7 +556,7 @@ __global__ void pinnsf_pack_tc_kernel(const __grid_constant__ TcPackTab T, const
             while (l + 1 < nlayers_per_branch && b >= T.r[l + 1].dst_b - T.r[0].dst_b) ++l;
             const TcPackRec &R = T.r[br * nlayers_per_branch + l];
             const int64_t o = b - (T.r[l].dst_b - T.r[0].dst_b);
-            if (o < R.N) v = src[R.src_b + o];
+            if (o < R.N) v = src[R.src_b + o] * R.scale;
         }
     }
     dst[i] = v;
@@ -590,20 +684,38 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     a.n_ped_tiles = (R + a.ag_ped - 1) / a.ag_ped;
     a.n_obs_tiles = has_obs ? (R + a.ag_obs - 1) / a.ag_obs : 0;
     a.sums = scratch; a.ped_msgs = ped_msgs; a.obs_msgs = has_obs ? obs_msgs : nullptr;
+    a.dbg = 0;
+    a.prof = nullptr;
+    if (const char *e = getenv("PIML_TC_DEBUG")) a.dbg = atoi(e);
+    if (getenv("PIML_TC_PROF")) {
+        static long long *prof_buf = nullptr;
+        if (!prof_buf) { PIML_CUDA(cudaMalloc(&prof_buf, 16 * sizeof(long long))); }
+        PIML_CUDA(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), st));
+        a.prof = prof_buf;
+    }
     const size_t smem = static_cast<size_t>(TC_STAGES) * TC_STAGE_BYTES +
-                        sizeof(float) * (2 * P.bias_floats + 256 + 128 * 33 + 1) + 8 * (2 * TC_STAGES + 2) + 64;
+                        sizeof(float) * (2 * P.bias_floats + 512 + 2 * 128 * TC_STAGE_LD) + 8 * (2 * TC_STAGES + 6) + 64;
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         attr_set = true;
     }
-    PIML_REQUIRE(smem <= 200 * 1024, "piml_pinnsf_forward_tc_f32: network too large for the shared-memory plan");
+    PIML_REQUIRE(smem <= 216 * 1024, "piml_pinnsf_forward_tc_f32: network too large for the shared-memory plan");
     const int64_t tiles = a.n_ped_tiles + a.n_obs_tiles;
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     pinnsf_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, a);
     count_launch();
     rc = check_launch("pinnsf_tc_kernel");
     if (rc) return rc;
+    if (a.prof) {
+        long long h[16];
+        PIML_CUDA(cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PIML_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[tc prof, CTA 0, %lld tiles] cycles/tile: producer wait empty %lld | mma wait A %lld, wait W %lld, issue %lld | "
+                "epilogue wait D per layer:", h[15], h[0] / h[15], h[1] / h[15], h[2] / h[15], h[3] / h[15]);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", h[4 + i] / h[15]);
+        fprintf(stderr, "\n");
+    }
     const int threads = 256;
     pinnsf_tc_finish_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
         scratch, self, dnorm, R, has_obs, tau, acc);

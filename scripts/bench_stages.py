@@ -60,10 +60,15 @@ def main():
     torch.manual_seed(666)
     net = M.PINNSF_bottleneck_multitask(bm_args()).to(dev).eval()
     packed = M.pack_device(net.state_dict(), net.spec, dev)
+    packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)
     slf = torch.cat([feats[2][0], v, acc, ds], -1)
     ms = timeit(lambda: M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False))
-    out["pinnsf_bm_forward_N%d" % N] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
-                                        "tflops": 1.52e6 * N / ms * 1e3 / 1e12}
+    out["pinnsf_bm_forward_fp32pipe_N%d" % N] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
+                                                 "tflops": 1.52e6 * N / ms * 1e3 / 1e12}
+    ms = timeit(lambda: M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False,
+                                         packed_tc=packed_tc))
+    out["pinnsf_bm_forward_tcgen05_N%d" % N] = {"ms": ms, "agent_steps_per_s": N / ms * 1e3,
+                                                "tflops_algorithmic": 1.52e6 * N / ms * 1e3 / 1e12}
     # GC-shaped scenes, one NN rollout step (forward + integrate + features) for S scenes of 122 slots
     S, Ns, Mo = a.scenes, 122, 100
     g = torch.Generator().manual_seed(1)
@@ -83,7 +88,7 @@ def main():
 
     def fwd():
         return M.pinnsf_forward(net.spec, packed, pf.view(S * Ns, 6, 6), of.view(S * Ns, 10, 6), sf.view(S * Ns, 7),
-                                need_msgs=False)[0].view(S, Ns, 2)
+                                need_msgs=False, packed_tc=packed_tc)[0].view(S, Ns, 2)
 
     def nn_step():
         a_next = fwd()
@@ -100,7 +105,8 @@ def main():
     pf1, of1, sf1 = state_features(one[0], one[1], one[2], one[3], ob, one[4], one[5], *fargs)
 
     def one_step():
-        a_next = M.pinnsf_forward(net.spec, packed, pf1[0], of1[0], sf1[0], need_msgs=False)[0][None]
+        a_next = M.pinnsf_forward(net.spec, packed, pf1[0], of1[0], sf1[0], need_msgs=False,
+                                  packed_tc=packed_tc)[0][None]
         integrate_step(one[0], one[1], one[2], a_next, one[3], one[6], one[7], one[8], 0.0, False, hist_v=one[4])
         state_features(one[0], one[1], one[2], one[3], ob, one[4], one[5], *fargs)
     ms = timeit(one_step, iters=50)
