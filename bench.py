@@ -36,6 +36,7 @@ FLOP_PER_PAIR = 51.0          # SURVEY.md 8d, MLAPM-GC per ordered pair
 MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)     # main_mlapm.py:16
 DT, RADIUS = 0.08, 0.3
 FLUSH_MB = 160                 # L2 is 126 MB
+MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ncu --set full, N = 100k, one launch (profiles/r01b_...)
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -350,9 +351,12 @@ def run_ours(a):
                        "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
                        "parallelism": f"agent-sharded rows x{world}" + (" + NCCL all-gather/step" if world > 1 else ""),
                        "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
-            "roofline": {"bound": "fp32", "kernel": "mlapm_pairs_kernel<GC,R=4,fast> (+finalize)",
+            "roofline": {"bound": "fp32", "kernel": "mlapm_pairs2_kernel<GC, 4 rows/thread, packed FP32> (+prep, finalize)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if peak else None, "traffic": None,
+                         "frac": (achieved / peak) if peak else None,
+                         "traffic": MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N) if N == 100000 else None,
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, "
+                                         "profiles/r01b_ncu_mlapm_pairs2_kernel.txt); algorithmic work is FLOPs",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
