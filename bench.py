@@ -103,8 +103,7 @@ def cpu_baseline(N, seconds=12.0, threads=None):
     """Oracle C port of MLAPM.step (mlapm.py:10-58) on the host cores, rows [0,R) against all N columns."""
     from oracle import oracle as O
     import numpy as np
-    if threads:
-        O.set_num_threads(threads)
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
     probe = max(64, cores * 16)
@@ -131,6 +130,8 @@ def run_reference(a):
     from oracle import oracle as O
     import numpy as np
     N = a.agents
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
     probe = max(64, cores * 16)
