@@ -257,10 +257,29 @@ def run_ours(a):
     model = P.MLAPM(**MLAPM_KW)
     flush = torch.empty(FLUSH_MB << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     pos_next, vel_next = torch.empty_like(pos), torch.empty_like(vel)
+    # Multi-GPU exchange: "push" = the finalize kernel stores each new row into every rank's next-state arrays over
+    # NVLink peer memory (piml_mlapm_advance_push_f32) + one barrier; "nccl" = separate all-gathers after the step.
+    crowd, exchange, exchange_note = None, "none", ""
+    if world > 1:
+        exchange = a.exchange
+        if exchange == "push":
+            try:
+                from piml_b200.sharded import ShardedCrowd
+                crowd = ShardedCrowd(N, device=dev)
+                crowd.load(pos, vel)
+            except Exception as e:                                      # no peer mapping on this box: use NCCL
+                crowd, exchange, exchange_note = None, "nccl", f"push unavailable: {type(e).__name__}: {e}"[:200]
+            ok = torch.tensor([1 if crowd is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0 and crowd is not None:
+                crowd, exchange, exchange_note = None, "nccl", "push unavailable on another rank"
 
-    def step():
+    def advance_step():
+        """One step incl. the exchange; returns nothing (state is updated in place / swapped)."""
         nonlocal pos, vel, pos_next, vel_next
-        flush.zero_()                                                   # L2 flush between steps
+        if crowd is not None:
+            crowd.step(model, ds, dest, DT, RADIUS)
+            return
         act, pnew, arrived = model.advance(pos, vel, ds, dest, DT, RADIUS, rows=(r0, r1))
         if world > 1:                                                   # the path's one exchange step
             dist.all_gather_into_tensor(pos_next, pnew)
@@ -269,7 +288,10 @@ def run_ours(a):
             vel, vel_next = vel_next, vel
         else:
             pos, vel = pnew, act
-        return arrived
+
+    def step():
+        flush.zero_()                                                   # L2 flush between steps
+        advance_step()
 
     def sync_all():
         if world > 1:
@@ -292,15 +314,8 @@ def run_ours(a):
     for s in range(a.steps):
         flush.zero_()
         k_ev[s][0].record()
-        act, pnew, arrived = model.advance(pos, vel, ds, dest, DT, RADIUS, rows=(r0, r1))
+        advance_step()
         k_ev[s][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(pos_next, pnew)
-            dist.all_gather_into_tensor(vel_next, act)
-            pos, pos_next = pos_next, pos
-            vel, vel_next = vel_next, vel
-        else:
-            pos, vel = pnew, act
     e1.record()
     sync_all()
     launches = L.launch_count() - launches0
@@ -310,7 +325,14 @@ def run_ours(a):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
     ms, kernel_ms = float(ms), float(kernel_ms)
-    assert torch.isfinite(pos).all(), "non-finite positions after the timed rollout"
+    final_pos = crowd.position if crowd is not None else pos
+    assert torch.isfinite(final_pos).all(), "non-finite positions after the timed rollout"
+    if world > 1:                       # every rank must hold the same crowd after the exchange
+        chk = final_pos.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float(hi - lo) == 0.0, "ranks disagree on the crowd state after the exchange"
 
     # ---- end-to-end through the public host-buffer API ------------------------------------------------------------
     act_h = torch.empty(shard, 2).pin_memory()
@@ -350,7 +372,11 @@ def run_ours(a):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "obstacle_points": int(obs_h.shape[0]),
                        "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
-                       "parallelism": f"agent-sharded rows x{world}" + (" + NCCL all-gather/step" if world > 1 else ""),
+                       "parallelism": f"agent-sharded rows x{world}" + (
+                           "" if world == 1 else (" + exchange fused into the finalize kernel (NVLink peer stores) + "
+                                                  "1 barrier/step" if exchange == "push" else
+                                                  " + NCCL all-gather/step")),
+                       "exchange": exchange, "exchange_note": exchange_note,
                        "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
             "roofline": {"bound": "fp32", "kernel": "mlapm_pairs2_kernel<GC, 4 rows/thread, packed FP32> (+prep, finalize)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -385,6 +411,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=100000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="multi-GPU exchange: fused peer-memory push (default) or NCCL all-gather")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

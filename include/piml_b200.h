@@ -149,6 +149,19 @@ PIML_API int piml_mlapm_advance_f32(const float *pos, const float *vel, const fl
                            const piml_mlapm_params *prm, float dt, float radius, float *action, float *pos_new,
                            uint8_t *arrived, void *workspace, void *stream);
 
+/* piml_mlapm_advance_f32 for an agent-sharded crowd with the path's one exchange FUSED into it: the
+ * finalize kernel stores the new position and velocity of its rows [row0,row1) straight into every rank's next-state
+ * arrays over NVLink / NVSwitch peer memory, instead of a separate all-gather.
+ * peer_pos_next_host / peer_vel_next_host: HOST arrays of `world` (<= 16) device addresses -- rank g's (N,2) next-state
+ * position / velocity arrays as mapped into this process (e.g. torch symmetric memory `buffer_ptrs` + offset), the
+ * calling rank included.  The caller double-buffers the state and places one cross-rank barrier after the call.
+ * Production math path only (prm->exact_math == 0). */
+PIML_API int piml_mlapm_advance_push_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                const piml_mlapm_params *prm, float dt, float radius, int world,
+                                const uint64_t *peer_pos_next_host, const uint64_t *peer_vel_next_host,
+                                uint8_t *arrived, void *workspace, void *stream);
+
 /* ---- SFM repulsion: src/utils/utils.py:31-100 ------------------------------------------------------------ */
 
 /* UTILS.calc_acceleration.  rel (S, stride) with stride >= 4 floats per slot -> out (S,2).

@@ -403,13 +403,18 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
     }
 }
 
+// Exchange step of an agent-sharded crowd fused into the finalize kernel: rank g's NEXT-state arrays, mapped into this
+// process over NVLink peer memory.  world == 0: no exchange.
+constexpr int ML_MAX_PEERS = 16;
+struct PeerPush { int world; float2 *pos[ML_MAX_PEERS]; float2 *vel[ML_MAX_PEERS]; };
+
 // force = (v0*ed - v)/tau - A*R(sum partial) ; action = v + force*dt ; optional p' = p + action*dt and arrival.
 __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
                                        const float *__restrict__ ds, int ds_dim, const float2 *__restrict__ dest,
                                        int row0, int row1, int nsplit, const float4 *__restrict__ partial, float A,
                                        float cos_t, float sin_t, int version, float tau, float dt, float radius,
                                        float2 *__restrict__ action, float2 *__restrict__ pos_new,
-                                       uint8_t *__restrict__ arrived) {
+                                       uint8_t *__restrict__ arrived, const __grid_constant__ PeerPush push) {
     const int rl = blockIdx.x * blockDim.x + threadIdx.x;
     const int nrows = row1 - row0;
     if (rl >= nrows) return;
@@ -438,13 +443,21 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     fy = __fsub_rn(fy, __fmul_rn(A, sy));
     const float ax = __fadd_rn(v.x, __fmul_rn(fx, dt));           // action = velocity + force*dt (mlapm.py:57)
     const float ay = __fadd_rn(v.y, __fmul_rn(fy, dt));
-    action[rl] = make_float2(ax, ay);
-    if (pos_new || arrived) {
+    if (action) action[rl] = make_float2(ax, ay);
+    if (pos_new || arrived || push.world > 0) {
         const float qx = __fadd_rn(p.x, __fmul_rn(ax, dt));       // p = position + v*dt          (main_mlapm.py:26)
         const float qy = __fadd_rn(p.y, __fmul_rn(ay, dt));
         if (pos_new) pos_new[rl] = make_float2(qx, qy);
         if (arrived)                                              // ||p - destination|| < radius (main_mlapm.py:34)
             arrived[rl] = norm2_rn(__fsub_rn(qx, d.x), __fsub_rn(qy, d.y)) < radius ? 1 : 0;
+        if (push.world > 0) {
+            // the path's one exchange, fused: store this row's new state into every rank's next-state arrays
+            for (int g = 0; g < push.world; ++g) {
+                push.pos[g][n] = make_float2(qx, qy);
+                push.vel[g][n] = make_float2(ax, ay);
+            }
+            __threadfence_system();                               // visible to the peers before the step barrier
+        }
     }
 }
 
@@ -522,11 +535,12 @@ extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
     return npad * M2_COLF * sizeof(float) + static_cast<int64_t>(ML_MAX_SPLIT) * N * 4 * sizeof(float) + 256;
 }
 
-extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
-                                      const float *dest, int64_t N, int64_t row0, int64_t row1,
-                                      const piml_mlapm_params *prm, float dt, float radius, float *action,
-                                      float *pos_new, uint8_t *arrived, void *workspace, void *stream) {
-    PIML_REQUIRE(pos && vel && desired_speed && dest && prm && action && workspace, "piml_mlapm: null pointer");
+static int mlapm_advance_impl(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                              const float *dest, int64_t N, int64_t row0, int64_t row1, const piml_mlapm_params *prm,
+                              float dt, float radius, float *action, float *pos_new, uint8_t *arrived, void *workspace,
+                              const PeerPush &push, void *stream) {
+    PIML_REQUIRE(pos && vel && desired_speed && dest && prm && (action || push.world > 0) && workspace,
+                 "piml_mlapm: null pointer");
     PIML_REQUIRE(ds_dim == 1 || ds_dim == 2, "piml_mlapm: desired_speed must be (N,1) or (N,2), got ds_dim=%d", ds_dim);
     PIML_REQUIRE(N >= 0 && N < (1LL << 31), "piml_mlapm: N=%lld out of range", static_cast<long long>(N));
     PIML_REQUIRE(0 <= row0 && row0 <= row1 && row1 <= N, "piml_mlapm: bad row range [%lld,%lld) for N=%lld",
@@ -558,6 +572,7 @@ extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const 
     const int iN = static_cast<int>(N), r0 = static_cast<int>(row0), r1 = static_cast<int>(row1);
     int rc;
     if (prm->exact_math) {
+        PIML_REQUIRE(push.world == 0, "piml_mlapm: the fused exchange is only available on the production math path");
         // validation variant: IEEE arithmetic in the reference's operation order
         const int R = pick_rows_per_thread(nrows);
         int nsplit, cps;
@@ -621,9 +636,40 @@ extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const 
     const int threads = 256;
     mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
         p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial4, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
-        dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived);
+        dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push);
     count_launch();
     return check_launch("mlapm_finalize2_kernel");
+}
+
+extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                      const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                      const piml_mlapm_params *prm, float dt, float radius, float *action,
+                                      float *pos_new, uint8_t *arrived, void *workspace, void *stream) {
+    PeerPush none;
+    none.world = 0;
+    return mlapm_advance_impl(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, radius, action, pos_new,
+                              arrived, workspace, none, stream);
+}
+
+extern "C" int piml_mlapm_advance_push_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                           const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                           const piml_mlapm_params *prm, float dt, float radius, int world,
+                                           const uint64_t *peer_pos_next_host, const uint64_t *peer_vel_next_host,
+                                           uint8_t *arrived, void *workspace, void *stream) {
+    PIML_REQUIRE(world >= 1 && world <= ML_MAX_PEERS, "piml_mlapm_advance_push_f32: world=%d not in [1,%d]", world,
+                 ML_MAX_PEERS);
+    PIML_REQUIRE(peer_pos_next_host && peer_vel_next_host, "piml_mlapm_advance_push_f32: null peer pointer table");
+    PeerPush push;
+    push.world = world;
+    for (int g = 0; g < ML_MAX_PEERS; ++g) {
+        push.pos[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_pos_next_host[g])) : nullptr;
+        push.vel[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_vel_next_host[g])) : nullptr;
+        PIML_REQUIRE(g >= world || (push.pos[g] && push.vel[g] && (peer_pos_next_host[g] & 7u) == 0 &&
+                                    (peer_vel_next_host[g] & 7u) == 0),
+                     "piml_mlapm_advance_push_f32: bad peer pointer for rank %d", g);
+    }
+    return mlapm_advance_impl(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, radius, nullptr, nullptr,
+                              arrived, workspace, push, stream);
 }
 
 extern "C" int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,

@@ -1,0 +1,72 @@
+"""Agent-sharded MLAPM crowd across the GPUs of one node (BASELINE config 5a).
+
+Rank g owns rows [g N/G, (g+1) N/G) and needs every agent's (position, velocity) each step -- the path's only exchange.
+Instead of a separate all-gather, the finalize kernel of `piml_mlapm_advance_push_f32` stores each new row straight
+into EVERY rank's next-state arrays over NVLink / NVSwitch peer memory (torch symmetric memory provides the peer
+mappings), so the transfer rides on the kernel's own epilogue; a step then needs one cross-rank barrier only.
+
+One process per GPU (`torchrun`), `torch.distributed` initialised with the NCCL backend.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+class ShardedCrowd(object):
+    """Double-buffered crowd state in symmetric memory: buf[parity][0] = positions (N,2), buf[parity][1] = velocities."""
+
+    def __init__(self, N, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if N % self.world:
+            raise ValueError(f"{N} agents are not divisible by {self.world} ranks")
+        self.N, self.shard = N, N // self.world
+        self.device = device if device is not None else L.cuda_device()
+        self.buf = symm.empty((2, 2, N, 2), dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.ptrs) != self.world:
+            raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peer buffers")
+        self.parity = 0
+        self.rows = (self.rank * self.shard, (self.rank + 1) * self.shard)
+        self.arrived = torch.empty(self.shard, dtype=torch.uint8, device=self.device)
+        plane = N * 2 * 4                                        # bytes of one (N,2) fp32 array
+        self._tables = []
+        for par in (0, 1):
+            pos = (C.c_uint64 * self.world)(*[p + (par * 2) * plane for p in self.ptrs])
+            vel = (C.c_uint64 * self.world)(*[p + (par * 2 + 1) * plane for p in self.ptrs])
+            self._tables.append((pos, vel))
+
+    def load(self, position, velocity):
+        """Every rank passes the full initial state (N,2)."""
+        self.buf[self.parity, 0].copy_(position)
+        self.buf[self.parity, 1].copy_(velocity)
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(self.group)
+
+    @property
+    def position(self):
+        return self.buf[self.parity, 0]
+
+    @property
+    def velocity(self):
+        return self.buf[self.parity, 1]
+
+    def step(self, model, desired_speed, destination, dt, radius=0.3):
+        """One iteration of src/main_mlapm.py:18-36 for this rank's rows, exchange included.  Returns arrived[bool]
+        for the local rows; afterwards .position / .velocity hold the new state of ALL agents."""
+        nxt = 1 - self.parity
+        pos_tab, vel_tab = self._tables[nxt]
+        ds = desired_speed if desired_speed.dim() == 2 else desired_speed.unsqueeze(-1)
+        r0, r1 = self.rows
+        L.check(L.load().piml_mlapm_advance_push_f32(
+            L.ptr(self.position), L.ptr(self.velocity), L.ptr(ds), ds.shape[1], L.ptr(destination), self.N, r0, r1,
+            C.byref(model._params()), float(dt), float(radius), self.world, pos_tab, vel_tab, L.ptr(self.arrived),
+            L.ptr(model._workspace(self.N, self.device)), L.stream_ptr(self.device)), "piml_mlapm_advance_push_f32")
+        self.hdl.barrier(channel=0)        # every rank's rows have landed in every rank's next-state arrays
+        self.parity = nxt
+        return self.arrived.bool()
