@@ -496,12 +496,12 @@ static int pick_split2(const void *kernel, int64_t nrows, int64_t N, int rows_pe
         cached_occ = occ < 1 ? 1 : occ;
         cached_kernel = kernel;
     }
-    const int64_t slots = static_cast<int64_t>(cached_occ) * sm_count();
-    const int64_t B = (nrows + rows_per_cta - 1) / rows_per_cta;
+    (void)nrows; (void)rows_per_cta;
+    // The column partition depends on N ONLY: a row's sum is then evaluated in the same order whichever row range
+    // (rank) it is computed in, so an agent-sharded crowd is bit-identical to the unsharded one.
+    // As many splits as allowed also gives every rank of an 8-way shard enough CTAs to fill its GPU.
     const int64_t tiles = (N + M2_TILE - 1) / M2_TILE;
-    int64_t s = (8 * slots + B - 1) / B;
-    if (s > tiles) s = tiles;
-    if (s > ML_MAX_SPLIT) s = ML_MAX_SPLIT;
+    int64_t s = tiles < ML_MAX_SPLIT ? tiles : ML_MAX_SPLIT;
     if (s < 1) s = 1;
     if (const char *e = getenv("PIML_MLAPM_SPLIT")) {
         const int64_t f = atoll(e);
