@@ -262,6 +262,33 @@ PIML_API int piml_integrate_step_f32(float *p, float *v, float *a, const float *
                             const float *a_gt, const float *dest_gt, const int64_t *dest_idx_gt, float *hist_v,
                             float *rec_p, float *rec_v, float *rec_a, float *rec_mask, void *stream);
 
+/* ---- whole rollout loop: src/models/simulators.py:595-652 ---------------------------------------------------------- */
+
+/* Everything BaseSimulator.get_multiple_rollouts' `for t in range(t_start, T)` loop touches, for S scenes of N slots
+ * rolled together.  Time-major ground truth (frame t of all scenes contiguous); all pointers are device pointers. */
+typedef struct {
+    const piml_net_desc *desc;      /* network */
+    const float *packed;            /* piml_pinnsf_pack_f32 vector (FP32-pipe kernel), or NULL if packed_tc is given */
+    const float *packed_tc;         /* piml_pinnsf_pack_tc_f32 vector (tensor-core kernel), or NULL */
+    int has_obs; float tau;
+    int S, N, M, D, T, t_start; float dt;
+    int kp; float cos_p, thr_p; int ko; float cos_o, thr_o;            /* topk / cos(sight angle) / distance threshold */
+    const float *obstacles; int obs_per_scene;                          /* (M,2) or (S,M,2) */
+    const float *pos_tm, *vel_tm, *acc_tm, *dest_tm;                    /* (T,S,N,2) data.position ... data.destination */
+    const int64_t *dest_idx_tm;                                         /* (T,S,N) */
+    const int64_t *entry_tm;                                            /* (T,S,N) mask_p - mask_p_pred (simulators.py:593) */
+    const int64_t *dest_num;                                            /* (S,N) */
+    const float *waypoints;                                             /* (S,D,N,2) */
+    const float *desired_speed;                                         /* (S,N) */
+    float *p, *v, *a, *dest; int64_t *dest_idx; float *hist_v;          /* (S,N,..) state at t_start, updated in place */
+    float *ped_f, *obs_f, *self_f, *dest_f;                             /* features of the state at t_start, in/out */
+    float *a_next;                                                      /* (S,N,2) scratch */
+    float *rec_p, *rec_v, *rec_a, *rec_mask;                            /* (T,S,N,2) x3, (T,S,N): rows t >= t_start written */
+} piml_rollout_args;
+
+/* Enqueues the whole loop (3-4 launches per step, no host synchronisation) on `stream`. */
+PIML_API int piml_rollout_f32(const piml_rollout_args *args, void *stream);
+
 /* Backward of the differentiable rollout's state update (simulators.py:741-769: v' = v + a dt, p' = p + v dt,
  * a' = model output; agents overwritten by teacher-forced entry get no gradient).  n = S*N agents.
  * entry (n) int64 or NULL; g_p2,g_v2,g_a2 (n,2) = gradients of the updated state -> g_p,g_v,g_a,g_a_next (n,2). */

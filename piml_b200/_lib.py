@@ -28,6 +28,19 @@ class NetDesc(C.Structure):
                 ("n_coll", i32), ("coll_dims", i32 * 5), ("kind", i32)]
 
 
+class RolloutArgs(C.Structure):
+    """piml_rollout_args"""
+    _fields_ = [("desc", C.POINTER(NetDesc)), ("packed", vp), ("packed_tc", vp), ("has_obs", i32), ("tau", f32),
+                ("S", i32), ("N", i32), ("M", i32), ("D", i32), ("T", i32), ("t_start", i32), ("dt", f32),
+                ("kp", i32), ("cos_p", f32), ("thr_p", f32), ("ko", i32), ("cos_o", f32), ("thr_o", f32),
+                ("obstacles", vp), ("obs_per_scene", i32),
+                ("pos_tm", vp), ("vel_tm", vp), ("acc_tm", vp), ("dest_tm", vp), ("dest_idx_tm", vp),
+                ("entry_tm", vp), ("dest_num", vp), ("waypoints", vp), ("desired_speed", vp),
+                ("p", vp), ("v", vp), ("a", vp), ("dest", vp), ("dest_idx", vp), ("hist_v", vp),
+                ("ped_f", vp), ("obs_f", vp), ("self_f", vp), ("dest_f", vp), ("a_next", vp),
+                ("rec_p", vp), ("rec_v", vp), ("rec_a", vp), ("rec_mask", vp)]
+
+
 # name -> (restype, argtypes); must list every symbol include/piml_b200.h declares (tests check this).
 SIGNATURES = {
     "piml_version": (i32, []),
@@ -70,6 +83,7 @@ SIGNATURES = {
                                        vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_relative_features_backward_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_collision_detection_f32": (i32, [vp, vp, i32, i32, i32, f32, i32, vp, vp, vp]),
+    "piml_rollout_f32": (i32, [C.POINTER(RolloutArgs), vp]),
     "piml_integrate_step_backward_f32": (i32, [vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_integrate_step_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp,
                                       vp, vp, vp, vp, vp, vp, vp]),

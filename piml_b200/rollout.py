@@ -107,20 +107,35 @@ def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed
                             L.f32c(scene["self_features0"]))
     hist = torch.empty(S, N, 2, device=dev)
     kp, ko = ped_f.shape[-2], obs_f.shape[-2]
-    feat_out = (torch.empty(S, N, kp, 6, device=dev), torch.empty(S, N, ko, 6, device=dev),
-                torch.empty(S, N, 7, device=dev), torch.empty(S, N, 2, device=dev))
-    for t in range(t_start, T):
-        a_next = M.pinnsf_forward(spec, packed, ped_f.view(S * N, kp, 6), obs_f.view(S * N, ko, 6),
-                                  self_f.view(S * N, 7), need_msgs=False, packed_tc=packed_tc)[0].view(S, N, 2)  # :602
-        last = t >= T - 1
-        integrate_step(p, v, a, a_next, dest, didx, dnum, wp, dt, True,
-                       None if last else flag_tm[t + 1],
-                       None if last else tm["position"][t + 1], None if last else tm["velocity"][t + 1],
-                       None if last else tm["acceleration"][t + 1], None if last else tm["destination"][t + 1],
-                       None if last else didx_tm[t + 1], hist, p_res[t], v_res[t], a_res[t], mask_new[t])
-        ped_f, obs_f, self_f = state_features(p, v, a, dest, obstacles, hist, ds, args.topk_ped,
-                                              args.sight_angle_ped, args.dist_threshold_ped, args.topk_obs,
-                                              args.sight_angle_obs, args.dist_threshold_obs, out=feat_out)
+    Mo = obstacles.shape[-2] if obstacles.numel() else 0
+    # feature buffers: hold the features of the state at t_start, then are rewritten in place every step
+    ped_f, self_f = ped_f.reshape(S, N, kp, 6).clone(), self_f.reshape(S, N, 7).clone()
+    obs_f = obs_f.reshape(S, N, ko, 6).clone() if Mo else None
+    dest_f = torch.empty(S, N, 2, device=dev)
+    a_next = torch.empty(S, N, 2, device=dev)
+    if dnum.numel() != S * N:
+        dnum = dnum.expand(S, N).contiguous()
+    desc = spec.desc()
+    r = L.RolloutArgs()
+    r.desc = L.C.pointer(desc)
+    r.packed, r.packed_tc = L.ptr(packed), (L.ptr(packed_tc) if (packed_tc is not None and M.tc_enabled()) else None)
+    r.has_obs, r.tau = (1 if (spec.has_obs and Mo) else 0), spec.tau
+    r.S, r.N, r.M, r.D, r.T, r.t_start, r.dt = S, N, Mo, wp.shape[-3], T, t_start, dt
+    r.kp, r.cos_p, r.thr_p = args.topk_ped, cos_threshold(args.sight_angle_ped), float(args.dist_threshold_ped)
+    r.ko, r.cos_o, r.thr_o = args.topk_obs, cos_threshold(args.sight_angle_obs), float(args.dist_threshold_obs)
+    r.obstacles, r.obs_per_scene = (L.ptr(obstacles) if Mo else None), (1 if (obstacles.dim() == 3 and Mo) else 0)
+    r.pos_tm, r.vel_tm, r.acc_tm, r.dest_tm = [L.ptr(tm[k]) for k in ("position", "velocity", "acceleration",
+                                                                        "destination")]
+    r.dest_idx_tm, r.entry_tm, r.dest_num = L.ptr(didx_tm), L.ptr(flag_tm), L.ptr(dnum)
+    r.waypoints, r.desired_speed = L.ptr(wp), L.ptr(ds)
+    r.p, r.v, r.a, r.dest, r.dest_idx, r.hist_v = [L.ptr(x) for x in (p, v, a, dest, didx, hist)]
+    r.ped_f, r.obs_f, r.self_f, r.dest_f, r.a_next = L.ptr(ped_f), L.ptr(obs_f), L.ptr(self_f), L.ptr(dest_f), \
+        L.ptr(a_next)
+    r.rec_p, r.rec_v, r.rec_a, r.rec_mask = L.ptr(p_res), L.ptr(v_res), L.ptr(a_res), L.ptr(mask_new)
+    if spec.has_obs and not Mo:
+        raise ValueError("the network has an obstacle branch but the scene has no obstacles")
+    # the whole `for t in range(t_start, T)` loop of simulators.py:595-652: one C call, 3-4 launches per step
+    L.check(L.load().piml_rollout_f32(L.C.byref(r), L.stream_ptr(dev)), "piml_rollout_f32")
     return (p_res.transpose(0, 1), v_res.transpose(0, 1), a_res.transpose(0, 1), mask_new.transpose(0, 1))
 
 

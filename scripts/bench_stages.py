@@ -111,6 +111,31 @@ def main():
         state_features(one[0], one[1], one[2], one[3], ob, one[4], one[5], *fargs)
     ms = timeit(one_step, iters=50)
     out["nn_rollout_step_S1_N122"] = {"ms": ms, "agent_steps_per_s": Ns / ms * 1e3}
+    # whole rollouts through the C-side loop (piml_rollout_f32): S scenes x 122 slots x 300 frames
+    from piml_b200.rollout import rollout_scenes
+    rargs = argparse.Namespace(time_unit=0.08, topk_ped=6, sight_angle_ped=90, dist_threshold_ped=4, topk_obs=10,
+                               sight_angle_obs=90, dist_threshold_obs=4)
+    for S2 in (1, 64):
+        T2 = 300
+        g = torch.Generator().manual_seed(3)
+        P0 = (torch.rand(S2, T2, Ns, 2, generator=g) * 20).to(dev)
+        P0[:, :, 30:] = float('nan')
+        scene = {"position": P0, "velocity": torch.randn(S2, T2, Ns, 2, generator=g).to(dev) * 0.5,
+                 "acceleration": torch.zeros(S2, T2, Ns, 2, device=dev),
+                 "destination": (torch.rand(S2, T2, Ns, 2, generator=g) * 20).to(dev),
+                 "dest_idx": torch.zeros(S2, T2, Ns, dtype=torch.int64, device=dev),
+                 "waypoints": (torch.rand(S2, 1, Ns, 2, generator=g) * 20).to(dev),
+                 "dest_num": torch.ones(S2, Ns, dtype=torch.int64, device=dev), "obstacles": ob,
+                 "mask_p": torch.ones(S2, T2, Ns, device=dev), "mask_p_pred": torch.ones(S2, T2, Ns, device=dev),
+                 "desired_speed": torch.full((S2, Ns), 1.3, device=dev)}
+        f0 = state_features(P0[:, 0].contiguous(), scene["velocity"][:, 0].contiguous(),
+                            scene["acceleration"][:, 0].contiguous(), scene["destination"][:, 0].contiguous(), ob,
+                            scene["velocity"][:, 0].contiguous(), scene["desired_speed"], *fargs)
+        scene["ped_features0"], scene["obs_features0"], scene["self_features0"] = f0
+        for tc in (packed_tc, None):
+            ms = timeit(lambda: rollout_scenes(net.spec, packed, rargs, scene, 0, T2, packed_tc=tc), iters=3, warm=1)
+            out["rollout_S%d_N%d_T%d_%s" % (S2, Ns, T2, "tcgen05" if tc is not None else "fp32pipe")] = {
+                "ms_per_step": ms / T2, "agent_steps_per_s": S2 * Ns * T2 / ms * 1e3}
     print(json.dumps(out, indent=1))
 
 
