@@ -249,8 +249,9 @@ def run_ours(a):
     N = a.agents
     if N % world:
         raise SystemExit(f"--agents {N} must be divisible by the number of ranks {world}")
+    from piml_b200.sharded import allgather_state, shard_rows
     shard = N // world
-    r0, r1 = rank * shard, (rank + 1) * shard
+    r0, r1 = shard_rows(N, world, rank)
 
     p_h, v_h, ds_h, dest_h, obs_h = [x.pin_memory() for x in synthetic_crowd(N)]
     pos, vel, ds, dest = p_h.to(dev), v_h.to(dev), ds_h.to(dev), dest_h.to(dev)
@@ -282,8 +283,7 @@ def run_ours(a):
             return
         act, pnew, arrived = model.advance(pos, vel, ds, dest, DT, RADIUS, rows=(r0, r1))
         if world > 1:                                                   # the path's one exchange step
-            dist.all_gather_into_tensor(pos_next, pnew)
-            dist.all_gather_into_tensor(vel_next, act)
+            allgather_state(pos_next, vel_next, pnew, act)
             pos, pos_next = pos_next, pos
             vel, vel_next = vel_next, vel
         else:

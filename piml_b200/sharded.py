@@ -15,6 +15,29 @@ import torch.distributed as dist
 from . import _lib as L
 
 
+def shard_rows(N, world, rank):
+    """Block partition of the agents: rank g owns rows [g N/G, (g+1) N/G)."""
+    if N % world:
+        raise ValueError(f"{N} agents are not divisible by {world} ranks")
+    shard = N // world
+    return rank * shard, (rank + 1) * shard
+
+
+def allgather_state(pos_next, vel_next, pos_rows, vel_rows, group=None):
+    """The exchange as a separate collective (the baseline the fused push replaces; also what a backend without peer
+    memory uses): every rank contributes its rows' new positions / velocities, all ranks end with the full (N,2)
+    arrays.  Works on NCCL (GPU) and gloo (CPU tests of the partition logic)."""
+    if dist.get_backend(group) == "gloo":
+        world = dist.get_world_size(group)
+        for full, part in ((pos_next, pos_rows), (vel_next, vel_rows)):
+            chunks = list(full.chunk(world, dim=0))
+            dist.all_gather(chunks, part.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(pos_next, pos_rows, group=group)
+        dist.all_gather_into_tensor(vel_next, vel_rows, group=group)
+    return pos_next, vel_next
+
+
 class ShardedCrowd(object):
     """Double-buffered crowd state in symmetric memory: buf[parity][0] = positions (N,2), buf[parity][1] = velocities."""
 
@@ -22,8 +45,7 @@ class ShardedCrowd(object):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        if N % self.world:
-            raise ValueError(f"{N} agents are not divisible by {self.world} ranks")
+        self.rows = shard_rows(N, self.world, self.rank)
         self.N, self.shard = N, N // self.world
         self.device = device if device is not None else L.cuda_device()
         self.buf = symm.empty((2, 2, N, 2), dtype=torch.float32, device=self.device)
@@ -32,7 +54,6 @@ class ShardedCrowd(object):
         if len(self.ptrs) != self.world:
             raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peer buffers")
         self.parity = 0
-        self.rows = (self.rank * self.shard, (self.rank + 1) * self.shard)
         self.arrived = torch.empty(self.shard, dtype=torch.uint8, device=self.device)
         plane = N * 2 * 4                                        # bytes of one (N,2) fp32 array
         self._tables = []
