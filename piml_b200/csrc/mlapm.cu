@@ -254,12 +254,13 @@ __global__ void mlapm_finalize_kernel(const float2 *__restrict__ pos, const floa
 // sigma = +1, the reference's masked_fill_(theta == 0, +theta)).
 // =====================================================================================================================
 constexpr int M2_THREADS = 128;
-constexpr int M2_TILE = 512;                      // columns per stage: 512 * 32 B = 16 KB
-constexpr int M2_COLF = 8;                        // floats per column record {cx,cx,cy,cy,cvx,cvx,cvy,cvy}
+constexpr int M2_TILE = 512;                      // columns per stage: 512 * 16 B = 8 KB
+constexpr int M2_COLF = 4;                        // floats per column record {px,py,vx,vy}; the packed instructions
+                                                  // read them as scalar-broadcast operands (SASS `Rn.F32`)
 
 __device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
 
-// col8[j] = {px,px,py,py,vx,vx,vy,vy} for j < N, padded up to Npad with copies of the last agent (never evaluated:
+// col8[j] = {px,py,vx,vy} for j < N, padded up to Npad with copies of the last agent (never evaluated:
 // the pair loop stops at N; the padding only keeps the fixed-size TMA bulk copies in bounds).
 __global__ void mlapm_prep_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel, int N, int Npad,
                                   float4 *__restrict__ col8) {
@@ -267,8 +268,7 @@ __global__ void mlapm_prep_kernel(const float2 *__restrict__ pos, const float2 *
     if (j >= Npad) return;
     const int s = j < N ? j : N - 1;
     const float2 p = pos[s], v = vel[s];
-    col8[2 * j] = make_float4(p.x, p.x, p.y, p.y);
-    col8[2 * j + 1] = make_float4(v.x, v.x, v.y, v.y);
+    col8[j] = make_float4(p.x, p.y, v.x, v.y);
 }
 
 struct M2Const {
@@ -279,11 +279,11 @@ struct M2Const {
 template <int VERSION>
 __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const float2 vx, const float2 vy,
                                       const float2 nvx, const float2 nvy, const float2 ex, const float2 ey,
-                                      const float4 cp, const float4 cv, const float2 Bl, const float2 Cl,
+                                      const float4 cp, const float2 Bl, const float2 Cl,
                                       const float2 Dl, float2 &Sx, float2 &Sy, float2 &Tx, float2 &Ty) {
     const float2 eps = splat(1e-30f);
-    const float2 rx = __fadd2_rn(make_float2(cp.x, cp.y), npx);            // vr = p_m - p_n          (mlapm.py:25)
-    const float2 ry = __fadd2_rn(make_float2(cp.z, cp.w), npy);
+    const float2 rx = __fadd2_rn(make_float2(cp.x, cp.x), npx);            // vr = p_m - p_n          (mlapm.py:25)
+    const float2 ry = __fadd2_rn(make_float2(cp.y, cp.y), npy);
     const float2 g = __ffma2_rn(vy, ry, __fmul2_rn(vx, rx));               // einsum('nk,nmk->nm')    (mlapm.py:27)
     const float2 r2 = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, eps));
     const float2 ir = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
@@ -297,15 +297,17 @@ __device__ __forceinline__ void pair2(const float2 npx, const float2 npy, const 
         Sx = __ffma2_rn(w, rx, Sx);
         Sy = __ffma2_rn(w, ry, Sy);
     } else {
-        const float2 ux = __fadd2_rn(make_float2(cv.x, cv.y), nvx);        // vv = v_m - v_n          (mlapm.py:31)
-        const float2 uy = __fadd2_rn(make_float2(cv.z, cv.w), nvy);
+        const float2 ux = __fadd2_rn(make_float2(cp.z, cp.z), nvx);        // vv = v_m - v_n          (mlapm.py:31)
+        const float2 uy = __fadd2_rn(make_float2(cp.w, cp.w), nvy);
         const float2 u2 = __ffma2_rn(uy, uy, __ffma2_rn(ux, ux, eps));
         const float2 iu = make_float2(rsqrt_approx(u2.x), rsqrt_approx(u2.y));
         const float2 dot = __ffma2_rn(ry, uy, __fmul2_rn(rx, ux));
-        const float2 cs = __fmul2_rn(__fmul2_rn(dot, ir), iu);             // cosine_similarity        (mlapm.py:32)
+        // cosine_similarity cs = dot*ir*iu (mlapm.py:32); B r + (C + D r) cs = B r + (dot*iu) (C/r + D): one
+        // packed instruction fewer than forming cs (r*ir == 1 to 2^-22, far inside the 1e-5 gate)
+        const float2 q = __fmul2_rn(dot, iu);
         // vr x e = fl(rx*ey) - fl(ry*ex) un-fused: its sign is the order of the two rounded products    (mlapm.py:33)
         const float2 m1 = __fmul2_rn(rx, ey), m2 = __fmul2_rn(ry, ex);
-        const float2 arg = __ffma2_rn(__ffma2_rn(Dl, r, Cl), cs, __fmul2_rn(Bl, r));
+        const float2 arg = __ffma2_rn(q, __ffma2_rn(Cl, ir, Dl), __fmul2_rn(Bl, r));
         w = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ir);
         w.x = g.x > 0.f ? w.x : 0.f;                                       // view gate
         w.y = g.y > 0.f ? w.y : 0.f;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
                                                                   const float4 *__restrict__ col8, int N, int row0,
                                                                   int row1, int cols_per_split, M2Const k,
                                                                   float4 *__restrict__ partial) {
-    __shared__ __align__(128) float4 tile[2][M2_TILE * 2];
+    __shared__ __align__(128) float4 tile[2][M2_TILE];
     __shared__ __align__(8) uint64_t bars[2];
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -368,14 +370,14 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
     constexpr uint32_t TILE_BYTES = M2_TILE * M2_COLF * sizeof(float);
     if (threadIdx.x == 0 && ntiles > 0) {
         mbar_expect_tx(&bars[0], TILE_BYTES);
-        tma_bulk_g2s(tile[0], col8 + static_cast<int64_t>(c0) * 2, TILE_BYTES, &bars[0]);
+        tma_bulk_g2s(tile[0], col8 + static_cast<int64_t>(c0), TILE_BYTES, &bars[0]);
     }
     uint32_t phase_bits = 0;
     for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         if (threadIdx.x == 0 && t + 1 < ntiles) {               // tile[buf^1] was released by the barrier below
             mbar_expect_tx(&bars[buf ^ 1], TILE_BYTES);
-            tma_bulk_g2s(tile[buf ^ 1], col8 + static_cast<int64_t>(c0 + (t + 1) * M2_TILE) * 2, TILE_BYTES,
+            tma_bulk_g2s(tile[buf ^ 1], col8 + static_cast<int64_t>(c0 + (t + 1) * M2_TILE), TILE_BYTES,
                          &bars[buf ^ 1]);
         }
         mbar_wait(&bars[buf], (phase_bits >> buf) & 1u);
@@ -384,11 +386,10 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
         const float4 *tl = tile[buf];
 #pragma unroll(UNROLL)
         for (int j = 0; j < tn; ++j) {
-            const float4 cp = tl[2 * j];
-            const float4 cv = tl[2 * j + 1];
+            const float4 cp = tl[j];
 #pragma unroll
             for (int i = 0; i < RP; ++i)
-                pair2<VERSION>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, cv, Bl, Cl, Dl, Sx[i],
+                pair2<VERSION>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, Bl, Cl, Dl, Sx[i],
                                Sy[i], Tx[i], Ty[i]);
         }
         __syncthreads();
@@ -603,7 +604,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     // production: packed-FP32 kernel on SoA-duplicated column records
     const int64_t npad = (N + M2_TILE - 1) / M2_TILE * M2_TILE;
     float4 *col8 = reinterpret_cast<float4 *>(workspace);
-    float4 *partial4 = col8 + npad * 2;
+    float4 *partial4 = col8 + npad;
     {
         const int threads = 256;
         mlapm_prep_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
