@@ -36,7 +36,8 @@ FLOP_PER_PAIR = 51.0          # SURVEY.md 8d, MLAPM-GC per ordered pair
 MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)     # main_mlapm.py:16
 DT, RADIUS = 0.08, 0.3
 FLUSH_MB = 160                 # L2 is 126 MB
-MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ncu --set full, N = 100k, one launch (profiles/r01b_...)
+MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ordered-pair kernel: ncu --set full, N = 100k (profiles/r01b_...)
+MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 3558144 + 138325248  # symmetric kernel (profiles/r01c_ncu_mlapm_sym_kernel.txt)
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -378,12 +379,23 @@ def run_ours(a):
                                                   " + NCCL all-gather/step")),
                        "exchange": exchange, "exchange_note": exchange_note,
                        "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
-            "roofline": {"bound": "fp32", "kernel": "mlapm_pairs2_kernel<GC, 4 rows/thread, packed FP32> (+prep, finalize)",
+            "roofline": {"bound": "fp32",
+                         "kernel": ("mlapm_sym_kernel<GC> (every unordered pair once for both rows, packed FP32; +prep, "
+                                    "finalize)" if world == 1 and N >= 16384 else
+                                    "mlapm_pairs2_kernel<GC, packed FP32> (ordered pairs of this rank's rows; +prep, "
+                                    "finalize)"),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if peak else None,
-                         "traffic": MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N) if N == 100000 else None,
-                         "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, "
-                                         "profiles/r01b_ncu_mlapm_pairs2_kernel.txt); algorithmic work is FLOPs",
+                         "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH if world == 1 else
+                                     MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, profiles/"
+                                         "r01c_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
+                                         "algorithmic work is FLOPs",
+                         "note": "achieved = 51 algorithmic FLOP per ORDERED pair (SURVEY 8d) x N^2 / kernel time.  "
+                                 "The symmetric kernel evaluates the n<->m-symmetric part of the formula once per "
+                                 "unordered pair, so it executes fewer FLOP than the algorithmic count and the "
+                                 "fraction can exceed 1; ncu: FMA pipe 66.5 % busy, MUFU 47 % "
+                                 "(profiles/r01c_ncu_mlapm_sym_kernel.txt)",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,

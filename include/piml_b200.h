@@ -149,6 +149,19 @@ PIML_API int piml_mlapm_advance_f32(const float *pos, const float *vel, const fl
                            const piml_mlapm_params *prm, float dt, float radius, float *action, float *pos_new,
                            uint8_t *arrived, void *workspace, void *stream);
 
+/* piml_mlapm_advance_f32 with the size of the caller's workspace stated.  With workspace_bytes >=
+ * piml_mlapm_workspace_bytes_sym(N) and the whole crowd (row0 = 0, row1 = N) the library may evaluate every UNORDERED
+ * pair once for both rows (the smooth part of mlapm.py:25-39 is symmetric under n <-> m; the two gates keep the
+ * reference's exact fp32 arithmetic in both directions), which needs room for the column-direction sums
+ * (N * N / 64 bytes).  Same results to fp32 summation order (row sums are added in a different, still fixed order).
+ * piml_set_mlapm_algorithm: 0 = automatic (symmetric from 16 384 agents), 1 = ordered pairs, 2 = symmetric. */
+PIML_API int64_t piml_mlapm_workspace_bytes_sym(int64_t N);
+PIML_API int piml_set_mlapm_algorithm(int algo);
+PIML_API int piml_mlapm_advance_ws_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                              const float *dest, int64_t N, int64_t row0, int64_t row1,
+                              const piml_mlapm_params *prm, float dt, float radius, float *action, float *pos_new,
+                              uint8_t *arrived, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* piml_mlapm_advance_f32 for an agent-sharded crowd with the path's one exchange FUSED into it: the
  * finalize kernel stores the new position and velocity of its rows [row0,row1) straight into every rank's next-state
  * arrays over NVLink / NVSwitch peer memory, instead of a separate all-gather.

@@ -61,6 +61,10 @@ SIGNATURES = {
     "piml_mlapm_step_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, vp, vp, vp]),
     "piml_mlapm_advance_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, vp, vp,
                                      vp, vp, vp]),
+    "piml_mlapm_workspace_bytes_sym": (i64, [i64]),
+    "piml_set_mlapm_algorithm": (i32, [i32]),
+    "piml_mlapm_advance_ws_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, vp, vp,
+                                        vp, vp, i64, vp]),
     "piml_mlapm_advance_push_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, i32,
                                           vp, vp, vp, vp, vp]),
     "piml_calc_acceleration_f32": (i32, [vp, i64, i32, i32, f32, f32, f32, f32, f32, f32, vp, vp]),

@@ -404,10 +404,255 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
     }
 }
 
+// =====================================================================================================================
+// Symmetric pair kernel (v3): every UNORDERED pair {n,m} is evaluated once and feeds both rows.
+//
+// Everything smooth in the GC formula is symmetric under n <-> m: vr -> -vr, vv -> -vv, so r, |vv|, cos(vr,vv) and
+// the exponent B r + C cos + D r cos are the same numbers for (n,m) and (m,n); only the two discontinuous gates (the
+// view test of the row's own velocity and the sign of vr x e of the row's own destination direction) and the
+// accumulation differ.  The 16 packed instructions + 3 MUFU of the shared part are therefore spent once per unordered
+// pair, and each direction adds 8 packed instructions (gate products, cross products, 4 accumulations):
+// 32 packed instructions + 6 MUFU per 128 ordered pairs instead of 48 + 12.  The gates keep the reference's exact
+// fp32 arithmetic in BOTH directions because fp32 subtraction, multiplication and fma are odd-symmetric:
+//   vr[m,n] = fl(p_n - p_m) = -fl(p_m - p_n),  v_m . vr[m,n] = -fmaf(v_my, ry, fl(v_mx rx))  ->  view' = (gc < 0),
+//   vr[m,n] x e_m = fl(fl(ry e_mx) - fl(rx e_my))                                          ->  sigma' = -1 iff m2c > m1c.
+//
+// Schedule: agents are cut into blocks of 512; block pair (I, J = I + d mod T) is evaluated by the CTA of row block I
+// for d = 0 .. floor(T/2) (a circulant schedule: every unordered block pair exactly once, every row block the same
+// amount of work; for even T the pairs at d = T/2 belong to I < T/2).  d = 0 is the diagonal block, evaluated one
+// direction at a time like v2.  A thread keeps 4 rows (2 packed lane pairs) in registers and streams J's columns from
+// shared memory (TMA bulk copies, double buffered), so the row direction accumulates in registers as before.  The
+// column direction needs, per column, the sum over all 512 rows of the CTA: the two packed lanes are added, each lane
+// parks its 4 sums for a batch of 8 columns in a per-warp shared-memory scratch, the warp transposes (lane -> column
+// lane/4, every 4th entry) and finishes with two shuffle stages; the 4 warps' column sums are added in a fixed order
+// and written to partialC[(I, d)][column] -- deterministic, no atomics.  Cost of the reduction per column and warp:
+// 9 FADD + 1 SHFL + 2 x 128-bit shared accesses against 64 packed instructions of pair work.
+// The finalize kernel subtracts the column-direction sums (vr' = -vr) from the row-direction sums.
+// =====================================================================================================================
+constexpr int MS_THREADS = 128;
+constexpr int MS_BLOCK = 512;                     // agents per block of the schedule = rows per CTA (4 per thread)
+constexpr int MS_CT = 128;                        // default columns per shared-memory stage (4 KB; 35 KB per CTA)
+constexpr int MS_BATCH = 8;                       // default columns per warp-level reduction
+constexpr int MS_RED_STRIDE = 36;                 // float4 per column of the scratch: 32 lanes + 64 B skew (no conflicts)
+constexpr int MS_RECF = 8;                        // floats per agent record {px,py,vx,vy, ex,ey,0,0}
+constexpr float MS_FAR = 1.0e18f;                 // padding agents sit here: exp(B r) == 0 exactly, nothing overflows
+
+template <int CT, int BATCH>
+struct MsSmem {
+    float4 tile[2][CT * 2];
+    float4 red[MS_THREADS / 32][BATCH * MS_RED_STRIDE];
+    float4 colacc[MS_THREADS / 32][CT];
+    uint64_t bars[2];
+};
+
+// rec[j] = {px,py,vx,vy},{ex,ey,0,0}, e = F.normalize(destination - position) (mlapm.py:21); j >= N: padding agents
+// far away (their weight underflows to exactly 0 in both directions), so block tails need no masks.
+__global__ void mlapm_prep_sym_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
+                                      const float2 *__restrict__ dest, int N, int Npad, float4 *__restrict__ rec) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    if (j >= N) {
+        rec[2 * j] = make_float4(MS_FAR, MS_FAR, 0.f, 0.f);
+        rec[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float2 p = pos[j], v = vel[j], d = dest[j];
+    const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
+    const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
+    rec[2 * j] = make_float4(p.x, p.y, v.x, v.y);
+    rec[2 * j + 1] = make_float4(__fdiv_rn(dx, dn), __fdiv_rn(dy, dn), 0.f, 0.f);
+}
+
+// Two rows (packed lanes) against one column, both directions.  Row sums accumulate in S/T; the column's share is
+// returned in cS/cT (FIRST: overwritten, else accumulated) in the row's sign convention (the caller subtracts it).
+template <int VERSION, bool FIRST>
+__device__ __forceinline__ void pair2sym(const float2 npx, const float2 npy, const float2 vx, const float2 vy,
+                                         const float2 nvx, const float2 nvy, const float2 ex, const float2 ey,
+                                         const float4 cp, const float4 ce, const float2 Bl, const float2 Cl,
+                                         const float2 Dl, float2 &Sx, float2 &Sy, float2 &Tx, float2 &Ty,
+                                         float2 &cSx, float2 &cSy, float2 &cTx, float2 &cTy) {
+    const float2 eps = splat(1e-30f);
+    const float2 rx = __fadd2_rn(splat(cp.x), npx);                        // vr[n,m] = p_m - p_n     (mlapm.py:25)
+    const float2 ry = __fadd2_rn(splat(cp.y), npy);
+    const float2 g = __ffma2_rn(vy, ry, __fmul2_rn(vx, rx));               // v_n . vr[n,m]           (mlapm.py:27)
+    const float2 gc = __ffma2_rn(splat(cp.w), ry, __fmul2_rn(splat(cp.z), rx));   // = -(v_m . vr[m,n])
+    const float2 r2 = __ffma2_rn(ry, ry, __ffma2_rn(rx, rx, eps));
+    const float2 ir = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    const float2 r = __fmul2_rn(r2, ir);
+    float2 w0;
+    if (VERSION == 0) {
+        const float2 arg = __fmul2_rn(Bl, r);
+        w0 = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ir);
+    } else {
+        const float2 ux = __fadd2_rn(splat(cp.z), nvx);                    // vv[n,m] = v_m - v_n     (mlapm.py:31)
+        const float2 uy = __fadd2_rn(splat(cp.w), nvy);
+        const float2 u2 = __ffma2_rn(uy, uy, __ffma2_rn(ux, ux, eps));
+        const float2 iu = make_float2(rsqrt_approx(u2.x), rsqrt_approx(u2.y));
+        const float2 dot = __ffma2_rn(ry, uy, __fmul2_rn(rx, ux));
+        const float2 q = __fmul2_rn(dot, iu);
+        const float2 arg = __ffma2_rn(q, __ffma2_rn(Cl, ir, Dl), __fmul2_rn(Bl, r));
+        w0 = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ir);
+    }
+    float2 w, wc;
+    w.x = g.x > 0.f ? w0.x : 0.f;                                          // view gate of the row
+    w.y = g.y > 0.f ? w0.y : 0.f;
+    wc.x = gc.x < 0.f ? w0.x : 0.f;                                        // view gate of the column
+    wc.y = gc.y < 0.f ? w0.y : 0.f;
+    Sx = __ffma2_rn(w, rx, Sx);
+    Sy = __ffma2_rn(w, ry, Sy);
+    cSx = FIRST ? __fmul2_rn(wc, rx) : __ffma2_rn(wc, rx, cSx);
+    cSy = FIRST ? __fmul2_rn(wc, ry) : __ffma2_rn(wc, ry, cSy);
+    if (VERSION != 0) {
+        // sign of vr x e from the order of the two rounded products, both directions             (mlapm.py:33-34)
+        const float2 m1 = __fmul2_rn(rx, ey), m2 = __fmul2_rn(ry, ex);
+        const float2 m1c = __fmul2_rn(rx, splat(ce.y)), m2c = __fmul2_rn(ry, splat(ce.x));
+        float2 ws, wcs;
+        ws.x = m1.x > m2.x ? -w.x : w.x;
+        ws.y = m1.y > m2.y ? -w.y : w.y;
+        wcs.x = m2c.x > m1c.x ? -wc.x : wc.x;
+        wcs.y = m2c.y > m1c.y ? -wc.y : wc.y;
+        Tx = __ffma2_rn(ws, rx, Tx);
+        Ty = __ffma2_rn(ws, ry, Ty);
+        cTx = FIRST ? __fmul2_rn(wcs, rx) : __ffma2_rn(wcs, rx, cTx);
+        cTy = FIRST ? __fmul2_rn(wcs, ry) : __ffma2_rn(wcs, ry, cTy);
+    } else if (FIRST) {
+        cTx = cTy = make_float2(0.f, 0.f);
+    }
+}
+
+// partialR[split][local row] = row-direction (Sx,Sy,Tx',Ty') over the split's block pairs;
+// partialC[(I - I0) * D + d - 1][column of block J] = column-direction sums of block pair (I, J = I + d mod T).
+template <int VERSION, int CT, int BATCH>
+__global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__restrict__ rec, int T, int D, int I0,
+                                                               int per, M2Const k, float4 *__restrict__ partialR,
+                                                               int nrows_pad, float4 *__restrict__ partialC) {
+    static_assert(MS_BLOCK % CT == 0 && CT % BATCH == 0 && (BATCH == 8 || BATCH == 4), "bad stage shape");
+    constexpr int SPB = MS_BLOCK / CT;                      // stages per block pair
+    constexpr int LPC = 32 / BATCH;                         // lanes that share a column in the transposed sum
+    extern __shared__ __align__(128) unsigned char ms_smem_raw[];
+    MsSmem<CT, BATCH> &sm = *reinterpret_cast<MsSmem<CT, BATCH> *>(ms_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&sm.bars[0], 1);
+        mbar_init(&sm.bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int I = I0 + blockIdx.x;
+    int L = D + 1;                                          // d = 0 .. D
+    if (!(T & 1) && 2 * I >= T) L = D;                      // even T: the pairs at d = T/2 belong to I < T/2
+    const int d_lo = blockIdx.y * per;
+    const int d_hi = min(d_lo + per, L);
+
+    float2 npx[2], npy[2], vx[2], vy[2], nvx[2], nvy[2], ex[2], ey[2], Sx[2], Sy[2], Tx[2], Ty[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int64_t na = static_cast<int64_t>(I) * MS_BLOCK + (2 * i) * MS_THREADS + tid;
+        const int64_t nb = na + MS_THREADS;
+        const float4 a0 = rec[2 * na], a1 = rec[2 * na + 1], b0 = rec[2 * nb], b1 = rec[2 * nb + 1];
+        npx[i] = make_float2(-a0.x, -b0.x); npy[i] = make_float2(-a0.y, -b0.y);
+        vx[i] = make_float2(a0.z, b0.z); vy[i] = make_float2(a0.w, b0.w);
+        nvx[i] = make_float2(-a0.z, -b0.z); nvy[i] = make_float2(-a0.w, -b0.w);
+        ex[i] = make_float2(a1.x, b1.x); ey[i] = make_float2(a1.y, b1.y);
+        Sx[i] = Sy[i] = Tx[i] = Ty[i] = make_float2(0.f, 0.f);
+    }
+    const float2 Bl = splat(k.Bl), Cl = splat(k.Cl), Dl = splat(k.Dl);
+
+    const int nst = d_hi > d_lo ? (d_hi - d_lo) * SPB : 0;
+    constexpr uint32_t STAGE_BYTES = CT * MS_RECF * sizeof(float);
+    auto stage_src = [&](int s) {
+        int J = I + d_lo + s / SPB;
+        J = J >= T ? J - T : J;
+        return rec + (static_cast<int64_t>(J) * MS_BLOCK + (s % SPB) * CT) * 2;
+    };
+    if (tid == 0 && nst > 0) {
+        mbar_expect_tx(&sm.bars[0], STAGE_BYTES);
+        tma_bulk_g2s(sm.tile[0], stage_src(0), STAGE_BYTES, &sm.bars[0]);
+    }
+    uint32_t phase_bits = 0;
+    for (int s = 0; s < nst; ++s) {
+        const int buf = s & 1;
+        if (tid == 0 && s + 1 < nst) {                      // tile[buf^1] was released by the barrier below
+            mbar_expect_tx(&sm.bars[buf ^ 1], STAGE_BYTES);
+            tma_bulk_g2s(sm.tile[buf ^ 1], stage_src(s + 1), STAGE_BYTES, &sm.bars[buf ^ 1]);
+        }
+        mbar_wait(&sm.bars[buf], (phase_bits >> buf) & 1u);
+        phase_bits ^= (1u << buf);
+        const float4 *tl = sm.tile[buf];
+        const int d = d_lo + s / SPB;
+        if (d == 0) {
+            // diagonal block: rows and columns are the same agents, every ordered pair appears -> one direction each
+#pragma unroll 4
+            for (int j = 0; j < CT; ++j) {
+                const float4 cp = tl[2 * j];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    pair2<VERSION>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, Bl, Cl, Dl, Sx[i],
+                                   Sy[i], Tx[i], Ty[i]);
+            }
+        } else {
+            float4 *red = sm.red[warp];
+            for (int b = 0; b < CT / BATCH; ++b) {
+#pragma unroll
+                for (int c = 0; c < BATCH; ++c) {
+                    const float4 cp = tl[2 * (b * BATCH + c)];
+                    const float4 ce = tl[2 * (b * BATCH + c) + 1];
+                    float2 cSx, cSy, cTx, cTy;
+                    pair2sym<VERSION, true>(npx[0], npy[0], vx[0], vy[0], nvx[0], nvy[0], ex[0], ey[0], cp, ce, Bl, Cl,
+                                            Dl, Sx[0], Sy[0], Tx[0], Ty[0], cSx, cSy, cTx, cTy);
+                    pair2sym<VERSION, false>(npx[1], npy[1], vx[1], vy[1], nvx[1], nvy[1], ex[1], ey[1], cp, ce, Bl,
+                                             Cl, Dl, Sx[1], Sy[1], Tx[1], Ty[1], cSx, cSy, cTx, cTy);
+                    red[c * MS_RED_STRIDE + lane] = make_float4(cSx.x + cSx.y, cSy.x + cSy.y, cTx.x + cTx.y,
+                                                                cTy.x + cTy.y);
+                }
+                __syncwarp();
+                // lane -> column lane/LPC, entries (lane%LPC), (lane%LPC)+LPC, ...: 32/LPC of the 32 row lanes each
+                const float4 *col = red + (lane / LPC) * MS_RED_STRIDE + (lane % LPC);
+                float4 acc = col[0];
+#pragma unroll
+                for (int e = 1; e < 32 / LPC; ++e) {
+                    const float4 t = col[LPC * e];
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                }
+#pragma unroll
+                for (int o = 1; o < LPC; o <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                }
+                if (lane % LPC == 0) sm.colacc[warp][b * BATCH + lane / LPC] = acc;
+                __syncwarp();
+            }
+            __syncthreads();
+            float4 *dst = partialC + (static_cast<int64_t>(blockIdx.x) * D + (d - 1)) * MS_BLOCK + (s % SPB) * CT;
+            for (int c = tid; c < CT; c += MS_THREADS) {
+                float4 a = sm.colacc[0][c];
+#pragma unroll
+                for (int wv = 1; wv < MS_THREADS / 32; ++wv) {
+                    const float4 t = sm.colacc[wv][c];
+                    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                }
+                dst[c] = a;
+            }
+        }
+        __syncthreads();
+    }
+    float4 *out = partialR + static_cast<int64_t>(blockIdx.y) * nrows_pad + static_cast<int64_t>(blockIdx.x) * MS_BLOCK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        out[(2 * i) * MS_THREADS + tid] = make_float4(Sx[i].x, Sy[i].x, Tx[i].x, Ty[i].x);
+        out[(2 * i + 1) * MS_THREADS + tid] = make_float4(Sx[i].y, Sy[i].y, Tx[i].y, Ty[i].y);
+    }
+}
+
 // Exchange step of an agent-sharded crowd fused into the finalize kernel: rank g's NEXT-state arrays, mapped into this
 // process over NVLink peer memory.  world == 0: no exchange.
 constexpr int ML_MAX_PEERS = 16;
 struct PeerPush { int world; float2 *pos[ML_MAX_PEERS]; float2 *vel[ML_MAX_PEERS]; };
+// Column-direction sums of the symmetric kernel (partialC == nullptr: ordered-pair kernel, row sums only).
+struct SymPartials { const float4 *partialC; int T, D, I0, nrows_pad; };
 
 // force = (v0*ed - v)/tau - A*R(sum partial) ; action = v + force*dt ; optional p' = p + action*dt and arrival.
 __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
@@ -415,7 +660,8 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
                                        int row0, int row1, int nsplit, const float4 *__restrict__ partial, float A,
                                        float cos_t, float sin_t, int version, float tau, float dt, float radius,
                                        float2 *__restrict__ action, float2 *__restrict__ pos_new,
-                                       uint8_t *__restrict__ arrived, const __grid_constant__ PeerPush push) {
+                                       uint8_t *__restrict__ arrived, const __grid_constant__ PeerPush push,
+                                       const __grid_constant__ SymPartials sym) {
     const int rl = blockIdx.x * blockDim.x + threadIdx.x;
     const int nrows = row1 - row0;
     if (rl >= nrows) return;
@@ -430,9 +676,24 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
     float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t pstride = sym.partialC ? sym.nrows_pad : nrows;
     for (int q = 0; q < nsplit; ++q) {                            // fixed order: deterministic
-        const float4 t = partial[static_cast<int64_t>(q) * nrows + rl];
+        const float4 t = partial[static_cast<int64_t>(q) * pstride + rl];
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (sym.partialC) {
+        // symmetric evaluation: this agent was a COLUMN of the block pairs (I = J - d mod T, J), d = 1..D; their
+        // column-direction sums enter with the opposite sign (vr[m,n] = -vr[n,m]).  Fixed order again.
+        const int J = n / MS_BLOCK, c = n % MS_BLOCK;
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int d = 1; d <= sym.D; ++d) {
+            int I = J - d;
+            I = I < 0 ? I + sym.T : I;
+            if (d == sym.D && !(sym.T & 1) && 2 * I >= sym.T) continue;      // even T: d = T/2 only for I < T/2
+            const float4 t = sym.partialC[(static_cast<int64_t>(I - sym.I0) * sym.D + (d - 1)) * MS_BLOCK + c];
+            u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
+        }
+        s.x -= u.x; s.y -= u.y; s.z -= u.z; s.w -= u.w;
     }
     float sx, sy;
     if (version == 0) { sx = s.x; sy = s.y; }
@@ -537,6 +798,39 @@ static void launch_pairs(int R, dim3 grid, cudaStream_t st, const float2 *pos, c
 
 using namespace piml;
 
+// ---- symmetric evaluation: selection and workspace ------------------------------------------------------------------
+static int g_mlapm_algorithm = 0;                 // 0 automatic, 1 ordered pairs (v2), 2 symmetric (v3)
+constexpr int64_t MS_AUTO_MIN_AGENTS = 16384;     // below this the ordered-pair kernel fills the GPU better
+
+static int64_t sym_blocks(int64_t N) { return (N + MS_BLOCK - 1) / MS_BLOCK; }
+static int sym_per(int64_t T) {                   // block pairs per CTA: >= 64 CTAs per SM (measured best at N = 100k: 2)
+    if (const char *e = getenv("PIML_MLAPM_SYM_PER")) {
+        const int f = atoi(e);
+        if (f >= 1) return f;
+    }
+    const int64_t pairs = T * (T / 2 + 1), want = 64LL * sm_count();
+    const int64_t per = pairs / want;
+    return per < 1 ? 1 : static_cast<int>(per);
+}
+static int64_t sym_workspace_bytes(int64_t N) {
+    const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
+    const int64_t per = sym_per(T), S = (D + 1 + per - 1) / per;
+    return npad * MS_RECF * sizeof(float) + (S + D) * npad * 4 * sizeof(float) + 256;
+}
+
+extern "C" int piml_set_mlapm_algorithm(int algo) {
+    PIML_REQUIRE(algo >= 0 && algo <= 2,
+                 "piml_set_mlapm_algorithm: 0 = automatic, 1 = ordered pairs, 2 = symmetric (unordered pairs)");
+    g_mlapm_algorithm = algo;
+    return PIML_OK;
+}
+
+extern "C" int64_t piml_mlapm_workspace_bytes_sym(int64_t N) {
+    if (N <= 0) return 0;
+    const int64_t a = piml_mlapm_workspace_bytes(N), b = sym_workspace_bytes(N);
+    return a > b ? a : b;
+}
+
 extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
     if (N < 0) return 0;
     // column records (32 B per agent, padded to a tile) + per-split partial sums (16 B per row and split)
@@ -547,7 +841,7 @@ extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
 static int mlapm_advance_impl(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
                               const float *dest, int64_t N, int64_t row0, int64_t row1, const piml_mlapm_params *prm,
                               float dt, float radius, float *action, float *pos_new, uint8_t *arrived, void *workspace,
-                              const PeerPush &push, void *stream) {
+                              int64_t workspace_bytes, const PeerPush &push, void *stream) {
     PIML_REQUIRE(pos && vel && desired_speed && dest && prm && (action || push.world > 0) && workspace,
                  "piml_mlapm: null pointer");
     PIML_REQUIRE(ds_dim == 1 || ds_dim == 2, "piml_mlapm: desired_speed must be (N,1) or (N,2), got ds_dim=%d", ds_dim);
@@ -601,7 +895,57 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
         count_launch();
         return check_launch("mlapm_finalize_kernel");
     }
-    // production: packed-FP32 kernel on SoA-duplicated column records
+    // production, whole crowd: symmetric evaluation (every unordered pair once) when the caller's workspace holds
+    // the column-direction sums; row ranges (agent-sharded ranks) and small crowds use the ordered-pair kernel.
+    SymPartials symp{nullptr, 0, 0, 0, 0};
+    const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) &&
+                        (prm->version == 0 ? k.Bl < 0.f : k.Bl + fabsf(k.Dl) < 0.f);   // padding agents need w -> 0
+    if (sym_ok && (g_mlapm_algorithm == 2 || (g_mlapm_algorithm == 0 && N >= MS_AUTO_MIN_AGENTS))) {
+        const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
+        const int per = sym_per(T);
+        const int S = static_cast<int>((D + 1 + per - 1) / per);
+        float4 *rec = reinterpret_cast<float4 *>(workspace);
+        float4 *partialR = rec + npad * 2;
+        float4 *partialC = partialR + static_cast<int64_t>(S) * npad;
+        const int threads = 256;
+        mlapm_prep_sym_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
+            p2, v2, d2, iN, static_cast<int>(npad), rec);
+        count_launch();
+        rc = check_launch("mlapm_prep_sym_kernel");
+        if (rc) return rc;
+        M2Const k2{k.Bl, k.Cl, k.Dl};
+        dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(S));
+        int cfg = 0;                                               // tuning: PIML_MLAPM_SYM_CFG = 0..3
+        if (const char *e = getenv("PIML_MLAPM_SYM_CFG")) cfg = atoi(e);
+#define PIML_LAUNCH_SYM(V, CT, BATCH)                                                                              \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH>,                                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                           static_cast<int>(sizeof(MsSmem<CT, BATCH>))));                          \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        mlapm_sym_kernel<V, CT, BATCH><<<grid, MS_THREADS, sizeof(MsSmem<CT, BATCH>), st>>>(                       \
+            rec, static_cast<int>(T), static_cast<int>(D), 0, per, k2, partialR, static_cast<int>(npad), partialC); \
+    } while (0)
+        if (prm->version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH);
+        else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8);
+        else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 4);
+        else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 4);
+        else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH);
+#undef PIML_LAUNCH_SYM
+        count_launch();
+        rc = check_launch("mlapm_sym_kernel");
+        if (rc) return rc;
+        symp = SymPartials{partialC, static_cast<int>(T), static_cast<int>(D), 0, static_cast<int>(npad)};
+        mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+            p2, v2, desired_speed, ds_dim, d2, r0, r1, S, partialR, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
+            dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
+        count_launch();
+        return check_launch("mlapm_finalize2_kernel");
+    }
+    // ordered pairs: packed-FP32 kernel on 16 B column records
     const int64_t npad = (N + M2_TILE - 1) / M2_TILE * M2_TILE;
     float4 *col8 = reinterpret_cast<float4 *>(workspace);
     float4 *partial4 = col8 + npad;
@@ -645,7 +989,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     const int threads = 256;
     mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
         p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial4, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
-        dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push);
+        dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
     count_launch();
     return check_launch("mlapm_finalize2_kernel");
 }
@@ -657,7 +1001,21 @@ extern "C" int piml_mlapm_advance_f32(const float *pos, const float *vel, const 
     PeerPush none;
     none.world = 0;
     return mlapm_advance_impl(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, radius, action, pos_new,
-                              arrived, workspace, none, stream);
+                              arrived, workspace, 0, none, stream);
+}
+
+extern "C" int piml_mlapm_advance_ws_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
+                                         const float *dest, int64_t N, int64_t row0, int64_t row1,
+                                         const piml_mlapm_params *prm, float dt, float radius, float *action,
+                                         float *pos_new, uint8_t *arrived, void *workspace, int64_t workspace_bytes,
+                                         void *stream) {
+    PIML_REQUIRE(workspace_bytes >= piml_mlapm_workspace_bytes(N),
+                 "piml_mlapm_advance_ws_f32: workspace of %lld bytes, need >= %lld",
+                 static_cast<long long>(workspace_bytes), static_cast<long long>(piml_mlapm_workspace_bytes(N)));
+    PeerPush none;
+    none.world = 0;
+    return mlapm_advance_impl(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, radius, action, pos_new,
+                              arrived, workspace, workspace_bytes, none, stream);
 }
 
 extern "C" int piml_mlapm_advance_push_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
@@ -678,7 +1036,7 @@ extern "C" int piml_mlapm_advance_push_f32(const float *pos, const float *vel, c
                      "piml_mlapm_advance_push_f32: bad peer pointer for rank %d", g);
     }
     return mlapm_advance_impl(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, radius, nullptr, nullptr,
-                              arrived, workspace, push, stream);
+                              arrived, workspace, 0, push, stream);
 }
 
 extern "C" int piml_mlapm_step_f32(const float *pos, const float *vel, const float *desired_speed, int ds_dim,

@@ -1,4 +1,6 @@
 """Drop-in for the reference's `MLAPM` (src/models/mlapm.py:5-58) on the CUDA all-pairs kernel."""
+import os
+
 import torch
 
 from . import _lib as L
@@ -25,8 +27,17 @@ class MLAPM:
         return L.MlapmParams(_VERSIONS[ver], float(a['tau']), float(a['A']), float(a['B']), float(a.get('C', 0.0)),
                              float(a.get('D', 0.0)), float(a.get('theta', 0.0)), 1 if a.get('exact_math') else 0)
 
-    def _workspace(self, N, device):
-        need = int(L.load().piml_mlapm_workspace_bytes(N))
+    # the symmetric (unordered-pair) evaluation needs N^2/64 bytes for its column-direction sums; above this cap the
+    # ordered-pair kernel is used instead (PIML_MLAPM_SYM_MAX_BYTES overrides; 0 disables the symmetric path)
+    SYM_MAX_BYTES = int(os.environ.get("PIML_MLAPM_SYM_MAX_BYTES", 40 << 30))
+
+    def _workspace(self, N, device, whole_crowd=False):
+        lib = L.load()
+        need = int(lib.piml_mlapm_workspace_bytes(N))
+        if whole_crowd and not self.args.get('exact_math'):
+            sym = int(lib.piml_mlapm_workspace_bytes_sym(N))
+            if sym <= self.SYM_MAX_BYTES:
+                need = max(need, sym)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
@@ -53,10 +64,11 @@ class MLAPM:
         r0, r1 = rows if rows is not None else (0, N)
         action = torch.empty(r1 - r0, 2, dtype=torch.float32, device=dev)
         prm = self._params()
-        L.check(L.load().piml_mlapm_step_f32(L.ptr(pos), L.ptr(vel), L.ptr(ds), ds.shape[1], L.ptr(dest), N, r0, r1,
-                                             L.C.byref(prm), float(dt), L.ptr(action),
-                                             L.ptr(self._workspace(N, dev)), L.stream_ptr(dev)),
-                "piml_mlapm_step_f32")
+        ws = self._workspace(N, dev, whole_crowd=(r0 == 0 and r1 == N))
+        L.check(L.load().piml_mlapm_advance_ws_f32(L.ptr(pos), L.ptr(vel), L.ptr(ds), ds.shape[1], L.ptr(dest), N, r0,
+                                                   r1, L.C.byref(prm), float(dt), 0.0, L.ptr(action), None, None,
+                                                   L.ptr(ws), ws.numel(), L.stream_ptr(dev)),
+                "piml_mlapm_advance_ws_f32")
         return action if origin == dev else action.to(origin)
 
     def advance(self, position, velocity, desired_speed, destination, dt, radius=0.3, rows=None):
@@ -68,10 +80,11 @@ class MLAPM:
         pnew = torch.empty(r1 - r0, 2, dtype=torch.float32, device=dev)
         arrived = torch.empty(r1 - r0, dtype=torch.uint8, device=dev)
         prm = self._params()
-        L.check(L.load().piml_mlapm_advance_f32(L.ptr(pos), L.ptr(vel), L.ptr(ds), ds.shape[1], L.ptr(dest), N, r0,
-                                                r1, L.C.byref(prm), float(dt), float(radius), L.ptr(action),
-                                                L.ptr(pnew), L.ptr(arrived), L.ptr(self._workspace(N, dev)),
-                                                L.stream_ptr(dev)), "piml_mlapm_advance_f32")
+        ws = self._workspace(N, dev, whole_crowd=(r0 == 0 and r1 == N))
+        L.check(L.load().piml_mlapm_advance_ws_f32(L.ptr(pos), L.ptr(vel), L.ptr(ds), ds.shape[1], L.ptr(dest), N, r0,
+                                                   r1, L.C.byref(prm), float(dt), float(radius), L.ptr(action),
+                                                   L.ptr(pnew), L.ptr(arrived), L.ptr(ws), ws.numel(),
+                                                   L.stream_ptr(dev)), "piml_mlapm_advance_ws_f32")
         if origin != dev:
             return action.to(origin), pnew.to(origin), arrived.bool().to(origin)
         return action, pnew, arrived.bool()

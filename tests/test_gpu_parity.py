@@ -280,6 +280,65 @@ def test_mlapm_nan_poisons_like_reference():
     assert np.isnan(want).all() and np.isnan(act).all()
 
 
+def _mlapm_algorithm(algo):
+    from piml_b200 import _lib as L
+    L.check(L.load().piml_set_mlapm_algorithm(algo), "piml_set_mlapm_algorithm")
+
+
+@pytest.mark.parametrize("ver", ["GC", "raw"])
+@pytest.mark.parametrize("N", [257, 1024, 1500, 2048, 2049, 5000, 8192])
+def test_mlapm_symmetric_evaluation(N, ver):
+    """The unordered-pair kernel (every pair once, both directions; odd / even / single block schedules, padded block
+    tails) against the oracle and against the ordered-pair kernel, incl. stationary agents (view gate false)."""
+    import piml_b200 as P
+    rng = np.random.default_rng(7 * N + len(ver))
+    L = np.sqrt(N / 0.5)
+    p = (rng.random((N, 2)) * L).astype(np.float32)
+    d = (rng.random((N, 2)) * L).astype(np.float32)
+    v = rng.normal(0, 1, (N, 2)).astype(np.float32)
+    v[rng.random(N) < 0.05] = 0.0
+    ds = (1.34 + 0.3 * rng.normal(0, 1, (N, 1))).astype(np.float32)
+    want = O.mlapm_step(p, v, ds, d, 0.08, ver)
+    model = P.MLAPM(**dict(GC_KW, version=ver))
+    try:
+        _mlapm_algorithm(2)
+        before = P._lib.launch_count()
+        sym, pnew, arrived = model.advance(cu(p), cu(v), cu(ds), cu(d), 0.08, 0.3)
+        sym = npy(sym)
+        again = npy(model.step(cu(p), cu(v), cu(ds), cu(d), 0.08))
+        _mlapm_algorithm(1)
+        ordered, pnew_o, arrived_o = model.advance(cu(p), cu(v), cu(ds), cu(d), 0.08, 0.3)
+    finally:
+        _mlapm_algorithm(0)
+    # action = v + F dt: where the two nearly cancel, fp32 rounding is relative to the operand v, not to the small
+    # result (the reference's own fp32 result is 2.6e-6 of |action| away from an fp64 evaluation on such an agent,
+    # scripts/diag_sym.py), so the scale of the gate is max(|action|, |v|)
+    def err(got, ref):
+        num = np.linalg.norm(np.asarray(got, np.float64) - ref, axis=-1)
+        den = np.maximum(np.maximum(np.linalg.norm(ref, axis=-1), np.linalg.norm(v, axis=-1)), 1e-6)
+        return float((num / den).max())
+    assert np.isfinite(sym).all()
+    assert err(sym, want) < TOL
+    assert rel_vec_err(sym, want) < 3 * TOL
+    assert np.array_equal(sym, again)                       # deterministic: fixed summation order, no atomics
+    assert err(sym, npy(ordered)) < TOL
+    assert np.array_equal(npy(arrived), npy(arrived_o))
+    assert np.allclose(npy(pnew), npy(pnew_o), rtol=0, atol=1e-5)
+
+
+def test_mlapm_symmetric_nan_poisons_like_reference():
+    import piml_b200 as P
+    g = group(golden("mlapm"), "syn1000")
+    p = g["position"].copy()
+    p[801] = np.nan
+    try:
+        _mlapm_algorithm(2)
+        act = npy(P.MLAPM(**GC_KW).step(cu(p), cu(g["velocity"]), cu(g["desired_speed"]), cu(g["destination"]), 0.08))
+    finally:
+        _mlapm_algorithm(0)
+    assert np.isnan(act).all()
+
+
 # ---- SFM -----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("key", ["v0/gc1560", "v0/ucy", "v1/gc2344", "v1/ucy", "v2/gc2344"])
 def test_calc_acceleration_golden(key):
