@@ -340,7 +340,19 @@ def run_ours(a):
     pnew_h = torch.empty(shard, 2).pin_memory()
     arr_h = torch.empty(shard, dtype=torch.bool).pin_memory()
 
+    if crowd is not None:                  # the agent-sharded public API: host state in, this rank's rows out
+        cr0, cr1 = crowd.rows
+        act_h = torch.empty(cr1 - cr0, 2).pin_memory()
+        pnew_h = torch.empty(cr1 - cr0, 2).pin_memory()
+        arr_h = torch.empty(cr1 - cr0, dtype=torch.bool).pin_memory()
+
     def e2e_step():
+        if crowd is not None:
+            crowd.position.copy_(p_h, non_blocking=True); crowd.velocity.copy_(v_h, non_blocking=True)
+            ds.copy_(ds_h, non_blocking=True); dest.copy_(dest_h, non_blocking=True)
+            arrived = crowd.step(model, ds, dest, DT, RADIUS)
+            act_h.copy_(crowd.velocity[cr0:cr1]); pnew_h.copy_(crowd.position[cr0:cr1]); arr_h.copy_(arrived)
+            return
         act, pnew, arrived = model.advance(p_h, v_h, ds_h, dest_h, DT, RADIUS, rows=(r0, r1))   # host in, host out
         act_h.copy_(act); pnew_h.copy_(pnew); arr_h.copy_(arrived)
     for _ in range(2):
@@ -363,6 +375,7 @@ def run_ours(a):
     h2d = (p_h.numel() + v_h.numel() + ds_h.numel() + dest_h.numel()) * 4
     d2h = (act_h.numel() + pnew_h.numel()) * 4 + arr_h.numel()
 
+    sym_used = (world == 1 and N >= 16384) or (crowd is not None and crowd.symmetric)
     if rank == 0:
         pairs = float(shard) * N                       # ordered pairs one launch of the pairs kernel evaluates
         achieved = FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12
@@ -375,19 +388,22 @@ def run_ours(a):
                        "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
                        "parallelism": f"agent-sharded rows x{world}" + (
                            "" if world == 1 else (" + exchange fused into the finalize kernel (NVLink peer stores) + "
-                                                  "1 barrier/step" if exchange == "push" else
+                                                  "1 barrier/step" if exchange == "push" and not sym_used else
+                                                  " + symmetric evaluation: column-direction shares and new state "
+                                                  "stored into the owners' buffers over NVLink peer memory by the "
+                                                  "pair / finalize stages + 2 barriers/step" if exchange == "push" else
                                                   " + NCCL all-gather/step")),
                        "exchange": exchange, "exchange_note": exchange_note,
                        "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
             "roofline": {"bound": "fp32",
                          "kernel": ("mlapm_sym_kernel<GC> (every unordered pair once for both rows, packed FP32; +prep, "
-                                    "finalize)" if world == 1 and N >= 16384 else
+                                    "finalize)" if sym_used else
                                     "mlapm_pairs2_kernel<GC, packed FP32> (ordered pairs of this rank's rows; +prep, "
                                     "finalize)"),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if peak else None,
-                         "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH if world == 1 else
-                                     MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
+                         "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH / world if sym_used
+                                     else MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
                          "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, profiles/"
                                          "r01c_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
                                          "algorithmic work is FLOPs",
@@ -402,7 +418,8 @@ def run_ours(a):
                          "pairs_per_sec": pairs / (kernel_ms * 1e-3), "mufu_peak_tops": peaks.get("mufu_tops")},
             "e2e": {"value": N * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
-                    "api": "piml_b200.MLAPM.advance(pinned host tensors) -> host tensors"},
+                    "api": ("piml_b200.MLAPM.advance(pinned host tensors) -> host tensors" if crowd is None else
+                            "piml_b200.sharded.ShardedCrowd: pinned host state in, step, this rank's rows out")},
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
         }

@@ -175,6 +175,30 @@ PIML_API int piml_mlapm_advance_push_f32(const float *pos, const float *vel, con
                                 const uint64_t *peer_pos_next_host, const uint64_t *peer_vel_next_host,
                                 uint8_t *arrived, void *workspace, void *stream);
 
+/* Agent-sharded crowd on the symmetric (unordered-pair) evaluation.  Rank g owns the 512-agent blocks
+ * [g T / G, (g+1) T / G), T = ceil(N / 512) (piml_mlapm_sym_shard_rows), and evaluates the block pairs of its own row
+ * blocks; the exchange is fused into two kernels over NVLink / NVSwitch peer memory:
+ *   piml_mlapm_sym_pairs_push_f32     pair kernel + per-rank reduction of the column-direction sums, stored into the
+ *                                     inbox of the rank that owns each agent (peer_inbox_host: `world` device
+ *                                     addresses of the ranks' inboxes, piml_mlapm_sym_inbox_bytes(N, world) each);
+ *   -- cross-rank barrier (caller) --
+ *   piml_mlapm_sym_finalize_push_f32  adds the ranks' shares in rank order, destination term, Euler update, arrival
+ *                                     test (main_mlapm.py:26,34) and stores the new rows into every rank's next-state
+ *                                     arrays like piml_mlapm_advance_push_f32;
+ *   -- cross-rank barrier (caller) --
+ * workspace >= piml_mlapm_sym_shard_workspace_bytes(N, world), the same buffer for both calls. */
+PIML_API int piml_mlapm_sym_shard_rows(int64_t N, int world, int rank, int64_t *row0, int64_t *row1);
+PIML_API int64_t piml_mlapm_sym_inbox_bytes(int64_t N, int world);
+PIML_API int64_t piml_mlapm_sym_shard_workspace_bytes(int64_t N, int world);
+PIML_API int piml_mlapm_sym_pairs_push_f32(const float *pos, const float *vel, const float *dest, int64_t N, int world,
+                                  int rank, const piml_mlapm_params *prm, const uint64_t *peer_inbox_host,
+                                  void *workspace, int64_t workspace_bytes, void *stream);
+PIML_API int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *vel, const float *desired_speed,
+                                     int ds_dim, const float *dest, int64_t N, int world, int rank,
+                                     const piml_mlapm_params *prm, float dt, float radius, const float *inbox_local,
+                                     const uint64_t *peer_pos_next_host, const uint64_t *peer_vel_next_host,
+                                     uint8_t *arrived, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- SFM repulsion: src/utils/utils.py:31-100 ------------------------------------------------------------ */
 
 /* UTILS.calc_acceleration.  rel (S, stride) with stride >= 4 floats per slot -> out (S,2).

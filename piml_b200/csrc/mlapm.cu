@@ -652,7 +652,35 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
 constexpr int ML_MAX_PEERS = 16;
 struct PeerPush { int world; float2 *pos[ML_MAX_PEERS]; float2 *vel[ML_MAX_PEERS]; };
 // Column-direction sums of the symmetric kernel (partialC == nullptr: ordered-pair kernel, row sums only).
-struct SymPartials { const float4 *partialC; int T, D, I0, nrows_pad; };
+// inbox != nullptr (agent-sharded crowd): the column-direction sums were reduced per rank and delivered to the owner
+// of the rows (mlapm_sym_colpush_kernel); inbox[g * inbox_stride + local row] is rank g's share.
+struct SymPartials { const float4 *partialC; int T, D, I0, nrows_pad; const float4 *inbox; int world;
+                     int64_t inbox_stride; };
+// Owners of the 512-agent blocks (rank g owns blocks [Ib[g], Ib[g+1])) and every rank's inbox as mapped here.
+struct PeerInbox { int world, rank; int Ib[ML_MAX_PEERS + 1]; float4 *inbox[ML_MAX_PEERS]; int64_t stride; };
+
+// Agent-sharded symmetric evaluation, first half of the exchange: this rank evaluated the block pairs (I, I + d) of
+// ITS row blocks I in [I0, I1); the column-direction sums of every agent m (its own or another rank's) are added over
+// those block pairs in a fixed order and stored into the inbox of the rank that owns m, over NVLink peer memory.
+__global__ void mlapm_sym_colpush_kernel(const float4 *__restrict__ partialC, int N, int T, int D, int I0, int I1,
+                                         const __grid_constant__ PeerInbox peers) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= N) return;
+    const int J = m / MS_BLOCK, c = m % MS_BLOCK;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 1; d <= D; ++d) {
+        int I = J - d;
+        I = I < 0 ? I + T : I;
+        if (I < I0 || I >= I1) continue;
+        if (d == D && !(T & 1) && 2 * I >= T) continue;                  // even T: d = T/2 only for I < T/2
+        const float4 t = partialC[(static_cast<int64_t>(I - I0) * D + (d - 1)) * MS_BLOCK + c];
+        u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
+    }
+    int h = 0;
+    while (h + 1 < peers.world && J >= peers.Ib[h + 1]) ++h;
+    peers.inbox[h][peers.rank * peers.stride + (m - peers.Ib[h] * MS_BLOCK)] = u;
+    __threadfence_system();                                               // visible to the owner before the barrier
+}
 
 // force = (v0*ed - v)/tau - A*R(sum partial) ; action = v + force*dt ; optional p' = p + action*dt and arrival.
 __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
@@ -676,12 +704,20 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
     float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t pstride = sym.partialC ? sym.nrows_pad : nrows;
+    const int64_t pstride = (sym.partialC || sym.inbox) ? sym.nrows_pad : nrows;
     for (int q = 0; q < nsplit; ++q) {                            // fixed order: deterministic
         const float4 t = partial[static_cast<int64_t>(q) * pstride + rl];
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     }
-    if (sym.partialC) {
+    if (sym.inbox) {
+        // agent-sharded symmetric evaluation: one pre-reduced share per rank, added in rank order
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < sym.world; ++g) {
+            const float4 t = sym.inbox[g * sym.inbox_stride + rl];
+            u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
+        }
+        s.x -= u.x; s.y -= u.y; s.z -= u.z; s.w -= u.w;
+    } else if (sym.partialC) {
         // symmetric evaluation: this agent was a COLUMN of the block pairs (I = J - d mod T, J), d = 1..D; their
         // column-direction sums enter with the opposite sign (vr[m,n] = -vr[n,m]).  Fixed order again.
         const int J = n / MS_BLOCK, c = n % MS_BLOCK;
@@ -838,6 +874,64 @@ extern "C" int64_t piml_mlapm_workspace_bytes(int64_t N) {
     return npad * M2_COLF * sizeof(float) + static_cast<int64_t>(ML_MAX_SPLIT) * N * 4 * sizeof(float) + 256;
 }
 
+static MlConst mlapm_consts(const piml_mlapm_params *prm) {
+    MlConst k;
+    k.version = prm->version;
+    k.A = prm->A; k.B = prm->B; k.C = prm->C; k.D = prm->D;
+    const double log2e = 1.4426950408889634;
+    k.Bl = static_cast<float>(prm->B * log2e); k.Cl = static_cast<float>(prm->C * log2e);
+    k.Dl = static_cast<float>(prm->D * log2e);
+    // theta tensor as the reference builds it in fp32: ((+-1 * theta) / 180) * pi   (mlapm.py:33)
+    const float th = (prm->theta_deg / 180.0f) * 3.14159274101257324f;
+    k.cos_t = static_cast<float>(cos(static_cast<double>(th)));
+    k.sin_t = static_cast<float>(sin(static_cast<double>(th)));
+    k.tau = prm->tau; k.inv_tau = 1.0f / prm->tau;
+    return k;
+}
+
+// The padding agents of the symmetric kernel need a weight that underflows to 0 at large r.
+static bool sym_params_ok(const piml_mlapm_params *prm, const MlConst &k) {
+    return !prm->exact_math && (prm->version == 0 ? k.Bl < 0.f : k.Bl + fabsf(k.Dl) < 0.f);
+}
+
+// prep + symmetric pair kernel for the row blocks [I0, I0 + nI) of a crowd of T blocks.
+static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, const float2 *d2, int N, int64_t T,
+                            int64_t I0, int64_t nI, int per, int S, const MlConst &k, float4 *rec, float4 *partialR,
+                            float4 *partialC, cudaStream_t st) {
+    const int64_t D = T / 2, npad = T * MS_BLOCK;
+    const int threads = 256;
+    mlapm_prep_sym_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
+        p2, v2, d2, N, static_cast<int>(npad), rec);
+    count_launch();
+    int rc = check_launch("mlapm_prep_sym_kernel");
+    if (rc) return rc;
+    M2Const k2{k.Bl, k.Cl, k.Dl};
+    dim3 grid(static_cast<unsigned>(nI), static_cast<unsigned>(S));
+    int cfg = 0;                                               // tuning: PIML_MLAPM_SYM_CFG = 0..3
+    if (const char *e = getenv("PIML_MLAPM_SYM_CFG")) cfg = atoi(e);
+#define PIML_LAUNCH_SYM(V, CT, BATCH)                                                                              \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH>,                                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                           static_cast<int>(sizeof(MsSmem<CT, BATCH>))));                          \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        mlapm_sym_kernel<V, CT, BATCH><<<grid, MS_THREADS, sizeof(MsSmem<CT, BATCH>), st>>>(                       \
+            rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, k2, partialR,                \
+            static_cast<int>(nI * MS_BLOCK), partialC);                                                            \
+    } while (0)
+    if (version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH);
+    else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8);
+    else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 4);
+    else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 4);
+    else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH);
+#undef PIML_LAUNCH_SYM
+    count_launch();
+    return check_launch("mlapm_sym_kernel");
+}
+
 static int mlapm_advance_impl(const float *pos, const float *vel, const float *desired_speed, int ds_dim,
                               const float *dest, int64_t N, int64_t row0, int64_t row1, const piml_mlapm_params *prm,
                               float dt, float radius, float *action, float *pos_new, uint8_t *arrived, void *workspace,
@@ -857,17 +951,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     const int64_t nrows = row1 - row0;
     if (nrows == 0) return PIML_OK;
 
-    MlConst k;
-    k.version = prm->version;
-    k.A = prm->A; k.B = prm->B; k.C = prm->C; k.D = prm->D;
-    const double log2e = 1.4426950408889634;
-    k.Bl = static_cast<float>(prm->B * log2e); k.Cl = static_cast<float>(prm->C * log2e);
-    k.Dl = static_cast<float>(prm->D * log2e);
-    // theta tensor as the reference builds it in fp32: ((+-1 * theta) / 180) * pi   (mlapm.py:33)
-    const float th = (prm->theta_deg / 180.0f) * 3.14159274101257324f;
-    k.cos_t = static_cast<float>(cos(static_cast<double>(th)));
-    k.sin_t = static_cast<float>(sin(static_cast<double>(th)));
-    k.tau = prm->tau; k.inv_tau = 1.0f / prm->tau;
+    const MlConst k = mlapm_consts(prm);
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float2 *p2 = reinterpret_cast<const float2 *>(pos), *v2 = reinterpret_cast<const float2 *>(vel);
@@ -897,9 +981,8 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     }
     // production, whole crowd: symmetric evaluation (every unordered pair once) when the caller's workspace holds
     // the column-direction sums; row ranges (agent-sharded ranks) and small crowds use the ordered-pair kernel.
-    SymPartials symp{nullptr, 0, 0, 0, 0};
-    const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) &&
-                        (prm->version == 0 ? k.Bl < 0.f : k.Bl + fabsf(k.Dl) < 0.f);   // padding agents need w -> 0
+    SymPartials symp{nullptr, 0, 0, 0, 0, nullptr, 0, 0};
+    const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) && sym_params_ok(prm, k);
     if (sym_ok && (g_mlapm_algorithm == 2 || (g_mlapm_algorithm == 0 && N >= MS_AUTO_MIN_AGENTS))) {
         const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
         const int per = sym_per(T);
@@ -907,38 +990,10 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
         float4 *rec = reinterpret_cast<float4 *>(workspace);
         float4 *partialR = rec + npad * 2;
         float4 *partialC = partialR + static_cast<int64_t>(S) * npad;
+        rc = launch_sym_pairs(prm->version, p2, v2, d2, iN, T, 0, T, per, S, k, rec, partialR, partialC, st);
+        if (rc) return rc;
         const int threads = 256;
-        mlapm_prep_sym_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
-            p2, v2, d2, iN, static_cast<int>(npad), rec);
-        count_launch();
-        rc = check_launch("mlapm_prep_sym_kernel");
-        if (rc) return rc;
-        M2Const k2{k.Bl, k.Cl, k.Dl};
-        dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(S));
-        int cfg = 0;                                               // tuning: PIML_MLAPM_SYM_CFG = 0..3
-        if (const char *e = getenv("PIML_MLAPM_SYM_CFG")) cfg = atoi(e);
-#define PIML_LAUNCH_SYM(V, CT, BATCH)                                                                              \
-    do {                                                                                                           \
-        static bool attr_done = false;                                                                             \
-        if (!attr_done) {                                                                                          \
-            PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH>,                                         \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
-                                           static_cast<int>(sizeof(MsSmem<CT, BATCH>))));                          \
-            attr_done = true;                                                                                      \
-        }                                                                                                          \
-        mlapm_sym_kernel<V, CT, BATCH><<<grid, MS_THREADS, sizeof(MsSmem<CT, BATCH>), st>>>(                       \
-            rec, static_cast<int>(T), static_cast<int>(D), 0, per, k2, partialR, static_cast<int>(npad), partialC); \
-    } while (0)
-        if (prm->version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH);
-        else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8);
-        else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 4);
-        else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 4);
-        else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH);
-#undef PIML_LAUNCH_SYM
-        count_launch();
-        rc = check_launch("mlapm_sym_kernel");
-        if (rc) return rc;
-        symp = SymPartials{partialC, static_cast<int>(T), static_cast<int>(D), 0, static_cast<int>(npad)};
+        symp = SymPartials{partialC, static_cast<int>(T), static_cast<int>(D), 0, static_cast<int>(npad), nullptr, 0, 0};
         mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
             p2, v2, desired_speed, ds_dim, d2, r0, r1, S, partialR, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
             dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
@@ -1045,4 +1100,148 @@ extern "C" int piml_mlapm_step_f32(const float *pos, const float *vel, const flo
                                    void *stream) {
     return piml_mlapm_advance_f32(pos, vel, desired_speed, ds_dim, dest, N, row0, row1, prm, dt, 0.f, action,
                                   nullptr, nullptr, workspace, stream);
+}
+
+// ---- agent-sharded symmetric evaluation ------------------------------------------------------------------------------
+// Rank g owns the 512-agent blocks [g T / G, (g+1) T / G) and evaluates the block pairs (I, I + d mod T) of its own
+// row blocks.  Row-direction sums stay local; the column-direction sums of OTHER ranks' agents are reduced per rank and
+// stored into the owner's inbox over NVLink peer memory (phase A).  After one barrier the owner's finalize kernel adds
+// the ranks' shares in rank order and pushes the new state into every rank's next-state arrays (phase B); a second
+// barrier ends the step.  Traffic per step and rank: 16 B per agent (shares) + 16 B per agent (state) to each peer.
+
+static void sym_block_bounds(int64_t T, int world, int *Ib) {
+    for (int g = 0; g <= world; ++g) Ib[g] = static_cast<int>(T * g / world);
+}
+
+extern "C" int piml_mlapm_sym_shard_rows(int64_t N, int world, int rank, int64_t *row0, int64_t *row1) {
+    PIML_REQUIRE(N > 0 && world >= 1 && world <= ML_MAX_PEERS && rank >= 0 && rank < world && row0 && row1,
+                 "piml_mlapm_sym_shard_rows: bad arguments (N=%lld, world=%d, rank=%d)", static_cast<long long>(N),
+                 world, rank);
+    const int64_t T = sym_blocks(N);
+    PIML_REQUIRE(T >= world, "piml_mlapm_sym_shard_rows: %lld blocks of %d agents cannot be split over %d ranks",
+                 static_cast<long long>(T), MS_BLOCK, world);
+    int Ib[ML_MAX_PEERS + 1];
+    sym_block_bounds(T, world, Ib);
+    *row0 = static_cast<int64_t>(Ib[rank]) * MS_BLOCK;
+    *row1 = static_cast<int64_t>(Ib[rank + 1]) * MS_BLOCK;
+    if (*row1 > N) *row1 = N;
+    return PIML_OK;
+}
+
+// Floats4 per (rank, row) slot of an inbox: the largest shard, so every rank's inbox has the same shape.
+static int64_t sym_inbox_stride(int64_t N, int world) {
+    const int64_t T = sym_blocks(N);
+    return ((T + world - 1) / world) * MS_BLOCK;
+}
+
+extern "C" int64_t piml_mlapm_sym_inbox_bytes(int64_t N, int world) {
+    if (N <= 0 || world < 1 || world > ML_MAX_PEERS) return 0;
+    return sym_inbox_stride(N, world) * world * 4 * sizeof(float);
+}
+
+extern "C" int64_t piml_mlapm_sym_shard_workspace_bytes(int64_t N, int world) {
+    if (N <= 0 || world < 1 || world > ML_MAX_PEERS) return 0;
+    const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
+    const int64_t nI = (T + world - 1) / world;
+    const int64_t per = sym_per(T), S = (D + 1 + per - 1) / per;
+    return npad * MS_RECF * sizeof(float) + (S + D) * nI * MS_BLOCK * 4 * sizeof(float) + 256;
+}
+
+struct SymShardPlan { int64_t T, D, npad, I0, nI; int per, S; float4 *rec, *partialR, *partialC; };
+
+static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64_t workspace_bytes, SymShardPlan *pl) {
+    PIML_REQUIRE(N > 0 && N < (1LL << 31) && world >= 1 && world <= ML_MAX_PEERS && rank >= 0 && rank < world,
+                 "piml_mlapm_sym: bad shard (N=%lld, world=%d, rank=%d)", static_cast<long long>(N), world, rank);
+    PIML_REQUIRE(workspace && workspace_bytes >= piml_mlapm_sym_shard_workspace_bytes(N, world),
+                 "piml_mlapm_sym: workspace of %lld bytes, need >= %lld", static_cast<long long>(workspace_bytes),
+                 static_cast<long long>(piml_mlapm_sym_shard_workspace_bytes(N, world)));
+    pl->T = sym_blocks(N);
+    PIML_REQUIRE(pl->T >= world, "piml_mlapm_sym: fewer blocks than ranks");
+    pl->D = pl->T / 2;
+    pl->npad = pl->T * MS_BLOCK;
+    int Ib[ML_MAX_PEERS + 1];
+    sym_block_bounds(pl->T, world, Ib);
+    pl->I0 = Ib[rank];
+    pl->nI = Ib[rank + 1] - Ib[rank];
+    pl->per = sym_per(pl->T);
+    pl->S = static_cast<int>((pl->D + 1 + pl->per - 1) / pl->per);
+    pl->rec = reinterpret_cast<float4 *>(workspace);
+    pl->partialR = pl->rec + pl->npad * 2;
+    pl->partialC = pl->partialR + static_cast<int64_t>(pl->S) * pl->nI * MS_BLOCK;
+    return PIML_OK;
+}
+
+extern "C" int piml_mlapm_sym_pairs_push_f32(const float *pos, const float *vel, const float *dest, int64_t N,
+                                             int world, int rank, const piml_mlapm_params *prm,
+                                             const uint64_t *peer_inbox_host, void *workspace,
+                                             int64_t workspace_bytes, void *stream) {
+    PIML_REQUIRE(pos && vel && dest && prm && peer_inbox_host, "piml_mlapm_sym_pairs_push_f32: null pointer");
+    PIML_REQUIRE(prm->version == 0 || prm->version == 1, "piml_mlapm_sym_pairs_push_f32: version %d unsupported",
+                 prm->version);
+    const MlConst k = mlapm_consts(prm);
+    PIML_REQUIRE(sym_params_ok(prm, k), "piml_mlapm_sym_pairs_push_f32: parameters outside the symmetric kernel's "
+                                         "domain (exact_math, or a weight that does not decay with distance)");
+    SymShardPlan pl;
+    int rc = sym_shard_plan(N, world, rank, workspace, workspace_bytes, &pl);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_sym_pairs(prm->version, reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel),
+                          reinterpret_cast<const float2 *>(dest), static_cast<int>(N), pl.T, pl.I0, pl.nI, pl.per, pl.S,
+                          k, pl.rec, pl.partialR, pl.partialC, st);
+    if (rc) return rc;
+    PeerInbox peers;
+    peers.world = world;
+    peers.rank = rank;
+    sym_block_bounds(pl.T, world, peers.Ib);
+    for (int g = world + 1; g <= ML_MAX_PEERS; ++g) peers.Ib[g] = peers.Ib[world];
+    peers.stride = sym_inbox_stride(N, world);
+    for (int g = 0; g < ML_MAX_PEERS; ++g) {
+        peers.inbox[g] = g < world ? reinterpret_cast<float4 *>(static_cast<uintptr_t>(peer_inbox_host[g])) : nullptr;
+        PIML_REQUIRE(g >= world || (peers.inbox[g] && (peer_inbox_host[g] & 15u) == 0),
+                     "piml_mlapm_sym_pairs_push_f32: bad inbox pointer for rank %d", g);
+    }
+    const int threads = 256;
+    mlapm_sym_colpush_kernel<<<static_cast<unsigned>((N + threads - 1) / threads), threads, 0, st>>>(
+        pl.partialC, static_cast<int>(N), static_cast<int>(pl.T), static_cast<int>(pl.D), static_cast<int>(pl.I0),
+        static_cast<int>(pl.I0 + pl.nI), peers);
+    count_launch();
+    return check_launch("mlapm_sym_colpush_kernel");
+}
+
+extern "C" int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *vel, const float *desired_speed,
+                                                int ds_dim, const float *dest, int64_t N, int world, int rank,
+                                                const piml_mlapm_params *prm, float dt, float radius,
+                                                const float *inbox_local, const uint64_t *peer_pos_next_host,
+                                                const uint64_t *peer_vel_next_host, uint8_t *arrived, void *workspace,
+                                                int64_t workspace_bytes, void *stream) {
+    PIML_REQUIRE(pos && vel && desired_speed && dest && prm && inbox_local && peer_pos_next_host && peer_vel_next_host,
+                 "piml_mlapm_sym_finalize_push_f32: null pointer");
+    PIML_REQUIRE(ds_dim == 1 || ds_dim == 2, "piml_mlapm_sym_finalize_push_f32: ds_dim=%d", ds_dim);
+    SymShardPlan pl;
+    int rc = sym_shard_plan(N, world, rank, workspace, workspace_bytes, &pl);
+    if (rc) return rc;
+    const MlConst k = mlapm_consts(prm);
+    PeerPush push;
+    push.world = world;
+    for (int g = 0; g < ML_MAX_PEERS; ++g) {
+        push.pos[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_pos_next_host[g])) : nullptr;
+        push.vel[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_vel_next_host[g])) : nullptr;
+        PIML_REQUIRE(g >= world || (push.pos[g] && push.vel[g]), "piml_mlapm_sym_finalize_push_f32: bad peer pointer");
+    }
+    const int64_t row0 = pl.I0 * MS_BLOCK;
+    int64_t row1 = (pl.I0 + pl.nI) * MS_BLOCK;
+    row1 = row1 > N ? N : row1;
+    const int64_t nrows = row1 - row0;
+    if (nrows <= 0) return PIML_OK;
+    SymPartials symp{nullptr, static_cast<int>(pl.T), static_cast<int>(pl.D), static_cast<int>(pl.I0),
+                     static_cast<int>(pl.nI * MS_BLOCK), reinterpret_cast<const float4 *>(inbox_local), world,
+                     sym_inbox_stride(N, world)};
+    const int threads = 256;
+    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0,
+                             static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel), desired_speed, ds_dim,
+        reinterpret_cast<const float2 *>(dest), static_cast<int>(row0), static_cast<int>(row1), pl.S, pl.partialR,
+        prm->A, k.cos_t, k.sin_t, prm->version, prm->tau, dt, radius, nullptr, nullptr, arrived, push, symp);
+    count_launch();
+    return check_launch("mlapm_finalize2_kernel");
 }

@@ -5,6 +5,12 @@ Instead of a separate all-gather, the finalize kernel of `piml_mlapm_advance_pus
 into EVERY rank's next-state arrays over NVLink / NVSwitch peer memory (torch symmetric memory provides the peer
 mappings), so the transfer rides on the kernel's own epilogue; a step then needs one cross-rank barrier only.
 
+`symmetric=True` (the default for crowds of >= 16 384 agents per the library's own rule): every UNORDERED pair is
+evaluated once for both rows.  Rank g then owns whole 512-agent blocks and evaluates the block pairs of its own row
+blocks; the column-direction sums that belong to other ranks' agents are reduced per rank and stored into the owners'
+inboxes by the pair stage (`piml_mlapm_sym_pairs_push_f32`), a barrier, and the owners' finalize kernel
+(`piml_mlapm_sym_finalize_push_f32`) adds the shares in rank order and pushes the new state as above.
+
 One process per GPU (`torchrun`), `torch.distributed` initialised with the NCCL backend.
 """
 import ctypes as C
@@ -41,13 +47,29 @@ def allgather_state(pos_next, vel_next, pos_rows, vel_rows, group=None):
 class ShardedCrowd(object):
     """Double-buffered crowd state in symmetric memory: buf[parity][0] = positions (N,2), buf[parity][1] = velocities."""
 
-    def __init__(self, N, group=None, device=None):
+    SYM_MIN_AGENTS = 16384
+
+    def __init__(self, N, group=None, device=None, symmetric=None):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.rows = shard_rows(N, self.world, self.rank)
-        self.N, self.shard = N, N // self.world
         self.device = device if device is not None else L.cuda_device()
+        self.N = N
+        self.symmetric = (N >= self.SYM_MIN_AGENTS) if symmetric is None else bool(symmetric)
+        if self.symmetric:
+            r0, r1 = C.c_int64(), C.c_int64()
+            L.check(L.load().piml_mlapm_sym_shard_rows(N, self.world, self.rank, C.byref(r0), C.byref(r1)),
+                    "piml_mlapm_sym_shard_rows")
+            self.rows = (int(r0.value), int(r1.value))
+            self.inbox = symm.empty((int(L.load().piml_mlapm_sym_inbox_bytes(N, self.world)) // 4,),
+                                    dtype=torch.float32, device=self.device)
+            self.inbox_hdl = symm.rendezvous(self.inbox, self.group)
+            self._inbox_tab = (C.c_uint64 * self.world)(*[int(p) for p in self.inbox_hdl.buffer_ptrs])
+            self._sym_ws = torch.empty(int(L.load().piml_mlapm_sym_shard_workspace_bytes(N, self.world)),
+                                       dtype=torch.uint8, device=self.device)
+        else:
+            self.rows = shard_rows(N, self.world, self.rank)
+        self.shard = self.rows[1] - self.rows[0]
         self.buf = symm.empty((2, 2, N, 2), dtype=torch.float32, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
@@ -84,6 +106,21 @@ class ShardedCrowd(object):
         pos_tab, vel_tab = self._tables[nxt]
         ds = desired_speed if desired_speed.dim() == 2 else desired_speed.unsqueeze(-1)
         r0, r1 = self.rows
+        if self.symmetric:
+            lib, prm, st = L.load(), model._params(), L.stream_ptr(self.device)
+            L.check(lib.piml_mlapm_sym_pairs_push_f32(
+                L.ptr(self.position), L.ptr(self.velocity), L.ptr(destination), self.N, self.world, self.rank,
+                C.byref(prm), self._inbox_tab, L.ptr(self._sym_ws), self._sym_ws.numel(), st),
+                "piml_mlapm_sym_pairs_push_f32")
+            self.hdl.barrier(channel=0)    # every rank's column-direction shares have landed in the owners' inboxes
+            L.check(lib.piml_mlapm_sym_finalize_push_f32(
+                L.ptr(self.position), L.ptr(self.velocity), L.ptr(ds), ds.shape[1], L.ptr(destination), self.N,
+                self.world, self.rank, C.byref(prm), float(dt), float(radius), L.ptr(self.inbox), pos_tab, vel_tab,
+                L.ptr(self.arrived), L.ptr(self._sym_ws), self._sym_ws.numel(), st),
+                "piml_mlapm_sym_finalize_push_f32")
+            self.hdl.barrier(channel=0)    # ... and every rank's new rows in every rank's next-state arrays
+            self.parity = nxt
+            return self.arrived.bool()
         L.check(L.load().piml_mlapm_advance_push_f32(
             L.ptr(self.position), L.ptr(self.velocity), L.ptr(ds), ds.shape[1], L.ptr(destination), self.N, r0, r1,
             C.byref(model._params()), float(dt), float(radius), self.world, pos_tab, vel_tab, L.ptr(self.arrived),

@@ -16,6 +16,8 @@ world, rank = dist.get_world_size(), dist.get_rank()
 N, steps = 8192 * world, 6
 p, v, ds, dest, _ = [x.to(dev) for x in bench.synthetic_crowd(N)]
 model = P.MLAPM(**bench.MLAPM_KW)
+from piml_b200 import _lib as L
+L.check(L.load().piml_set_mlapm_algorithm(1), "piml_set_mlapm_algorithm")      # ordered pairs: bit-identity checks
 # reference: unsharded
 pu, vu = p.clone(), v.clone()
 for _ in range(steps):
@@ -31,7 +33,7 @@ for _ in range(steps):
     dist.all_gather_into_tensor(pn2, pn); dist.all_gather_into_tensor(vn2, act)
     pa, va = pn2, vn2
 # fused push path
-crowd = ShardedCrowd(N, device=dev)
+crowd = ShardedCrowd(N, device=dev, symmetric=False)
 crowd.load(p, v)
 for _ in range(steps):
     crowd.step(model, ds, dest, bench.DT, bench.RADIUS)
@@ -42,5 +44,30 @@ dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"push exchange == NCCL all-gather == unsharded on all {world} ranks after {steps} steps: {bool(int(t))}"
           f"  (peer buffers: {len(crowd.ptrs)})")
+# symmetric (unordered-pair) evaluation, agent-sharded with the two-stage fused exchange: every rank must hold the
+# SAME state bit for bit, and it must agree with the unsharded symmetric and the ordered results to fp32 rounding
+L.check(L.load().piml_set_mlapm_algorithm(2), "piml_set_mlapm_algorithm")
+ps, vs = p.clone(), v.clone()
+for _ in range(steps):
+    act, pn, arr = model.advance(ps, vs, ds, dest, bench.DT, bench.RADIUS)
+    ps, vs = pn, act
+L.check(L.load().piml_set_mlapm_algorithm(0), "piml_set_mlapm_algorithm")
+sym = ShardedCrowd(N, device=dev, symmetric=True)
+sym.load(p, v)
+for _ in range(steps):
+    sym.step(model, ds, dest, bench.DT, bench.RADIUS)
+torch.cuda.synchronize()
+gathered = [torch.empty_like(sym.position) for _ in range(world)]
+dist.all_gather(gathered, sym.position.contiguous())
+same = all(torch.equal(g_, gathered[0]) for g_ in gathered)
+e_sym = float((sym.position - ps).norm(dim=-1).max())
+e_ord = float((sym.position - pu).norm(dim=-1).max())
+e_v = float(((sym.velocity - vu).norm(dim=-1) / vu.norm(dim=-1).clamp_min(1e-3)).max())
+ok2 = same and e_sym < 1e-4 and e_ord < 1e-4 and bool(torch.isfinite(sym.position).all())
+t2 = torch.tensor([1 if ok2 else 0], device=dev)
+dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"symmetric sharded: identical on all ranks {same}; max |dp| vs unsharded symmetric {e_sym:.2e} m, vs "
+          f"ordered {e_ord:.2e} m, max rel dv {e_v:.2e} after {steps} steps (rows of rank 0: {sym.rows}): {bool(int(t2))}")
 dist.destroy_process_group()
-sys.exit(0 if int(t) else 1)
+sys.exit(0 if int(t) and int(t2) else 1)
