@@ -206,6 +206,18 @@ PIML_API int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *vel
 PIML_API int piml_calc_acceleration_f32(const float *rel, int64_t S, int stride, int version, float A, float B, float C,
                                float D, float theta, float eps, float *out, void *stream);
 
+/* Pure social-force "model" with the model(ped, obs, self) -> [acc, ped_msgs, obs_msgs] interface of model.py:1185
+ * (BASELINE config 2).  The reference's own simulator (models.socialforce) is not shipped; this is the composition of
+ * shipped reference code that SURVEY.md 8c names: per slot the v0 repulsion of utils.py:53-58 with the ped constants
+ * (A_ped, B_ped = 8.75, -2.5 for GC; 10.67, -3.33 for UCY, utils.py:47-52) and with the obstacle constants
+ * (src/configs/socialforce.yaml:52-56: intensity 10 / radius 0.2 -> A_obs = 50, B_obs = -5), summed over slots, plus
+ * the destination term model.py:1205-1210 (tau = 0.5, socialforce.yaml:29).  ped_f (R,kp,6), obs_f (R,ko,6) or NULL
+ * with ko = 0, self_f (R,7) -> acc (R,2); ped_msgs (R,kp,2) / obs_msgs (R,ko,2) may be NULL. */
+typedef struct { float A_ped, B_ped, A_obs, B_obs, eps, tau; } piml_sfm_params;
+PIML_API int piml_sfm_forward_f32(const piml_sfm_params *prm, const float *ped_f, const float *obs_f,
+                         const float *self_f, int64_t R, int kp, int ko, float *acc, float *ped_msgs,
+                         float *obs_msgs, void *stream);
+
 /* ---- interaction networks: src/models/model.py:40-119, :720-792, :1062-1305 -------------------------------- */
 
 typedef struct {
@@ -304,7 +316,7 @@ PIML_API int piml_integrate_step_f32(float *p, float *v, float *a, const float *
 /* Everything BaseSimulator.get_multiple_rollouts' `for t in range(t_start, T)` loop touches, for S scenes of N slots
  * rolled together.  Time-major ground truth (frame t of all scenes contiguous); all pointers are device pointers. */
 typedef struct {
-    const piml_net_desc *desc;      /* network */
+    const piml_net_desc *desc;      /* network (NULL when sfm is given) */
     const float *packed;            /* piml_pinnsf_pack_f32 vector (FP32-pipe kernel), or NULL if packed_tc is given */
     const float *packed_tc;         /* piml_pinnsf_pack_tc_f32 vector (tensor-core kernel), or NULL */
     int has_obs; float tau;
@@ -321,6 +333,7 @@ typedef struct {
     float *ped_f, *obs_f, *self_f, *dest_f;                             /* features of the state at t_start, in/out */
     float *a_next;                                                      /* (S,N,2) scratch */
     float *rec_p, *rec_v, *rec_a, *rec_mask;                            /* (T,S,N,2) x3, (T,S,N): rows t >= t_start written */
+    const piml_sfm_params *sfm;     /* non-NULL: the pure social-force model replaces the network (desc, packed* unused) */
 } piml_rollout_args;
 
 /* Enqueues the whole loop (3-4 launches per step, no host synchronisation) on `stream`. */

@@ -173,6 +173,26 @@ def calc_acceleration(relative_data, equation_version="v0", dataset="gc1560", ep
     return out
 
 
+SFM_CONSTS = {"gc1560": (8.75, -2.5), "gc2344": (8.75, -2.5), "ucy": (10.67, -3.33)}     # utils.py:47-52
+
+
+def sfm_forward(ped, obs, slf, dataset="gc1560", tau=0.5, A_obs=10 / 0.2, B_obs=-1 / 0.2, eps=1e-6):
+    """The composed social-force module (tests/golden/make_golden.py: SocialForceComposed) for (N,..) inputs.
+    Returns [acc (N,2), ped_msgs (N,kp,2), obs_msgs (N,ko,2)]."""
+    ped, slf = _f32(ped), _f32(slf)
+    obs = _f32(obs) if obs is not None and np.asarray(obs).size else None
+    R, kp = ped.shape[0], ped.shape[1]
+    ko = obs.shape[1] if obs is not None else 0
+    A, B = SFM_CONSTS[dataset]
+    acc = np.empty((R, 2), np.float32)
+    pm = np.empty((R, kp, 2), np.float32)
+    om = np.empty((R, ko, 2), np.float32)
+    lib().orc_sfm_forward(_ptr(ped), _ptr(obs), _ptr(slf), C.c_int64(R), C.c_int(kp), C.c_int(ko), C.c_float(A),
+                          C.c_float(B), C.c_float(A_obs), C.c_float(B_obs), C.c_float(eps), C.c_float(tau), _ptr(acc),
+                          _ptr(pm), _ptr(om) if ko else None)
+    return [acc, pm, om]
+
+
 def net_desc(enc_dims, proc_mode, dec_dims, coll_dims, kind):
     d = NetDesc()
     d.n_enc = len(enc_dims) - 1

@@ -481,6 +481,43 @@ ORC_API void orc_pinnsf_forward(const orc_net_t *net, const float *params, int h
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Pure social-force "model" with the model(ped, obs, self) -> [acc, ped_msgs, obs_msgs] interface (BASELINE config 2,
+ * SURVEY.md 8c): per slot the v0 repulsion of utils.py:53-58 (ped constants A_p,B_p; the same form with the obstacle
+ * constants A_o,B_o of socialforce.yaml:52-56), summed over slots in slot order (torch.sum over dim -2), plus the
+ * destination term model.py:1205-1210 for (N,7) inputs.  Padded slots (dr = 0) give exactly 0.
+ * ped (R,kp,6), obs (R,ko,6) or NULL, self (R,7) -> acc (R,2), ped_msgs (R,kp,2), obs_msgs (R,ko,2) (may be NULL). */
+ORC_API void orc_sfm_forward(const float *ped, const float *obs, const float *self, int64_t R, int kp, int ko,
+                             float A_p, float B_p, float A_o, float B_o, float eps, float tau, float *acc,
+                             float *ped_msgs, float *obs_msgs) {
+    for (int64_t r = 0; r < R; ++r) {
+        float ax = 0.f, ay = 0.f, ox = 0.f, oy = 0.f;
+        for (int j = 0; j < kp; ++j) {
+            const float *f = ped + (r * kp + j) * 6;
+            float rr = norm2f(f[0], f[1]) + eps;
+            float a = A_p * expf(B_p * rr);
+            float mx = -a * (f[0] / rr), my = -a * (f[1] / rr);
+            if (ped_msgs) { ped_msgs[(r * kp + j) * 2] = mx; ped_msgs[(r * kp + j) * 2 + 1] = my; }
+            ax += mx; ay += my;
+        }
+        for (int j = 0; obs && j < ko; ++j) {
+            const float *f = obs + (r * ko + j) * 6;
+            float rr = norm2f(f[0], f[1]) + eps;
+            float a = A_o * expf(B_o * rr);
+            float mx = -a * (f[0] / rr), my = -a * (f[1] / rr);
+            if (obs_msgs) { obs_msgs[(r * ko + j) * 2] = mx; obs_msgs[(r * ko + j) * 2 + 1] = my; }
+            ox += mx; oy += my;
+        }
+        const float *s = self + r * 7;
+        float n = norm2f(s[0], s[1]);
+        if (n == 0.f) n = n + 0.1f;
+        float dxs = (s[6] * (s[0] / n) - s[2]) / tau;
+        float dys = (s[6] * (s[1] / n) - s[3]) / tau;
+        acc[2 * r] = (ax + ox) + dxs;
+        acc[2 * r + 1] = (ay + oy) + dys;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * One inference-rollout state update, simulators.py:603-639, everything except the model
  * forward and the feature rebuild.  All arrays for ONE scene of N slots.
  *   p,v,a (N,2) in/out ; a_next (N,2) model output ; dest (N,2) in/out ; dest_idx (N) in/out ; dest_num (N)

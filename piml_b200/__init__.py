@@ -6,8 +6,8 @@ include/piml_b200.h, sources in piml_b200/csrc).  There is no CPU fallback: comp
 from . import _lib
 from .features import Pedestrians, cos_threshold
 from .mlapm import MLAPM
-from .sfm import calc_acceleration
+from .sfm import SocialForce, calc_acceleration
 from . import models
 
-__all__ = ["Pedestrians", "MLAPM", "calc_acceleration", "models", "cos_threshold", "_lib"]
+__all__ = ["Pedestrians", "MLAPM", "calc_acceleration", "SocialForce", "models", "cos_threshold", "_lib"]
 __version__ = "0.1.0"

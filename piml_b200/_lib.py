@@ -38,7 +38,12 @@ class RolloutArgs(C.Structure):
                 ("entry_tm", vp), ("dest_num", vp), ("waypoints", vp), ("desired_speed", vp),
                 ("p", vp), ("v", vp), ("a", vp), ("dest", vp), ("dest_idx", vp), ("hist_v", vp),
                 ("ped_f", vp), ("obs_f", vp), ("self_f", vp), ("dest_f", vp), ("a_next", vp),
-                ("rec_p", vp), ("rec_v", vp), ("rec_a", vp), ("rec_mask", vp)]
+                ("rec_p", vp), ("rec_v", vp), ("rec_a", vp), ("rec_mask", vp), ("sfm", vp)]
+
+
+class SfmParams(C.Structure):
+    """piml_sfm_params"""
+    _fields_ = [("A_ped", f32), ("B_ped", f32), ("A_obs", f32), ("B_obs", f32), ("eps", f32), ("tau", f32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/piml_b200.h declares (tests check this).
@@ -74,6 +79,7 @@ SIGNATURES = {
     "piml_mlapm_advance_push_f32": (i32, [vp, vp, vp, i32, vp, i64, i64, i64, C.POINTER(MlapmParams), f32, f32, i32,
                                           vp, vp, vp, vp, vp]),
     "piml_calc_acceleration_f32": (i32, [vp, i64, i32, i32, f32, f32, f32, f32, f32, f32, vp, vp]),
+    "piml_sfm_forward_f32": (i32, [C.POINTER(SfmParams), vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "piml_pinnsf_packed_floats": (i64, [C.POINTER(NetDesc)]),
     "piml_pinnsf_pack_f32": (i32, [C.POINTER(NetDesc), vp, vp, vp]),
     "piml_pinnsf_forward_f32": (i32, [C.POINTER(NetDesc), vp, i32, f32, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp,

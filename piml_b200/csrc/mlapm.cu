@@ -839,18 +839,20 @@ static int g_mlapm_algorithm = 0;                 // 0 automatic, 1 ordered pair
 constexpr int64_t MS_AUTO_MIN_AGENTS = 16384;     // below this the ordered-pair kernel fills the GPU better
 
 static int64_t sym_blocks(int64_t N) { return (N + MS_BLOCK - 1) / MS_BLOCK; }
-static int sym_per(int64_t T) {                   // block pairs per CTA: >= 64 CTAs per SM (measured best at N = 100k: 2)
+// Block pairs per CTA for nI row blocks of a crowd of T blocks: >= 64 CTAs per SM (measured best at N = 100k on one
+// GPU: 2; an 8-way shard of the same crowd gets 1).
+static int sym_per(int64_t nI, int64_t T) {
     if (const char *e = getenv("PIML_MLAPM_SYM_PER")) {
         const int f = atoi(e);
         if (f >= 1) return f;
     }
-    const int64_t pairs = T * (T / 2 + 1), want = 64LL * sm_count();
+    const int64_t pairs = nI * (T / 2 + 1), want = 64LL * sm_count();
     const int64_t per = pairs / want;
     return per < 1 ? 1 : static_cast<int>(per);
 }
 static int64_t sym_workspace_bytes(int64_t N) {
     const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
-    const int64_t per = sym_per(T), S = (D + 1 + per - 1) / per;
+    const int64_t per = sym_per(T, T), S = (D + 1 + per - 1) / per;
     return npad * MS_RECF * sizeof(float) + (S + D) * npad * 4 * sizeof(float) + 256;
 }
 
@@ -985,7 +987,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) && sym_params_ok(prm, k);
     if (sym_ok && (g_mlapm_algorithm == 2 || (g_mlapm_algorithm == 0 && N >= MS_AUTO_MIN_AGENTS))) {
         const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
-        const int per = sym_per(T);
+        const int per = sym_per(T, T);
         const int S = static_cast<int>((D + 1 + per - 1) / per);
         float4 *rec = reinterpret_cast<float4 *>(workspace);
         float4 *partialR = rec + npad * 2;
@@ -1143,7 +1145,7 @@ extern "C" int64_t piml_mlapm_sym_shard_workspace_bytes(int64_t N, int world) {
     if (N <= 0 || world < 1 || world > ML_MAX_PEERS) return 0;
     const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
     const int64_t nI = (T + world - 1) / world;
-    const int64_t per = sym_per(T), S = (D + 1 + per - 1) / per;
+    const int64_t per = sym_per(nI, T), S = (D + 1 + per - 1) / per;
     return npad * MS_RECF * sizeof(float) + (S + D) * nI * MS_BLOCK * 4 * sizeof(float) + 256;
 }
 
@@ -1163,7 +1165,7 @@ static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64
     sym_block_bounds(pl->T, world, Ib);
     pl->I0 = Ib[rank];
     pl->nI = Ib[rank + 1] - Ib[rank];
-    pl->per = sym_per(pl->T);
+    pl->per = sym_per((pl->T + world - 1) / world, pl->T);
     pl->S = static_cast<int>((pl->D + 1 + pl->per - 1) / pl->per);
     pl->rec = reinterpret_cast<float4 *>(workspace);
     pl->partialR = pl->rec + pl->npad * 2;

@@ -8,7 +8,8 @@
 using namespace piml;
 
 extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
-    PIML_REQUIRE(r && r->desc && (r->packed || r->packed_tc), "piml_rollout_f32: null descriptor / parameters");
+    PIML_REQUIRE(r && (r->sfm || (r->desc && (r->packed || r->packed_tc))),
+                 "piml_rollout_f32: null descriptor / parameters");
     PIML_REQUIRE(r->S >= 1 && r->N >= 1 && r->T >= 1 && r->D >= 1 && r->M >= 0 && r->t_start >= 0 && r->t_start < r->T,
                  "piml_rollout_f32: bad dimensions S=%d N=%d T=%d D=%d M=%d t_start=%d", r->S, r->N, r->T, r->D, r->M,
                  r->t_start);
@@ -26,7 +27,10 @@ extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
     for (int t = r->t_start; t < r->T; ++t) {
         int rc;
         // a_next = model(*state_features)[0]                                               (simulators.py:602)
-        if (r->packed_tc)
+        if (r->sfm)                            // pure social-force mode (BASELINE config 2)
+            rc = piml_sfm_forward_f32(r->sfm, r->ped_f, has_obs ? r->obs_f : nullptr, r->self_f, SN, kp,
+                                      has_obs ? ko : 0, r->a_next, nullptr, nullptr, stream);
+        else if (r->packed_tc)
             rc = piml_pinnsf_forward_tc_f32(r->desc, r->packed_tc, has_obs, r->tau, r->ped_f, r->obs_f, r->self_f, SN,
                                             kp, ko, 0, r->a_next, nullptr, nullptr, stream);
         else

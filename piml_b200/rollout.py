@@ -10,6 +10,7 @@ import torch
 from . import _lib as L
 from .features import cos_threshold
 from . import models as M
+from .sfm import SfmSpec, SocialForce
 
 
 def integrate_step(p, v, a, a_next, dest, dest_idx, dest_num, waypoints, dt, remove_on_arrival=True, entry=None,
@@ -115,10 +116,15 @@ def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed
     a_next = torch.empty(S, N, 2, device=dev)
     if dnum.numel() != S * N:
         dnum = dnum.expand(S, N).contiguous()
-    desc = spec.desc()
     r = L.RolloutArgs()
-    r.desc = L.C.pointer(desc)
-    r.packed, r.packed_tc = L.ptr(packed), (L.ptr(packed_tc) if (packed_tc is not None and M.tc_enabled()) else None)
+    if isinstance(spec, SfmSpec):              # pure social-force mode (BASELINE config 2): no network
+        sfm_prm = spec.params()
+        r.sfm = L.C.cast(L.C.pointer(sfm_prm), L.C.c_void_p)
+    else:
+        desc = spec.desc()
+        r.desc = L.C.pointer(desc)
+        r.packed = L.ptr(packed)
+        r.packed_tc = L.ptr(packed_tc) if (packed_tc is not None and M.tc_enabled()) else None
     r.has_obs, r.tau = (1 if (spec.has_obs and Mo) else 0), spec.tau
     r.S, r.N, r.M, r.D, r.T, r.t_start, r.dt = S, N, Mo, wp.shape[-3], T, t_start, dt
     r.kp, r.cos_p, r.thr_p = args.topk_ped, cos_threshold(args.sight_angle_ped), float(args.dist_threshold_ped)
@@ -172,9 +178,12 @@ def get_multiple_rollouts(simulator, data, t_start=0, load_model=True, result_cl
         raise NotImplementedError("channelled rollouts: use rollout_scenes")
     dev = torch.device("cuda", torch.cuda.current_device())
     module = simulator.model.module if isinstance(simulator.model, torch.nn.DataParallel) else simulator.model
-    spec = M.spec_from_module(module)
-    packed = M.pack_device(module.state_dict(), spec, dev)
-    packed_tc = M.pack_device_tc(module.state_dict(), spec, dev)        # None if the net cannot use the tensor cores
+    if isinstance(module, SocialForce):
+        spec, packed, packed_tc = module.spec, None, None
+    else:
+        spec = M.spec_from_module(module)
+        packed = M.pack_device(module.state_dict(), spec, dev)
+        packed_tc = M.pack_device_tc(module.state_dict(), spec, dev)    # None if the net cannot use the tensor cores
     if not hasattr(args, "time_unit"):
         args.time_unit = data.time_unit
     scene = scene_from_data(data, t_start, dev)

@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by running the UNMODIFIED reference (imported from /root/reference).
 
 Run in the build container only:   python tests/golden/make_golden.py [group ...]
-Groups: features models mlapm sfm rollout training.   Output: tests/golden/*.npz (small, compressed).
+Groups: features models mlapm sfm rollout sfm_rollout training.   Output: tests/golden/*.npz (small, compressed).
 
 The reference ships no tests and no golden vectors, so these files ARE the pin: they
 hold the reference's own outputs on its own data files (GC / UCY / toy clips) and on seeded synthetic crowds.
@@ -230,7 +230,7 @@ def gen_sfm():
     save("sfm", **out)
 
 
-def rollout_case(clip, kind, dataset_name, t_start=25, seed=666, max_frames=None):
+def rollout_case(clip, kind, dataset_name, t_start=25, seed=666, max_frames=None, module=None):
     """BaseSimulator.get_multiple_rollouts (simulators.py:556-657) on a deepcopy of the clip, recording the state
     handed to get_relative_features each step (= the reference's own p/v/a/dest after update + entry)."""
     raw = H.load_raw(clip)
@@ -242,6 +242,8 @@ def rollout_case(clip, kind, dataset_name, t_start=25, seed=666, max_frames=None
     torch.manual_seed(seed)
     with H.quiet():
         sim = SIM.BaseSimulator(args)
+    if module is not None:
+        sim.model = module
     sim.model.eval()
     inp = {}
     for k in ("position", "velocity", "acceleration", "destination", "waypoints", "obstacles", "mask_p",
@@ -278,6 +280,61 @@ def rollout_case(clip, kind, dataset_name, t_start=25, seed=666, max_frames=None
     out["out/mask_p"] = res.mask_p[:T]
     out["out/dest_after_step"] = torch.stack(rec_dest, 0)     # (T - t_start, N, 2): dest_cur after step t
     return out
+
+
+class SocialForceComposed(torch.nn.Module):
+    """BASELINE config 2: the generator of data/synthetic_data/*_simulation.npy (models.socialforce) is
+    not shipped, so the pure social-force mode is pinned against a module COMPOSED OF SHIPPED REFERENCE CODE with the
+    model(ped, obs, self) -> list interface (model.py:1185):
+        ped messages   UTILS.calc_acceleration(ped_features, 'v0', dataset)        utils.py:46-58
+        obs messages   the same v0 form with the obstacle constants of socialforce.yaml:52-56
+                       (intensity 10, radius 0.2  ->  A = 10/0.2, B = -1/0.2, exactly as the shipped ped-ped constants
+                       8.75 = 3.5/0.4, -2.5 = -1/0.4 relate to that file's intensity / radius)
+        dest term      the lines model.py:1205-1210, verbatim, tau = 1/desired_speed_intensity = 0.5 (socialforce.yaml:29)
+    rolled out by the UNMODIFIED BaseSimulator.get_multiple_rollouts."""
+
+    def __init__(self, dataset, tau=0.5, A_obs=10 / 0.2, B_obs=-1 / 0.2):
+        super().__init__()
+        self.dataset, self.tau, self.A_obs, self.B_obs = dataset, tau, A_obs, B_obs
+
+    def forward(self, ped_features, obs_features, self_features):
+        ped_msgs = UTILS.calc_acceleration(ped_features, 'v0', self.dataset)
+        pred_acc_ped = torch.sum(ped_msgs, dim=-2)
+        dr = obs_features[..., 0:2]                                    # utils.py:53-58 with the obstacle constants
+        r = torch.linalg.norm(dr, ord=2, dim=-1, keepdim=True)
+        r += 1e-6
+        obs_msgs = -(self.A_obs * torch.exp(self.B_obs * r)) * (dr / r)
+        pred_acc_ped = pred_acc_ped + torch.sum(obs_msgs, dim=-2)
+        desired_speed = self_features[..., -1].unsqueeze(-1)           # model.py:1205-1210
+        temp = torch.norm(self_features[..., :2], p=2, dim=1, keepdim=True)
+        temp_ = temp.clone()
+        temp_[temp_ == 0] = temp_[temp_ == 0] + 0.1
+        dest_direction = self_features[..., :2] / temp_
+        pred_acc_dest = (desired_speed * dest_direction - self_features[..., 2:4]) / self.tau
+        return [pred_acc_ped + pred_acc_dest, ped_msgs, obs_msgs]
+
+
+def sfm_rollout_case(clip, dataset_name, t_start):
+    """get_multiple_rollouts of the composed social-force module from the clip's own state at t_start."""
+    out = rollout_case(clip, "pinnsf_bm", dataset_name, t_start=t_start, module=SocialForceComposed(dataset_name))
+    out = {k: v for k, v in out.items() if not k.startswith("sd/")}
+    out["in/model"] = np.array("sfm")
+    out["in/tau"] = np.float64(0.5)
+    out["in/sfm_consts"] = np.array([8.75, -2.5, 10 / 0.2, -1 / 0.2, 1e-6], np.float64)   # A_p, B_p, A_o, B_o, eps
+    # one forward of the module on the features of frame 300, all three outputs
+    raw = H.load_raw(clip)
+    data = H.make_time_indexed(H.default_args(dataset_name=dataset_name), raw)
+    with torch.no_grad():
+        res = SocialForceComposed(dataset_name)(data.ped_features[300].clone(), data.obs_features[300].clone(),
+                                                data.self_features[300].clone())
+    out["fwd/ped"], out["fwd/obs"], out["fwd/self"] = data.ped_features[300], data.obs_features[300], \
+        data.self_features[300]
+    out["fwd/acc"], out["fwd/ped_msgs"], out["fwd/obs_msgs"] = res
+    return out
+
+
+def gen_sfm_rollout():
+    save("rollout_syn_sfm", **sfm_rollout_case(H.SYN_CLIP, "gc1560", 25))
 
 
 def gen_rollout():
@@ -422,7 +479,7 @@ def gen_training():
 
 
 GROUPS = {"features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
-          "rollout": gen_rollout, "training": gen_training}
+          "rollout": gen_rollout, "sfm_rollout": gen_sfm_rollout, "training": gen_training}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GROUPS)

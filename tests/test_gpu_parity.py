@@ -541,3 +541,80 @@ def test_rollout_free_running(name):
     assert np.array_equal(np.isnan(p_res[:first]), np.isnan(o["position"][:first]))
     assert np.nanmax(drift[:first]) < 1e-4
     assert np.nanmax(drift) < 0.5
+
+
+# ---- pure social-force mode (BASELINE config 2) ------------------------------------------------------------------------
+def test_sfm_forward_golden_and_oracle():
+    """piml_b200.SocialForce against the composed reference module's own outputs and the oracle."""
+    import piml_b200 as P
+    g = group(golden("rollout_syn_sfm"), "fwd")
+    net = P.SocialForce("gc1560")
+    acc, pm, om = net(cu(g["ped"]), cu(g["obs"]), cu(g["self"]))
+    assert rel_vec_err(npy(pm), g["ped_msgs"], floor=1e-4) < TOL
+    assert rel_vec_err(npy(om), g["obs_msgs"], floor=1e-4) < TOL
+    assert np.array_equal(npy(pm) == 0, g["ped_msgs"] == 0) and np.array_equal(npy(om) == 0, g["obs_msgs"] == 0)
+    assert accel_err(npy(acc), g["acc"], g["self"], 0.5) < TOL
+    want = O.sfm_forward(g["ped"], g["obs"], g["self"], "gc1560")
+    assert accel_err(npy(acc), want[0], g["self"], 0.5) < TOL
+    # host tensors in -> host tensors out, scene-batched leading dimension
+    acc2 = net(torch.from_numpy(g["ped"])[None], torch.from_numpy(g["obs"])[None], torch.from_numpy(g["self"])[None])[0]
+    assert not acc2.is_cuda and np.array_equal(acc2[0].numpy(), npy(acc))
+
+
+def _sfm_scene(i):
+    scene = {k: cu(i[k])[None] for k in ("position", "velocity", "acceleration", "destination", "waypoints",
+                                          "mask_p", "mask_p_pred", "desired_speed")}
+    scene["dest_idx"] = cu(i["dest_idx"], torch.int64)[None]
+    scene["dest_num"] = cu(i["dest_num"], torch.int64)[None]
+    scene["obstacles"] = cu(i["obstacles"])
+    for k in ("ped_features0", "obs_features0", "self_features0"):
+        scene[k] = cu(i[k])[None]
+    return scene
+
+
+def test_sfm_rollout_resynchronised_steps():
+    """From the reference's recorded state at t (composed social-force module rolled out by the unmodified
+    get_multiple_rollouts, synthetic GC clip, 725 steps): feature rebuild + SFM forward reproduce a[t+1] within 1e-5
+    (the state update itself is covered bit for bit by test_integrate_resynchronised_steps on the other clips and by
+    the oracle test of this clip)."""
+    import piml_b200 as P
+    from piml_b200.rollout import state_features
+    z = golden("rollout_syn_sfm")
+    i, o = group(z, "in"), group(z, "out")
+    T, t0, dt = int(i["num_frames"]), int(i["t_start"]), float(i["time_unit"])
+    net = P.SocialForce("gc1560")
+    P_, V_, A_ = cu(o["position"]), cu(o["velocity"]), cu(o["acceleration"])
+    flag = (i["mask_p"] - i["mask_p_pred"]).astype(np.int64)
+    ds, obs = cu(i["desired_speed"])[None], cu(i["obstacles"])
+    worst = 0.0
+    for t in range(t0 + 1, T - 1, 7):
+        p, v, a = P_[t][None].clone(), V_[t][None].clone(), A_[t][None].clone()
+        dest = cu(o["dest_after_step"][t - t0 - 1])[None]
+        ped_f, obs_f, self_f = state_features(p, v, a, dest, obs, v.clone(), ds, 6, 90, 4, 10, 90, 4)
+        acc = net(ped_f[0], obs_f[0], self_f[0])[0]
+        sim = flag[t + 1] == 0
+        worst = max(worst, accel_err(npy(acc)[sim], o["acceleration"][t + 1][sim], npy(self_f[0])[sim], 0.5))
+    assert worst < TOL, worst
+
+
+def test_sfm_rollout_free_running():
+    """BASELINE config 2: the whole 725-step pure social-force rollout in one C call against the reference's run of
+    the composed module: arrival / entry pattern (mask_p, NaNs) identical, drift reported."""
+    import piml_b200 as P
+    from piml_b200.rollout import rollout_scenes
+    from tests.golden_args import base_args
+    z = golden("rollout_syn_sfm")
+    i, o = group(z, "in"), group(z, "out")
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    args = base_args(model="sfm", dataset_name="gc1560", time_unit=float(i["time_unit"]))
+    net = P.SocialForce("gc1560")
+    before = P._lib.launch_count()
+    p_res, v_res, a_res, mask = rollout_scenes(net.spec, None, args, _sfm_scene(i), t0, T)
+    assert P._lib.launch_count() - before >= 3 * (T - t0)
+    p_res, v_res, mask = npy(p_res[0]), npy(v_res[0]), npy(mask[0])
+    assert np.array_equal(mask, o["mask_p"])
+    assert np.array_equal(np.isnan(p_res), np.isnan(o["position"]))
+    drift = np.linalg.norm(p_res - o["position"], axis=-1)
+    print(f"rollout_syn_sfm: max drift {np.nanmax(drift):.3e} m, mean {np.nanmean(drift):.3e} m over {T - t0} steps")
+    assert np.nanmax(drift[:t0 + 26]) < 1e-4
+    assert np.nanmax(drift) < 0.05

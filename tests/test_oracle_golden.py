@@ -179,3 +179,45 @@ def test_rollout_resynchronised_network_output(name):
         sim = flag[t + 1] == 0
         worst = max(worst, accel_err(acc[sim], o["acceleration"][t + 1][sim], slf[sim], spec.tau))
     assert worst < 1e-5, worst
+
+
+# ---- pure social-force mode (BASELINE config 2) ------------------------------------------------------------------------
+def test_sfm_forward_matches_composed_reference_module():
+    g = group(golden("rollout_syn_sfm"), "fwd")
+    acc, pm, om = O.sfm_forward(g["ped"], g["obs"], g["self"], "gc1560")
+    assert rel_vec_err(pm, g["ped_msgs"], floor=1e-4) < 1e-5
+    assert rel_vec_err(om, g["obs_msgs"], floor=1e-4) < 1e-5
+    assert np.array_equal(pm == 0, g["ped_msgs"] == 0) and np.array_equal(om == 0, g["obs_msgs"] == 0)
+    assert accel_err(acc, g["acc"], g["self"], 0.5) < 1e-5
+
+
+def test_sfm_rollout_resynchronised():
+    """From the reference's recorded state at t: oracle features + oracle social-force module reproduce a[t+1], and
+    one oracle state update reproduces p, v at t+1 bit for bit (the composed module rolled out by the unmodified
+    get_multiple_rollouts on the synthetic clip, 725 steps)."""
+    z = golden("rollout_syn_sfm")
+    i, o = group(z, "in"), group(z, "out")
+    T, t0, dt = int(i["num_frames"]), int(i["t_start"]), float(i["time_unit"])
+    assert str(i["model"]) == "sfm" and T == 750
+    flag = (i["mask_p"] - i["mask_p_pred"]).astype(np.int64)
+    P, V, A = o["position"], o["velocity"], o["acceleration"]
+    dest = i["destination"][t0].copy()
+    didx = i["dest_idx"][t0].astype(np.int64)
+    worst = 0.0
+    for t in range(t0, T - 1):
+        p, v, a, dest, didx, hist = O.integrate_step(
+            P[t], V[t], A[t], A[t + 1], dest, didx, i["dest_num"], i["waypoints"], dt, True, flag[t + 1],
+            i["position"][t + 1], i["velocity"][t + 1], i["acceleration"][t + 1], i["destination"][t + 1],
+            i["dest_idx"][t + 1].astype(np.int64))
+        assert np.array_equal(p, P[t + 1], equal_nan=True), t
+        assert np.array_equal(v, V[t + 1]), t
+        assert np.array_equal(dest, o["dest_after_step"][t - t0], equal_nan=True), t
+        if t > t0 and (t - t0) % 12 == 0:
+            pp, vv, aa = P[t][None], V[t][None].copy(), A[t][None].copy()
+            d_prev = o["dest_after_step"][t - t0 - 1][None]
+            pf, of, df = O.relative_features(pp, vv, aa, d_prev, i["obstacles"])
+            slf = np.concatenate([df[0], vv[0], aa[0], i["desired_speed"][:, None]], -1)
+            acc = O.sfm_forward(pf[0], of[0], slf, "gc1560")[0]
+            sim = flag[t + 1] == 0
+            worst = max(worst, accel_err(acc[sim], A[t + 1][sim], slf[sim], 0.5))
+    assert worst < 1e-5, worst
