@@ -39,6 +39,22 @@ for name in ("rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"):
         lines.append(f"| {name} | {label} | {T - t0} | {mx(1):.2e} / {mx(10):.2e} / {mx(100):.2e} / {mx(300):.2e} / "
                      f"{np.nanmax(drift):.2e} | {end_mean:.2e} | {np.array_equal(mask, o['mask_p'])} | "
                      f"{np.array_equal(np.isnan(p_res), np.isnan(o['position']))} |")
+# pure social-force rollout (BASELINE config 2): the composed reference module on the synthetic clip
+import piml_b200 as P                                         # noqa: E402
+from tests.golden_args import base_args                       # noqa: E402
+from tests.test_gpu_parity import _sfm_scene                  # noqa: E402
+from tests.util import golden, group                          # noqa: E402
+z = golden("rollout_syn_sfm")
+i, o = group(z, "in"), group(z, "out")
+T, t0 = int(i["num_frames"]), int(i["t_start"])
+args = base_args(model="sfm", dataset_name="gc1560", time_unit=float(i["time_unit"]))
+p_res, v_res, a_res, mask = rollout_scenes(P.SocialForce("gc1560").spec, None, args, _sfm_scene(i), t0, T)
+p_res, mask = npy(p_res[0]), npy(mask[0])
+drift = np.linalg.norm(p_res - o["position"], axis=-1)
+mx = lambda k: np.nanmax(drift[:min(T - 1, t0 + k) + 1])
+lines.append(f"| rollout_syn_sfm (pure social force) | sfm_forward_kernel | {T - t0} | {mx(1):.2e} / {mx(10):.2e} / "
+             f"{mx(100):.2e} / {mx(300):.2e} / {np.nanmax(drift):.2e} | {np.nanmean(drift[np.isfinite(drift).any(1)][-1]):.2e} | "
+             f"{np.array_equal(mask, o['mask_p'])} | {np.array_equal(np.isnan(p_res), np.isnan(o['position']))} |")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "rollout_drift.md"), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
