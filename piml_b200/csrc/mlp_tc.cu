@@ -201,6 +201,13 @@ struct TcArgs {
     float *sums; float *ped_msgs; float *obs_msgs;
     long long *prof;                               // optional cycle counters of CTA 0 (bring-up only)
     int dbg;                                       // timing experiments only (PIML_TC_DEBUG): 1 = skip epilogue math, 2 = one MMA term
+    // Compact mode (kind 0): zero-padded slot rows all produce the same message f(0), so only the non-zero rows (+ one
+    // zero row per branch that yields f(0)) go through the network; the slot sums are formed by the finish kernel.
+    int compact; int has_obs;
+    const int *list_ped, *list_obs;                // indices of the non-zero slot rows of each branch
+    const int *counts;                             // [2] their number (written by tc_compact_kernel)
+    float *cmsg_ped, *cmsg_obs;                    // per-row messages (R*kp,2), (R*ko,2): non-zero rows are written
+    float *f0;                                     // [2][2] message of a zero row per branch
 };
 
 // mbarrier wait that can never hang the GPU: a protocol bug traps (launch error) after ~seconds instead of spinning.
@@ -242,20 +249,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
     }
     for (int e = tid; e < 2 * P.bias_floats; e += TC_THREADS) {
         const int br = e / P.bias_floats, i = e - br * P.bias_floats;
-        biasb[e] = (br == 0 || a.n_obs_tiles > 0) ? a.params[P.b_off[br] + i] : 0.f;
+        biasb[e] = (br == 0 || a.has_obs) ? a.params[P.b_off[br] + i] : 0.f;
     }
+    // compact mode: rows = the listed non-zero rows followed by ONE zero row (index -1) per branch
+    const int64_t cnt_ped = a.compact ? a.counts[0] + 1 : 0, cnt_obs = (a.compact && a.has_obs) ? a.counts[1] + 1 : 0;
+    const int64_t n_ped_tiles = a.compact ? (cnt_ped + 127) / 128 : a.n_ped_tiles;
+    const int64_t n_obs_tiles = a.compact ? (cnt_obs + 127) / 128 : a.n_obs_tiles;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
-    const int64_t ntiles = a.n_ped_tiles + a.n_obs_tiles;
+    const int64_t ntiles = n_ped_tiles + n_obs_tiles;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t pc = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int br = tile < a.n_ped_tiles ? 0 : 1;
+                const int br = tile < n_ped_tiles ? 0 : 1;
                 const float *wbase = a.params + P.w_off[br];
                 for (int c = 0; c < P.nch; ++c, ++pc) {
                     const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
@@ -330,20 +341,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
         float *stg = stage + half * 128 * TC_STAGE_LD;
         uint32_t dph = 0;                                          // phase bit per d_ready barrier
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int br = tile < a.n_ped_tiles ? 0 : 1;
+            const int br = tile < n_ped_tiles ? 0 : 1;
             const int k = br == 0 ? a.kp : a.ko;
             const int AG = br == 0 ? a.ag_ped : a.ag_obs;
-            const int64_t agent0 = (br == 0 ? tile : tile - a.n_ped_tiles) * AG;
-            const int na = static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
-            const int nrows = na * k;
+            const int64_t tloc = br == 0 ? tile : tile - n_ped_tiles;
+            const int64_t agent0 = tloc * AG;
+            const int na = a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
+            const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
+            const int nrows = a.compact ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
             const int64_t row0 = agent0 * k;
+            // compact mode: the slot row this tile row stands for (-1: the zero row that yields f(0))
+            int64_t crow = -1;
+            if (a.compact && m < nrows && tloc * 128 + m < cnt - 1) crow = (br == 0 ? a.list_ped : a.list_obs)[tloc * 128 + m];
             const float *bb = biasb + br * P.bias_floats;
             if (half == 0) {   // stage the 6-d features of this row as the first A operand (K padded to 8 with zeros)
                 uint32_t hi[8], lo[8];
-                const float *f = (br == 0 ? a.ped : a.obs) + (row0 + m) * 6;
+                const float *f = (br == 0 ? a.ped : a.obs) + (a.compact ? (crow < 0 ? 0 : crow) : row0 + m) * 6;
+                const bool live = a.compact ? crow >= 0 : m < nrows;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float x = (q < 6 && m < nrows) ? f[q] : 0.f;
+                    const float x = (q < 6 && live) ? f[q] : 0.f;
                     tc::split_tf32(x, hi[q], lo[q]);
                 }
                 tc::st8(tl + TC_COL_AH, hi);
@@ -419,7 +436,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
             if (half == 0) {
                 m0 = small[m * 2] + small[(128 + m) * 2] + bb[P.predb_off];
                 m1 = small[m * 2 + 1] + small[(128 + m) * 2 + 1] + bb[P.predb_off + 1];
-                if (P.kind == 0) {
+                if (P.kind == 0 && a.compact) {
+                    if (m < nrows) {                               // slot sums are formed by the finish kernel
+                        float *dst = crow >= 0 ? (br == 0 ? a.cmsg_ped : a.cmsg_obs) + crow * 2 : a.f0 + br * 2;
+                        dst[0] = m0; dst[1] = m1;
+                    }
+                } else if (P.kind == 0) {
                     float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
                     if (msgs_out && m < nrows) { msgs_out[(row0 + m) * 2] = m0; msgs_out[(row0 + m) * 2 + 1] = m1; }
                     half_barrier(0);                               // every partial read before the totals overwrite
@@ -598,6 +620,69 @@ __global__ void tc_colnorm_kernel(const float *__restrict__ self, int group, flo
     for (int i = threadIdx.x; i < group; i += blockDim.x) { dnorm[(base + i) * 2] = n0; dnorm[(base + i) * 2 + 1] = n1; }
 }
 
+// Compact mode, pass 1: list the slot rows that are not all-zero (warp-aggregated append; a row's message does not
+// depend on its place in a tile, so the order is irrelevant) and flag the zero rows for the finish kernel.
+__global__ void tc_compact_kernel(const float *__restrict__ ped, const float *__restrict__ obs, int64_t rows_ped,
+                                  int64_t rows_obs, int *__restrict__ list_ped, int *__restrict__ list_obs,
+                                  int *__restrict__ counts, uint8_t *__restrict__ zero_ped,
+                                  uint8_t *__restrict__ zero_obs) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int br = i < rows_ped ? 0 : 1;
+    const int64_t r = br == 0 ? i : i - rows_ped;
+    const bool in = i < rows_ped + rows_obs;
+    bool nz = false;
+    if (in) {
+        const float2 *f = reinterpret_cast<const float2 *>((br == 0 ? ped : obs) + r * 6);
+        const float2 a = f[0], b = f[1], c = f[2];
+        nz = !(a.x == 0.f && a.y == 0.f && b.x == 0.f && b.y == 0.f && c.x == 0.f && c.y == 0.f);
+        (br == 0 ? zero_ped : zero_obs)[r] = nz ? 0 : 1;
+    }
+    // a warp may straddle the two branches: append per branch
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2) {
+        const unsigned mask = __ballot_sync(0xffffffffu, in && nz && br == b2);
+        if (!mask) continue;
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&counts[b2], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (in && nz && br == b2) (b2 == 0 ? list_ped : list_obs)[base + __popc(mask & ((1u << lane) - 1))] = static_cast<int>(r);
+    }
+}
+
+// Compact mode, finish: acc = sum over the k slots (in slot order, f(0) for the zero rows) of both branches + the
+// destination term -- the same additions in the same order as the in-tile sums of the dense mode.
+__global__ void pinnsf_tc_finish_compact_kernel(const float *__restrict__ cmsg_ped, const float *__restrict__ cmsg_obs,
+                                                const uint8_t *__restrict__ zero_ped,
+                                                const uint8_t *__restrict__ zero_obs, const float *__restrict__ f0,
+                                                const float *__restrict__ self, const float *__restrict__ dnorm,
+                                                int64_t R, int kp, int ko, int has_obs, float tau,
+                                                float *__restrict__ acc) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= 2 * R) return;
+    const int64_t ag = i >> 1;
+    const int c = static_cast<int>(i & 1);
+    const float *s = self + ag * 7;
+    float nrm = dnorm ? dnorm[ag * 2 + c] : norm2_rn(s[0], s[1]);
+    if (nrm == 0.f) nrm = __fadd_rn(nrm, 0.1f);
+    const float dir = __fdiv_rn(s[c], nrm);
+    const float dterm = __fdiv_rn(__fsub_rn(__fmul_rn(s[6], dir), s[2 + c]), tau);
+    float mm = 0.f;
+    for (int j = 0; j < kp; ++j) {
+        const int64_t r = ag * kp + j;
+        mm += zero_ped[r] ? f0[c] : cmsg_ped[r * 2 + c];
+    }
+    if (has_obs) {
+        float mo = 0.f;
+        for (int j = 0; j < ko; ++j) {
+            const int64_t r = ag * ko + j;
+            mo += zero_obs[r] ? f0[2 + c] : cmsg_obs[r * 2 + c];
+        }
+        mm = __fadd_rn(mm, mo);
+    }
+    acc[i] = __fadd_rn(mm, dterm);
+}
+
 struct TcScratch { cudaStream_t st; int dev; float *buf; int64_t cap; };
 static int tc_scratch_get(cudaStream_t st, int64_t floats, float **out) {
     static thread_local TcScratch slots[8] = {};
@@ -666,7 +751,17 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     if (R == 0) return PIML_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *scratch = nullptr;
-    rc = tc_scratch_get(st, R * 4 + (norm_group > 0 ? R * 2 : 0), &scratch);
+    // compact mode: network kind 0, messages not requested (PIML_TC_COMPACT=0 disables it)
+    static const bool compact_env = [] { const char *e = getenv("PIML_TC_COMPACT"); return !(e && atoi(e) == 0); }();
+    // (a scene whose dense tiles fit one wave gains nothing from it and would pay two more launches)
+    const int64_t dense_tiles = (R + 128 / kp - 1) / (128 / kp) + ((has_obs && ko) ? (R + 128 / ko - 1) / (128 / ko) : 0);
+    const bool compact = compact_env && P.kind == 0 && !ped_msgs && !obs_msgs && dense_tiles > sm_count() &&
+                         R * static_cast<int64_t>(kp > ko ? kp : ko) < (1LL << 31);
+    const int64_t rows_ped = R * kp, rows_obs = has_obs ? R * ko : 0, rows_all = rows_ped + rows_obs;
+    // scratch (floats): sums R*4 | dnorm R*2 | messages rows_all*2 | lists rows_all | f0 4 + counts 2 (+2 pad) | flags
+    const int64_t f_sums = R * 4, f_norm = norm_group > 0 ? R * 2 : 0;
+    const int64_t f_extra = compact ? rows_all * 2 + rows_all + 8 + (rows_all + 3) / 4 + 4 : 0;
+    rc = tc_scratch_get(st, f_sums + f_norm + f_extra, &scratch);
     if (rc) return rc;
     const float *dnorm = nullptr;
     if (norm_group > 0) {
@@ -686,6 +781,26 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     a.sums = scratch; a.ped_msgs = ped_msgs; a.obs_msgs = has_obs ? obs_msgs : nullptr;
     a.dbg = 0;
     a.prof = nullptr;
+    a.compact = compact ? 1 : 0;
+    a.has_obs = has_obs ? 1 : 0;
+    a.list_ped = a.list_obs = nullptr; a.counts = nullptr; a.cmsg_ped = a.cmsg_obs = a.f0 = nullptr;
+    uint8_t *zero_ped = nullptr, *zero_obs = nullptr;
+    if (compact) {
+        float *x = scratch + f_sums + f_norm;
+        a.cmsg_ped = x; a.cmsg_obs = x + rows_ped * 2; x += rows_all * 2;
+        int *lists = reinterpret_cast<int *>(x); x += rows_all;
+        a.list_ped = lists; a.list_obs = lists + rows_ped;
+        a.f0 = x; int *counts = reinterpret_cast<int *>(x + 4); x += 8;
+        a.counts = counts;
+        zero_ped = reinterpret_cast<uint8_t *>(x); zero_obs = zero_ped + rows_ped;
+        PIML_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+        const int threads = 256;
+        tc_compact_kernel<<<static_cast<unsigned>((rows_all + threads - 1) / threads), threads, 0, st>>>(
+            ped, obs, rows_ped, rows_obs, lists, lists + rows_ped, counts, zero_ped, zero_obs);
+        count_launch();
+        rc = check_launch("tc_compact_kernel");
+        if (rc) return rc;
+    }
     if (const char *e = getenv("PIML_TC_DEBUG")) a.dbg = atoi(e);
     if (getenv("PIML_TC_PROF")) {
         static long long *prof_buf = nullptr;
@@ -701,7 +816,9 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
         attr_set = true;
     }
     PIML_REQUIRE(smem <= 216 * 1024, "piml_pinnsf_forward_tc_f32: network too large for the shared-memory plan");
-    const int64_t tiles = a.n_ped_tiles + a.n_obs_tiles;
+    // compact mode: the tile count is only known on the device (at most (rows + 1) / 128 + 1 per branch)
+    const int64_t tiles = compact ? (rows_ped + 128) / 128 + (has_obs ? (rows_obs + 128) / 128 : 0)
+                                  : a.n_ped_tiles + a.n_obs_tiles;
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     pinnsf_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, a);
     count_launch();
@@ -717,6 +834,12 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
         fprintf(stderr, "\n");
     }
     const int threads = 256;
+    if (compact) {
+        pinnsf_tc_finish_compact_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
+            a.cmsg_ped, a.cmsg_obs, zero_ped, zero_obs, a.f0, self, dnorm, R, kp, ko, has_obs, tau, acc);
+        count_launch();
+        return check_launch("pinnsf_tc_finish_compact_kernel");
+    }
     pinnsf_tc_finish_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
         scratch, self, dnorm, R, has_obs, tau, acc);
     count_launch();

@@ -446,6 +446,42 @@ def test_pinnsf_forward_tensor_cores_vs_fp32_kernel(kind, R, kp, ko, chan, has_o
             assert float((got[2] - ref[2]).abs().max()) < TOL * float(ref[2].abs().max())
 
 
+@pytest.mark.parametrize("R,kp,ko,pz,chan", [(3001, 6, 10, 0.6, 0), (700, 6, 10, 1.0, 0), (129, 6, 10, 0.0, 0),
+                                             (5000, 6, 0, 0.3, 0), (1280, 4, 7, 0.8, 5)])
+def test_tensor_core_compact_mode_is_bit_identical(R, kp, ko, pz, chan):
+    """Zero-padded slot rows all yield the same message f(0) (model.py:1188-1194 does not mask them), so the tensor-core
+    forward only runs the non-zero rows (+ one zero row per branch) when no per-slot output is requested.  A row's
+    result does not depend on its place in a tile and the slot sums are formed in the same order, so the acceleration
+    must be BIT-identical to the dense evaluation (which the messages request forces)."""
+    from piml_b200 import models as M
+    from .golden_args import base_args
+    has_obs = ko > 0
+    args = base_args(model="pinnsf_bottleneck", dataset_name="gc1560", obs_feature_dim=6 if has_obs else 0)
+    torch.manual_seed(R)
+    net = M.CLASSES["pinnsf_bottleneck"](args).cuda().eval()
+    g = torch.Generator().manual_seed(R + 7)
+    lead = (chan, R // chan) if chan else (R,)
+    ped = torch.randn(*lead, kp, 6, generator=g)
+    ped[torch.rand(*lead, kp, generator=g) < pz] = 0
+    obs = torch.randn(*lead, max(ko, 1), 6, generator=g)[..., :ko, :]
+    if ko:
+        obs[torch.rand(*lead, ko, generator=g) < pz] = 0
+    ped.view(-1, kp, 6)[:3] = 0                                # whole agents without neighbours
+    slf = torch.randn(*lead, 7, generator=g)
+    ped, obs, slf = ped.cuda(), obs.cuda(), slf.cuda()
+    packed = M.pack_device(net.state_dict(), net.spec)
+    ptc = M.pack_device_tc(net.state_dict(), net.spec)
+    assert ptc is not None
+    dense = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True, packed_tc=ptc)
+    compact = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=False, packed_tc=ptc)
+    assert torch.equal(dense[0], compact[0])
+    again = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=False, packed_tc=ptc)
+    assert torch.equal(again[0], compact[0])                   # independent of the (atomic) row order
+    ref = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True)
+    err = accel_err(npy(compact[0]).reshape(-1, 2), npy(ref[0]).reshape(-1, 2), npy(slf).reshape(-1, 7), net.spec.tau)
+    assert err < TOL, err
+
+
 # ---- integrator ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
 def test_integrate_step_golden(name):
