@@ -90,6 +90,17 @@ PIML_API int piml_state_features_f32(const float *pos, float *vel, float *acc, c
                             const float *desired_speed, float *ped_f, float *obs_f, float *self_f, float *dest_f,
                             void *stream);
 
+/* piml_state_features_f32 for the rows [row0,row1) of ONE scene of N slots against all N agents and M obstacles
+ * (agent-sharded crowd): ped_f (row1-row0,kp,6), obs_f, self_f (row1-row0,7), dest_f (row1-row0,2) hold
+ * only those rows.  pos / vel / acc / dest / hist_v / desired_speed are the WHOLE scene (every rank keeps all of it);
+ * the in-place NaN -> 0 of data.py:483-484 is applied to all N rows so that the replicas stay identical.
+ * Always the cell-list evaluation (needs finite distance thresholds); identical results to the unsharded call. */
+PIML_API int piml_state_features_rows_f32(const float *pos, float *vel, float *acc, const float *dest, const float *obs,
+                                 int N, int M, int64_t row0, int64_t row1, int kp, float cos_thr_ped,
+                                 float dist_thr_ped, int ko, float cos_thr_obs, float dist_thr_obs,
+                                 const float *hist_v, const float *desired_speed, float *ped_f, float *obs_f,
+                                 float *self_f, float *dest_f, void *stream);
+
 /* Pedestrians.calculate_collision_label (data.py:515-535). ped_f (S,6) -> out (S) in {0,1}. */
 PIML_API int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream);
 

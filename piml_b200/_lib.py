@@ -59,6 +59,8 @@ SIGNATURES = {
                                          f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_state_features_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, vp, vp,
                                       vp, vp, vp, vp, vp]),
+    "piml_state_features_rows_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i64, i64, i32, f32, f32, i32, f32, f32, vp,
+                                           vp, vp, vp, vp, vp, vp]),
     "piml_collision_label_f32": (i32, [vp, i64, vp, vp]),
     "piml_set_feature_algorithm": (i32, [i32]),
     "piml_free_workspace": (i32, []),

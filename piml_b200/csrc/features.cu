@@ -428,7 +428,7 @@ static int relative_features_impl(const float *pos, float *vel, float *acc, cons
                                           float cos_thr_obs, float dist_thr_obs, float *ped_f, float *obs_f,
                                           float *dest_f, int64_t *ped_idx, float *ped_dist, int64_t *obs_idx,
                                           float *obs_dist, const float *hist_v, const float *desired_speed,
-                                          float *self_f, void *stream) {
+                                          float *self_f, void *stream, int64_t row0 = 0, int64_t row1 = 0) {
     PIML_REQUIRE(pos && vel && acc && dest && ped_f && dest_f, "piml_relative_features_f32: null pointer");
     PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0 && M >= 0 && kp >= 0 && ko >= 0,
                  "piml_relative_features_f32: negative dimension");
@@ -450,11 +450,17 @@ static int relative_features_impl(const float *pos, float *vel, float *acc, cons
     a.ped_f = ped_f; a.obs_f = obs_f; a.dest_f = dest_f;
     a.ped_idx = ped_idx; a.ped_dist = ped_dist; a.obs_idx = obs_idx; a.obs_dist = obs_dist;
     a.hist_v = hist_v; a.desired_speed = desired_speed; a.self_f = self_f;
+    a.row0 = row0; a.row1 = row1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // large crowds: uniform-grid cell list (identical neighbour set, see features_cells.cu); small scenes: all pairs
     const int algo = g_feature_algo.load(std::memory_order_relaxed);
     const float thr_max = fmaxf(dist_thr_ped, M > 0 ? dist_thr_obs : 0.f);
     const bool cells_ok = thr_max > 0.f && thr_max < 1e18f;
+    if (row1 > 0) {
+        PIML_REQUIRE(0 <= row0 && row0 < row1 && row1 <= B * N, "piml_state_features_rows_f32: bad row range");
+        PIML_REQUIRE(cells_ok, "piml_state_features_rows_f32: row ranges need a finite distance threshold (cell list)");
+        return relative_features_cells(a, obs_per_channel ? C : 1, st);
+    }
     if (cells_ok && (algo == 2 || (algo == 0 && N >= CELLS_MIN_AGENTS)))
         return relative_features_cells(a, obs_per_channel ? C : 1, st);
     const int G = pick_group(B, N);
@@ -485,6 +491,18 @@ extern "C" int piml_state_features_f32(const float *pos, float *vel, float *acc,
     return relative_features_impl(pos, vel, acc, dest, nullptr, obs, obs_per_scene, S, 1, N, M, kp, cos_thr_ped,
                                   dist_thr_ped, ko, cos_thr_obs, dist_thr_obs, ped_f, obs_f, dest_f, nullptr,
                                   nullptr, nullptr, nullptr, hist_v, desired_speed, self_f, stream);
+}
+
+extern "C" int piml_state_features_rows_f32(const float *pos, float *vel, float *acc, const float *dest,
+                                            const float *obs, int N, int M, int64_t row0, int64_t row1, int kp,
+                                            float cos_thr_ped, float dist_thr_ped, int ko, float cos_thr_obs,
+                                            float dist_thr_obs, const float *hist_v, const float *desired_speed,
+                                            float *ped_f, float *obs_f, float *self_f, float *dest_f, void *stream) {
+    PIML_REQUIRE(hist_v && desired_speed && self_f, "piml_state_features_rows_f32: null pointer");
+    PIML_REQUIRE(row1 > row0, "piml_state_features_rows_f32: empty row range");
+    return relative_features_impl(pos, vel, acc, dest, nullptr, obs, 0, 1, 1, N, M, kp, cos_thr_ped, dist_thr_ped, ko,
+                                  cos_thr_obs, dist_thr_obs, ped_f, obs_f, dest_f, nullptr, nullptr, nullptr, nullptr,
+                                  hist_v, desired_speed, self_f, stream, row0, row1);
 }
 
 extern "C" int piml_collision_label_f32(const float *ped_f, int64_t S, float *out, void *stream) {

@@ -160,8 +160,24 @@ __device__ __forceinline__ void scan_cells(TopK<KMAX> &best, const HashGrid &g, 
 template <int KP, int KO>
 __global__ void __launch_bounds__(CELL_THREADS) features_cells_kernel(FeatArgs a, HashGrid gp, HashGrid go,
                                                                       double inv_cs) {
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (row >= static_cast<int64_t>(a.B) * a.N) return;
+    const int64_t all_rows = static_cast<int64_t>(a.B) * a.N;
+    const int64_t first = a.row1 > 0 ? a.row0 : 0, last = a.row1 > 0 ? a.row1 : all_rows;
+    if (a.row1 > 0) {
+        // a row range leaves the other rows' velocities / accelerations to other ranks, but every rank keeps the whole
+        // state: apply the in-place NaN -> 0 of data.py:483-484 to ALL rows so that the replicas stay identical
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < all_rows;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            if (i >= first && i < last) continue;
+            const float2 vi = reinterpret_cast<const float2 *>(a.vel)[i], ai = reinterpret_cast<const float2 *>(a.acc)[i];
+            if (vi.x != vi.x || vi.y != vi.y)
+                reinterpret_cast<float2 *>(a.vel)[i] = make_float2(nan_to_zero(vi.x), nan_to_zero(vi.y));
+            if (ai.x != ai.x || ai.y != ai.y)
+                reinterpret_cast<float2 *>(a.acc)[i] = make_float2(nan_to_zero(ai.x), nan_to_zero(ai.y));
+        }
+    }
+    const int64_t row = first + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= last) return;
+    const int64_t orow = row - first;                               // where this row's outputs go
     const int b = static_cast<int>(row / a.N);
     const float2 p = reinterpret_cast<const float2 *>(a.pos)[row];
     float2 v = reinterpret_cast<const float2 *>(a.vel)[row];
@@ -207,20 +223,20 @@ __global__ void __launch_bounds__(CELL_THREADS) features_cells_kernel(FeatArgs a
                 f1 = make_float2(__fsub_rn(nan_to_zero(vm.x), v.x), __fsub_rn(nan_to_zero(vm.y), v.y));
                 f2 = make_float2(__fsub_rn(nan_to_zero(am.x), ac.x), __fsub_rn(nan_to_zero(am.y), ac.y));
             }
-            float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + j) * 3;
+            float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (orow * a.kp + j) * 3;
             out[0] = f0; out[1] = f1; out[2] = f2;
-            if (a.ped_idx) a.ped_idx[row * a.kp + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
-            if (a.ped_dist) a.ped_dist[row * a.kp + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+            if (a.ped_idx) a.ped_idx[orow * a.kp + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+            if (a.ped_dist) a.ped_dist[orow * a.kp + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
         }
     }
     // ---- destination ----
     {
         const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
         const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
-        reinterpret_cast<float2 *>(a.dest_f)[row] = df;
+        reinterpret_cast<float2 *>(a.dest_f)[orow] = df;
         if (a.self_f) {
             const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
-            float *sf = a.self_f + row * 7;
+            float *sf = a.self_f + orow * 7;
             sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
             sf[6] = a.desired_speed[row];
         }
@@ -243,10 +259,10 @@ __global__ void __launch_bounds__(CELL_THREADS) features_cells_kernel(FeatArgs a
                 f1 = make_float2(__fsub_rn(0.f, v.x), __fsub_rn(0.f, v.y));
                 f2 = make_float2(__fsub_rn(0.f, ac.x), __fsub_rn(0.f, ac.y));
             }
-            float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + j) * 3;
+            float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (orow * a.ko + j) * 3;
             out[0] = f0; out[1] = f1; out[2] = f2;
-            if (a.obs_idx) a.obs_idx[row * a.ko + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
-            if (a.obs_dist) a.obs_dist[row * a.ko + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
+            if (a.obs_idx) a.obs_idx[orow * a.ko + j] = (w != EMPTY_KEY) ? key_idx(w) : -1;
+            if (a.obs_dist) a.obs_dist[orow * a.ko + j] = (w != EMPTY_KEY) ? key_dist(w) : CUDART_INF_F;
         }
     }
 }
@@ -361,7 +377,7 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st) 
         if (rc) return rc;
         ho = HashGrid{go.H, obs_frames, a.M, go.start, go.rec};
     }
-    const int64_t rows = static_cast<int64_t>(a.B) * a.N;
+    const int64_t rows = a.row1 > 0 ? a.row1 - a.row0 : static_cast<int64_t>(a.B) * a.N;
     const unsigned blocks = static_cast<unsigned>((rows + CELL_THREADS - 1) / CELL_THREADS);
     if (a.kp <= 8 && a.ko <= 16) features_cells_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);
     else if (a.kp <= 16 && a.ko <= 16) features_cells_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);

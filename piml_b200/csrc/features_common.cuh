@@ -77,6 +77,9 @@ struct FeatArgs {
     int64_t *ped_idx; float *ped_dist; int64_t *obs_idx; float *obs_dist;
     // optional rollout extras: self_f (B,N,7) = [dest_f, hist_v, acceleration, desired_speed]  (simulators.py:651)
     const float *hist_v; const float *desired_speed; float *self_f;
+    // row range of the flattened (B*N) rows this call evaluates (agent-sharded ranks): outputs are indexed by
+    // row - row0; row1 == 0 means all rows.  Cell-list evaluation only.
+    int64_t row0, row1;
 };
 
 // slack so that sqrtf(d2) <= thr  =>  d2 <= pre2 for every fp32 d2 (prefilter must be a superset)

@@ -128,3 +128,77 @@ class ShardedCrowd(object):
         self.hdl.barrier(channel=0)        # every rank's rows have landed in every rank's next-state arrays
         self.parity = nxt
         return self.arrived.bool()
+
+
+class ShardedNNCrowd(object):
+    """Agent-sharded NN-augmented (or pure social-force) rollout of ONE large scene: the loop body of
+    `get_multiple_rollouts` (simulators.py:602-652) with rank g computing rows [g N/G, (g+1) N/G).
+
+    Every rank keeps the whole state.  Per step: feature rebuild of the OWN rows against all agents
+    (`piml_state_features_rows_f32`, cell list) -> network forward of the own rows -> the path's one exchange, an
+    all-gather of the new accelerations (8 B per agent -- the only quantity a rank cannot compute for rows it does not
+    own) -> the cheap elementwise state update (Euler / arrival / waypoints, `piml_integrate_step_f32`) replicated on
+    every rank, which keeps the replicas bit-identical without exchanging positions and velocities.
+    Works on NCCL; results are bit-identical to the unsharded step sequence (`scripts/check_nn_sharded.py`)."""
+
+    def __init__(self, model, args, N, obstacles, group=None, device=None):
+        from . import models as M
+        from .sfm import SocialForce
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = device if device is not None else L.cuda_device()
+        self.N, self.rows = N, shard_rows(N, self.world, self.rank)
+        self.args, self.model = args, model
+        self.sfm = isinstance(model, SocialForce)
+        if not self.sfm:
+            self.spec = model.spec if hasattr(model, "spec") else M.spec_from_module(model)
+            self.packed = M.pack_device(model.state_dict(), self.spec, self.device)
+            self.packed_tc = M.pack_device_tc(model.state_dict(), self.spec, self.device)
+        self.obstacles = L.f32c(obstacles.to(self.device))
+        self.Mo = self.obstacles.shape[-2] if self.obstacles.numel() else 0
+        n = self.rows[1] - self.rows[0]
+        kp, ko = min(args.topk_ped, N), (min(args.topk_obs, self.Mo) if self.Mo else 0)
+        dev = self.device
+        self.ped_f, self.obs_f = torch.empty(n, kp, 6, device=dev), torch.empty(n, ko, 6, device=dev)
+        self.self_f, self.dest_f = torch.empty(n, 7, device=dev), torch.empty(n, 2, device=dev)
+        self.a_next = torch.empty(1, N, 2, device=dev)
+
+    def load(self, position, velocity, acceleration, destination, dest_idx, dest_num, waypoints, desired_speed,
+             hist_v=None):
+        """Every rank passes the whole initial state: (N,2) x4, dest_idx / dest_num (N) int64, waypoints (D,N,2),
+        desired_speed (N)."""
+        dv = lambda x, dt=torch.float32: x.to(self.device, dt).contiguous()
+        self.p, self.v, self.a, self.dest = [dv(x)[None].clone() for x in (position, velocity, acceleration,
+                                                                           destination)]
+        self.didx, self.dnum = dv(dest_idx, torch.int64)[None].clone(), dv(dest_num, torch.int64)[None].clone()
+        self.wp, self.ds = dv(waypoints)[None].clone(), dv(desired_speed).reshape(1, self.N).clone()
+        self.hist = (dv(hist_v)[None] if hist_v is not None else self.v).clone()
+        self._features()
+
+    def _features(self):
+        from .features import cos_threshold
+        a, (r0, r1) = self.args, self.rows
+        L.check(L.load().piml_state_features_rows_f32(
+            L.ptr(self.p), L.ptr(self.v), L.ptr(self.a), L.ptr(self.dest), L.ptr(self.obstacles) if self.Mo else None,
+            self.N, self.Mo, r0, r1, a.topk_ped, cos_threshold(a.sight_angle_ped), float(a.dist_threshold_ped),
+            a.topk_obs, cos_threshold(a.sight_angle_obs), float(a.dist_threshold_obs), L.ptr(self.hist),
+            L.ptr(self.ds), L.ptr(self.ped_f), L.ptr(self.obs_f) if self.Mo else None, L.ptr(self.self_f),
+            L.ptr(self.dest_f), L.stream_ptr(self.device)), "piml_state_features_rows_f32")
+
+    def step(self, dt=None, remove_on_arrival=True):
+        """One rollout step; afterwards .p / .v / .a hold the new state of ALL agents on every rank."""
+        from . import models as M
+        from .rollout import integrate_step
+        dt = float(self.args.time_unit if dt is None else dt)
+        if self.sfm:
+            a_own = self.model(self.ped_f, self.obs_f, self.self_f)[0]
+        else:
+            a_own = M.pinnsf_forward(self.spec, self.packed, self.ped_f, self.obs_f, self.self_f, need_msgs=False,
+                                     packed_tc=self.packed_tc)[0]
+        if self.world > 1:                   # the path's one exchange: 8 B per agent
+            dist.all_gather_into_tensor(self.a_next.view(self.N, 2), a_own.contiguous(), group=self.group)
+        else:
+            self.a_next.view(self.N, 2).copy_(a_own)
+        integrate_step(self.p, self.v, self.a, self.a_next, self.dest, self.didx, self.dnum, self.wp, dt,
+                       remove_on_arrival, hist_v=self.hist)
+        self._features()
