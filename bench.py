@@ -243,6 +243,7 @@ def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
                         processor_hidden_layers=16, decoder_hidden_layers=2, ped_feature_dim=6, obs_feature_dim=6,
                         self_feature_dim=7, topk_ped=6, topk_obs=10, sight_angle_ped=90, sight_angle_obs=90,
                         dist_threshold_ped=4, dist_threshold_obs=4, time_unit=DT)
+    crowd, err = None, ""
     try:
         torch.manual_seed(666)
         net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
@@ -250,6 +251,15 @@ def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
         crowd = ShardedNNCrowd(net, args, N, obs_h.to(dev), device=dev)
         crowd.load(p, v, torch.zeros_like(v), dest, torch.zeros(N, dtype=torch.int64),
                    torch.ones(N, dtype=torch.int64), dest[None], ds)
+        with torch.no_grad():
+            crowd.step(remove_on_arrival=False) if world == 1 else None
+    except Exception as e:
+        crowd, err = None, f"{type(e).__name__}: {e}"[:300]
+    ok = torch.tensor([1 if crowd is not None else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # all ranks take the collective steps, or none does
+    if int(ok) == 0:
+        return {"error": err or "setup failed on another rank"}
+    try:
         with torch.no_grad():
             for _ in range(3):
                 crowd.step(remove_on_arrival=False)
