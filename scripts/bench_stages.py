@@ -136,6 +136,39 @@ def main():
             ms = timeit(lambda: rollout_scenes(net.spec, packed, rargs, scene, 0, T2, packed_tc=tc), iters=3, warm=1)
             out["rollout_S%d_N%d_T%d_%s" % (S2, Ns, T2, "tcgen05" if tc is not None else "fp32pipe")] = {
                 "ms_per_step": ms / T2, "agent_steps_per_s": S2 * Ns * T2 / ms * 1e3}
+        if S2 in (1, 64):                                   # BASELINE config 2: the pure social-force model
+            sf_spec = P.SocialForce("gc1560").spec
+            ms = timeit(lambda: rollout_scenes(sf_spec, None, rargs, scene, 0, T2), iters=3, warm=1)
+            out["rollout_S%d_N%d_T%d_socialforce" % (S2, Ns, T2)] = {
+                "ms_per_step": ms / T2, "agent_steps_per_s": S2 * Ns * T2 / ms * 1e3}
+    # f-1: the feature build of make_dataset over a whole GC-sized clip (data.py:766-771; 7.2 s in the reference)
+    T3 = 750
+    g = torch.Generator().manual_seed(5)
+    Pc = (torch.rand(T3, Ns, 2, generator=g) * 20).to(dev)
+    Pc[:, 30:] = float('nan')
+    Vc, Ac = torch.randn(T3, Ns, 2, generator=g).to(dev), torch.zeros(T3, Ns, 2, device=dev)
+    Dc = (torch.rand(T3, Ns, 2, generator=g) * 20).to(dev)
+    ms = timeit(lambda: ped.get_relative_features(Pc, Vc, Ac, Dc, ob, *fargs), iters=5)
+    out["make_dataset_features_T%d_N%d_M%d" % (T3, Ns, Mo)] = {"ms": ms, "agent_steps_per_s": T3 * Ns / ms * 1e3}
+    # training: forward + backward of one batch (single-step training, simulators.py:327-360; batch 128 as main.py,
+    # and the 32 x 144 agent rows of one UCY rollout-training step)
+    for kind, cls in (("pinnsf_m", M.PINNSF_multitask), ("pinnsf_bm", M.PINNSF_bottleneck_multitask)):
+        targs = bm_args()
+        targs.model = kind
+        torch.manual_seed(666)
+        tnet = cls(targs).to(dev).train()
+        for Bt in (128, 4608):
+            g = torch.Generator().manual_seed(Bt)
+            tp = torch.randn(Bt, 6, 6, generator=g).to(dev)
+            to = torch.randn(Bt, 10, 6, generator=g).to(dev)
+            ts = torch.randn(Bt, 7, generator=g).to(dev)
+
+            def train_step():
+                tnet.zero_grad(set_to_none=True)
+                res = tnet(tp, to, ts)
+                (res[0].square().sum() + res[-1].sum()).backward()
+            ms = timeit(train_step, iters=10)
+            out["train_fwd_bwd_%s_B%d" % (kind, Bt)] = {"ms": ms, "rows_per_s": Bt / ms * 1e3}
     print(json.dumps(out, indent=1))
 
 
