@@ -37,7 +37,7 @@ MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
 DT, RADIUS = 0.08, 0.3
 FLUSH_MB = 160                 # L2 is 126 MB
 MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ordered-pair kernel: ncu --set full, N = 100k (profiles/r01b_...)
-MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 3558144 + 138325248  # symmetric kernel (profiles/r01c_ncu_mlapm_sym_kernel.txt)
+MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 3592704 + 178046720  # symmetric kernel (profiles/r01c_ncu_mlapm_sym_kernel.txt)
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -459,7 +459,7 @@ def run_ours(a):
                          "note": "achieved = 51 algorithmic FLOP per ORDERED pair (SURVEY 8d) x N^2 / kernel time.  "
                                  "The symmetric kernel evaluates the n<->m-symmetric part of the formula once per "
                                  "unordered pair, so it executes fewer FLOP than the algorithmic count and the "
-                                 "fraction can exceed 1; ncu: FMA pipe 66.5 % busy, MUFU 47 % "
+                                 "fraction can exceed 1; ncu: FMA pipe 67.4 % busy, MUFU 47 %, ALU 33 % "
                                  "(profiles/r01c_ncu_mlapm_sym_kernel.txt)",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",

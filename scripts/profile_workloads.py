@@ -32,8 +32,11 @@ def main():
     model = P.MLAPM(**bench.MLAPM_KW)
     torch.manual_seed(666)
     net = M.PINNSF_bottleneck_multitask(bm_args()).to(dev).train()
+    packed = M.pack_device(net.state_dict(), net.spec, dev)
+    packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)
+    sfm = P.SocialForce("gc1560")
     for _ in range(a.reps):
-        model.advance(p, v, ds, dest, bench.DT, bench.RADIUS)                       # mlapm_pairs2_kernel
+        model.advance(p, v, ds, dest, bench.DT, bench.RADIUS)                       # mlapm_sym_kernel
         for algo in (1, 2):                                                         # relative_features / cells
             L.check(L.load().piml_set_feature_algorithm(algo), "algo")
             feats = ped.get_relative_features(p[None], v[None], acc[None], dest[None], obs, *fargs)
@@ -42,6 +45,9 @@ def main():
         with torch.no_grad():
             net.eval()
             net(feats[0][0], feats[1][0], slf)                                      # pinnsf_tile_kernel (inference)
+            M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False,
+                             packed_tc=packed_tc)                                   # pinnsf_tc_kernel (compact mode)
+            sfm(feats[0][0], feats[1][0], slf)                                      # sfm_forward_kernel
         net.train()
         out = net(feats[0][0], feats[1][0], slf)                                    # pinnsf_tile_kernel (+ stash)
         (out[0].sum() + out[1].sum() + out[3].sum()).backward()                     # pinnsf_bwd_tile / dw kernels
