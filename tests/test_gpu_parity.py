@@ -654,3 +654,50 @@ def test_sfm_rollout_free_running():
     print(f"rollout_syn_sfm: max drift {np.nanmax(drift):.3e} m, mean {np.nanmean(drift):.3e} m over {T - t0} steps")
     assert np.nanmax(drift[:t0 + 26]) < 1e-4
     assert np.nanmax(drift) < 0.05
+
+
+# ---- agent-sharded NN step: row-range features ---------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,rows", [(5000, 300, (1234, 3001)), (4099, 0, (0, 17)), (9000, 2000, (8000, 9000))])
+def test_state_features_row_range_matches_full_call(N, M, rows):
+    """piml_state_features_rows_f32 (what a rank of an agent-sharded crowd calls for its own rows) returns exactly the
+    rows of the unsharded call, and applies the in-place NaN -> 0 of data.py:483-484 to ALL rows so that every rank's
+    copy of the state stays the same."""
+    from piml_b200 import _lib as L
+    from piml_b200.features import cos_threshold
+    from piml_b200.rollout import state_features
+    rng = np.random.default_rng(N + M)
+    side = np.sqrt(N / 0.5)
+    p = (rng.random((1, N, 2)) * side).astype(np.float32)
+    p[0, rng.random(N) < 0.05] = np.nan                               # absent agents
+    v = rng.normal(0, 1, (1, N, 2)).astype(np.float32)
+    v[0, rng.random(N) < 0.03] = np.nan
+    a = rng.normal(0, 1, (1, N, 2)).astype(np.float32)
+    a[0, rng.random(N) < 0.03] = np.nan
+    d = (rng.random((1, N, 2)) * side).astype(np.float32)
+    obs = (rng.random((M, 2)) * side).astype(np.float32)
+    ds = np.full((1, N), 1.3, np.float32)
+    L.check(L.load().piml_set_feature_algorithm(2), "piml_set_feature_algorithm")
+    try:
+        vf, af = cu(v), cu(a)
+        pf, of, sf = state_features(cu(p), vf, af, cu(d), cu(obs), vf.clone(), cu(ds), 6, 90, 4, 10, 90, 4)
+    finally:
+        L.check(L.load().piml_set_feature_algorithm(0), "piml_set_feature_algorithm")
+    r0, r1 = rows
+    n = r1 - r0
+    kp, ko = min(6, N), min(10, M)
+    vr, ar = cu(v), cu(a)
+    hist = vr.clone()
+    ped_f, obs_f = torch.empty(n, kp, 6).cuda(), torch.empty(n, max(ko, 1), 6).cuda()
+    self_f, dest_f = torch.empty(n, 7).cuda(), torch.empty(n, 2).cuda()
+    pos, dst, ob, dsp = cu(p), cu(d), cu(obs), cu(ds)
+    L.check(L.load().piml_state_features_rows_f32(
+        L.ptr(pos), L.ptr(vr), L.ptr(ar), L.ptr(dst), L.ptr(ob) if M else None, N, M, r0, r1, 6, cos_threshold(90), 4.0,
+        10, cos_threshold(90), 4.0, L.ptr(hist), L.ptr(dsp), L.ptr(ped_f), L.ptr(obs_f) if M else None, L.ptr(self_f),
+        L.ptr(dest_f), L.stream_ptr(pos.device)), "piml_state_features_rows_f32")
+    assert torch.equal(ped_f, pf[0, r0:r1])
+    if M:
+        assert torch.equal(obs_f[:, :ko], of[0, r0:r1])
+    # self_f holds hist_v, which was captured before the NaN -> 0 (NaN == NaN is False): compare bitwise
+    assert torch.equal(self_f.view(torch.int32), sf[0, r0:r1].contiguous().view(torch.int32))
+    assert torch.equal(vr.view(torch.int32), vf.view(torch.int32)) and torch.equal(ar.view(torch.int32), af.view(torch.int32))
+    assert not torch.isnan(vr).any() and not torch.isnan(ar).any()
