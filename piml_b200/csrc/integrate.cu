@@ -4,9 +4,7 @@
 // (reference src/models/simulators.py:596-639, ~25 eager launches and 5 host syncs per step) by one kernel: record
 // the state at t, lagged explicit Euler, arrival / waypoint switch, removal on arrival, teacher-forced entry and the
 // history-velocity update.  One thread per (scene, slot); state is read and written once.
-#include <math_constants.h>
-
-#include "common.cuh"
+#include "integrate_common.cuh"
 
 namespace piml {
 
@@ -27,20 +25,11 @@ __global__ void integrate_kernel(IntArgs g) {
     if (g.rec_v) g.rec_v[i] = v;
     if (g.rec_a) g.rec_a[i] = a;
     if (g.rec_mask && !(p.x != p.x)) g.rec_mask[i] = 1.0f;
-    // v_next = v + a*dt ; p_next = p + v*dt  with the OLD a and v   (simulators.py:603-604)
-    float2 vn = make_float2(__fadd_rn(v.x, __fmul_rn(a.x, g.dt)), __fadd_rn(v.y, __fmul_rn(a.y, g.dt)));
-    float2 pn = make_float2(__fadd_rn(p.x, __fmul_rn(v.x, g.dt)), __fadd_rn(p.y, __fmul_rn(v.y, g.dt)));
-    float2 an = g.a_next[i];
-    float2 d = g.dest[i];
-    int64_t di = g.dest_idx[i];
-    const float dis = norm2_rn(__fsub_rn(p.x, d.x), __fsub_rn(p.y, d.y));      // :608
-    if (dis < 0.5f) di += 1;                                                   // :609
-    if (di > g.dest_num[i] - 1) {
-        if (g.remove_on_arrival) pn = make_float2(CUDART_NAN_F, CUDART_NAN_F); // :611
-        di -= 1;                                                               // :613
-    }
-    d = g.waypoints[(static_cast<int64_t>(s) * g.D + di) * g.N + n];           // :614-616
-    float2 hv = vn;                                                            // :624-626
+    AgentState st{p, v, a, g.dest[i], g.dest_idx[i], make_float2(0.f, 0.f)};
+    integrate_update(st, g.a_next[i], g.dt, g.remove_on_arrival, g.dest_num[i],
+                     g.waypoints + static_cast<int64_t>(s) * g.D * g.N + n, g.N);
+    float2 pn = st.p, vn = st.v, an = st.a, d = st.dest, hv = st.hv;
+    int64_t di = st.di;
     if (g.entry && g.entry[i] == 1) {                                          // :629-639
         pn = g.p_gt[i]; vn = g.v_gt[i]; an = g.a_gt[i]; d = g.dest_gt[i]; di = g.dest_idx_gt[i];
         hv = vn;

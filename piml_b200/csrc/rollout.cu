@@ -5,6 +5,11 @@
 // step t+1 are queued while step t runs.
 #include "common.cuh"
 
+namespace piml {
+bool sfm_rollout_fits(const piml_rollout_args *r);                 // rollout_sfm.cu
+int sfm_rollout_launch(const piml_rollout_args *r, cudaStream_t st);
+}  // namespace piml
+
 using namespace piml;
 
 extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
@@ -24,6 +29,8 @@ extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
     const int kp = r->kp < r->N ? r->kp : r->N;
     const int ko = r->M > 0 ? (r->ko < r->M ? r->ko : r->M) : 0;
     const int has_obs = (r->has_obs && ko > 0) ? 1 : 0;
+    // pure social-force model on GC-shaped scenes: the whole loop in one persistent kernel (rollout_sfm.cu)
+    if (r->sfm && sfm_rollout_fits(r)) return sfm_rollout_launch(r, static_cast<cudaStream_t>(stream));
     for (int t = r->t_start; t < r->T; ++t) {
         int rc;
         // a_next = model(*state_features)[0]                                               (simulators.py:602)

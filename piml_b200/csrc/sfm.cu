@@ -1,6 +1,6 @@
 // sfm.cu -- social-force pairwise repulsion per neighbour slot for sm_100a.
 // Replaces UTILS.calc_acceleration (reference src/utils/utils.py:31-100).
-#include "common.cuh"
+#include "sfm_common.cuh"
 
 namespace piml {
 
@@ -35,12 +35,6 @@ __global__ void calc_acceleration_kernel(const float *__restrict__ rel, int64_t 
 
 // Pure social-force "model" (BASELINE config 2): v0 repulsion per ped / obstacle slot (utils.py:53-58), slot sums,
 // destination term (model.py:1205-1210).  One thread per agent: 16 slots x 8 B + 28 B read, 8 B written (+ messages).
-__device__ __forceinline__ float2 sfm_v0(float dx, float dy, float A, float B, float eps) {
-    const float r = __fadd_rn(norm2_rn(dx, dy), eps);                          // r += eps        (utils.py:56)
-    const float a = __fmul_rn(A, expf(__fmul_rn(B, r)));                       // A*exp(B*r)      (:57)
-    return make_float2(__fmul_rn(-a, __fdiv_rn(dx, r)), __fmul_rn(-a, __fdiv_rn(dy, r)));   // -acc * dr/r   (:58-59)
-}
-
 __global__ void sfm_forward_kernel(const float *__restrict__ ped, const float *__restrict__ obs,
                                    const float *__restrict__ self, int64_t R, int kp, int ko, piml_sfm_params c,
                                    float2 *__restrict__ acc, float2 *__restrict__ ped_msgs,
@@ -61,11 +55,7 @@ __global__ void sfm_forward_kernel(const float *__restrict__ ped, const float *_
         ox = __fadd_rn(ox, m.x); oy = __fadd_rn(oy, m.y);
     }
     const float *s = self + r * 7;
-    float n = norm2_rn(s[0], s[1]);
-    if (n == 0.f) n = 0.1f;                                                    // temp_[temp_ == 0] += 0.1   (:1208)
-    const float dxs = __fdiv_rn(__fsub_rn(__fmul_rn(s[6], __fdiv_rn(s[0], n)), s[2]), c.tau);
-    const float dys = __fdiv_rn(__fsub_rn(__fmul_rn(s[6], __fdiv_rn(s[1], n)), s[3]), c.tau);
-    acc[r] = make_float2(__fadd_rn(__fadd_rn(ax, ox), dxs), __fadd_rn(__fadd_rn(ay, oy), dys));
+    acc[r] = sfm_total(ax, ay, ox, oy, s[0], s[1], s[2], s[3], s[6], c.tau);
 }
 
 }  // namespace piml

@@ -646,7 +646,7 @@ def test_sfm_rollout_free_running():
     net = P.SocialForce("gc1560")
     before = P._lib.launch_count()
     p_res, v_res, a_res, mask = rollout_scenes(net.spec, None, args, _sfm_scene(i), t0, T)
-    assert P._lib.launch_count() - before >= 3 * (T - t0)
+    assert P._lib.launch_count() - before >= 1
     p_res, v_res, mask = npy(p_res[0]), npy(v_res[0]), npy(mask[0])
     assert np.array_equal(mask, o["mask_p"])
     assert np.array_equal(np.isnan(p_res), np.isnan(o["position"]))
@@ -701,3 +701,54 @@ def test_state_features_row_range_matches_full_call(N, M, rows):
     assert torch.equal(self_f.view(torch.int32), sf[0, r0:r1].contiguous().view(torch.int32))
     assert torch.equal(vr.view(torch.int32), vf.view(torch.int32)) and torch.equal(ar.view(torch.int32), af.view(torch.int32))
     assert not torch.isnan(vr).any() and not torch.isnan(ar).any()
+
+
+@pytest.mark.parametrize("S", [1, 5])
+def test_sfm_persistent_rollout_kernel_matches_per_step_path(S):
+    """The persistent one-launch rollout kernel (rollout_sfm.cu) against the three-launches-per-step route of
+    piml_rollout_f32: every recorded p, v, a and mask bit for bit, for S scenes (the golden clip and jittered copies)."""
+    import os
+    import piml_b200 as P
+    from piml_b200.rollout import rollout_scenes
+    from tests.golden_args import base_args
+    z = golden("rollout_syn_sfm")
+    i, o = group(z, "in"), group(z, "out")
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    T = min(T, t0 + 260)
+    args = base_args(model="sfm", dataset_name="gc1560", time_unit=float(i["time_unit"]))
+    scene = _sfm_scene(i)
+    if S > 1:
+        g = torch.Generator().manual_seed(S)
+        rep = {}
+        for k, v in scene.items():
+            if k == "obstacles":
+                rep[k] = v
+                continue
+            v = v.expand(S, *v.shape[1:]).clone()
+            if k == "position":
+                v = v + 0.05 * torch.randn(v.shape, generator=g).to(v.device)          # NaNs stay NaN
+            rep[k] = v
+        scene = rep
+        from piml_b200.rollout import state_features
+        fargs = (args.topk_ped, args.sight_angle_ped, args.dist_threshold_ped, args.topk_obs, args.sight_angle_obs,
+                 args.dist_threshold_obs)
+        v0 = scene["velocity"][:, t0].contiguous()
+        pf, of, sf = state_features(scene["position"][:, t0].contiguous(), v0, scene["acceleration"][:, t0].contiguous(),
+                                    scene["destination"][:, t0].contiguous(), scene["obstacles"], v0.clone(),
+                                    scene["desired_speed"], *fargs)
+        scene["ped_features0"], scene["obs_features0"], scene["self_features0"] = pf, of, sf
+    spec = P.SocialForce("gc1560").spec
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["PIML_SFM_PERSISTENT"] = mode
+        try:
+            before = P._lib.launch_count()
+            outs[mode] = [npy(x) for x in rollout_scenes(spec, None, args, scene, t0, T)]
+            launches = P._lib.launch_count() - before
+        finally:
+            os.environ.pop("PIML_SFM_PERSISTENT", None)
+        assert (launches == 1) if mode == "1" else (launches >= 3 * (T - t0))
+    for a_, b_ in zip(outs["1"], outs["0"]):
+        assert np.array_equal(a_, b_, equal_nan=True)
+    if S == 1:
+        assert np.array_equal(outs["1"][3][0], o["mask_p"][:T])
