@@ -752,3 +752,76 @@ def test_sfm_persistent_rollout_kernel_matches_per_step_path(S):
         assert np.array_equal(a_, b_, equal_nan=True)
     if S == 1:
         assert np.array_equal(outs["1"][3][0], o["mask_p"][:T])
+
+
+def test_predicate_arithmetic_against_torch_primitives_gpu():
+    """SURVEY.md A.2b row 1 on the CUDA path: the k smallest gated distances of get_nearby_obj_in_sight on random pairs
+    incl. zero / huge / tiny / inf / NaN coordinates equal torch's CPU norm + cosine_similarity bit for bit."""
+    import piml_b200 as P
+    rng = np.random.default_rng(11)
+    N, M, k = 256, 4096, 32
+    pos = rng.normal(0, 3, (1, N, 2)).astype(np.float32)
+    obj = rng.normal(0, 3, (1, M, 2)).astype(np.float32)
+    obj[0, :64] = pos[0, :64]
+    obj[0, 64:96] *= 1e18
+    obj[0, 96:128] *= 1e-30
+    obj[0, 128:140] = np.nan
+    obj[0, 140:150, 0] = np.inf
+    pos[0, -3:] = np.nan
+    head = rng.normal(0, 1, (1, N, 2)).astype(np.float32)
+    head[0, :16] = 0.0
+    for angle in (90, 100):
+        dist, idx = P.Pedestrians().get_nearby_obj_in_sight(cu(pos), cu(obj), cu(head), k, angle)
+        p, o, h = torch.from_numpy(pos), torch.from_numpy(obj), torch.from_numpy(head)
+        rel = o[:, None, :, :] - p[:, :, None, :]
+        rel[torch.isnan(rel)] = float('inf')
+        d = torch.norm(rel, p=2, dim=-1)
+        cos = torch.cosine_similarity(rel, h[:, :, None, :].expand_as(rel), dim=-1)
+        cos[torch.isnan(cos)] = -1
+        d[cos < torch.tensor(np.float32(np.cos(3.14 * angle / 180)))] = float('inf')
+        want = torch.sort(d, dim=-1)[0][..., :k].numpy()
+        assert np.array_equal(npy(dist).view(np.uint32), want.view(np.uint32)), angle
+
+
+@pytest.mark.parametrize("model", ["sfm", "pinnsf_bm"])
+def test_scene_sharded_rollouts_equal_the_unsharded_batch(model):
+    """SURVEY.md A.2b multi-GPU row, scene parallelism: rolling S scenes together and rolling two halves of them
+    separately (what two ranks do, no communication) give bit-identical trajectories."""
+    import os
+    import piml_b200 as P
+    from piml_b200 import models as M
+    from piml_b200.rollout import rollout_scenes, state_features
+    from tests.golden_args import base_args
+    z = golden("rollout_syn_sfm")
+    i = group(z, "in")
+    T, t0, S = 60 + int(i["t_start"]), int(i["t_start"]), 6
+    args = base_args(model="pinnsf_bm", dataset_name="gc1560", time_unit=float(i["time_unit"]))
+    scene = _sfm_scene(i)
+    g = torch.Generator().manual_seed(9)
+    rep = {}
+    for k_, v in scene.items():
+        if k_ == "obstacles":
+            rep[k_] = v
+            continue
+        v = v.expand(S, *v.shape[1:]).clone()
+        if k_ == "position":
+            v = v + 0.05 * torch.randn(v.shape, generator=g).to(v.device)
+        rep[k_] = v
+    scene = rep
+    v0 = scene["velocity"][:, t0].contiguous()
+    pf, of, sf = state_features(scene["position"][:, t0].contiguous(), v0, scene["acceleration"][:, t0].contiguous(),
+                                scene["destination"][:, t0].contiguous(), scene["obstacles"], v0.clone(),
+                                scene["desired_speed"], 6, 90, 4, 10, 90, 4)
+    scene["ped_features0"], scene["obs_features0"], scene["self_features0"] = pf, of, sf
+    if model == "sfm":
+        spec, packed, ptc = P.SocialForce("gc1560").spec, None, None
+    else:
+        torch.manual_seed(666)
+        net = M.CLASSES["pinnsf_bm"](args).cuda().eval()
+        spec, packed, ptc = net.spec, M.pack_device(net.state_dict(), net.spec), M.pack_device_tc(net.state_dict(), net.spec)
+    full = [npy(x) for x in rollout_scenes(spec, packed, args, scene, t0, T, packed_tc=ptc)]
+    for lo, hi in ((0, 3), (3, 6)):
+        part_scene = {k_: (v if k_ == "obstacles" else v[lo:hi].contiguous()) for k_, v in scene.items()}
+        part = [npy(x) for x in rollout_scenes(spec, packed, args, part_scene, t0, T, packed_tc=ptc)]
+        for a_, b_ in zip(full, part):
+            assert np.array_equal(a_[lo:hi], b_, equal_nan=True)

@@ -221,3 +221,35 @@ def test_sfm_rollout_resynchronised():
             sim = flag[t + 1] == 0
             worst = max(worst, accel_err(acc[sim], A[t + 1][sim], slf[sim], 0.5))
     assert worst < 1e-5, worst
+
+
+def test_predicate_arithmetic_against_torch_primitives():
+    """the fp32 evaluation of the neighbour-selection predicate (torch.norm over a 2-vector,
+    torch.cosine_similarity, the 3.14-based threshold; data.py:432-443) on ~10^6 random pairs incl. zero, huge, tiny,
+    inf and NaN coordinates: the oracle's gated distances must equal torch's CPU kernels bit for bit."""
+    import torch
+    rng = np.random.default_rng(11)
+    N, M = 256, 4096
+    pos = rng.normal(0, 3, (1, N, 2)).astype(np.float32)
+    obj = rng.normal(0, 3, (1, M, 2)).astype(np.float32)
+    obj[0, :64] = pos[0, :64]                                  # coincident points (distance 0, cos of a zero vector)
+    obj[0, 64:96] *= 1e18
+    obj[0, 96:128] *= 1e-30
+    obj[0, 128:140] = np.nan
+    obj[0, 140:150, 0] = np.inf
+    pos[0, -3:] = np.nan                                       # absent agents
+    head = rng.normal(0, 1, (1, N, 2)).astype(np.float32)
+    head[0, :16] = 0.0                                         # stationary agents see nobody at <= 90 degrees
+    for angle in (90, 100):
+        dist, idx = O.select(pos, obj, head, M, angle)
+        p, o, h = torch.from_numpy(pos), torch.from_numpy(obj), torch.from_numpy(head)
+        rel = o[:, None, :, :] - p[:, :, None, :]              # (1,N,M,2) = B - A
+        rel[torch.isnan(rel)] = float('inf')
+        d = torch.norm(rel, p=2, dim=-1)
+        cos = torch.cosine_similarity(rel, h[:, :, None, :].expand_as(rel), dim=-1)
+        cos[torch.isnan(cos)] = -1
+        d[cos < torch.tensor(np.float32(np.cos(3.14 * angle / 180)))] = float('inf')
+        want = torch.sort(d, dim=-1)[0].numpy()
+        assert np.array_equal(np.asarray(dist).view(np.uint32), want.view(np.uint32)), angle
+        fin = np.isfinite(want)
+        assert fin.sum() > 1e5
