@@ -309,6 +309,26 @@ PIML_API int piml_pinnsf_backward_f32(const piml_net_desc *desc, const float *pa
                              const float *g_coll, float *g_params, float *g_ped, float *g_obs, float *g_self,
                              float *workspace, void *stream);
 
+/* ---- rollout losses: src/models/simulators.py:172-249 --------------------------------------------------------- */
+
+/* multiple_rollout_mse_loss (:172), multiple_rollout_collision_loss (:195) for the collision and the hard-collision
+ * counts, each with reduction 'sum', as test_multiple_rollouts_for_training calls them (:795-813), in one pass:
+ *   out[0] = sum decay_t (pred - labels)^2,  decay_t = time_decay^(T-t-1)  (time_decay^t if reverse, :822-823)
+ *   out[1] = sum w_cn decay_t (P pred - P labels)^2 with w from `collisions` (C,T,N), out[2] likewise from
+ *            `hard_collisions`; either may be NULL (-> 0); abnormal_mask (N) or NULL (:222-224).
+ * pred (C,T,N,2) contiguous; labels: row (c,t,n) starts at labels + ((c*T+t)*N+n)*label_stride and its first two
+ * floats are used (data.labels[..., :2] has stride 6 + k; pass labels + 4 for the acceleration labels of :822).
+ * workspace >= piml_rollout_losses_workspace_floats(C, N) floats.  T <= 256.
+ * Backward: g_pred (C,T,N,2) = d(g_out[0] out[0] + g_out[1] out[1] + g_out[2] out[2]) / d pred, g_out on the device. */
+PIML_API int64_t piml_rollout_losses_workspace_floats(int C, int N);
+PIML_API int piml_rollout_losses_f32(const float *pred, const float *labels, int64_t label_stride, int C, int T, int N,
+                            float time_decay, int reverse, const float *collisions, const float *hard_collisions,
+                            const float *abnormal_mask, float *out, float *workspace, void *stream);
+PIML_API int piml_rollout_losses_backward_f32(const float *pred, const float *labels, int64_t label_stride, int C, int T,
+                                     int N, float time_decay, int reverse, const float *collisions,
+                                     const float *hard_collisions, const float *abnormal_mask, const float *g_out,
+                                     float *g_pred, void *stream);
+
 /* ---- integrator: src/models/simulators.py:603-639 ---------------------------------------------------------- */
 
 /* One state update of get_multiple_rollouts for S scenes of N slots: lagged explicit

@@ -171,3 +171,42 @@ class IntegrateTrainFunction(torch.autograd.Function):
             L.ptr(entry), gs[0].numel() // 2, ctx.dt, *[L.ptr(g) for g in gs], *[L.ptr(o) for o in outs],
             L.stream_ptr(dev)), "piml_integrate_step_backward_f32")
         return (outs[0], outs[1], outs[2], outs[3]) + (None,) * 11
+
+
+class RolloutLossesFunction(torch.autograd.Function):
+    """The 'sum'-reduced rollout losses of test_multiple_rollouts_for_training (simulators.py:172-249, called at
+    :795-824) in one pass: returns a (3,) tensor [mse, collision, hard collision] (piml_rollout_losses_f32); the
+    backward is one kernel (piml_rollout_losses_backward_f32).  `labels` may be a strided view whose last dimension is
+    a slice of a wider tensor (data.labels[..., :2], data.labels[..., 4:6]): it is read in place."""
+
+    @staticmethod
+    def forward(ctx, pred, labels, time_decay, reverse, collisions, hard_collisions, abnormal_mask):
+        dev = L.require_cuda(pred, labels)
+        pred = L.f32c(pred)
+        C, T, N = pred.shape[0], pred.shape[1], pred.shape[2]
+        if labels.dtype != torch.float32 or labels.stride(-1) != 1 or labels.shape[:3] != pred.shape[:3] or \
+                labels.stride(1) != N * labels.stride(2) or labels.stride(0) != T * N * labels.stride(2):
+            labels = labels.float().contiguous()
+        stride = labels.stride(2)
+        coll = L.f32c(collisions) if collisions is not None else None
+        hard = L.f32c(hard_collisions) if hard_collisions is not None else None
+        ab = L.f32c(abnormal_mask).reshape(-1) if abnormal_mask is not None else None
+        out = torch.empty(3, device=dev)
+        ws = torch.empty(int(L.load().piml_rollout_losses_workspace_floats(C, N)), device=dev)
+        L.check(L.load().piml_rollout_losses_f32(L.ptr(pred), L.ptr(labels), stride, C, T, N, float(time_decay),
+                                                 1 if reverse else 0, L.ptr(coll), L.ptr(hard), L.ptr(ab), L.ptr(out),
+                                                 L.ptr(ws), L.stream_ptr(dev)), "piml_rollout_losses_f32")
+        ctx.save_for_backward(pred, labels, coll, hard, ab)
+        ctx.cfg = (stride, C, T, N, float(time_decay), 1 if reverse else 0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pred, labels, coll, hard, ab = ctx.saved_tensors
+        stride, C, T, N, time_decay, reverse = ctx.cfg
+        g_out = L.f32c(g_out)
+        g_pred = torch.empty_like(pred)
+        L.check(L.load().piml_rollout_losses_backward_f32(
+            L.ptr(pred), L.ptr(labels), stride, C, T, N, time_decay, reverse, L.ptr(coll), L.ptr(hard), L.ptr(ab),
+            L.ptr(g_out), L.ptr(g_pred), L.stream_ptr(pred.device)), "piml_rollout_losses_backward_f32")
+        return g_pred, None, None, None, None, None, None

@@ -6,14 +6,15 @@ Per step the reference runs the model, four N x N `collision_detection` passes, 
 bookkeeping and a differentiable `get_relative_features`, all as eager ops recorded by autograd.  Here every one of
 those stages is a kernel of libpiml_b200.so wrapped in a `torch.autograd.Function` (piml_b200/autograd.py), so
 `loss.backward()` (:359) also runs in the library: network backward (dX chain, dW, db), feature scatter, Euler chain.
-The loss reductions themselves are small elementwise expressions over (C,T,N,2) tensors and stay in torch
-(fusing them is "next").
+The 'sum'-reduced position / collision / teacher losses (:795-824) are one fused kernel each way
+(`RolloutLossesFunction`); the torch restatements below remain for the other reductions
+('none', 'mean') and as the reference of the fused kernel's tests.
 """
 import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .autograd import IntegrateTrainFunction
+from .autograd import IntegrateTrainFunction, RolloutLossesFunction
 from .features import Pedestrians
 
 _PEDS = Pedestrians()
@@ -164,24 +165,25 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
     p_res[mask_p_ == 0] = 0.                                                      # :792-793
     data.labels[mask_p_ == 0] = 0.
     labels_p = data.labels[:, :, :, :2]
-    mse_loss = multiple_rollout_mse_loss(p_res, labels_p, args.time_decay, 'sum')
-    loss = loss + mse_loss
+    # the three 'sum'-reduced position losses of :795-813 in ONE fused pass (piml_rollout_losses_f32); the collision
+    # weights are only needed when their loss is switched on
     zero = torch.tensor(0., device=dev)
     collision_loss, hard_collision_loss, collision_pred_loss, collision_pred_acc = zero, zero, zero, zero
+    want_coll = args.collision_loss_weight > 0 and args.collision_loss_version in ('v0', 'v2')
+    am = data.abnormal_mask if (want_coll and args.collision_loss_version == 'v2') else None
+    fused = RolloutLossesFunction.apply(p_res, labels_p, args.time_decay, False, collisions if want_coll else None,
+                                        hard_collisions if want_coll else None, am)
+    mse_loss = fused[0]
+    loss = loss + mse_loss
     if args.collision_loss_weight > 0:                                            # :799-819
-        am = None
-        if args.collision_loss_version == 'v2':
-            am = data.abnormal_mask
-        if args.collision_loss_version in ('v0', 'v2'):
-            collision_loss = multiple_rollout_collision_loss(
-                p_res, labels_p, args.time_decay, args.collision_focus_weight, collisions, 'sum', am)
-            hard_collision_loss = multiple_rollout_collision_loss(
-                p_res, labels_p, args.time_decay, args.collision_focus_weight, hard_collisions, 'sum', am)
+        if want_coll:
+            collision_loss, hard_collision_loss = fused[1], fused[2]
         collision_loss = collision_loss * args.collision_loss_weight
         hard_collision_loss = hard_collision_loss * args.collision_loss_weight * args.hard_collision_penalty
         loss = loss + collision_loss + hard_collision_loss
     if args.teacher_weight > 0:                                                   # :821-824
-        a_mse_loss = multiple_rollout_mse_loss(a_res, data.labels[..., 4:6], args.time_decay, 'sum', reverse=True)
+        a_mse_loss = RolloutLossesFunction.apply(a_res, data.labels[..., 4:6], args.time_decay, True, None, None,
+                                                 None)[0]
         loss = loss + a_mse_loss * args.teacher_weight
     if args.collision_pred_weight > 0:                                            # :826-830
         collision_pred_loss = F.binary_cross_entropy(pred_collisions, true_collision,

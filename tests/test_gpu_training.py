@@ -239,3 +239,42 @@ def test_training_rollout_golden(case):
         if k.startswith("grad/"):
             worst = max(worst, max_rel(named[k[5:]].grad.cpu().numpy(), v))
     assert worst < 5e-5, worst
+
+
+@pytest.mark.parametrize("C,T,N,reverse,with_coll,with_mask", [(32, 10, 144, False, True, False),
+                                                               (6, 5, 122, False, True, True),
+                                                               (4, 7, 33, True, False, False),
+                                                               (1, 1, 5, False, True, False)])
+def test_fused_rollout_losses_match_the_torch_restatement(C, T, N, reverse, with_coll, with_mask):
+    """piml_rollout_losses_f32 / _backward_f32 (simulators.py:172-249 with reduction 'sum', fused) against the plain
+    torch restatement of the same three losses (piml_b200.train_rollout.multiple_rollout_*), values and d/d pred, with
+    labels read in place from a wider (.., 6 + k) tensor like data.labels[..., :2]."""
+    from piml_b200 import train_rollout as TR
+    from piml_b200.autograd import RolloutLossesFunction
+    g = torch.Generator().manual_seed(C * 100 + T)
+    pred = (torch.randn(C, T, N, 2, generator=g) * 3).cuda().requires_grad_(True)
+    wide = (torch.randn(C, T, N, 12, generator=g) * 3).cuda()
+    labels = wide[..., 4:6] if reverse else wide[..., :2]
+    coll = hard = am = None
+    if with_coll:
+        coll = (torch.rand(C, T, N, generator=g) < 0.1).float().cuda() * 2
+        hard = (torch.rand(C, T, N, generator=g) < 0.03).float().cuda()
+    if with_mask:
+        am = (torch.rand(N, generator=g) < 0.7).float().cuda()
+    decay = 0.9
+    out = RolloutLossesFunction.apply(pred, labels, decay, reverse, coll, hard, am)
+    gw = torch.tensor([1.0, 10.0, 100.0]).cuda()
+    (out * gw).sum().backward()
+    got_g = pred.grad.clone()
+    pred.grad = None
+    want0 = TR.multiple_rollout_mse_loss(pred, labels, decay, 'sum', reverse=reverse)
+    want = [want0, torch.zeros((), device="cuda"), torch.zeros((), device="cuda")]
+    if with_coll:
+        want[1] = TR.multiple_rollout_collision_loss(pred, labels, decay, 10, coll.clone(), 'sum', am)
+        want[2] = TR.multiple_rollout_collision_loss(pred, labels, decay, 10, hard.clone(), 'sum', am)
+    (want[0] * gw[0] + want[1] * gw[1] + want[2] * gw[2]).backward()
+    for q in range(3):
+        ref = float(want[q])
+        assert abs(float(out[q]) - ref) <= 2e-5 * max(abs(ref), 1.0), (q, float(out[q]), ref)
+    scale = float(pred.grad.abs().max())
+    assert float((got_g - pred.grad).abs().max()) <= 2e-5 * max(scale, 1.0)
