@@ -329,6 +329,19 @@ PIML_API int piml_rollout_losses_backward_f32(const float *pred, const float *la
                                      const float *hard_collisions, const float *abnormal_mask, const float *g_out,
                                      float *g_pred, void *stream);
 
+/* ---- evaluation metrics: src/functions/metrics.py ----------------------------------------------------------------- */
+
+/* Per frame t of a rollout, over the agents with mask[t][n] == 1 (p, q (T,N,2); mask (T,N) uint8):
+ *   out_mae[t]  sum ||p - q||_2                      mae_with_time_mask  metrics.py:29-42
+ *   out_ot[t]   SinkhornDistance(eps, max_iter)      ot_with_time_mask   :45-67, :108-199 (log-domain updates, equal
+ *               weights, stops when sum |u - u_prev| < 0.1, exactly the reference's per-frame loop)
+ *   out_mmd[t]  MaximumMeanDiscrepancy, kernel_mul / kernel_num bandwidths   mmd_with_time_mask :70-91, :207-273
+ *   out_count[t] number of masked agents; frames with count <= 1 are skipped by the reference: ot / mmd are NaN there
+ *   (count > 1024 is not supported: NaN as well).  out_ot / out_mmd may be NULL.  One CTA per frame. */
+PIML_API int piml_metrics_frames_f32(const float *p, const float *q, const uint8_t *mask, int T, int N, float eps,
+                            int max_iter, float kernel_mul, int kernel_num, float *out_mae, float *out_ot,
+                            float *out_mmd, int *out_count, void *stream);
+
 /* ---- integrator: src/models/simulators.py:603-639 ---------------------------------------------------------- */
 
 /* One state update of get_multiple_rollouts for S scenes of N slots: lagged explicit

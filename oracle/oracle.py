@@ -255,3 +255,81 @@ def integrate_step(p, v, a, a_next, dest, dest_idx, dest_num, waypoints, dt, rem
                              C.c_int(N), C.c_float(dt), C.c_int(1 if remove_on_arrival else 0), _ptr(en),
                              _ptr(gts[0]), _ptr(gts[1]), _ptr(gts[2]), _ptr(gts[3]), _ptr(dig), _ptr(hist))
     return p, v, a, dest, di, hist
+
+
+# ---- f-4: evaluation metrics (reference src/functions/metrics.py), numpy fp32 restatement -----------------------------
+def mae_with_time_mask(p, q, mask):
+    """metrics.py:29-42 with reduction 'sum': sum over mask == 1 of ||p - q||_2."""
+    p, q, mask = _f32(p), _f32(q), np.asarray(mask)
+    d = (p - q)[mask == 1]
+    return float(np.sqrt((d * d).sum(-1, dtype=np.float32)).sum(dtype=np.float32))
+
+
+def _logsumexp(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    return (np.log(np.exp(x - m).sum(axis=axis, dtype=np.float32)) + np.squeeze(m, axis)).astype(np.float32)
+
+
+def sinkhorn_distance(x, y, eps=0.1, max_iter=100):
+    """SinkhornDistance.forward (metrics.py:131-192) for one frame: x (n,2), y (n,2) -> entropic OT cost.
+    Log-domain updates, equal weights, stops when sum |u - u_prev| < 0.1."""
+    x, y = _f32(x), _f32(y)
+    eps32 = np.float32(eps)
+    C = (np.abs(x[:, None, :] - y[None, :, :]) ** 2).sum(-1, dtype=np.float32)            # :194-199
+    n, m = x.shape[0], y.shape[0]
+    lmu = np.log(np.float32(1.0 / n) + np.float32(1e-8), dtype=np.float32)
+    lnu = np.log(np.float32(1.0 / m) + np.float32(1e-8), dtype=np.float32)
+    u, v = np.zeros(n, np.float32), np.zeros(m, np.float32)
+    M = lambda: ((-C + u[:, None]) + v[None, :]) / eps32                                 # :186-189
+    for _ in range(max_iter):
+        u1 = u
+        u = eps32 * (lmu - _logsumexp(M(), 1)) + u
+        v = eps32 * (lnu - _logsumexp(M().T, 1)) + v
+        if float(np.abs(u - u1).sum(dtype=np.float32)) < 1e-1:                            # :166-170
+            break
+    pi = np.exp(M())
+    return float((pi * C).sum(dtype=np.float32))
+
+
+def ot_with_time_mask(p, q, mask, eps=0.1, max_iter=100):
+    """metrics.py:45-67: one Sinkhorn problem per frame with more than one masked point; returns (frames, costs)."""
+    p, q, mask = _f32(p), _f32(q), np.asarray(mask)
+    frames, out = [], []
+    for t in range(mask.shape[0]):
+        sel = mask[t] == 1
+        if sel.sum() > 1:
+            frames.append(t)
+            out.append(sinkhorn_distance(p[t][sel], q[t][sel], eps, max_iter))
+    return np.asarray(frames), np.asarray(out, np.float64)
+
+
+def mmd(source, target, kernel_mul=2.0, kernel_num=5):
+    """MaximumMeanDiscrepancy.__call__ (metrics.py:213-273): multi-bandwidth Gaussian-kernel MMD of two point sets."""
+    s, t = _f32(source), _f32(target)
+    n, m = s.shape[0], t.shape[0]
+    tot = np.concatenate([s, t], 0)
+    L2 = ((tot[None, :, :] - tot[:, None, :]) ** 2).sum(2, dtype=np.float32)
+    ns = n + m
+    bw = np.float32(L2.sum(dtype=np.float32) / np.float32(ns * ns - ns))
+    bw = np.float32(bw / np.float32(kernel_mul ** (kernel_num // 2)))
+    K = np.zeros_like(L2)
+    for i in range(kernel_num):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            K = K + np.exp(-L2 / np.float32(bw * np.float32(kernel_mul ** i)))
+    XX = (K[:n, :n] / np.float32(n * n)).sum(1, dtype=np.float32)
+    XY = (K[:n, n:] / np.float32(-n * m)).sum(1, dtype=np.float32)
+    YX = (K[n:, :n] / np.float32(-m * n)).sum(1, dtype=np.float32)
+    YY = (K[n:, n:] / np.float32(m * m)).sum(1, dtype=np.float32)
+    return float((XX + XY).sum(dtype=np.float32) + (YX + YY).sum(dtype=np.float32))
+
+
+def mmd_with_time_mask(p, q, mask):
+    """metrics.py:70-91; returns (frames, values)."""
+    p, q, mask = _f32(p), _f32(q), np.asarray(mask)
+    frames, out = [], []
+    for t in range(mask.shape[0]):
+        sel = mask[t] == 1
+        if sel.sum() > 1:
+            frames.append(t)
+            out.append(mmd(p[t][sel], q[t][sel]))
+    return np.asarray(frames), np.asarray(out, np.float64)

@@ -7,7 +7,7 @@ from . import _lib
 from .features import Pedestrians, cos_threshold
 from .mlapm import MLAPM
 from .sfm import SocialForce, calc_acceleration
-from . import models
+from . import metrics, models
 
-__all__ = ["Pedestrians", "MLAPM", "calc_acceleration", "SocialForce", "models", "cos_threshold", "_lib"]
+__all__ = ["Pedestrians", "MLAPM", "calc_acceleration", "SocialForce", "metrics", "models", "cos_threshold", "_lib"]
 __version__ = "0.1.0"

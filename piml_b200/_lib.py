@@ -84,6 +84,7 @@ SIGNATURES = {
     "piml_rollout_losses_workspace_floats": (i64, [i32, i32]),
     "piml_rollout_losses_f32": (i32, [vp, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "piml_rollout_losses_backward_f32": (i32, [vp, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
+    "piml_metrics_frames_f32": (i32, [vp, vp, vp, i32, i32, f32, i32, f32, i32, vp, vp, vp, vp, vp]),
     "piml_sfm_forward_f32": (i32, [C.POINTER(SfmParams), vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "piml_pinnsf_packed_floats": (i64, [C.POINTER(NetDesc)]),
     "piml_pinnsf_pack_f32": (i32, [C.POINTER(NetDesc), vp, vp, vp]),

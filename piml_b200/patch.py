@@ -3,6 +3,7 @@
     import data.data as DATA, models.mlapm as MLAPM_MOD, models.model as MODEL, models.simulators as SIM, utils.utils as UTILS
     import piml_b200.patch as patch
     patch.install(DATA=DATA, MLAPM_MOD=MLAPM_MOD, MODEL=MODEL, SIM=SIM, UTILS=UTILS)     # or patch.install_from_env(...)
+    (optionally METRIC=functions.metrics for the evaluation metrics)
 
 After `install` the unmodified reference scripts (src/main.py, src/main_mlapm.py) run their hot path in
 libpiml_b200.so: the five signatures below keep their names, argument order and return types; everything else
@@ -18,6 +19,8 @@ switch off the reference is byte-for-byte itself.  Opt-in only: `install_from_en
     BaseSimulator.get_multiple_rollouts                            (src/models/simulators.py:556)
     BaseSimulator.test_multiple_rollouts_for_training              (src/models/simulators.py:659)
     Pedestrians.collision_detection                                (src/data/data.py:538)
+    METRIC.collision_count / mae_with_time_mask / ot_with_time_mask / mmd_with_time_mask   (src/functions/metrics.py:16-91;
+                                                                   pass METRIC=functions.metrics; (T,N,2) inputs)
 
 Training: the patched model forwards record a CUDA backward (piml_b200.autograd), so the reference's own
 `loss.backward(); optimizer.step()` (simulators.py:359-360) runs the library's backward kernels unchanged.
@@ -25,6 +28,7 @@ Training: the patched model forwards record a CUDA backward (piml_b200.autograd)
 import os
 
 from . import features as _features
+from . import metrics as _metrics
 from . import mlapm as _mlapm
 from . import models as _models
 from . import rollout as _rollout
@@ -50,7 +54,7 @@ def _swap(owner, name, new):
     setattr(owner, name, new)
 
 
-def install(DATA=None, MLAPM_MOD=None, MODEL=None, SIM=None, UTILS=None):
+def install(DATA=None, MLAPM_MOD=None, MODEL=None, SIM=None, UTILS=None, METRIC=None):
     """Patch whichever of the reference modules are given.  Returns the list of patched qualified names."""
     done = []
     if DATA is not None:
@@ -89,6 +93,10 @@ def install(DATA=None, MLAPM_MOD=None, MODEL=None, SIM=None, UTILS=None):
             return _train_rollout.test_multiple_rollouts_for_training(self, data, t_start)
         _swap(SIM.BaseSimulator, "test_multiple_rollouts_for_training", test_multiple_rollouts_for_training)
         done.append("models.simulators.BaseSimulator.test_multiple_rollouts_for_training")
+    if METRIC is not None:
+        for m in ("collision_count", "mae_with_time_mask", "ot_with_time_mask", "mmd_with_time_mask"):
+            _swap(METRIC, m, getattr(_metrics, m))
+            done.append(f"functions.metrics.{m}")
     return done
 
 

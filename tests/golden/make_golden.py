@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by running the UNMODIFIED reference (imported from /root/reference).
 
 Run in the build container only:   python tests/golden/make_golden.py [group ...]
-Groups: features models mlapm sfm rollout sfm_rollout training.   Output: tests/golden/*.npz (small, compressed).
+Groups: features models mlapm sfm rollout sfm_rollout training metrics.   Output: tests/golden/*.npz (small, compressed).
 
 The reference ships no tests and no golden vectors, so these files ARE the pin: they
 hold the reference's own outputs on its own data files (GC / UCY / toy clips) and on seeded synthetic crowds.
@@ -478,7 +478,45 @@ def gen_training():
     save("training_rollout", **out)
 
 
-GROUPS = {"features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
+def gen_metrics():
+    """f-4: the evaluation metrics of test_multiple_rollouts (simulators.py:505-531) on the reference's own rollouts
+    (golden trajectories): post_process (:443-463), then METRIC.mae / ot / mmd _with_time_mask (metrics.py:29-91) and
+    METRIC.collision_count (:16-26), per frame where the reference loops over frames."""
+    import functions.metrics as METRIC
+    import types
+    out = {}
+    for name in ("rollout_gc_bm", "rollout_ucy_bm", "rollout_syn_sfm"):
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        T = int(z["in/num_frames"])
+        p_pred = torch.from_numpy(z["out/position"][:T].copy())
+        pred_mask = torch.from_numpy(z["out/mask_p"][:T].copy())
+        mask = torch.from_numpy(z["in/mask_p_pred"][:T].copy()).long()
+        labels = torch.from_numpy(z["in/position"][:T].copy())
+        stub = types.SimpleNamespace(waypoints=torch.from_numpy(z["in/waypoints"].copy()),
+                                     dest_num=torch.from_numpy(z["in/dest_num"].copy()).long())
+        t0 = int(z["in/t_start"])
+        coll = METRIC.collision_count(p_pred[t0:].clone(), 0.5, reduction='sum')
+        hard = METRIC.collision_count(p_pred[t0:].clone(), 0.25, reduction='sum')
+        p_pp = SIM.BaseSimulator.post_process(stub, p_pred.clone(), pred_mask, mask)
+        g = name + "/"
+        out[g + "p_pred"], out[g + "labels"], out[g + "mask"] = p_pp, labels, mask
+        out[g + "p_raw"], out[g + "t_start"] = p_pred, np.int64(t0)
+        out[g + "collision_count"], out[g + "hard_collision_count"] = np.float64(coll), np.float64(hard)
+        out[g + "mae_sum"] = np.float64(METRIC.mae_with_time_mask(p_pp, labels, mask, reduction='sum'))
+        ot = METRIC.ot_with_time_mask(p_pp, labels, mask, reduction=None, dvs='cpu')
+        mmd = METRIC.mmd_with_time_mask(p_pp, labels, mask, reduction=None)
+        frames = [t for t in range(mask.shape[0]) if int(mask[t].sum()) > 1]
+        assert len(ot) == len(frames) == len(mmd)
+        out[g + "frames"] = np.asarray(frames, np.int64)
+        out[g + "ot"], out[g + "mmd"] = np.asarray(ot, np.float64), np.asarray(mmd, np.float64)
+        out[g + "ot_sum"] = np.float64(METRIC.ot_with_time_mask(p_pp, labels, mask, reduction='sum', dvs='cpu'))
+        out[g + "mmd_sum"] = np.float64(METRIC.mmd_with_time_mask(p_pp, labels, mask, reduction='sum'))
+        print(name, "frames", len(frames), "mae", out[g + "mae_sum"], "ot", out[g + "ot_sum"], "mmd", out[g + "mmd_sum"],
+              "coll", coll, hard)
+    save("metrics", **out)
+
+
+GROUPS = {"metrics": gen_metrics, "features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
           "rollout": gen_rollout, "sfm_rollout": gen_sfm_rollout, "training": gen_training}
 
 if __name__ == "__main__":

@@ -825,3 +825,52 @@ def test_scene_sharded_rollouts_equal_the_unsharded_batch(model):
         part = [npy(x) for x in rollout_scenes(spec, packed, args, part_scene, t0, T, packed_tc=ptc)]
         for a_, b_ in zip(full, part):
             assert np.array_equal(a_[lo:hi], b_, equal_nan=True)
+
+
+# ---- f-4: evaluation metrics -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_ucy_bm", "rollout_syn_sfm"])
+def test_metrics_match_reference_gpu(name):
+    """piml_b200.metrics (one launch for all frames) against the reference's own METRIC values on its own rollouts:
+    every frame's Sinkhorn OT cost and MMD, the MAE sum and the collision counts."""
+    from piml_b200 import metrics as MT
+    g = group(golden("metrics"), name)
+    p, q, mask = cu(g["p_pred"]), cu(g["labels"]), cu(g["mask"], torch.int64)
+    mae = MT.mae_with_time_mask(p, q, mask, reduction='sum')
+    assert abs(mae - float(g["mae_sum"])) <= 1e-5 * float(g["mae_sum"])
+    ot = np.asarray(MT.ot_with_time_mask(p, q, mask, reduction=None))
+    assert ot.shape == g["ot"].shape
+    assert np.allclose(ot, g["ot"], rtol=2e-4, atol=1e-6), float(np.abs(ot - g["ot"]).max())
+    assert abs(MT.ot_with_time_mask(p, q, mask, reduction='sum') - float(g["ot_sum"])) <= 1e-4 * float(g["ot_sum"])
+    mmd = np.asarray(MT.mmd_with_time_mask(p, q, mask, reduction=None))
+    assert np.allclose(mmd, g["mmd"], rtol=2e-4, atol=2e-6), float(np.abs(mmd - g["mmd"]).max())
+    assert abs(MT.mmd_with_time_mask(p, q, mask, reduction='sum') - float(g["mmd_sum"])) <= 1e-4 * float(g["mmd_sum"]) + 1e-5
+    t0 = int(g["t_start"])
+    raw = cu(g["p_raw"])
+    assert MT.collision_count(raw[t0:], 0.5, reduction='sum') == float(g["collision_count"])
+    assert MT.collision_count(raw[t0:], 0.25, reduction='sum') == float(g["hard_collision_count"])
+    # host tensors in: staged like every other adapter
+    assert abs(MT.mae_with_time_mask(torch.from_numpy(g["p_pred"]), torch.from_numpy(g["labels"]),
+                                     torch.from_numpy(g["mask"]), reduction='sum') - mae) < 1e-3
+
+
+def test_metrics_against_oracle_on_random_frames():
+    """Random point sets incl. frames with 0 / 1 / many masked agents, against the numpy restatement."""
+    from piml_b200 import metrics as MT
+    rng = np.random.default_rng(5)
+    T, N = 40, 200
+    p = rng.normal(0, 4, (T, N, 2)).astype(np.float32)
+    q = (p + rng.normal(0, 0.7, (T, N, 2))).astype(np.float32)
+    mask = (rng.random((T, N)) < rng.random((T, 1))).astype(np.int64)
+    mask[0] = 0
+    mask[1] = 0
+    mask[1, 7] = 1
+    mask[2] = 1
+    fr, want_ot = O.ot_with_time_mask(p, q, mask)
+    _, want_mmd = O.mmd_with_time_mask(p, q, mask)
+    ot = np.asarray(MT.ot_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction=None))
+    mmd = np.asarray(MT.mmd_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction=None))
+    assert len(ot) == len(fr) == len(mmd)
+    assert np.allclose(ot, want_ot, rtol=2e-4, atol=1e-6), float(np.abs(ot - want_ot).max())
+    assert np.allclose(mmd, want_mmd, rtol=2e-4, atol=2e-6), float(np.abs(mmd - want_mmd).max())
+    want_mae = O.mae_with_time_mask(p, q, mask)
+    assert abs(MT.mae_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum') - want_mae) <= 1e-5 * want_mae

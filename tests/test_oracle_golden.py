@@ -253,3 +253,23 @@ def test_predicate_arithmetic_against_torch_primitives():
         assert np.array_equal(np.asarray(dist).view(np.uint32), want.view(np.uint32)), angle
         fin = np.isfinite(want)
         assert fin.sum() > 1e5
+
+
+# ---- f-4: evaluation metrics -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_ucy_bm", "rollout_syn_sfm"])
+def test_metrics_match_reference(name):
+    """The numpy restatement of METRIC.mae / ot / mmd _with_time_mask against the reference's own values on its own
+    rollouts (per frame where the reference loops over frames)."""
+    g = group(golden("metrics"), name)
+    p, q, mask = g["p_pred"], g["labels"], g["mask"]
+    assert abs(O.mae_with_time_mask(p, q, mask) - float(g["mae_sum"])) <= 1e-5 * float(g["mae_sum"])
+    step = 5 if name != "rollout_ucy_bm" else 2                  # every 5th frame keeps the CPU suite short
+    sub = np.zeros_like(mask)
+    sub[::step] = mask[::step]
+    frames, ot = O.ot_with_time_mask(p, q, sub)
+    idx = np.searchsorted(g["frames"], frames)
+    assert np.array_equal(g["frames"][idx], frames)
+    assert np.allclose(ot, g["ot"][idx], rtol=2e-4, atol=1e-6)
+    frames2, mm = O.mmd_with_time_mask(p, q, sub)
+    assert np.array_equal(frames2, frames)
+    assert np.allclose(mm, g["mmd"][idx], rtol=2e-4, atol=2e-6)
