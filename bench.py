@@ -227,9 +227,27 @@ def nn_path_step(torch, dev, N, obs_h, iters=10):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     assert torch.isfinite(p).all()
+    # algorithmic HBM bytes per agent-step of the three stages: features read 44 B state and write
+    # (6 + 10) slots x 24 B + 28 B self + 8 B dest; the forward reads those 420 B and writes 8 B; integrate reads 68 B and
+    # writes 48 B
+    bytes_per_agent = 44 + 384 + 28 + 8 + 420 + 8 + 68 + 48
+    peak_gbs, peak_src = 6550.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_gbs, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    gbs = bytes_per_agent * N / (ms * 1e-3) / 1e9
     return {"workload": f"pinnsf_bm NN rollout step, N={N}, M={int(obs.shape[0])}, k=6/10 (forward + integrate + "
-                        "cell-list feature rebuild); forward on tcgen05 tensor cores (3xTF32)", "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
-            "forward_flop_per_agent": 1.52e6, "tflops_algorithmic": 1.52e6 * N / ms * 1e3 / 1e12}
+                        "cell-list feature rebuild); forward on tcgen05 tensor cores (3xTF32), compact mode",
+            "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
+            "forward_flop_per_agent": 1.52e6, "tflops_algorithmic": 1.52e6 * N / ms * 1e3 / 1e12,
+            "hbm": {"bound": "hbm", "bytes_per_agent_step": bytes_per_agent, "achieved": gbs, "peak": peak_gbs,
+                    "unit": "GB/s", "frac": gbs / peak_gbs, "peak_source": peak_src,
+                    "note": "the gather / MLP / integrate stages are NOT HBM-bound at this size: the step is bound by "
+                            "the tensor-core forward (tensor pipe 29 % busy, MMA-issue and epilogue latency) and the "
+                            "latency-bound cell-list gather (profiles/r01c_ncu_pinnsf_tc_kernel.txt, "
+                            "r01c_ncu_features_cells_kernel.txt)"}}
 
 
 def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
