@@ -429,9 +429,10 @@ static int relative_features_impl(const float *pos, float *vel, float *acc, cons
                                           float *dest_f, int64_t *ped_idx, float *ped_dist, int64_t *obs_idx,
                                           float *obs_dist, const float *hist_v, const float *desired_speed,
                                           float *self_f, void *stream, int64_t row0 = 0, int64_t row1 = 0) {
-    PIML_REQUIRE(pos && vel && acc && dest && ped_f && dest_f, "piml_relative_features_f32: null pointer");
     PIML_REQUIRE(C >= 0 && T >= 0 && N >= 0 && M >= 0 && kp >= 0 && ko >= 0,
                  "piml_relative_features_f32: negative dimension");
+    if (static_cast<int64_t>(C) * T * N == 0) return PIML_OK;         // empty batch: pointers may be null
+    PIML_REQUIRE(pos && vel && acc && dest && ped_f && dest_f, "piml_relative_features_f32: null pointer");
     PIML_REQUIRE(M == 0 || (obs && obs_f), "piml_relative_features_f32: obstacles given but obs/obs_f is null");
     PIML_REQUIRE(head || T == 1, "piml_relative_features_f32: head may only be NULL when T == 1 (got T=%d)", T);
     const int kpp = kp < N ? kp : N;

@@ -157,6 +157,7 @@ using namespace piml;
 extern "C" int piml_metrics_frames_f32(const float *p, const float *q, const uint8_t *mask, int T, int N, float eps,
                                        int max_iter, float kernel_mul, int kernel_num, float *out_mae, float *out_ot,
                                        float *out_mmd, int *out_count, void *stream) {
+    if (T == 0) return PIML_OK;
     PIML_REQUIRE(p && q && mask && out_mae && out_count, "piml_metrics_frames_f32: null pointer");
     PIML_REQUIRE(T >= 0 && N >= 0, "piml_metrics_frames_f32: negative dimension");
     PIML_REQUIRE(!out_ot || (eps > 0.f && max_iter >= 1), "piml_metrics_frames_f32: eps must be > 0, max_iter >= 1");

@@ -938,6 +938,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
                               const float *dest, int64_t N, int64_t row0, int64_t row1, const piml_mlapm_params *prm,
                               float dt, float radius, float *action, float *pos_new, uint8_t *arrived, void *workspace,
                               int64_t workspace_bytes, const PeerPush &push, void *stream) {
+    if (N == 0) return PIML_OK;                                    // empty crowd: nothing to do, pointers may be null
     PIML_REQUIRE(pos && vel && desired_speed && dest && prm && (action || push.world > 0) && workspace,
                  "piml_mlapm: null pointer");
     PIML_REQUIRE(ds_dim == 1 || ds_dim == 2, "piml_mlapm: desired_speed must be (N,1) or (N,2), got ds_dim=%d", ds_dim);
@@ -1066,6 +1067,7 @@ extern "C" int piml_mlapm_advance_ws_f32(const float *pos, const float *vel, con
                                          const piml_mlapm_params *prm, float dt, float radius, float *action,
                                          float *pos_new, uint8_t *arrived, void *workspace, int64_t workspace_bytes,
                                          void *stream) {
+    if (N == 0) return PIML_OK;
     PIML_REQUIRE(workspace_bytes >= piml_mlapm_workspace_bytes(N),
                  "piml_mlapm_advance_ws_f32: workspace of %lld bytes, need >= %lld",
                  static_cast<long long>(workspace_bytes), static_cast<long long>(piml_mlapm_workspace_bytes(N)));

@@ -65,6 +65,7 @@ using namespace piml;
 extern "C" int piml_sfm_forward_f32(const piml_sfm_params *prm, const float *ped_f, const float *obs_f,
                                     const float *self_f, int64_t R, int kp, int ko, float *acc, float *ped_msgs,
                                     float *obs_msgs, void *stream) {
+    if (R == 0) return PIML_OK;
     PIML_REQUIRE(prm && ped_f && self_f && acc, "piml_sfm_forward_f32: null pointer");
     PIML_REQUIRE(R >= 0 && kp >= 0 && ko >= 0 && (ko == 0 || obs_f), "piml_sfm_forward_f32: bad sizes R=%lld kp=%d ko=%d",
                  static_cast<long long>(R), kp, ko);
@@ -85,6 +86,7 @@ extern "C" int piml_sfm_forward_f32(const piml_sfm_params *prm, const float *ped
 
 extern "C" int piml_calc_acceleration_f32(const float *rel, int64_t S, int stride, int version, float A, float B,
                                           float C, float D, float theta, float eps, float *out, void *stream) {
+    if (S == 0) return PIML_OK;
     PIML_REQUIRE(rel && out, "piml_calc_acceleration_f32: null pointer");
     PIML_REQUIRE(S >= 0 && stride >= 2, "piml_calc_acceleration_f32: bad size/stride");
     PIML_REQUIRE(version >= 0 && version <= 2, "piml_calc_acceleration_f32: equation version %d unknown", version);

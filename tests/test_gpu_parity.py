@@ -874,3 +874,38 @@ def test_metrics_against_oracle_on_random_frames():
     assert np.allclose(mmd, want_mmd, rtol=2e-4, atol=2e-6), float(np.abs(mmd - want_mmd).max())
     want_mae = O.mae_with_time_mask(p, q, mask)
     assert abs(MT.mae_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum') - want_mae) <= 1e-5 * want_mae
+
+
+# ---- edge sizes ----------------------------------------------------------------------------------------------------------
+def test_edge_sizes_do_not_break_the_adapters():
+    """Empty and minimal inputs through every adapter (the reference's own tensors can be this small: toy clips have
+    N = 3, M = 2; a frame can have 0 or 1 agents)."""
+    import piml_b200 as P
+    from piml_b200 import metrics as MT
+    ped = P.Pedestrians()
+    # one agent, two obstacle points: k' = min(k, N|M)
+    p1, v1 = cu([[[1.0, 2.0]]]), cu([[[0.5, 0.0]]])
+    a1, d1, ob = cu([[[0.0, 0.0]]]), cu([[[3.0, 2.0]]]), cu([[2.0, 2.0], [9.0, 9.0]])
+    pf, of, df = ped.get_relative_features(p1, v1, a1, d1, ob, 6, 90, 4, 10, 90, 4)
+    assert pf.shape == (1, 1, 1, 6) and of.shape == (1, 1, 2, 6) and df.shape == (1, 1, 2)
+    want = O.relative_features(npy(p1), npy(v1).copy(), npy(a1).copy(), npy(d1), npy(ob))
+    for w, g_ in zip(want, (pf, of, df)):
+        assert np.array_equal(npy(g_), w)
+    # MLAPM with 1 and 2 agents (no pair / one pair), both kernels' entry point
+    for N in (1, 2):
+        p = cu(np.array([[0.0, 0.0], [1.0, 0.5]][:N], np.float32))
+        v = cu(np.array([[1.0, 0.0], [-1.0, 0.0]][:N], np.float32))
+        ds, d = cu(np.full((N, 1), 1.3, np.float32)), cu(np.array([[5.0, 0.0], [-5.0, 0.5]][:N], np.float32))
+        act = P.MLAPM(**GC_KW).step(p, v, ds, d, 0.08)
+        ref = O.mlapm_step(npy(p), npy(v), npy(ds), npy(d), 0.08, "GC")
+        assert rel_vec_err(npy(act), ref) < TOL
+    # empty batches
+    e = torch.empty(0, 2).cuda()
+    assert P.MLAPM(**GC_KW).step(e, e, torch.empty(0, 1).cuda(), e, 0.08).shape == (0, 2)
+    net = P.SocialForce("gc1560")
+    out = net(torch.empty(0, 6, 6).cuda(), torch.empty(0, 10, 6).cuda(), torch.empty(0, 7).cuda())
+    assert out[0].shape == (0, 2) and out[1].shape == (0, 6, 2)
+    assert P.calc_acceleration(torch.empty(0, 6, 6).cuda()).shape == (0, 6, 2)
+    z = torch.zeros(3, 4, 2).cuda()
+    m0 = torch.zeros(3, 4, dtype=torch.int64).cuda()
+    assert MT.ot_with_time_mask(z, z, m0, reduction=None) == [] and MT.mae_with_time_mask(z, z, m0, reduction='sum') == 0.0
