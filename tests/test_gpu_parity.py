@@ -909,3 +909,34 @@ def test_edge_sizes_do_not_break_the_adapters():
     z = torch.zeros(3, 4, 2).cuda()
     m0 = torch.zeros(3, 4, dtype=torch.int64).cuda()
     assert MT.ot_with_time_mask(z, z, m0, reduction=None) == [] and MT.mae_with_time_mask(z, z, m0, reduction='sum') == 0.0
+
+
+def test_mlapm_symmetric_vs_ordered_at_bench_size():
+    """BASELINE config 4 size (N = 100 000, T = 196 blocks): the symmetric kernel the bench times against the ordered-pair
+    kernel (itself checked against the oracle up to N = 8192), two consecutive steps on one workspace."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import piml_b200 as P
+    N = 100000
+    p, v, ds, dest, _ = [x.cuda() for x in bench.synthetic_crowd(N)]
+    model = P.MLAPM(**bench.MLAPM_KW)
+    res = {}
+    for algo in (2, 1):
+        _mlapm_algorithm(algo)
+        try:
+            pp, vv = p.clone(), v.clone()
+            for _ in range(2):
+                act, pn, arr = model.advance(pp, vv, ds, dest, bench.DT, bench.RADIUS)
+                pp, vv = pn, act
+            res[algo] = (npy(vv), npy(pp), npy(arr))
+        finally:
+            _mlapm_algorithm(0)
+    vs, vo = res[2][0], res[1][0]
+    assert np.isfinite(vs).all()
+    num = np.linalg.norm(vs.astype(np.float64) - vo, axis=-1)
+    den = np.maximum(np.maximum(np.linalg.norm(vo, axis=-1), np.linalg.norm(npy(v), axis=-1)), 1e-6)
+    assert float((num / den).max()) < TOL
+    assert np.abs(res[2][1] - res[1][1]).max() < 1e-4            # positions up to 450 m: a few fp32 ulps
+    assert (res[2][2] != res[1][2]).sum() <= 2                    # arrival test at the radius boundary
