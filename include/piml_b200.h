@@ -109,7 +109,9 @@ PIML_API int piml_collision_label_f32(const float *ped_f, int64_t S, float *out,
  * as the larger distance threshold; only the 3 x 3 cells around an agent are scanned) used from 4096 agents per frame.
  * algo: 0 = automatic (default), 1 = always all pairs, 2 = always cell list.  Process-wide setting. */
 PIML_API int piml_set_feature_algorithm(int algo);
-/* Frees the stream-keyed device scratch the cell-list path caches between calls (grid arrays). */
+/* Frees the device scratch the library caches between calls: the cell-list path's grid arrays (per stream) and the
+ * tensor-core forward's per-agent sums / compact-mode lists (per calling thread, device and stream).  Everything else
+ * the library touches is passed in by the caller. */
 PIML_API int piml_free_workspace(void);
 
 /* Backward of piml_relative_features_f32 / the feature rebuild inside the differentiable rollout

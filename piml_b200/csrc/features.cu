@@ -570,7 +570,10 @@ extern "C" int piml_set_feature_algorithm(int algo) {
     return PIML_OK;
 }
 
+namespace piml { void tc_scratch_free(); }                        // mlp_tc.cu
+
 extern "C" int piml_free_workspace(void) {
     cell_scratch_free();
+    piml::tc_scratch_free();
     return PIML_OK;
 }

@@ -913,13 +913,10 @@ static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, con
     if (const char *e = getenv("PIML_MLAPM_SYM_CFG")) cfg = atoi(e);
 #define PIML_LAUNCH_SYM(V, CT, BATCH)                                                                              \
     do {                                                                                                           \
-        static bool attr_done = false;                                                                             \
-        if (!attr_done) {                                                                                          \
+        if (sizeof(MsSmem<CT, BATCH>) > 48 * 1024)       /* per device: a process may drive several GPUs */        \
             PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH>,                                         \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
                                            static_cast<int>(sizeof(MsSmem<CT, BATCH>))));                          \
-            attr_done = true;                                                                                      \
-        }                                                                                                          \
         mlapm_sym_kernel<V, CT, BATCH><<<grid, MS_THREADS, sizeof(MsSmem<CT, BATCH>), st>>>(                       \
             rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, k2, partialR,                \
             static_cast<int>(nI * MS_BLOCK), partialC);                                                            \

@@ -683,10 +683,29 @@ __global__ void pinnsf_tc_finish_compact_kernel(const float *__restrict__ cmsg_p
     acc[i] = __fadd_rn(mm, dterm);
 }
 
+// Internal scratch of the tensor-core forward (per-agent sums, compact-mode lists and messages), cached per calling
+// thread, device and stream; released by piml_free_workspace().
 struct TcScratch { cudaStream_t st; int dev; float *buf; int64_t cap; };
+static thread_local TcScratch g_tc_slots[8] = {};
+static thread_local int g_tc_used = 0;
+
+void tc_scratch_free() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    for (int i = 0; i < g_tc_used; ++i)
+        if (g_tc_slots[i].buf) {
+            cudaSetDevice(g_tc_slots[i].dev);
+            cudaStreamSynchronize(g_tc_slots[i].st);
+            cudaFree(g_tc_slots[i].buf);
+            g_tc_slots[i] = TcScratch{};
+        }
+    g_tc_used = 0;
+    cudaSetDevice(dev);
+}
+
 static int tc_scratch_get(cudaStream_t st, int64_t floats, float **out) {
-    static thread_local TcScratch slots[8] = {};
-    static thread_local int used = 0;
+    TcScratch *slots = g_tc_slots;
+    int &used = g_tc_used;
     int dev = 0;
     PIML_CUDA(cudaGetDevice(&dev));
     TcScratch *s = nullptr;
