@@ -481,6 +481,12 @@ def run_ours(a):
                                  "(profiles/r01c_ncu_mlapm_sym_kernel.txt)",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",
+                         "executed": ({"fp32_lane_instructions_per_ordered_pair": 16.6,
+                                       "fma_pipe_busy_ncu": 0.674, "mufu_pipe_busy_ncu": 0.474,
+                                       "source": "profiles/r01c_ncu_mlapm_sym_kernel.txt (32 packed FP32 instructions "
+                                                 "+ 9 FADD per 128 ordered pairs and warp)"} if sym_used else
+                                      {"fp32_lane_instructions_per_ordered_pair": 24.0, "fma_pipe_busy_ncu": 0.718,
+                                       "source": "profiles/r01b_ncu_mlapm_pairs2_kernel.txt"}),
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
                          "pairs_per_sec": pairs / (kernel_ms * 1e-3), "mufu_peak_tops": peaks.get("mufu_tops")},
             "e2e": {"value": N * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
