@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(M2_THREADS) mlapm_pairs2_kernel(const float2 *
 // Schedule: agents are cut into blocks of 512; block pair (I, J = I + d mod T) is evaluated by the CTA of row block I
 // for d = 0 .. floor(T/2) (a circulant schedule: every unordered block pair exactly once, every row block the same
 // amount of work; for even T the pairs at d = T/2 belong to I < T/2).  d = 0 is the diagonal block, evaluated one
-// direction at a time like v2.  A thread keeps 4 rows (2 packed lane pairs) in registers and streams J's columns from
+// direction at a time like v2.  A thread keeps 8 rows (4 packed lane pairs) in registers and streams J's columns from
 // shared memory (TMA bulk copies, double buffered), so the row direction accumulates in registers as before.  The
 // column direction needs, per column, the sum over all 512 rows of the CTA: the two packed lanes are added, each lane
 // parks its 4 sums for a batch of 8 columns in a per-warp shared-memory scratch, the warp transposes (lane -> column
@@ -437,11 +437,11 @@ constexpr int MS_RED_STRIDE = 36;                 // float4 per column of the sc
 constexpr int MS_RECF = 8;                        // floats per agent record {px,py,vx,vy, ex,ey,0,0}
 constexpr float MS_FAR = 1.0e18f;                 // padding agents sit here: exp(B r) == 0 exactly, nothing overflows
 
-template <int CT, int BATCH>
+template <int CT, int BATCH, int THREADS = MS_THREADS>
 struct MsSmem {
     float4 tile[2][CT * 2];
-    float4 red[MS_THREADS / 32][BATCH * MS_RED_STRIDE];
-    float4 colacc[MS_THREADS / 32][CT];
+    float4 red[THREADS / 32][BATCH * MS_RED_STRIDE];
+    float4 colacc[THREADS / 32][CT];
     uint64_t bars[2];
 };
 
@@ -522,15 +522,18 @@ __device__ __forceinline__ void pair2sym(const float2 npx, const float2 npy, con
 
 // partialR[split][local row] = row-direction (Sx,Sy,Tx',Ty') over the split's block pairs;
 // partialC[(I - I0) * D + d - 1][column of block J] = column-direction sums of block pair (I, J = I + d mod T).
-template <int VERSION, int CT, int BATCH>
-__global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__restrict__ rec, int T, int D, int I0,
-                                                               int per, M2Const k, float4 *__restrict__ partialR,
-                                                               int nrows_pad, float4 *__restrict__ partialC) {
+// RPS = packed row pairs per thread (2 * RPS rows): the CTA's 512 rows are spread over THREADS = 256 / RPS threads.
+template <int VERSION, int CT, int BATCH, int RPS = 2>
+__global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const float4 *__restrict__ rec, int T, int D,
+                                                                         int I0, int per, M2Const k,
+                                                                         float4 *__restrict__ partialR, int nrows_pad,
+                                                                         float4 *__restrict__ partialC) {
+    constexpr int THREADS = MS_BLOCK / (2 * RPS);
     static_assert(MS_BLOCK % CT == 0 && CT % BATCH == 0 && (BATCH == 8 || BATCH == 4), "bad stage shape");
     constexpr int SPB = MS_BLOCK / CT;                      // stages per block pair
     constexpr int LPC = 32 / BATCH;                         // lanes that share a column in the transposed sum
     extern __shared__ __align__(128) unsigned char ms_smem_raw[];
-    MsSmem<CT, BATCH> &sm = *reinterpret_cast<MsSmem<CT, BATCH> *>(ms_smem_raw);
+    MsSmem<CT, BATCH, THREADS> &sm = *reinterpret_cast<MsSmem<CT, BATCH, THREADS> *>(ms_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&sm.bars[0], 1);
@@ -545,11 +548,12 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
     const int d_lo = blockIdx.y * per;
     const int d_hi = min(d_lo + per, L);
 
-    float2 npx[2], npy[2], vx[2], vy[2], nvx[2], nvy[2], ex[2], ey[2], Sx[2], Sy[2], Tx[2], Ty[2];
+    float2 npx[RPS], npy[RPS], vx[RPS], vy[RPS], nvx[RPS], nvy[RPS], ex[RPS], ey[RPS], Sx[RPS], Sy[RPS], Tx[RPS],
+        Ty[RPS];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int64_t na = static_cast<int64_t>(I) * MS_BLOCK + (2 * i) * MS_THREADS + tid;
-        const int64_t nb = na + MS_THREADS;
+    for (int i = 0; i < RPS; ++i) {
+        const int64_t na = static_cast<int64_t>(I) * MS_BLOCK + (2 * i) * THREADS + tid;
+        const int64_t nb = na + THREADS;
         const float4 a0 = rec[2 * na], a1 = rec[2 * na + 1], b0 = rec[2 * nb], b1 = rec[2 * nb + 1];
         npx[i] = make_float2(-a0.x, -b0.x); npy[i] = make_float2(-a0.y, -b0.y);
         vx[i] = make_float2(a0.z, b0.z); vy[i] = make_float2(a0.w, b0.w);
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
             for (int j = 0; j < CT; ++j) {
                 const float4 cp = tl[2 * j];
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < RPS; ++i)
                     pair2<VERSION>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, Bl, Cl, Dl, Sx[i],
                                    Sy[i], Tx[i], Ty[i]);
             }
@@ -601,8 +605,10 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
                     float2 cSx, cSy, cTx, cTy;
                     pair2sym<VERSION, true>(npx[0], npy[0], vx[0], vy[0], nvx[0], nvy[0], ex[0], ey[0], cp, ce, Bl, Cl,
                                             Dl, Sx[0], Sy[0], Tx[0], Ty[0], cSx, cSy, cTx, cTy);
-                    pair2sym<VERSION, false>(npx[1], npy[1], vx[1], vy[1], nvx[1], nvy[1], ex[1], ey[1], cp, ce, Bl,
-                                             Cl, Dl, Sx[1], Sy[1], Tx[1], Ty[1], cSx, cSy, cTx, cTy);
+#pragma unroll
+                    for (int i = 1; i < RPS; ++i)
+                        pair2sym<VERSION, false>(npx[i], npy[i], vx[i], vy[i], nvx[i], nvy[i], ex[i], ey[i], cp, ce,
+                                                 Bl, Cl, Dl, Sx[i], Sy[i], Tx[i], Ty[i], cSx, cSy, cTx, cTy);
                     red[c * MS_RED_STRIDE + lane] = make_float4(cSx.x + cSx.y, cSy.x + cSy.y, cTx.x + cTx.y,
                                                                 cTy.x + cTy.y);
                 }
@@ -627,10 +633,10 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
             }
             __syncthreads();
             float4 *dst = partialC + (static_cast<int64_t>(blockIdx.x) * D + (d - 1)) * MS_BLOCK + (s % SPB) * CT;
-            for (int c = tid; c < CT; c += MS_THREADS) {
+            for (int c = tid; c < CT; c += THREADS) {
                 float4 a = sm.colacc[0][c];
 #pragma unroll
-                for (int wv = 1; wv < MS_THREADS / 32; ++wv) {
+                for (int wv = 1; wv < THREADS / 32; ++wv) {
                     const float4 t = sm.colacc[wv][c];
                     a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                 }
@@ -641,9 +647,9 @@ __global__ void __launch_bounds__(MS_THREADS) mlapm_sym_kernel(const float4 *__r
     }
     float4 *out = partialR + static_cast<int64_t>(blockIdx.y) * nrows_pad + static_cast<int64_t>(blockIdx.x) * MS_BLOCK;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        out[(2 * i) * MS_THREADS + tid] = make_float4(Sx[i].x, Sy[i].x, Tx[i].x, Ty[i].x);
-        out[(2 * i + 1) * MS_THREADS + tid] = make_float4(Sx[i].y, Sy[i].y, Tx[i].y, Ty[i].y);
+    for (int i = 0; i < RPS; ++i) {
+        out[(2 * i) * THREADS + tid] = make_float4(Sx[i].x, Sy[i].x, Tx[i].x, Ty[i].x);
+        out[(2 * i + 1) * THREADS + tid] = make_float4(Sx[i].y, Sy[i].y, Tx[i].y, Ty[i].y);
     }
 }
 
@@ -911,21 +917,24 @@ static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, con
     dim3 grid(static_cast<unsigned>(nI), static_cast<unsigned>(S));
     int cfg = 0;                                               // tuning: PIML_MLAPM_SYM_CFG = 0..3
     if (const char *e = getenv("PIML_MLAPM_SYM_CFG")) cfg = atoi(e);
-#define PIML_LAUNCH_SYM(V, CT, BATCH)                                                                              \
+#define PIML_LAUNCH_SYM(V, CT, BATCH, RPS)                                                                         \
     do {                                                                                                           \
-        if (sizeof(MsSmem<CT, BATCH>) > 48 * 1024)       /* per device: a process may drive several GPUs */        \
-            PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH>,                                         \
+        using Smem = MsSmem<CT, BATCH, MS_BLOCK / (2 * RPS)>;                                                      \
+        if (sizeof(Smem) > 48 * 1024)                    /* per device: a process may drive several GPUs */        \
+            PIML_CUDA(cudaFuncSetAttribute(mlapm_sym_kernel<V, CT, BATCH, RPS>,                                    \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
-                                           static_cast<int>(sizeof(MsSmem<CT, BATCH>))));                          \
-        mlapm_sym_kernel<V, CT, BATCH><<<grid, MS_THREADS, sizeof(MsSmem<CT, BATCH>), st>>>(                       \
+                                           static_cast<int>(sizeof(Smem))));                                       \
+        mlapm_sym_kernel<V, CT, BATCH, RPS><<<grid, MS_BLOCK / (2 * RPS), sizeof(Smem), st>>>(                     \
             rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, k2, partialR,                \
             static_cast<int>(nI * MS_BLOCK), partialC);                                                            \
     } while (0)
-    if (version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH);
-    else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8);
-    else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 4);
-    else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 4);
-    else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH);
+    // measured at N = 100k (ms per step): 8 rows per thread (64 threads) 6.81, 4 rows (128 threads) 6.99, 2 rows 7.16
+    if (version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH, 2);
+    else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8, 2);
+    else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 8, 2);
+    else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 8, 4);
+    else if (cfg == 4) PIML_LAUNCH_SYM(1, 128, 8, 1);
+    else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH, 4);
 #undef PIML_LAUNCH_SYM
     count_launch();
     return check_launch("mlapm_sym_kernel");
