@@ -37,7 +37,7 @@ MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
 DT, RADIUS = 0.08, 0.3
 FLUSH_MB = 160                 # L2 is 126 MB
 MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ordered-pair kernel: ncu --set full, N = 100k (profiles/r01b_...)
-MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 3592704 + 178046720  # symmetric kernel (profiles/r01c_ncu_mlapm_sym_kernel.txt)
+MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 4000512 + 181217792  # symmetric kernel (profiles/r01d_ncu_mlapm_sym_kernel.txt)
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -472,19 +472,19 @@ def run_ours(a):
                          "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH / world if sym_used
                                      else MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
                          "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, profiles/"
-                                         "r01c_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
+                                         "r01d_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
                                          "algorithmic work is FLOPs",
                          "note": "achieved = 51 algorithmic FLOP per ORDERED pair (SURVEY 8d) x N^2 / kernel time.  "
                                  "The symmetric kernel evaluates the n<->m-symmetric part of the formula once per "
                                  "unordered pair, so it executes fewer FLOP than the algorithmic count and the "
-                                 "fraction can exceed 1; ncu: FMA pipe 67.4 % busy, MUFU 47 %, ALU 33 % "
-                                 "(profiles/r01c_ncu_mlapm_sym_kernel.txt)",
+                                 "fraction can exceed 1; ncu: FMA pipe 67.0 % busy, MUFU 49 %, ALU 33 % "
+                                 "(profiles/r01d_ncu_mlapm_sym_kernel.txt)",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",
-                         "executed": ({"fp32_lane_instructions_per_ordered_pair": 16.6,
-                                       "fma_pipe_busy_ncu": 0.674, "mufu_pipe_busy_ncu": 0.474,
-                                       "source": "profiles/r01c_ncu_mlapm_sym_kernel.txt (32 packed FP32 instructions "
-                                                 "+ 9 FADD per 128 ordered pairs and warp)"} if sym_used else
+                         "executed": ({"fp32_lane_instructions_per_ordered_pair": 16.3,
+                                       "fma_pipe_busy_ncu": 0.670, "mufu_pipe_busy_ncu": 0.488,
+                                       "source": "profiles/r01d_ncu_mlapm_sym_kernel.txt (32 packed FP32 instructions "
+                                                 "per 128 ordered pairs + 9 FADD per 256 and warp)"} if sym_used else
                                       {"fp32_lane_instructions_per_ordered_pair": 24.0, "fma_pipe_busy_ncu": 0.718,
                                        "source": "profiles/r01b_ncu_mlapm_pairs2_kernel.txt"}),
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
