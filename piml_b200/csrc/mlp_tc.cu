@@ -340,6 +340,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
         const uint32_t tl = tbase + (static_cast<uint32_t>(q4 * 32) << 16);
         float *stg = stage + half * 128 * TC_STAGE_LD;
         uint32_t dph = 0;                                          // phase bit per d_ready barrier
+        // The 6-d features of a tile row (and, in compact mode, the row's index through the list) are two dependent
+        // global loads at the head of a tile's critical path: fetch them one tile ahead, into registers.
+        struct RowFeat { int64_t crow; float f[6]; bool live; };
+        auto load_row = [&](int64_t tile) {
+            RowFeat rf;
+            rf.crow = -1; rf.live = false;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) rf.f[q] = 0.f;
+            if (tile >= ntiles) return rf;
+            const int br = tile < n_ped_tiles ? 0 : 1;
+            const int k = br == 0 ? a.kp : a.ko;
+            const int AG = br == 0 ? a.ag_ped : a.ag_obs;
+            const int64_t tloc = br == 0 ? tile : tile - n_ped_tiles;
+            const int64_t agent0 = tloc * AG;
+            const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
+            int64_t src;
+            if (a.compact) {
+                const int nrows = static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128));
+                if (m < nrows && tloc * 128 + m < cnt - 1) rf.crow = (br == 0 ? a.list_ped : a.list_obs)[tloc * 128 + m];
+                rf.live = rf.crow >= 0;
+                src = rf.crow;
+            } else {
+                const int na = static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
+                rf.live = m < na * k;
+                src = agent0 * k + m;
+            }
+            if (rf.live) {
+                const float2 *f2 = reinterpret_cast<const float2 *>((br == 0 ? a.ped : a.obs) + src * 6);
+                const float2 x0 = f2[0], x1 = f2[1], x2 = f2[2];
+                rf.f[0] = x0.x; rf.f[1] = x0.y; rf.f[2] = x1.x; rf.f[3] = x1.y; rf.f[4] = x2.x; rf.f[5] = x2.y;
+            }
+            return rf;
+        };
+        RowFeat nxt = load_row(half == 0 ? static_cast<int64_t>(blockIdx.x) : ntiles);
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int br = tile < n_ped_tiles ? 0 : 1;
             const int k = br == 0 ? a.kp : a.ko;
@@ -351,16 +385,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
             const int nrows = a.compact ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
             const int64_t row0 = agent0 * k;
             // compact mode: the slot row this tile row stands for (-1: the zero row that yields f(0))
-            int64_t crow = -1;
-            if (a.compact && m < nrows && tloc * 128 + m < cnt - 1) crow = (br == 0 ? a.list_ped : a.list_obs)[tloc * 128 + m];
+            const int64_t crow = nxt.crow;
             const float *bb = biasb + br * P.bias_floats;
             if (half == 0) {   // stage the 6-d features of this row as the first A operand (K padded to 8 with zeros)
                 uint32_t hi[8], lo[8];
-                const float *f = (br == 0 ? a.ped : a.obs) + (a.compact ? (crow < 0 ? 0 : crow) : row0 + m) * 6;
-                const bool live = a.compact ? crow >= 0 : m < nrows;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float x = (q < 6 && live) ? f[q] : 0.f;
+                    const float x = (q < 6 && nxt.live) ? nxt.f[q] : 0.f;
                     tc::split_tf32(x, hi[q], lo[q]);
                 }
                 tc::st8(tl + TC_COL_AH, hi);
@@ -369,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                 tc::fence_before_sync();
             }
             tc::mbar_arrive(&a_ready[0]);
+            if (half == 0) nxt = load_row(tile + gridDim.x);       // in flight while this tile runs
             float m0 = 0.f, m1 = 0.f;
             for (int li = 0; li < P.nl; ++li) {
                 const TcLayer &Ly = P.L[li];
