@@ -252,9 +252,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
         biasb[e] = (br == 0 || a.has_obs) ? a.params[P.b_off[br] + i] : 0.f;
     }
     // compact mode: rows = the listed non-zero rows followed by ONE zero row (index -1) per branch
+    // (compact == 2, kind 1: the lists hold AGENTS with at least one non-zero slot, + one all-zero agent per branch)
     const int64_t cnt_ped = a.compact ? a.counts[0] + 1 : 0, cnt_obs = (a.compact && a.has_obs) ? a.counts[1] + 1 : 0;
-    const int64_t n_ped_tiles = a.compact ? (cnt_ped + 127) / 128 : a.n_ped_tiles;
-    const int64_t n_obs_tiles = a.compact ? (cnt_obs + 127) / 128 : a.n_obs_tiles;
+    const int64_t per_ped = a.compact == 2 ? a.ag_ped : 128, per_obs = a.compact == 2 ? a.ag_obs : 128;
+    const int64_t n_ped_tiles = a.compact ? (cnt_ped + per_ped - 1) / per_ped : a.n_ped_tiles;
+    const int64_t n_obs_tiles = a.compact ? (cnt_obs + per_obs - 1) / per_obs : a.n_obs_tiles;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -356,7 +358,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
             const int64_t agent0 = tloc * AG;
             const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
             int64_t src;
-            if (a.compact) {
+            if (a.compact == 2) {                                  // listed agent (m / k), its slot m % k
+                const int na = static_cast<int>(min(static_cast<int64_t>(AG), cnt - agent0));
+                const int64_t ai = agent0 + m / k;
+                int64_t ag = -1;
+                if (m < na * k && ai < cnt - 1) ag = (br == 0 ? a.list_ped : a.list_obs)[ai];
+                rf.live = ag >= 0;
+                src = ag * k + m % k;
+            } else if (a.compact) {
                 const int nrows = static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128));
                 if (m < nrows && tloc * 128 + m < cnt - 1) rf.crow = (br == 0 ? a.list_ped : a.list_obs)[tloc * 128 + m];
                 rf.live = rf.crow >= 0;
@@ -380,9 +389,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
             const int AG = br == 0 ? a.ag_ped : a.ag_obs;
             const int64_t tloc = br == 0 ? tile : tile - n_ped_tiles;
             const int64_t agent0 = tloc * AG;
-            const int na = a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
             const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
-            const int nrows = a.compact ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
+            const int na = a.compact == 2 ? static_cast<int>(min(static_cast<int64_t>(AG), cnt - agent0))
+                                          : (a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0)));
+            const int nrows = a.compact == 1 ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
             const int64_t row0 = agent0 * k;
             // compact mode: the slot row this tile row stands for (-1: the zero row that yields f(0))
             const int64_t crow = nxt.crow;
@@ -486,8 +496,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                         a.sums[(agent0 + ag) * 4 + br * 2 + c] = s;
                     }
                 } else if (m < na) {
-                    a.sums[(agent0 + m) * 4 + br * 2] = m0;
-                    a.sums[(agent0 + m) * 4 + br * 2 + 1] = m1;
+                    float *dst = a.sums + (agent0 + m) * 4 + br * 2;
+                    if (a.compact == 2) {                          // listed agent, or the all-zero agent -> g(0)
+                        const int64_t ag = agent0 + m < cnt - 1 ? (br == 0 ? a.list_ped : a.list_obs)[agent0 + m] : -1;
+                        dst = ag >= 0 ? a.sums + ag * 4 + br * 2 : a.f0 + br * 2;
+                    }
+                    dst[0] = m0; dst[1] = m1;
                 }
             }
             epi_barrier_all();                                     // small[] is free for the next tile
@@ -682,6 +696,58 @@ __global__ void tc_compact_kernel(const float *__restrict__ ped, const float *__
     }
 }
 
+// Compact mode 2 (summed-embedding networks, kind 1), pass 1: list the AGENTS of each branch that have a non-zero
+// slot; an agent whose slots are all zero yields the same per-branch output g(0) = pred(dec(k * 2 enc(0))).
+__global__ void tc_compact_agents_kernel(const float *__restrict__ ped, const float *__restrict__ obs, int64_t R,
+                                         int kp, int ko, int *__restrict__ list_ped, int *__restrict__ list_obs,
+                                         int *__restrict__ counts, uint8_t *__restrict__ zero_ped,
+                                         uint8_t *__restrict__ zero_obs) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int nb = obs ? 2 : 1;
+    const int br = i < R ? 0 : 1;
+    const int64_t ag = br == 0 ? i : i - R;
+    const bool in = i < R * nb;
+    bool nz = false;
+    if (in) {
+        const int k = br == 0 ? kp : ko;
+        const float2 *f = reinterpret_cast<const float2 *>((br == 0 ? ped : obs) + ag * k * 6);
+        for (int j = 0; j < 3 * k; ++j) {
+            const float2 x = f[j];
+            nz = nz || x.x != 0.f || x.y != 0.f;
+        }
+        (br == 0 ? zero_ped : zero_obs)[ag] = nz ? 0 : 1;
+    }
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2) {
+        const unsigned mask = __ballot_sync(0xffffffffu, in && nz && br == b2);
+        if (!mask) continue;
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&counts[b2], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (in && nz && br == b2) (b2 == 0 ? list_ped : list_obs)[base + __popc(mask & ((1u << lane) - 1))] = static_cast<int>(ag);
+    }
+}
+
+// Compact mode 2, finish: per-branch outputs of the listed agents, g(0) for the others, + the destination term.
+__global__ void pinnsf_tc_finish_compact2_kernel(const float *__restrict__ sums, const uint8_t *__restrict__ zero_ped,
+                                                 const uint8_t *__restrict__ zero_obs, const float *__restrict__ f0,
+                                                 const float *__restrict__ self, const float *__restrict__ dnorm,
+                                                 int64_t R, int has_obs, float tau, float *__restrict__ acc) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= 2 * R) return;
+    const int64_t ag = i >> 1;
+    const int c = static_cast<int>(i & 1);
+    const float *s = self + ag * 7;
+    float nrm = dnorm ? dnorm[ag * 2 + c] : norm2_rn(s[0], s[1]);
+    if (nrm == 0.f) nrm = __fadd_rn(nrm, 0.1f);
+    const float dir = __fdiv_rn(s[c], nrm);
+    const float dterm = __fdiv_rn(__fsub_rn(__fmul_rn(s[6], dir), s[2 + c]), tau);
+    float mm = zero_ped[ag] ? f0[c] : sums[ag * 4 + c];
+    if (has_obs) mm = __fadd_rn(mm, zero_obs[ag] ? f0[2 + c] : sums[ag * 4 + 2 + c]);
+    acc[i] = __fadd_rn(mm, dterm);
+}
+
 // Compact mode, finish: acc = sum over the k slots (in slot order, f(0) for the zero rows) of both branches + the
 // destination term -- the same additions in the same order as the in-tile sums of the dense mode.
 __global__ void pinnsf_tc_finish_compact_kernel(const float *__restrict__ cmsg_ped, const float *__restrict__ cmsg_obs,
@@ -803,15 +869,19 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *scratch = nullptr;
     // compact mode: network kind 0, messages not requested (PIML_TC_COMPACT=0 disables it)
-    static const bool compact_env = [] { const char *e = getenv("PIML_TC_COMPACT"); return !(e && atoi(e) == 0); }();
+    const char *cenv = getenv("PIML_TC_COMPACT");                  // read per call: tests compare both modes
+    const bool compact_env = !(cenv && atoi(cenv) == 0);
     // (a scene whose dense tiles fit one wave gains nothing from it and would pay two more launches)
     const int64_t dense_tiles = (R + 128 / kp - 1) / (128 / kp) + ((has_obs && ko) ? (R + 128 / ko - 1) / (128 / ko) : 0);
-    const bool compact = compact_env && P.kind == 0 && !ped_msgs && !obs_msgs && dense_tiles > sm_count() &&
-                         R * static_cast<int64_t>(kp > ko ? kp : ko) < (1LL << 31);
+    const bool compact_ok = compact_env && !ped_msgs && !obs_msgs && dense_tiles > sm_count() &&
+                            R * static_cast<int64_t>(kp > ko ? kp : ko) < (1LL << 31);
+    const bool compact = compact_ok && P.kind == 0;               // row level (per-slot decoders)
+    const bool compact2 = compact_ok && P.kind == 1;              // agent level (summed embeddings)
     const int64_t rows_ped = R * kp, rows_obs = has_obs ? R * ko : 0, rows_all = rows_ped + rows_obs;
     // scratch (floats): sums R*4 | dnorm R*2 | messages rows_all*2 | lists rows_all | f0 4 + counts 2 (+2 pad) | flags
     const int64_t f_sums = R * 4, f_norm = norm_group > 0 ? R * 2 : 0;
-    const int64_t f_extra = compact ? rows_all * 2 + rows_all + 8 + (rows_all + 3) / 4 + 4 : 0;
+    const int64_t f_extra = compact ? rows_all * 2 + rows_all + 8 + (rows_all + 3) / 4 + 4
+                                    : (compact2 ? 2 * R + 8 + (2 * R + 3) / 4 + 4 : 0);
     rc = tc_scratch_get(st, f_sums + f_norm + f_extra, &scratch);
     if (rc) return rc;
     const float *dnorm = nullptr;
@@ -832,7 +902,7 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     a.sums = scratch; a.ped_msgs = ped_msgs; a.obs_msgs = has_obs ? obs_msgs : nullptr;
     a.dbg = 0;
     a.prof = nullptr;
-    a.compact = compact ? 1 : 0;
+    a.compact = compact ? 1 : (compact2 ? 2 : 0);
     a.has_obs = has_obs ? 1 : 0;
     a.list_ped = a.list_obs = nullptr; a.counts = nullptr; a.cmsg_ped = a.cmsg_obs = a.f0 = nullptr;
     uint8_t *zero_ped = nullptr, *zero_obs = nullptr;
@@ -868,8 +938,24 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     }
     PIML_REQUIRE(smem <= 216 * 1024, "piml_pinnsf_forward_tc_f32: network too large for the shared-memory plan");
     // compact mode: the tile count is only known on the device (at most (rows + 1) / 128 + 1 per branch)
+    if (compact2) {
+        float *x = scratch + f_sums + f_norm;
+        int *lists = reinterpret_cast<int *>(x); x += 2 * R;
+        a.list_ped = lists; a.list_obs = lists + R;
+        a.f0 = x; int *counts = reinterpret_cast<int *>(x + 4); x += 8;
+        a.counts = counts;
+        zero_ped = reinterpret_cast<uint8_t *>(x); zero_obs = zero_ped + R;
+        PIML_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+        const int threads = 256;
+        const int64_t n = R * (has_obs ? 2 : 1);
+        tc_compact_agents_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, st>>>(
+            ped, has_obs ? obs : nullptr, R, kp, ko, lists, lists + R, counts, zero_ped, zero_obs);
+        count_launch();
+        rc = check_launch("tc_compact_agents_kernel");
+        if (rc) return rc;
+    }
     const int64_t tiles = compact ? (rows_ped + 128) / 128 + (has_obs ? (rows_obs + 128) / 128 : 0)
-                                  : a.n_ped_tiles + a.n_obs_tiles;
+                                  : a.n_ped_tiles + a.n_obs_tiles + (compact2 ? 2 : 0);
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     pinnsf_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, a);
     count_launch();
@@ -885,6 +971,12 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
         fprintf(stderr, "\n");
     }
     const int threads = 256;
+    if (compact2) {
+        pinnsf_tc_finish_compact2_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
+            scratch, zero_ped, zero_obs, a.f0, self, dnorm, R, has_obs, tau, acc);
+        count_launch();
+        return check_launch("pinnsf_tc_finish_compact2_kernel");
+    }
     if (compact) {
         pinnsf_tc_finish_compact_kernel<<<static_cast<unsigned>((2 * R + threads - 1) / threads), threads, 0, st>>>(
             a.cmsg_ped, a.cmsg_obs, zero_ped, zero_obs, a.f0, self, dnorm, R, kp, ko, has_obs, tau, acc);

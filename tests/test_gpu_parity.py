@@ -482,6 +482,44 @@ def test_tensor_core_compact_mode_is_bit_identical(R, kp, ko, pz, chan):
     assert err < TOL, err
 
 
+@pytest.mark.parametrize("R,kp,ko,pz,chan", [(6000, 6, 10, 0.75, 0), (3100, 6, 0, 0.5, 0), (5000, 4, 7, 0.9, 5)])
+def test_tensor_core_agent_compact_mode_is_bit_identical(R, kp, ko, pz, chan):
+    """Summed-embedding networks (pinnsf_m, model.py:1274-1279): an agent whose slots are all zero (an absent agent, or
+    one with no obstacle in range) yields the same per-branch output, so only the agents with a non-zero slot (+ one
+    all-zero agent per branch) go through the network.  Bit-identical to the dense evaluation (PIML_TC_COMPACT=0)."""
+    import os
+    from piml_b200 import models as M
+    from .golden_args import base_args
+    has_obs = ko > 0
+    args = base_args(model="pinnsf_m", dataset_name="gc1560", obs_feature_dim=6 if has_obs else 0)
+    torch.manual_seed(R)
+    net = M.CLASSES["pinnsf_m"](args).cuda().eval()
+    g = torch.Generator().manual_seed(R + 3)
+    lead = (chan, R // chan) if chan else (R,)
+    ped = torch.randn(*lead, kp, 6, generator=g)
+    ped[torch.rand(*lead, generator=g) < pz] = 0                   # whole agents without neighbours
+    ped[..., -1, :] = 0                                            # and a padded slot on everybody
+    obs = torch.randn(*lead, max(ko, 1), 6, generator=g)[..., :ko, :]
+    if ko:
+        obs[torch.rand(*lead, generator=g) < 0.95] = 0
+    slf = torch.randn(*lead, 7, generator=g)
+    ped, obs, slf = ped.cuda(), obs.cuda(), slf.cuda()
+    packed = M.pack_device(net.state_dict(), net.spec)
+    ptc = M.pack_device_tc(net.state_dict(), net.spec)
+    assert ptc is not None
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["PIML_TC_COMPACT"] = mode
+        try:
+            outs[mode] = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=False, packed_tc=ptc)[0].clone()
+        finally:
+            os.environ.pop("PIML_TC_COMPACT", None)
+    assert torch.equal(outs["1"], outs["0"])
+    ref = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True)
+    err = accel_err(npy(outs["1"]).reshape(-1, 2), npy(ref[0]).reshape(-1, 2), npy(slf).reshape(-1, 7), net.spec.tau)
+    assert err < TOL, err
+
+
 # ---- integrator ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"])
 def test_integrate_step_golden(name):
