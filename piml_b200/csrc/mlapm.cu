@@ -525,7 +525,7 @@ __device__ __forceinline__ void pair2sym(const float2 npx, const float2 npy, con
 // RPS = packed row pairs per thread (2 * RPS rows): the CTA's 512 rows are spread over THREADS = 256 / RPS threads.
 template <int VERSION, int CT, int BATCH, int RPS = 2>
 __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const float4 *__restrict__ rec, int T, int D,
-                                                                         int I0, int per, M2Const k,
+                                                                         int I0, int per, int sub, M2Const k,
                                                                          float4 *__restrict__ partialR, int nrows_pad,
                                                                          float4 *__restrict__ partialC) {
     constexpr int THREADS = MS_BLOCK / (2 * RPS);
@@ -545,7 +545,11 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
     const int I = I0 + blockIdx.x;
     int L = D + 1;                                          // d = 0 .. D
     if (!(T & 1) && 2 * I >= T) L = D;                      // even T: the pairs at d = T/2 belong to I < T/2
-    const int d_lo = blockIdx.y * per;
+    // blockIdx.y = (group of `per` block pairs) * sub + (which 1/sub of each pair's column stages): small shards use
+    // sub > 1 so that the grid still has several waves of CTAs
+    const int sy = blockIdx.y / sub, su = blockIdx.y - sy * sub;
+    const int spc = SPB / sub;                               // stages of a block pair this CTA handles
+    const int d_lo = sy * per;
     const int d_hi = min(d_lo + per, L);
 
     float2 npx[RPS], npy[RPS], vx[RPS], vy[RPS], nvx[RPS], nvy[RPS], ex[RPS], ey[RPS], Sx[RPS], Sy[RPS], Tx[RPS],
@@ -563,12 +567,12 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
     }
     const float2 Bl = splat(k.Bl), Cl = splat(k.Cl), Dl = splat(k.Dl);
 
-    const int nst = d_hi > d_lo ? (d_hi - d_lo) * SPB : 0;
+    const int nst = d_hi > d_lo ? (d_hi - d_lo) * spc : 0;
     constexpr uint32_t STAGE_BYTES = CT * MS_RECF * sizeof(float);
     auto stage_src = [&](int s) {
-        int J = I + d_lo + s / SPB;
+        int J = I + d_lo + s / spc;
         J = J >= T ? J - T : J;
-        return rec + (static_cast<int64_t>(J) * MS_BLOCK + (s % SPB) * CT) * 2;
+        return rec + (static_cast<int64_t>(J) * MS_BLOCK + (su * spc + s % spc) * CT) * 2;
     };
     if (tid == 0 && nst > 0) {
         mbar_expect_tx(&sm.bars[0], STAGE_BYTES);
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
         mbar_wait(&sm.bars[buf], (phase_bits >> buf) & 1u);
         phase_bits ^= (1u << buf);
         const float4 *tl = sm.tile[buf];
-        const int d = d_lo + s / SPB;
+        const int d = d_lo + s / spc;
         if (d == 0) {
             // diagonal block: rows and columns are the same agents, every ordered pair appears -> one direction each
 #pragma unroll 4
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
                 __syncwarp();
             }
             __syncthreads();
-            float4 *dst = partialC + (static_cast<int64_t>(blockIdx.x) * D + (d - 1)) * MS_BLOCK + (s % SPB) * CT;
+            float4 *dst = partialC + (static_cast<int64_t>(blockIdx.x) * D + (d - 1)) * MS_BLOCK + (su * spc + s % spc) * CT;
             for (int c = tid; c < CT; c += THREADS) {
                 float4 a = sm.colacc[0][c];
 #pragma unroll
@@ -856,9 +860,29 @@ static int sym_per(int64_t nI, int64_t T) {
     const int64_t per = pairs / want;
     return per < 1 ? 1 : static_cast<int>(per);
 }
+// CTAs per block pair (1, 2 or 4 = the 4 column stages of a pair split over that many CTAs): a shard with few row
+// blocks (8 ranks at N = 100k: 25 blocks x 99 pairs) would otherwise run ~2 waves of CTAs with a nearly empty last one.
+static int sym_sub(int64_t nI, int64_t T, int per) {
+    if (const char *e = getenv("PIML_MLAPM_SYM_SUB")) {
+        const int f = atoi(e);
+        if (f == 1 || f == 2 || f == 4) return f;
+    }
+    const int64_t ctas = nI * ((T / 2 + 1 + per - 1) / per), wave = 8LL * sm_count();
+    int sub = 1;
+    while (sub < MS_BLOCK / MS_CT && ctas * sub < 6 * wave) sub *= 2;
+    return sub;
+}
+// Row-partial splits of a launch over nI row blocks: (groups of `per` block pairs) x sub.
+static int sym_splits(int64_t nI, int64_t T, int *per, int *sub) {
+    *per = sym_per(nI, T);
+    *sub = sym_sub(nI, T, *per);
+    return static_cast<int>((T / 2 + 1 + *per - 1) / *per) * *sub;
+}
+
 static int64_t sym_workspace_bytes(int64_t N) {
     const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
-    const int64_t per = sym_per(T, T), S = (D + 1 + per - 1) / per;
+    int per_, sub_;
+    const int64_t S = sym_splits(T, T, &per_, &sub_);
     return npad * MS_RECF * sizeof(float) + (S + D) * npad * 4 * sizeof(float) + 256;
 }
 
@@ -904,7 +928,7 @@ static bool sym_params_ok(const piml_mlapm_params *prm, const MlConst &k) {
 
 // prep + symmetric pair kernel for the row blocks [I0, I0 + nI) of a crowd of T blocks.
 static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, const float2 *d2, int N, int64_t T,
-                            int64_t I0, int64_t nI, int per, int S, const MlConst &k, float4 *rec, float4 *partialR,
+                            int64_t I0, int64_t nI, int per, int sub, int S, const MlConst &k, float4 *rec, float4 *partialR,
                             float4 *partialC, cudaStream_t st) {
     const int64_t D = T / 2, npad = T * MS_BLOCK;
     const int threads = 256;
@@ -925,14 +949,12 @@ static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, con
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
                                            static_cast<int>(sizeof(Smem))));                                       \
         mlapm_sym_kernel<V, CT, BATCH, RPS><<<grid, MS_BLOCK / (2 * RPS), sizeof(Smem), st>>>(                     \
-            rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, k2, partialR,                \
+            rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, sub, k2, partialR,           \
             static_cast<int>(nI * MS_BLOCK), partialC);                                                            \
     } while (0)
     // measured at N = 100k (ms per step): 8 rows per thread (64 threads) 6.81, 4 rows (128 threads) 6.99, 2 rows 7.16
     if (version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH, 2);
-    else if (cfg == 1) PIML_LAUNCH_SYM(1, 256, 8, 2);
     else if (cfg == 2) PIML_LAUNCH_SYM(1, 128, 8, 2);
-    else if (cfg == 3) PIML_LAUNCH_SYM(1, 256, 8, 4);
     else if (cfg == 4) PIML_LAUNCH_SYM(1, 128, 8, 1);
     else PIML_LAUNCH_SYM(1, MS_CT, MS_BATCH, 4);
 #undef PIML_LAUNCH_SYM
@@ -994,12 +1016,12 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) && sym_params_ok(prm, k);
     if (sym_ok && (g_mlapm_algorithm == 2 || (g_mlapm_algorithm == 0 && N >= MS_AUTO_MIN_AGENTS))) {
         const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
-        const int per = sym_per(T, T);
-        const int S = static_cast<int>((D + 1 + per - 1) / per);
+        int per, sub;
+        const int S = sym_splits(T, T, &per, &sub);
         float4 *rec = reinterpret_cast<float4 *>(workspace);
         float4 *partialR = rec + npad * 2;
         float4 *partialC = partialR + static_cast<int64_t>(S) * npad;
-        rc = launch_sym_pairs(prm->version, p2, v2, d2, iN, T, 0, T, per, S, k, rec, partialR, partialC, st);
+        rc = launch_sym_pairs(prm->version, p2, v2, d2, iN, T, 0, T, per, sub, S, k, rec, partialR, partialC, st);
         if (rc) return rc;
         const int threads = 256;
         symp = SymPartials{partialC, static_cast<int>(T), static_cast<int>(D), 0, static_cast<int>(npad), nullptr, 0, 0};
@@ -1153,11 +1175,12 @@ extern "C" int64_t piml_mlapm_sym_shard_workspace_bytes(int64_t N, int world) {
     if (N <= 0 || world < 1 || world > ML_MAX_PEERS) return 0;
     const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
     const int64_t nI = (T + world - 1) / world;
-    const int64_t per = sym_per(nI, T), S = (D + 1 + per - 1) / per;
+    int per_, sub_;
+    const int64_t S = sym_splits(nI, T, &per_, &sub_);
     return npad * MS_RECF * sizeof(float) + (S + D) * nI * MS_BLOCK * 4 * sizeof(float) + 256;
 }
 
-struct SymShardPlan { int64_t T, D, npad, I0, nI; int per, S; float4 *rec, *partialR, *partialC; };
+struct SymShardPlan { int64_t T, D, npad, I0, nI; int per, sub, S; float4 *rec, *partialR, *partialC; };
 
 static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64_t workspace_bytes, SymShardPlan *pl) {
     PIML_REQUIRE(N > 0 && N < (1LL << 31) && world >= 1 && world <= ML_MAX_PEERS && rank >= 0 && rank < world,
@@ -1173,8 +1196,7 @@ static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64
     sym_block_bounds(pl->T, world, Ib);
     pl->I0 = Ib[rank];
     pl->nI = Ib[rank + 1] - Ib[rank];
-    pl->per = sym_per((pl->T + world - 1) / world, pl->T);
-    pl->S = static_cast<int>((pl->D + 1 + pl->per - 1) / pl->per);
+    pl->S = sym_splits((pl->T + world - 1) / world, pl->T, &pl->per, &pl->sub);
     pl->rec = reinterpret_cast<float4 *>(workspace);
     pl->partialR = pl->rec + pl->npad * 2;
     pl->partialC = pl->partialR + static_cast<int64_t>(pl->S) * pl->nI * MS_BLOCK;
@@ -1196,7 +1218,7 @@ extern "C" int piml_mlapm_sym_pairs_push_f32(const float *pos, const float *vel,
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     rc = launch_sym_pairs(prm->version, reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel),
-                          reinterpret_cast<const float2 *>(dest), static_cast<int>(N), pl.T, pl.I0, pl.nI, pl.per, pl.S,
+                          reinterpret_cast<const float2 *>(dest), static_cast<int>(N), pl.T, pl.I0, pl.nI, pl.per, pl.sub, pl.S,
                           k, pl.rec, pl.partialR, pl.partialC, st);
     if (rc) return rc;
     PeerInbox peers;
