@@ -3,7 +3,8 @@ dense vs compact mode.  Prints the per-tile breakdown of CTA 0 (stderr of the li
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["PIML_TC_PROF"] = "1"
+if "--no-prof" not in sys.argv:
+    os.environ["PIML_TC_PROF"] = "1"
 import bench
 import piml_b200 as P
 from piml_b200 import models as M
