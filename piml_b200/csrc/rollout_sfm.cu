@@ -91,15 +91,17 @@ __global__ void __launch_bounds__(RS_THREADS) sfm_rollout_kernel(const __grid_co
         float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;              // slot order, like torch.sum over dim -2
 #pragma unroll
         for (int j = 0; j < RS_KP; ++j) {
+            if (j >= kp) break;                                   // uniform
             const float mx = __shfl_sync(0xffffffffu, pm[j / G].x, j % G, G);
             const float my = __shfl_sync(0xffffffffu, pm[j / G].y, j % G, G);
-            if (j < kp) { ax = __fadd_rn(ax, mx); ay = __fadd_rn(ay, my); }
+            ax = __fadd_rn(ax, mx); ay = __fadd_rn(ay, my);
         }
 #pragma unroll
         for (int j = 0; j < RS_KO; ++j) {
+            if (j >= ko) break;
             const float mx = __shfl_sync(0xffffffffu, om[j / G].x, j % G, G);
             const float my = __shfl_sync(0xffffffffu, om[j / G].y, j % G, G);
-            if (j < ko) { bx = __fadd_rn(bx, mx); by = __fadd_rn(by, my); }
+            bx = __fadd_rn(bx, mx); by = __fadd_rn(by, my);
         }
         const float2 a_next = sfm_total(ax, ay, bx, by, dfx, dfy, hvx, hvy, v0, r.prm.tau);
         // ---- record the state at t, update, teacher-forced entry                           (:596-639)
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(RS_THREADS) sfm_rollout_kernel(const __grid_co
             }
 #pragma unroll
             for (int j = 0; j < RS_KP; ++j) {                     // merge the G lists: k smallest keys, smallest first
+                if (j >= kp) break;                               // uniform: slots beyond kp stay zero
                 const uint64_t w = group_min<G>(best.key[0]);
                 if (w != EMPTY_KEY && best.key[0] == w) best.pop_front();
                 if (j % G == g) {
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(RS_THREADS) sfm_rollout_kernel(const __grid_co
             }
 #pragma unroll
             for (int j = 0; j < RS_KO; ++j) {
+                if (j >= ko) break;
                 const uint64_t w = group_min<G>(best.key[0]);
                 if (w != EMPTY_KEY && best.key[0] == w) best.pop_front();
                 if (j % G == g) {
