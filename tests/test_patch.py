@@ -81,10 +81,28 @@ def test_install_on_the_real_reference_modules():
     DATA, MODEL, MLAPM, SIM, UTILS = H.import_reference()
     import piml_b200.patch as patch
     orig = DATA.Pedestrians.get_relative_features
-    names = patch.install(DATA=DATA, MLAPM_MOD=MLAPM, MODEL=MODEL, SIM=SIM, UTILS=UTILS)
+    import functions.metrics as METRIC
+    orig_ot = METRIC.ot_with_time_mask
+    names = patch.install(DATA=DATA, MLAPM_MOD=MLAPM, MODEL=MODEL, SIM=SIM, UTILS=UTILS, METRIC=METRIC)
     try:
-        assert len(names) == 14
+        assert len(names) == 14 + 4
         assert SIM.BaseSimulator.get_relative_features is not orig
+        import piml_b200.metrics as MT
+        assert METRIC.ot_with_time_mask is MT.ot_with_time_mask and METRIC.collision_count is MT.collision_count
+        # simulators.py calls METRIC.<name>(...) through the module object, so it sees the replacements
+        assert SIM.METRIC.mmd_with_time_mask is MT.mmd_with_time_mask
     finally:
         patch.uninstall()
-    assert DATA.Pedestrians.get_relative_features is orig
+    assert DATA.Pedestrians.get_relative_features is orig and METRIC.ot_with_time_mask is orig_ot
+
+
+def test_social_force_mirror_constants_and_errors():
+    """piml_b200.SocialForce: the ped constants are calc_acceleration's v0 constants per dataset (utils.py:47-52), the
+    obstacle constants socialforce.yaml's intensity / radius; unknown datasets are rejected (no GPU needed)."""
+    import piml_b200 as P
+    gc, ucy = P.SocialForce("gc1560").spec, P.SocialForce("ucy").spec
+    assert (gc.A_ped, gc.B_ped) == (8.75, -2.5) and (ucy.A_ped, ucy.B_ped) == (10.67, -3.33)
+    assert (gc.A_obs, gc.B_obs, gc.tau, gc.eps) == (50.0, -5.0, 0.5, 1e-6)
+    assert len(list(P.SocialForce("gc2344").parameters())) == 0
+    with pytest.raises(ValueError):
+        P.SocialForce("nope")
