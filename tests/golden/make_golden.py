@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by running the UNMODIFIED reference (imported from /root/reference).
 
 Run in the build container only:   python tests/golden/make_golden.py [group ...]
-Groups: features models mlapm sfm rollout sfm_rollout training metrics.   Output: tests/golden/*.npz (small, compressed).
+Groups: features models mlapm sfm rollout sfm_rollout training metrics losses.   Output: tests/golden/*.npz (small, compressed).
 
 The reference ships no tests and no golden vectors, so these files ARE the pin: they
 hold the reference's own outputs on its own data files (GC / UCY / toy clips) and on seeded synthetic crowds.
@@ -478,6 +478,44 @@ def gen_training():
     save("training_rollout", **out)
 
 
+def gen_losses():
+    """f-3: the reference's own rollout-loss methods (simulators.py:172-249) called directly on seeded tensors shaped
+    like a UCY / GC rollout-training batch: values with reduction 'sum' and d/d pred from the reference's autograd."""
+    import types
+    stub = types.SimpleNamespace(reduction=SIM.BaseSimulator.reduction)
+    for name in ("multiple_rollout_mse_loss", "multiple_rollout_collision_avoidance_loss",
+                 "multiple_rollout_collision_loss"):
+        setattr(stub, name, types.MethodType(getattr(SIM.BaseSimulator, name), stub))
+    out = {}
+    for case, (C, T, N, decay, mask) in {"ucy": (8, 10, 144, 0.9, False), "gc": (6, 5, 122, 1.0, True),
+                                         "tiny": (2, 1, 5, 0.5, False)}.items():
+        g = torch.Generator().manual_seed(C * 1000 + T)
+        wide = torch.randn(C, T, N, 12, generator=g) * 3
+        pred = (wide[..., :2] + 0.3 * torch.randn(C, T, N, 2, generator=g)).clone().requires_grad_(True)
+        a_pred = (wide[..., 4:6] + 0.1 * torch.randn(C, T, N, 2, generator=g)).clone().requires_grad_(True)
+        coll = (torch.rand(C, T, N, generator=g) < 0.1).float() * 2
+        hard = (torch.rand(C, T, N, generator=g) < 0.03).float()
+        am = (torch.rand(N, generator=g) < 0.7).float() if mask else None
+        labels = wide[..., :2]
+        mse = stub.multiple_rollout_mse_loss(pred, labels, decay, reduction='sum')
+        cl = stub.multiple_rollout_collision_loss(pred, labels, decay, 10, coll.clone(), reduction='sum',
+                                                  abnormal_mask=am)
+        hl = stub.multiple_rollout_collision_loss(pred, labels, decay, 10, hard.clone(), reduction='sum',
+                                                  abnormal_mask=am)
+        (mse + 10.0 * cl + 100.0 * hl).backward()
+        amse = stub.multiple_rollout_mse_loss(a_pred, wide[..., 4:6], decay, reduction='sum', reverse=True)
+        amse.backward()
+        k = case + "/"
+        out[k + "wide"], out[k + "pred"], out[k + "a_pred"] = wide, pred.detach(), a_pred.detach()
+        out[k + "coll"], out[k + "hard"] = coll, hard
+        if am is not None:
+            out[k + "abnormal_mask"] = am
+        out[k + "decay"] = np.float64(decay)
+        out[k + "mse"], out[k + "collision"], out[k + "hard_collision"], out[k + "a_mse"] = mse, cl, hl, amse
+        out[k + "g_pred"], out[k + "g_a_pred"] = pred.grad, a_pred.grad          # weights 1 / 10 / 100 and 1
+    save("losses", **out)
+
+
 def gen_metrics():
     """f-4: the evaluation metrics of test_multiple_rollouts (simulators.py:505-531) on the reference's own rollouts
     (golden trajectories): post_process (:443-463), then METRIC.mae / ot / mmd _with_time_mask (metrics.py:29-91) and
@@ -516,7 +554,7 @@ def gen_metrics():
     save("metrics", **out)
 
 
-GROUPS = {"metrics": gen_metrics, "features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
+GROUPS = {"metrics": gen_metrics, "losses": gen_losses, "features": gen_features, "models": gen_models, "mlapm": gen_mlapm, "sfm": gen_sfm,
           "rollout": gen_rollout, "sfm_rollout": gen_sfm_rollout, "training": gen_training}
 
 if __name__ == "__main__":

@@ -278,3 +278,27 @@ def test_fused_rollout_losses_match_the_torch_restatement(C, T, N, reverse, with
         assert abs(float(out[q]) - ref) <= 2e-5 * max(abs(ref), 1.0), (q, float(out[q]), ref)
     scale = float(pred.grad.abs().max())
     assert float((got_g - pred.grad).abs().max()) <= 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("case", ["ucy", "gc", "tiny"])
+def test_fused_rollout_losses_match_reference_methods(case):
+    """f-3 pinned to the reference: the fused loss kernels against the values and gradients of the reference's own
+    BaseSimulator.multiple_rollout_* methods (tests/golden/make_golden.py losses)."""
+    from piml_b200.autograd import RolloutLossesFunction
+    g = group(golden("losses"), case)
+    wide = torch.from_numpy(g["wide"]).to(dev())
+    pred = torch.from_numpy(g["pred"]).to(dev()).requires_grad_(True)
+    a_pred = torch.from_numpy(g["a_pred"]).to(dev()).requires_grad_(True)
+    am = torch.from_numpy(g["abnormal_mask"]).to(dev()) if "abnormal_mask" in g else None
+    decay = float(g["decay"])
+    out = RolloutLossesFunction.apply(pred, wide[..., :2], decay, False, torch.from_numpy(g["coll"]).to(dev()),
+                                      torch.from_numpy(g["hard"]).to(dev()), am)
+    (out * torch.tensor([1.0, 10.0, 100.0], device=dev())).sum().backward()
+    a_out = RolloutLossesFunction.apply(a_pred, wide[..., 4:6], decay, True, None, None, None)
+    a_out[0].backward()
+    for got, key in ((out[0], "mse"), (out[1], "collision"), (out[2], "hard_collision"), (a_out[0], "a_mse")):
+        ref = float(g[key])
+        assert abs(float(got.detach()) - ref) <= 2e-5 * max(abs(ref), 1.0), (key, float(got.detach()), ref)
+    scale = float(np.abs(g["g_pred"]).max())
+    assert float(np.abs(pred.grad.cpu().numpy() - g["g_pred"]).max()) <= 2e-5 * max(scale, 1.0)
+    assert np.allclose(a_pred.grad.cpu().numpy(), g["g_a_pred"], rtol=2e-5, atol=2e-6)

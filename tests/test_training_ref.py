@@ -78,3 +78,28 @@ def test_collision_detection_ref_shapes():
     c4 = TR.collision_detection_ref(p.reshape(2, 3, 9, 2), 0.5)
     assert c4.shape == (2, 3, 9, 9)
     assert set(np.unique(c3.numpy()).tolist()) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("case", ["ucy", "gc", "tiny"])
+def test_loss_restatements_match_reference_methods(case):
+    """f-3: the torch restatements of the rollout losses (piml_b200.train_rollout.multiple_rollout_*) against the
+    reference's own BaseSimulator methods (simulators.py:172-249) called on the same seeded tensors: values and d/d pred."""
+    from piml_b200 import train_rollout as TR
+    from tests.util import golden, group
+    g = group(golden("losses"), case)
+    wide = torch.from_numpy(g["wide"])
+    pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+    a_pred = torch.from_numpy(g["a_pred"]).requires_grad_(True)
+    am = torch.from_numpy(g["abnormal_mask"]) if "abnormal_mask" in g else None
+    decay = float(g["decay"])
+    labels = wide[..., :2]
+    mse = TR.multiple_rollout_mse_loss(pred, labels, decay, 'sum')
+    cl = TR.multiple_rollout_collision_loss(pred, labels, decay, 10, torch.from_numpy(g["coll"]).clone(), 'sum', am)
+    hl = TR.multiple_rollout_collision_loss(pred, labels, decay, 10, torch.from_numpy(g["hard"]).clone(), 'sum', am)
+    (mse + 10.0 * cl + 100.0 * hl).backward()
+    amse = TR.multiple_rollout_mse_loss(a_pred, wide[..., 4:6], decay, 'sum', reverse=True)
+    amse.backward()
+    for got, key in ((mse, "mse"), (cl, "collision"), (hl, "hard_collision"), (amse, "a_mse")):
+        assert abs(float(got.detach()) - float(g[key])) <= 1e-6 * max(abs(float(g[key])), 1.0), key
+    assert np.allclose(pred.grad.numpy(), g["g_pred"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(a_pred.grad.numpy(), g["g_a_pred"], rtol=1e-5, atol=1e-6)
