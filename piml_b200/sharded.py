@@ -44,6 +44,17 @@ def allgather_state(pos_next, vel_next, pos_rows, vel_rows, group=None):
     return pos_next, vel_next
 
 
+def allgather_rows(full, part, group=None):
+    """All-gather of equally sized row blocks: rank g contributes `part` = rows [g n/G, (g+1) n/G) of `full` (n, ...).
+    NCCL: one all_gather_into_tensor; gloo (CPU tests of the host logic): all_gather into row-block views."""
+    if dist.get_backend(group) == "gloo":
+        chunks = list(full.chunk(dist.get_world_size(group), dim=0))
+        dist.all_gather(chunks, part.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(full, part.contiguous(), group=group)
+    return full
+
+
 class ShardedCrowd(object):
     """Double-buffered crowd state in symmetric memory: buf[parity][0] = positions (N,2), buf[parity][1] = velocities."""
 
@@ -196,7 +207,7 @@ class ShardedNNCrowd(object):
             a_own = M.pinnsf_forward(self.spec, self.packed, self.ped_f, self.obs_f, self.self_f, need_msgs=False,
                                      packed_tc=self.packed_tc)[0]
         if self.world > 1:                   # the path's one exchange: 8 B per agent
-            dist.all_gather_into_tensor(self.a_next.view(self.N, 2), a_own.contiguous(), group=self.group)
+            allgather_rows(self.a_next.view(self.N, 2), a_own, self.group)
         else:
             self.a_next.view(self.N, 2).copy_(a_own)
         integrate_step(self.p, self.v, self.a, self.a_next, self.dest, self.didx, self.dnum, self.wp, dt,
