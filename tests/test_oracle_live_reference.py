@@ -64,3 +64,56 @@ def test_oracle_selection_equals_live_reference_on_gc_frames():
             od, oi = O.select(p.numpy(), p.numpy(), head.numpy(), 6, angle)
             assert np.array_equal(od, dist.numpy()), (t, angle)
             assert valid_sets(oi, od, 4) == valid_sets(idx.numpy(), dist.numpy(), 4), (t, angle)
+
+
+@pytest.mark.parametrize("N,ver,seed", [(5, "GC", 1), (333, "GC", 2), (1500, "GC", 3), (700, "raw", 4)])
+def test_oracle_mlapm_equals_live_reference(N, ver, seed):
+    """MLAPM.step (mlapm.py:10-58) live on seeded crowds (incl. stationary agents): 1e-5 per agent, operand-relative."""
+    H = _harness()
+    _, _, MLAPM, _, _ = H.import_reference()
+    g = torch.Generator().manual_seed(seed)
+    side = (N / 0.5) ** 0.5
+    p, d = torch.rand(N, 2, generator=g) * side, torch.rand(N, 2, generator=g) * side
+    v = torch.randn(N, 2, generator=g)
+    v[torch.rand(N, generator=g) < 0.1] = 0
+    ds = 1.34 + 0.3 * torch.randn(N, 1, generator=g)
+    kw = dict(version=ver, tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
+    ref = MLAPM.MLAPM(**kw).step(p.clone(), v.clone(), ds.clone(), d.clone(), 0.08).numpy()
+    got = O.mlapm_step(p.numpy(), v.numpy(), ds.numpy(), d.numpy(), 0.08, ver)
+    num = np.linalg.norm(got.astype(np.float64) - ref, axis=-1)
+    den = np.maximum(np.maximum(np.linalg.norm(ref, axis=-1), np.linalg.norm(v.numpy(), axis=-1)), 1e-6)
+    assert float((num / den).max()) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["pinnsf_bm", "pinnsf_m", "pinnsf_bottleneck", "pinnsf"])
+def test_oracle_network_equals_live_reference_module(kind):
+    """The four PINNSF forwards (model.py:762, :1104, :1185, :1271) instantiated live with a fresh seed, eval mode, on
+    random features with zero-padded slots: every output of the oracle within 1e-5."""
+    from piml_b200 import models as M
+    from tests.golden_args import base_args
+    from tests.util import accel_err, rel_vec_err
+    H = _harness()
+    _, MODEL, _, _, _ = H.import_reference()
+    cls = {"pinnsf_bm": "PINNSF_bottleneck_multitask", "pinnsf_m": "PINNSF_multitask",
+           "pinnsf_bottleneck": "PINNSF_bottleneck", "pinnsf": "PINNSF"}[kind]
+    args = base_args(model=kind, dataset_name="gc1560")
+    torch.manual_seed(1234)
+    net = getattr(MODEL, cls)(args).eval()
+    g = torch.Generator().manual_seed(5)
+    R = 37
+    ped, obs, slf = torch.randn(R, 6, 6, generator=g), torch.randn(R, 10, 6, generator=g), torch.randn(R, 7, generator=g)
+    ped[:, 4:] = 0
+    obs[::2] = 0
+    with torch.no_grad():
+        ref = net(ped.clone(), obs.clone(), slf.clone())
+    spec = M.spec_from_module(net)
+    desc = O.net_desc(spec.enc_dims, spec.proc_mode, spec.dec_dims, spec.coll_dims, spec.kind)
+    out = O.pinnsf_forward(desc, M.pack_state_dict(net.state_dict(), spec).numpy(), spec.tau, ped.numpy(), obs.numpy(),
+                           slf.numpy(), spec.has_obs)
+    assert len(out) == len(ref)
+    assert accel_err(out[0], ref[0].numpy(), slf.numpy(), spec.tau) < 1e-5
+    for o, r_ in zip(out[1:], ref[1:]):
+        r_ = r_.numpy()
+        o = o.reshape(r_.shape)
+        err = rel_vec_err(o, r_, floor=1e-3) if r_.ndim >= 2 and r_.shape[-1] > 1 else float(np.abs(o - r_).max())
+        assert err < 1e-5, (kind, err)
