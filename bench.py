@@ -13,9 +13,14 @@ force (N^2 ordered pairs), destination term, v' = v + F dt, p' = p + v' dt, arri
             FP32/MUFU-pipe bound, DRAM traffic is O(N)); algorithmic work = 51 FLOP per ordered pair
   cpu_baseline  the oracle's C port of MLAPM.step timed on the host cores on a bounded row sample (rank 0, N=1 only)
 
-Multi-GPU (--gpus N under torchrun): the crowd is agent-sharded -- rank g owns rows [g N/G, (g+1) N/G), computes them
-against all N columns, and the new positions/velocities are exchanged with ONE NCCL all-gather per step (strong
-scaling at fixed N).   --impl reference times the reference's CPU algorithm (oracle port, all host threads).
+  parity    the step the bench times, checked in the same run against oracle rows (action AND force level)
+  reference_pytorch  the UNMODIFIED reference (baseline/_ref, PyTorch CPU) timed on the host cores at the sizes it can run
+
+Multi-GPU (--gpus N under torchrun): the crowd is agent-sharded.  Default exchange "push": the symmetric evaluation
+splits the unordered block pairs over the ranks, column-direction shares and the new state are stored into the owners'
+buffers over NVLink peer memory by the pair / finalize kernels (no collective); "--exchange nccl": ordered rows + one NCCL
+all-gather per step.  Strong scaling at fixed N.  --impl reference times the reference's CPU algorithm (the oracle's
+C/OpenMP port of MLAPM.step on all host threads: the Python reference cannot run N = 100k).
 """
 import argparse
 import json
@@ -119,7 +124,123 @@ def cpu_baseline(N, seconds=12.0, threads=None):
     assert np.isfinite(out).all()
     return {"value": R / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle C port (OpenMP, {cores} threads) of MLAPM.step: rows [0,{R}) x all {N} columns, "
-                      f"{R * N / dt / 1e6:.1f} Mpairs/s, {dt:.1f} s"}
+                      f"{R * N / dt / 1e6:.1f} Mpairs/s, {dt:.1f} s"}, out
+
+
+BIG_DT = float(2 ** 20)       # F dt exact, v below the rounding of F dt: F = (action - v) / 2^20 to 6e-8
+
+
+def parity_block(torch, dev, N, model, oracle_rows=None):
+    """The timed step against the oracle, in the same run: action = v + F dt on the rows the cpu_baseline leg computed
+    anyway, and the FORCE (recovered through dt = 2^20) on row ranges spread over the symmetric kernel's block
+    schedule.  strict = ||dF|| / ||F|| per agent; kappa = S / ||F|| with S = |dest term| + sum |pair term| (fp32
+    rounding of a row sum is relative to S; tests/test_gpu_parity_sizes.py states the enforced gate)."""
+    from oracle import oracle as O
+    import numpy as np
+    p, v, ds, dest, _ = synthetic_crowd(N)
+    pn, vn, dsn, dn = [x.numpy() for x in (p, v, ds, dest)]
+    pc, vc, dsc, dc = [x.to(dev) for x in (p, v, ds, dest)]
+    act = model.step(pc, vc, dsc, dc, DT).cpu().numpy()
+    big = model.step(pc, vc, dsc, dc, BIG_DT).cpu().numpy().astype(np.float64)
+    res = {"oracle": "oracle/piml_oracle.c orc_mlapm_step (mlapm.py:10-58 in the reference's fp32 op order, row sums "
+                     "in fp64)"}
+    if oracle_rows is not None and len(oracle_rows):
+        R = len(oracle_rows)
+        num = np.linalg.norm(act[:R].astype(np.float64) - oracle_rows, axis=-1)
+        den = np.maximum(np.linalg.norm(oracle_rows, axis=-1), 1e-6)
+        res.update({"action_rows": R, "max_rel_action": float((num / den).max())})
+    block = 512
+    T = (N + block - 1) // block
+    e_all, nF_all, S_all = [], [], []
+    for b in sorted({0, 1, T // 3 | 1, T // 2, (2 * T) // 3, T - 2, T - 1} & set(range(T))):
+        lo, hi = b * block, min(N, b * block + block)
+        _, force, opsum = O.mlapm_step_diag(pn, vn, dsn, dn, DT, "GC", rows=(lo, hi))
+        F = (big[lo:hi] - vn[lo:hi].astype(np.float64)) / BIG_DT
+        e_all.append(np.linalg.norm(F - force, axis=-1)); nF_all.append(np.linalg.norm(force, axis=-1))
+        S_all.append(opsum)
+    e, nF, S = [np.concatenate(x) for x in (e_all, nF_all, S_all)]
+    strict = e / np.maximum(nF, 1e-30)
+    kappa = S / np.maximum(nF, 1e-30)
+    well = kappa <= 16.0
+    res.update({"force_rows": int(len(e)), "max_rel_force": float(strict.max()),
+                "max_rel_force_kappa": float(kappa[int(np.argmax(strict))]),
+                "p999_rel_force": float(np.quantile(strict, 0.999)),
+                "max_rel_force_well_conditioned": float(strict[well].max()) if well.any() else None,
+                "well_conditioned_share": float(well.mean()),
+                "max_force_err_over_operand_sum": float((e / S).max()),
+                "gate": "||dF|| <= 1e-5 max(||F||, S/16) per agent; ||d action|| / ||action|| <= 1e-5 per agent",
+                "pass": bool((e <= 1e-5 * np.maximum(nF, S / 16.0)).all()
+                             and res.get("max_rel_action", 0.0) < 1e-5)})
+    return res
+
+
+def _import_reference():
+    """The UNMODIFIED reference: /root/reference in the build container, its verbatim copy baseline/_ref on the GPU box
+    (staged by __graft_entry__.build()).  Returns the src dir or None."""
+    for root in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        src = os.path.join(root, "src")
+        if os.path.isdir(os.path.join(src, "models")):
+            if src not in sys.path:
+                sys.path.insert(0, src)
+            return src
+    return None
+
+
+def reference_pytorch(budget_s=60.0):
+    """Time the reference's own PyTorch CPU path on this box's host cores (north star): MLAPM.step at
+    N in {1024, 4096, 8192} and Pedestrians.get_relative_features at N in {512, 2048, 4096} (M = 2000), with 1 thread and
+    with all threads; min and max of the repeats.  Sizes that would blow the time budget are skipped and say so."""
+    import torch
+    src = _import_reference()
+    if src is None:
+        return {"unavailable": "no reference tree (baseline/_ref missing: run __graft_entry__.build() in the container)"}
+    from models.mlapm import MLAPM as RefMLAPM
+    import data.data as RDATA
+    cores = len(os.sched_getaffinity(0))
+    keep = torch.get_num_threads()
+    t_begin = time.perf_counter()
+    out = {"source": src, "torch": torch.__version__, "cores": cores, "mlapm_step": [], "get_relative_features": []}
+
+    def timed(fn, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts), max(ts)
+    ref = RefMLAPM(**MLAPM_KW)
+    peds = RDATA.Pedestrians()
+    try:
+        for threads in (cores, 1):
+            torch.set_num_threads(threads)
+            for N in (1024, 4096, 8192):
+                est = (N / 8192.0) ** 2 * (20.0 if threads == 1 else 5.0)
+                if time.perf_counter() - t_begin + 2 * est > budget_s:
+                    out["mlapm_step"].append({"N": N, "threads": threads, "skipped": "time budget"})
+                    continue
+                p, v, ds, dest, _ = synthetic_crowd(N)
+                with torch.no_grad():
+                    ref.step(p, v, ds, dest, DT)
+                    lo, hi = timed(lambda: ref.step(p, v, ds, dest, DT), 2)
+                out["mlapm_step"].append({"N": N, "threads": threads, "s_min": lo, "s_max": hi,
+                                          "mpairs_per_s": N * N / lo / 1e6, "agent_steps_per_s": N / lo})
+            for N in (512, 2048, 4096):
+                est = (N / 4096.0) ** 2 * (7.0 if threads == 1 else 3.0)
+                if time.perf_counter() - t_begin + 2 * est > budget_s:
+                    out["get_relative_features"].append({"N": N, "threads": threads, "skipped": "time budget"})
+                    continue
+                p, v, ds, dest, obs = synthetic_crowd(N)
+                a = torch.zeros_like(v)
+                f = lambda: peds.get_relative_features(p[None].clone(), v[None].clone(), a[None].clone(),
+                                                       dest[None].clone(), obs, 6, 90, 4, 10, 90, 4)
+                with torch.no_grad():
+                    lo, hi = timed(f, 2)
+                out["get_relative_features"].append({"N": N, "M": int(obs.shape[0]), "threads": threads, "s_min": lo,
+                                                     "s_max": hi, "agent_steps_per_s": N / lo})
+    finally:
+        torch.set_num_threads(keep)
+    out["seconds"] = time.perf_counter() - t_begin
+    return out
 
 
 def run_reference(a):
@@ -156,9 +277,21 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "sample_rows_per_step": R},
+        "config": bench_config(N, a.gpus),
+        "ms_per_full_step": N / val * 1e3, "sample_rows_per_step": R,
+        "note": "value = rows computed per second against all N columns (agent-steps/s of a full step is the same "
+                "number); ms_per_step is the time of one SAMPLED step of R rows, ms_per_full_step its extrapolation "
+                "to all N rows",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def bench_config(N, world):
+    """The workload both arms run (identical keys and values in `ours` and `--impl reference`)."""
+    return {"workload": f"mlapm_gc_rollout_N{N}", "agents": N,
+            "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
+            "crowd": "SURVEY 8d config 4: seed 666, rho 0.5 ped/m^2, dt 0.08",
+            "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region (GPU arm)"}
 
 
 def probe_peaks(L, torch, dev):
@@ -451,23 +584,22 @@ def run_ours(a):
             "metric": METRIC, "value": N * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mlapm_gc_rollout_N{N}", "agents": N, "obstacle_points": int(obs_h.shape[0]),
-                       "reference": "src/main_mlapm.py:18-36 + src/models/mlapm.py:10-58, version GC",
-                       "parallelism": f"agent-sharded rows x{world}" + (
-                           "" if world == 1 else (" + exchange fused into the finalize kernel (NVLink peer stores) + "
-                                                  "1 barrier/step" if exchange == "push" and not sym_used else
-                                                  " + symmetric evaluation: column-direction shares and new state "
-                                                  "stored into the owners' buffers over NVLink peer memory by the "
-                                                  "pair / finalize stages + 2 barriers/step" if exchange == "push" else
-                                                  " + NCCL all-gather/step")),
-                       "exchange": exchange, "exchange_note": exchange_note,
-                       "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region"},
+            "config": bench_config(N, world),
+            "parallelism": {"mode": f"agent-sharded rows x{world}" + (
+                                "" if world == 1 else (" + exchange fused into the finalize kernel (NVLink peer stores) + "
+                                                       "1 barrier/step" if exchange == "push" and not sym_used else
+                                                       " + symmetric evaluation: column-direction shares and new state "
+                                                       "stored into the owners' buffers over NVLink peer memory by the "
+                                                       "pair / finalize stages + 2 barriers/step" if exchange == "push"
+                                                       else " + NCCL all-gather/step")),
+                            "exchange": exchange, "exchange_note": exchange_note},
             "roofline": {"bound": "fp32",
                          "kernel": ("mlapm_sym_kernel<GC> (every unordered pair once for both rows, packed FP32; +prep, "
                                     "finalize)" if sym_used else
                                     "mlapm_pairs2_kernel<GC, packed FP32> (ordered pairs of this rank's rows; +prep, "
                                     "finalize)"),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "peak_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
                          "frac": (achieved / peak) if peak else None,
                          "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH / world if sym_used
                                      else MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
@@ -501,7 +633,9 @@ def run_ours(a):
         else:
             line["nn_path"] = nn_sharded
         if world == 1 and not a.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(N)
+            line["cpu_baseline"], rows = cpu_baseline(N)
+            line["parity"] = parity_block(torch, dev, N, model, rows)
+            line["cpu_baseline"]["reference_pytorch"] = reference_pytorch()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

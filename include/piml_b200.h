@@ -58,6 +58,21 @@ PIML_API int piml_pipe_probe(int which, int ctas, int iters, float *out, void *s
  * the nearest later, else nearest earlier, non-zero velocity of the same pedestrian; then v/||v|| (0 stays 0). */
 PIML_API int piml_heading_f32(const float *vel, int C, int T, int N, float *head, void *stream);
 
+/* The desired-speed double loop of TimeIndexedPedData.make_dataset (data.py:797-806).  vel (T,N,2) -> out (N):
+ * mean of ||v|| over frames [s, min(s+skip_frames,T)) with s the pedestrian's first frame of non-zero velocity
+ * (0 if none).  The mean is accumulated in fp64 (torch.mean's fp32 summation order is not specified): <= 1 ulp. */
+PIML_API int piml_desired_speed_f32(const float *vel, int T, int N, int skip_frames, float *out, void *stream);
+
+/* Pedestrians.get_relative_quantity (data.py:398-414): out (frames,N,M,d) = B (frames,M,d)[m] - A (frames,N,d)[n].
+ * Only for callers that ask for the dense tensor (the reference's polar / symbolic paths); the hot path fuses it. */
+PIML_API int piml_relative_quantity_f32(const float *A, const float *B, int64_t frames, int N, int M, int d, float *out,
+                                        void *stream);
+
+/* Pedestrians.get_filtered_features (data.py:449-464): features (rows,M,d), idx int64 / dist (rows,k) ->
+ * out (rows,k,d) = features[row, idx] with every slot of distance > dist_threshold zeroed. */
+PIML_API int piml_filtered_features_f32(const float *features, const int64_t *idx, const float *dist, int64_t rows, int M,
+                                        int k, int d, float dist_threshold, float *out, void *stream);
+
 /* Pedestrians.get_nearby_obj_in_sight (data.py:416-447).  pos (B,N,2), obj (B,M,2) [obj_frame_stride = M*2] or
  * (M,2) shared by all frames [obj_frame_stride = 0], head (B,N,2).  k <= 32.
  * out_dist (B,N,kk) fp32 / out_idx (B,N,kk) int64, kk = min(k,M): the kk nearest objects inside the field of view
@@ -331,6 +346,19 @@ PIML_API int piml_rollout_losses_backward_f32(const float *pred, const float *la
                                      const float *hard_collisions, const float *abnormal_mask, const float *g_out,
                                      float *g_pred, void *stream);
 
+/* l1_reg_loss(embeddings, weight, 'sum') (simulators.py:169-170, called at :735-737): out[0] = sum weight*|x|; and
+ * its gradient g_x = g_out[0] * weight * sign(x).  One CTA, fixed summation order. */
+PIML_API int piml_l1_sum_f32(const float *x, int64_t n, float weight, float *out, void *stream);
+PIML_API int piml_l1_sum_backward_f32(const float *x, int64_t n, float weight, const float *g_out, float *g_x,
+                                      void *stream);
+
+/* The collision-prediction loss of the training rollout (simulators.py:826-830):
+ * out[0] = F.binary_cross_entropy(pred, target, reduction='sum') (log clamped at -100 like ATen),
+ * out[1] = number of elements with round(pred) == target;  backward: g_pred = g_out[0] (p - t) / max((1-p) p, 1e-12). */
+PIML_API int piml_bce_sum_f32(const float *pred, const float *target, int64_t n, float *out, void *stream);
+PIML_API int piml_bce_sum_backward_f32(const float *pred, const float *target, int64_t n, const float *g_out,
+                                       float *g_pred, void *stream);
+
 /* ---- evaluation metrics: src/functions/metrics.py ----------------------------------------------------------------- */
 
 /* Per frame t of a rollout, over the agents with mask[t][n] == 1 (p, q (T,N,2); mask (T,N) uint8):
@@ -339,7 +367,10 @@ PIML_API int piml_rollout_losses_backward_f32(const float *pred, const float *la
  *               weights, stops when sum |u - u_prev| < 0.1, exactly the reference's per-frame loop)
  *   out_mmd[t]  MaximumMeanDiscrepancy, kernel_mul / kernel_num bandwidths   mmd_with_time_mask :70-91, :207-273
  *   out_count[t] number of masked agents; frames with count <= 1 are skipped by the reference: ot / mmd are NaN there
- *   (count > 1024 is not supported: NaN as well).  out_ot / out_mmd may be NULL.  One CTA per frame. */
+ *   (ot / mmd of a frame with more than PIML_METRICS_MAX_AGENTS = 1024 masked agents are NOT computed: NaN, and the
+ *   caller must treat count[t] > 1024 as an error; out_mae has no such limit).  out_ot / out_mmd may be NULL.
+ *   One CTA per frame. */
+#define PIML_METRICS_MAX_AGENTS 1024
 PIML_API int piml_metrics_frames_f32(const float *p, const float *q, const uint8_t *mask, int T, int N, float eps,
                             int max_iter, float kernel_mul, int kernel_num, float *out_mae, float *out_ot,
                             float *out_mmd, int *out_count, void *stream);

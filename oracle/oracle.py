@@ -128,6 +128,46 @@ def relative_features(position, velocity, acceleration, destination, obstacles, 
     return ped_f, obs_f, dest_f
 
 
+def relative_features_rows(position, velocity, acceleration, destination, obstacles, rows, topk_ped=6,
+                           sight_angle_ped=90, dist_threshold_ped=4, topk_obs=10, sight_angle_obs=90,
+                           dist_threshold_obs=4, return_selection=False):
+    """Rows [r0,r1) of get_relative_features for ONE frame: inputs (N,2) (or (1,N,2)); outputs carry r1-r0 rows.
+    Same arithmetic as relative_features; for crowds whose full N x N scan would take minutes on the CPU."""
+    pos, dest = _f32(position).reshape(-1, 2), _f32(destination).reshape(-1, 2)
+    vel, acc = _f32(velocity).reshape(-1, 2).copy(), _f32(acceleration).reshape(-1, 2).copy()
+    obs = _f32(obstacles).reshape(-1, 2)
+    N, M = pos.shape[0], obs.shape[0]
+    r0, r1 = rows
+    R = r1 - r0
+    kp, ko = min(topk_ped, N), (min(topk_obs, M) if M else 0)
+    ped_f, obs_f = np.empty((R, kp, 6), np.float32), np.empty((R, ko, 6), np.float32)
+    dest_f = np.empty((R, 2), np.float32)
+    pi, pd = np.empty((R, kp), np.int64), np.empty((R, kp), np.float32)
+    oi, od = np.empty((R, ko), np.int64), np.empty((R, ko), np.float32)
+    lib().orc_relative_features_rows(
+        _ptr(pos), _ptr(vel), _ptr(acc), _ptr(dest), _ptr(obs), C.c_int(N), C.c_int(M), C.c_int(topk_ped),
+        C.c_float(cos_threshold(sight_angle_ped)), C.c_float(dist_threshold_ped), C.c_int(topk_obs),
+        C.c_float(cos_threshold(sight_angle_obs)), C.c_float(dist_threshold_obs), C.c_int64(r0), C.c_int64(r1),
+        _ptr(ped_f), _ptr(obs_f), _ptr(dest_f), _ptr(pi), _ptr(pd), _ptr(oi), _ptr(od))
+    if return_selection:
+        return ped_f, obs_f, dest_f, (pi, pd, oi, od)
+    return ped_f, obs_f, dest_f
+
+
+def desired_speed(velocity, skip_frames=25):
+    """The double loop of TimeIndexedPedData.make_dataset (data.py:797-806): per pedestrian, mean ||v|| over the
+    `skip_frames` frames from its first moving frame (frame 0 if it never moves).  velocity (T,N,2) -> (N,)."""
+    v = _f32(velocity)
+    T, N = v.shape[0], v.shape[1]
+    speed = np.sqrt((v[..., 1] * v[..., 1] + v[..., 0] * v[..., 0]).astype(np.float32))       # norm2f
+    out = np.empty(N, np.float32)
+    for i in range(N):
+        moving = np.nonzero(speed[:, i] > 0)[0]
+        s = int(moving[0]) if len(moving) else 0
+        out[i] = np.float32(speed[s:s + skip_frames, i].astype(np.float64).mean())
+    return out
+
+
 def collision_label(ped_f):
     f = _f32(ped_f)
     out = np.empty(f.shape[:-1], np.float32)
@@ -153,6 +193,26 @@ def mlapm_step(position, velocity, desired_speed, destination, dt, version="GC",
                          C.c_float(C_), C.c_float(D), C.c_float(theta), C.c_float(dt), C.c_int64(r0),
                          C.c_int64(r1), _ptr(out))
     return out
+
+
+def mlapm_step_diag(position, velocity, desired_speed, destination, dt, version="GC", tau=0.5, A=7.55, B=-3.0,
+                    C_=0.2, D=-0.3, theta=56, rows=None):
+    """mlapm_step plus, per row, the force before the Euler step (fp64, (R,2)) and the operand magnitude
+    S = |dest term| + sum_m |pair term| (fp64, (R,)): returns (action, force, S)."""
+    pos, vel, dest = _f32(position), _f32(velocity), _f32(destination)
+    ds = _f32(desired_speed)
+    if ds.ndim == 1:
+        ds = ds[:, None]
+    N = pos.shape[0]
+    r0, r1 = rows if rows is not None else (0, N)
+    out = np.empty((r1 - r0, 2), np.float32)
+    force = np.empty((r1 - r0, 2), np.float64)
+    opsum = np.empty((r1 - r0,), np.float64)
+    lib().orc_mlapm_step_diag(_ptr(pos), _ptr(vel), _ptr(ds), C.c_int(ds.shape[1]), _ptr(dest), C.c_int64(N),
+                              C.c_int(MLAPM_VERSIONS[version]), C.c_float(tau), C.c_float(A), C.c_float(B),
+                              C.c_float(C_), C.c_float(D), C.c_float(theta), C.c_float(dt), C.c_int64(r0),
+                              C.c_int64(r1), _ptr(out), _ptr(force), _ptr(opsum))
+    return out, force, opsum
 
 
 _SFM = {("v0", "gc1560"): (8.75, -2.5, 0, 0, 0), ("v0", "gc2344"): (8.75, -2.5, 0, 0, 0),

@@ -220,6 +220,65 @@ ORC_API void orc_relative_features(const float *pos, float *vel, float *acc, con
     free(head); free(pd); free(pi); free(od); free(oi);
 }
 
+/* Row-range form of orc_relative_features for ONE frame (C = T = 1): rows [row0,row1) of the frame against all N
+ * agents / M obstacles -- the same arithmetic, used to check large crowds (N = 1e5) on a bounded row sample.
+ * vel / acc are sanitised in place over the WHOLE frame like the reference (data.py:483-484); outputs hold
+ * (row1-row0) rows. */
+ORC_API void orc_relative_features_rows(const float *pos, float *vel, float *acc, const float *dest,
+                                        const float *obs, int N, int M, int kp, float cos_p, float thr_p, int ko,
+                                        float cos_o, float thr_o, int64_t row0, int64_t row1, float *ped_f,
+                                        float *obs_f, float *dest_f, int64_t *ped_idx, float *ped_dist,
+                                        int64_t *obs_idx, float *obs_dist) {
+    int64_t R = row1 - row0;
+    orc_nan_to_zero(acc, (int64_t)N * 2);
+    orc_nan_to_zero(vel, (int64_t)N * 2);
+    float *head = (float *)malloc(sizeof(float) * (size_t)N * 2);
+    orc_heading(vel, 1, 1, N, head);
+    int kpp = kp < N ? kp : N;
+    int kop = (M > 0) ? (ko < M ? ko : M) : 0;
+    float *pd = (float *)malloc(sizeof(float) * R * (kpp > 0 ? kpp : 1));
+    int64_t *pi = (int64_t *)malloc(sizeof(int64_t) * R * (kpp > 0 ? kpp : 1));
+    float *od = (float *)malloc(sizeof(float) * R * (kop > 0 ? kop : 1));
+    int64_t *oi = (int64_t *)malloc(sizeof(int64_t) * R * (kop > 0 ? kop : 1));
+    orc_select(pos + row0 * 2, pos, 0, head + row0 * 2, 1, (int)R, N, kp, cos_p, pd, pi);
+    if (M > 0) orc_select(pos + row0 * 2, obs, 0, head + row0 * 2, 1, (int)R, M, ko, cos_o, od, oi);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < R; ++r) {
+        int64_t row = row0 + r;
+        const float *p = pos + row * 2, *v = vel + row * 2, *a = acc + row * 2;
+        for (int j = 0; j < kpp; ++j) {
+            float *f = ped_f + (r * kpp + j) * 6;
+            int64_t m = pi[r * kpp + j];
+            if (pd[r * kpp + j] > thr_p) {
+                for (int q = 0; q < 6; ++q) f[q] = 0.f;
+            } else {
+                f[0] = pos[2 * m] - p[0]; f[1] = pos[2 * m + 1] - p[1];
+                f[2] = vel[2 * m] - v[0]; f[3] = vel[2 * m + 1] - v[1];
+                f[4] = acc[2 * m] - a[0]; f[5] = acc[2 * m + 1] - a[1];
+            }
+        }
+        float dx = dest[row * 2] - p[0], dy = dest[row * 2 + 1] - p[1];
+        dest_f[r * 2] = isnan(dx) ? 0.f : dx;
+        dest_f[r * 2 + 1] = isnan(dy) ? 0.f : dy;
+        for (int j = 0; j < kop; ++j) {
+            float *f = obs_f + (r * kop + j) * 6;
+            int64_t m = oi[r * kop + j];
+            if (od[r * kop + j] > thr_o) {
+                for (int q = 0; q < 6; ++q) f[q] = 0.f;
+            } else {
+                f[0] = obs[2 * m] - p[0]; f[1] = obs[2 * m + 1] - p[1];
+                f[2] = 0.f - v[0]; f[3] = 0.f - v[1];
+                f[4] = 0.f - a[0]; f[5] = 0.f - a[1];
+            }
+        }
+    }
+    if (ped_idx) memcpy(ped_idx, pi, sizeof(int64_t) * R * kpp);
+    if (ped_dist) memcpy(ped_dist, pd, sizeof(float) * R * kpp);
+    if (obs_idx && kop) memcpy(obs_idx, oi, sizeof(int64_t) * R * kop);
+    if (obs_dist && kop) memcpy(obs_dist, od, sizeof(float) * R * kop);
+    free(head); free(pd); free(pi); free(od); free(oi);
+}
+
 /* data.py:515-535 calculate_collision_label: will the pair come within 0.5 m in the next second (10 samples) */
 ORC_API void orc_collision_label(const float *ped_f, int64_t slots, float *out) {
     for (int64_t s = 0; s < slots; ++s) {
@@ -243,9 +302,10 @@ ORC_API void orc_collision_label(const float *ped_f, int64_t slots, float *out) 
  * Per-pair terms follow the reference's fp32 op order; the row sum is accumulated in double (the reference's
  * fp32 .sum(dim=1) order is an ATen implementation detail; it differs from this by ~1e-6).
  * NaN semantics: view(bool)*A*exp(..)*direc is a product, so a NaN column poisons every row (0*NaN = NaN). */
-ORC_API void orc_mlapm_step(const float *pos, const float *vel, const float *ds, int ds_dim, const float *dest,
+static void mlapm_step_impl(const float *pos, const float *vel, const float *ds, int ds_dim, const float *dest,
                             int64_t N, int version, float tau, float A, float Bc, float Cc, float Dc,
-                            float theta_deg, float dt, int64_t row0, int64_t row1, float *out) {
+                            float theta_deg, float dt, int64_t row0, int64_t row1, float *out, double *force,
+                            double *opsum) {
     /* theta = -sign(cross) * theta/180*pi as fp32 tensor ops: (sign*theta)/180*pi ; theta==0 -> theta/180*pi (double->fp32) */
     const float pi_f = (float)3.141592653589793;
 #pragma omp parallel for schedule(dynamic, 16)
@@ -257,7 +317,7 @@ ORC_API void orc_mlapm_step(const float *pos, const float *vel, const float *ds,
         ex = ex / en; ey = ey / en;
         float dsx = ds[n * ds_dim], dsy = ds[n * ds_dim + (ds_dim > 1 ? 1 : 0)];
         float fx0 = (dsx * ex - vx) / tau, fy0 = (dsy * ey - vy) / tau;
-        double sx = 0.0, sy = 0.0;
+        double sx = 0.0, sy = 0.0, mag = 0.0;
         for (int64_t m = 0; m < N; ++m) {
             float rx = pos[2 * m] - px, ry = pos[2 * m + 1] - py;
             float r = norm2f(rx, ry);
@@ -285,11 +345,33 @@ ORC_API void orc_mlapm_step(const float *pos, const float *vel, const float *ds,
                 ty = ((viewf * A) * e) * dyr;
             }
             sx += (double)tx; sy += (double)ty;
+            if (opsum) mag += sqrt((double)tx * tx + (double)ty * ty);
         }
         float fx = fx0 - (float)sx, fy = fy0 - (float)sy;
         out[2 * (n - row0)] = vx + fx * dt;
         out[2 * (n - row0) + 1] = vy + fy * dt;
+        if (force) { force[2 * (n - row0)] = (double)fx0 - sx; force[2 * (n - row0) + 1] = (double)fy0 - sy; }
+        if (opsum) opsum[n - row0] = mag + sqrt((double)fx0 * fx0 + (double)fy0 * fy0);
     }
+}
+
+ORC_API void orc_mlapm_step(const float *pos, const float *vel, const float *ds, int ds_dim, const float *dest,
+                            int64_t N, int version, float tau, float A, float Bc, float Cc, float Dc,
+                            float theta_deg, float dt, int64_t row0, int64_t row1, float *out) {
+    mlapm_step_impl(pos, vel, ds, ds_dim, dest, N, version, tau, A, Bc, Cc, Dc, theta_deg, dt, row0, row1, out, NULL,
+                    NULL);
+}
+
+/* Diagnostic form for the force-level parity gate: additionally returns, per row, the force BEFORE the Euler step
+ * (fp32 pair terms summed in fp64, destination term added in fp64: (rows,2) doubles) and the operand magnitude
+ * S = |dest term| + sum_m |term_m| -- the scale fp32 rounding of the row sum is relative to (S / |F| is the
+ * condition number of the sum). */
+ORC_API void orc_mlapm_step_diag(const float *pos, const float *vel, const float *ds, int ds_dim, const float *dest,
+                                 int64_t N, int version, float tau, float A, float Bc, float Cc, float Dc,
+                                 float theta_deg, float dt, int64_t row0, int64_t row1, float *out, double *force,
+                                 double *opsum) {
+    mlapm_step_impl(pos, vel, ds, ds_dim, dest, N, version, tau, A, Bc, Cc, Dc, theta_deg, dt, row0, row1, out, force,
+                    opsum);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

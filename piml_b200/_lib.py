@@ -54,6 +54,9 @@ SIGNATURES = {
     "piml_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
     "piml_pipe_probe": (i32, [i32, i32, i32, vp, vp]),
     "piml_heading_f32": (i32, [vp, i32, i32, i32, vp, vp]),
+    "piml_desired_speed_f32": (i32, [vp, i32, i32, i32, vp, vp]),
+    "piml_relative_quantity_f32": (i32, [vp, vp, i64, i32, i32, i32, vp, vp]),
+    "piml_filtered_features_f32": (i32, [vp, vp, vp, i64, i32, i32, i32, f32, vp, vp]),
     "piml_select_neighbors_f32": (i32, [vp, vp, i64, vp, i32, i32, i32, i32, f32, vp, vp, vp]),
     "piml_relative_features_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, i32, f32,
                                          f32, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -84,6 +87,10 @@ SIGNATURES = {
     "piml_rollout_losses_workspace_floats": (i64, [i32, i32]),
     "piml_rollout_losses_f32": (i32, [vp, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "piml_rollout_losses_backward_f32": (i32, [vp, vp, i64, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp]),
+    "piml_l1_sum_f32": (i32, [vp, i64, f32, vp, vp]),
+    "piml_l1_sum_backward_f32": (i32, [vp, i64, f32, vp, vp, vp]),
+    "piml_bce_sum_f32": (i32, [vp, vp, i64, vp, vp]),
+    "piml_bce_sum_backward_f32": (i32, [vp, vp, i64, vp, vp, vp]),
     "piml_metrics_frames_f32": (i32, [vp, vp, vp, i32, i32, f32, i32, f32, i32, vp, vp, vp, vp, vp]),
     "piml_sfm_forward_f32": (i32, [C.POINTER(SfmParams), vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "piml_pinnsf_packed_floats": (i64, [C.POINTER(NetDesc)]),

@@ -210,3 +210,54 @@ class RolloutLossesFunction(torch.autograd.Function):
             L.ptr(pred), L.ptr(labels), stride, C, T, N, time_decay, reverse, L.ptr(coll), L.ptr(hard), L.ptr(ab),
             L.ptr(g_out), L.ptr(g_pred), L.stream_ptr(pred.device)), "piml_rollout_losses_backward_f32")
         return g_pred, None, None, None, None, None, None
+
+
+class L1SumFunction(torch.autograd.Function):
+    """l1_reg_loss(x, weight, 'sum') (simulators.py:169-170): weight * sum |x| -> scalar tensor."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        dev = L.require_cuda(x)
+        x = L.f32c(x)
+        out = torch.empty(1, device=dev)
+        L.check(L.load().piml_l1_sum_f32(L.ptr(x), x.numel(), float(weight), L.ptr(out), L.stream_ptr(dev)),
+                "piml_l1_sum_f32")
+        ctx.save_for_backward(x)
+        ctx.weight = float(weight)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        g = L.f32c(g).reshape(1)
+        L.check(L.load().piml_l1_sum_backward_f32(L.ptr(x), x.numel(), ctx.weight, L.ptr(g), L.ptr(gx),
+                                                  L.stream_ptr(x.device)), "piml_l1_sum_backward_f32")
+        return gx, None
+
+
+class BceSumFunction(torch.autograd.Function):
+    """F.binary_cross_entropy(pred, target, reduction='sum') and the number of correct rounded predictions
+    (simulators.py:826-830) in one launch: returns (loss, hits) scalars; gradient to `pred` only."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        dev = L.require_cuda(pred, target)
+        pred, target = L.f32c(pred), L.f32c(target)
+        out = torch.empty(2, device=dev)
+        L.check(L.load().piml_bce_sum_f32(L.ptr(pred), L.ptr(target), pred.numel(), L.ptr(out), L.stream_ptr(dev)),
+                "piml_bce_sum_f32")
+        ctx.save_for_backward(pred, target)
+        loss, hits = out[0].clone(), out[1].clone()
+        ctx.mark_non_differentiable(hits)
+        return loss, hits
+
+    @staticmethod
+    def backward(ctx, g, _):
+        pred, target = ctx.saved_tensors
+        gp = torch.empty_like(pred)
+        g = L.f32c(g).reshape(1)
+        L.check(L.load().piml_bce_sum_backward_f32(L.ptr(pred), L.ptr(target), pred.numel(), L.ptr(g), L.ptr(gp),
+                                                   L.stream_ptr(pred.device)), "piml_bce_sum_backward_f32")
+        return gp, None
+

@@ -403,6 +403,96 @@ extern "C" int piml_heading_f32(const float *vel, int C, int T, int N, float *he
     return check_launch("heading_kernel");
 }
 
+// TimeIndexedPedData.make_dataset, data.py:797-806: per pedestrian, the mean speed over the first `skip` frames
+// starting at its first frame with non-zero velocity (frame 0 when it never moves).  One thread per pedestrian; the
+// (T,N,2) reads of a warp are coalesced across pedestrians.
+__global__ void desired_speed_kernel(const float2 *__restrict__ vel, int T, int N, int skip, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int start = 0;
+    for (int j = 0; j < T; ++j) {
+        const float2 v = vel[static_cast<size_t>(j) * N + i];
+        if (piml::norm2_rn(v.x, v.y) > 0.0f) { start = j; break; }
+    }
+    const int end = min(start + skip, T);
+    double s = 0.0;                              // torch.mean's fp32 cascade order is an ATen detail: <= 1 ulp apart
+    for (int j = start; j < end; ++j) {
+        const float2 v = vel[static_cast<size_t>(j) * N + i];
+        s += static_cast<double>(piml::norm2_rn(v.x, v.y));
+    }
+    out[i] = static_cast<float>(s / static_cast<double>(end - start));      // empty slice -> NaN like torch.mean
+}
+
+extern "C" int piml_desired_speed_f32(const float *vel, int T, int N, int skip_frames, float *out, void *stream) {
+    PIML_REQUIRE(vel && out, "piml_desired_speed_f32: null pointer");
+    PIML_REQUIRE(T >= 0 && N >= 0 && skip_frames >= 0, "piml_desired_speed_f32: negative dimension");
+    if (N == 0) return PIML_OK;
+    const int threads = 128;
+    desired_speed_kernel<<<(N + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(vel), T, N, skip_frames, out);
+    count_launch();
+    return check_launch("desired_speed_kernel");
+}
+
+// Pedestrians.get_relative_quantity, data.py:398-414: out[b,n,m,:] = B[b,m,:] - A[b,n,:].  The hot path never
+// materialises this tensor (it is fused into the selection / feature kernels); this entry serves the reference's
+// polar / symbolic-regression callers that ask for it explicitly.
+__global__ void relative_quantity_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t total, int N,
+                                         int M, int d, float *__restrict__ out) {
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % d);
+        const int64_t r = e / d;
+        const int m = static_cast<int>(r % M);
+        const int64_t bn = r / M;
+        const int64_t b = bn / N;
+        out[e] = __fsub_rn(B[(b * M + m) * d + c], A[bn * d + c]);
+    }
+}
+
+extern "C" int piml_relative_quantity_f32(const float *A, const float *B, int64_t frames, int N, int M, int d,
+                                          float *out, void *stream) {
+    PIML_REQUIRE(A && B && out, "piml_relative_quantity_f32: null pointer");
+    PIML_REQUIRE(frames >= 0 && N >= 0 && M >= 0 && d >= 1, "piml_relative_quantity_f32: bad dimension");
+    const int64_t total = frames * N * M * d;
+    if (total == 0) return PIML_OK;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    relative_quantity_kernel<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), threads, 0,
+                               static_cast<cudaStream_t>(stream)>>>(A, B, total, N, M, d, out);
+    count_launch();
+    return check_launch("relative_quantity_kernel");
+}
+
+// Pedestrians.get_filtered_features, data.py:449-464: gather the k selected columns of (rows, M, d) and zero every
+// slot whose distance exceeds the threshold (NaN distances keep their slot, like `nearby_dist > thr`).
+__global__ void filtered_features_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx,
+                                         const float *__restrict__ dist, int64_t total, int M, int k, int d, float thr,
+                                         float *__restrict__ out) {
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % d);
+        const int64_t slot = e / d;
+        const int64_t row = slot / k;
+        out[e] = (dist[slot] > thr) ? 0.0f : feat[(row * M + idx[slot]) * d + c];
+    }
+}
+
+extern "C" int piml_filtered_features_f32(const float *features, const int64_t *idx, const float *dist, int64_t rows,
+                                          int M, int k, int d, float dist_threshold, float *out, void *stream) {
+    PIML_REQUIRE(features && idx && dist && out, "piml_filtered_features_f32: null pointer");
+    PIML_REQUIRE(rows >= 0 && M >= 1 && k >= 0 && d >= 1, "piml_filtered_features_f32: bad dimension");
+    const int64_t total = rows * k * d;
+    if (total == 0) return PIML_OK;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    filtered_features_kernel<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), threads, 0,
+                               static_cast<cudaStream_t>(stream)>>>(features, idx, dist, total, M, k, d, dist_threshold,
+                                                                    out);
+    count_launch();
+    return check_launch("filtered_features_kernel");
+}
+
 extern "C" int piml_select_neighbors_f32(const float *pos, const float *obj, int64_t obj_frame_stride,
                                          const float *head, int B, int N, int M, int k, float cos_thr,
                                          float *out_dist, int64_t *out_idx, void *stream) {

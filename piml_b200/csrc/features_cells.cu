@@ -15,6 +15,8 @@
 //      buckets are filtered by comparing the record's packed cell with the cell being visited.
 // Buckets are a hash of the integer cell coordinates (no bounding box needed => no device->host read of extents);
 // cell coordinates are computed in fp64 so that rounding can never move a candidate two cells away.
+#include <mutex>
+
 #include "features_common.cuh"
 
 namespace piml {
@@ -271,8 +273,10 @@ __global__ void __launch_bounds__(CELL_THREADS) features_cells_kernel(FeatArgs a
 struct ByteScratch { cudaStream_t st; int dev; char *buf; size_t cap; };
 static ByteScratch g_cell_scratch[8] = {};
 static int g_cell_used = 0;
+static std::mutex g_cell_mutex;                  // the cache is process-wide (freed by piml_free_workspace from any thread)
 
 static int cell_scratch_get(cudaStream_t st, size_t bytes, char **out) {
+    std::lock_guard<std::mutex> lock(g_cell_mutex);
     int dev = 0;
     PIML_CUDA(cudaGetDevice(&dev));
     ByteScratch *s = nullptr;
@@ -298,6 +302,7 @@ static int cell_scratch_get(cudaStream_t st, size_t bytes, char **out) {
 }
 
 void cell_scratch_free() {
+    std::lock_guard<std::mutex> lock(g_cell_mutex);
     for (int i = 0; i < g_cell_used; ++i)
         if (g_cell_scratch[i].buf) {
             int dev = 0;

@@ -192,3 +192,109 @@ extern "C" int piml_rollout_losses_backward_f32(const float *pred, const float *
     count_launch();
     return check_launch("rollout_losses_bwd_kernel");
 }
+
+// ---- the two small scalar losses of the training rollout -----------------------------------------------------------
+// l1_reg_loss (simulators.py:169-170, 'sum'): weight * sum |x|, and the collision-prediction head's
+// F.binary_cross_entropy(pred, target, reduction='sum') with its accuracy count (:826-830).  Both reduce a few hundred
+// thousand elements: ONE CTA, fixed summation order (deterministic), no workspace.
+namespace piml {
+
+constexpr int SL_THREADS = 1024;
+
+__device__ __forceinline__ double block_sum_d(double v, double *red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = SL_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double s = red[0];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(SL_THREADS) l1_sum_kernel(const float *__restrict__ x, int64_t n, float weight,
+                                                            float *__restrict__ out) {
+    __shared__ double red[SL_THREADS];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += SL_THREADS) s += static_cast<double>(__fmul_rn(weight, fabsf(x[i])));
+    s = block_sum_d(s, red);
+    if (threadIdx.x == 0) out[0] = static_cast<float>(s);
+}
+
+__global__ void l1_sum_bwd_kernel(const float *__restrict__ x, int64_t n, float weight, const float *__restrict__ g,
+                                  float *__restrict__ gx) {
+    const float gw = __fmul_rn(g[0], weight);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float v = x[i];
+        gx[i] = v > 0.f ? gw : (v < 0.f ? -gw : 0.f);              // d|x|/dx = sign(x), 0 at 0 like torch.abs
+    }
+}
+
+// binary_cross_entropy: -(t max(log p, -100) + (1 - t) max(log(1 - p), -100)), ATen's clamp; out[0] = sum,
+// out[1] = number of elements with round(p) == t (torch.round: half to even)
+__global__ void __launch_bounds__(SL_THREADS) bce_sum_kernel(const float *__restrict__ p, const float *__restrict__ t,
+                                                             int64_t n, float *__restrict__ out) {
+    __shared__ double red[SL_THREADS];
+    double s = 0.0, hit = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += SL_THREADS) {
+        const float pi = p[i], ti = t[i];
+        const float lp = fmaxf(logf(pi), -100.f), lq = fmaxf(log1pf(-pi), -100.f);
+        s += static_cast<double>(-(__fadd_rn(__fmul_rn(ti, lp), __fmul_rn(__fsub_rn(1.f, ti), lq))));
+        hit += (rintf(pi) == ti) ? 1.0 : 0.0;
+    }
+    s = block_sum_d(s, red);
+    hit = block_sum_d(hit, red);
+    if (threadIdx.x == 0) { out[0] = static_cast<float>(s); out[1] = static_cast<float>(hit); }
+}
+
+__global__ void bce_sum_bwd_kernel(const float *__restrict__ p, const float *__restrict__ t, int64_t n,
+                                   const float *__restrict__ g, float *__restrict__ gp) {
+    const float g0 = g[0];
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float pi = p[i];
+        gp[i] = g0 * (pi - t[i]) / fmaxf((1.f - pi) * pi, 1e-12f);  // ATen binary_cross_entropy_backward
+    }
+}
+
+}  // namespace piml
+
+static unsigned grid_for(int64_t n) {
+    const int64_t b = (n + 255) / 256;
+    return static_cast<unsigned>(b < 148 * 8 ? (b > 0 ? b : 1) : 148 * 8);
+}
+
+extern "C" int piml_l1_sum_f32(const float *x, int64_t n, float weight, float *out, void *stream) {
+    PIML_REQUIRE(out && (x || n == 0) && n >= 0, "piml_l1_sum_f32: bad argument");
+    l1_sum_kernel<<<1, SL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, n, weight, out);
+    count_launch();
+    return check_launch("l1_sum_kernel");
+}
+
+extern "C" int piml_l1_sum_backward_f32(const float *x, int64_t n, float weight, const float *g_out, float *g_x,
+                                        void *stream) {
+    PIML_REQUIRE(g_out && (n == 0 || (x && g_x)) && n >= 0, "piml_l1_sum_backward_f32: bad argument");
+    if (n == 0) return PIML_OK;
+    l1_sum_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, weight, g_out, g_x);
+    count_launch();
+    return check_launch("l1_sum_bwd_kernel");
+}
+
+extern "C" int piml_bce_sum_f32(const float *pred, const float *target, int64_t n, float *out, void *stream) {
+    PIML_REQUIRE(out && (n == 0 || (pred && target)) && n >= 0, "piml_bce_sum_f32: bad argument");
+    bce_sum_kernel<<<1, SL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(pred, target, n, out);
+    count_launch();
+    return check_launch("bce_sum_kernel");
+}
+
+extern "C" int piml_bce_sum_backward_f32(const float *pred, const float *target, int64_t n, const float *g_out,
+                                         float *g_pred, void *stream) {
+    PIML_REQUIRE(g_out && (n == 0 || (pred && target && g_pred)) && n >= 0, "piml_bce_sum_backward_f32: bad argument");
+    if (n == 0) return PIML_OK;
+    bce_sum_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, target, n, g_out, g_pred);
+    count_launch();
+    return check_launch("bce_sum_bwd_kernel");
+}
+

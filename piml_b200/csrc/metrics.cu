@@ -15,7 +15,7 @@
 namespace piml {
 
 constexpr int MT_THREADS = 128;
-constexpr int MT_MAXN = 1024;                     // masked agents per frame held in shared memory
+constexpr int MT_MAXN = PIML_METRICS_MAX_AGENTS;  // masked agents per frame held in shared memory
 
 struct MetricArgs {
     const float2 *p, *q; const uint8_t *mask; int T, N;
@@ -60,12 +60,17 @@ __global__ void __launch_bounds__(MT_THREADS) metrics_frames_kernel(const __grid
     if (tid == 0) a.count[t] = n;
     // ---- mae: sum over the masked agents of ||p - q||_2
     {
-        float s = 0.f;
-        for (int i = tid; i < n && i < MT_MAXN; i += MT_THREADS) s += norm2_rn(__fsub_rn(xs[i].x, ys[i].x), __fsub_rn(xs[i].y, ys[i].y));
+        float s = 0.f;                                             // straight from global memory: any number of agents
+        for (int j = tid; j < a.N; j += MT_THREADS) {
+            const int64_t e = static_cast<int64_t>(t) * a.N + j;
+            if (a.mask[e] == 1) s += norm2_rn(__fsub_rn(a.p[e].x, a.q[e].x), __fsub_rn(a.p[e].y, a.q[e].y));
+        }
         s = block_sum(s, red);
         if (tid == 0) a.mae[t] = s;
     }
-    if (n <= 1 || n > MT_MAXN) {                                   // the reference skips frames with fewer than 2 points
+    // the reference skips frames with fewer than 2 points; frames with more than MT_MAXN masked agents do not fit the
+    // shared-memory point arrays: OT / MMD are NaN there and the host adapter raises (count[t] tells it)
+    if (n <= 1 || n > MT_MAXN) {
         if (tid == 0) {
             if (a.ot) a.ot[t] = CUDART_NAN_F;
             if (a.mmd) a.mmd[t] = CUDART_NAN_F;

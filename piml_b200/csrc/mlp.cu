@@ -331,12 +331,9 @@ static int pinnsf_forward_impl(const piml_net_desc *desc, const float *params, i
     a.sums = sums; a.ped_msgs = ped_msgs; a.obs_msgs = has_obs ? obs_msgs : nullptr; a.coll = coll;
     a.stash = stash;
     const size_t smem = sizeof(float) * (2 * FT_MAXW * FT_TRP + 2 * FT_KC * FT_MAXW + FT_SMALL * FT_TRP) + 16;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-        attr_set = true;
-    }
+    // per launch: the attribute is per DEVICE, and a process may touch several (it costs well under a microsecond)
+    PIML_CUDA(cudaFuncSetAttribute(pinnsf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
     const int64_t tiles = a.n_ped_tiles + a.n_obs_tiles;
     PIML_REQUIRE(tiles < (1LL << 31), "piml_pinnsf_forward_f32: too many tiles");
     pinnsf_tile_kernel<<<static_cast<unsigned>(tiles), FT_THREADS, smem, st>>>(P, T, a, S);

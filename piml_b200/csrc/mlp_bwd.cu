@@ -447,12 +447,9 @@ extern "C" int piml_pinnsf_backward_f32(const piml_net_desc *desc, const float *
     a.n_obs_tiles = has_obs ? (R + a.ag_obs - 1) / a.ag_obs : 0;
     a.has_coll = coll ? 1 : 0;
     const size_t smem = sizeof(float) * (2 * FT_MAXW * FT_TRP + 2 * FT_KC * FT_MAXW + FT_SMALL * FT_TRP) + 16;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        PIML_CUDA(cudaFuncSetAttribute(pinnsf_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-        attr_set = true;
-    }
+    // per launch: the attribute is per DEVICE, and a process may touch several (it costs well under a microsecond)
+    PIML_CUDA(cudaFuncSetAttribute(pinnsf_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
     const int64_t tiles = a.n_ped_tiles + a.n_obs_tiles;
     PIML_REQUIRE(tiles < (1LL << 31), "piml_pinnsf_backward_f32: too many tiles");
     pinnsf_bwd_tile_kernel<<<static_cast<unsigned>(tiles), FT_THREADS, smem, st>>>(Pt, T, a, S, Gp);

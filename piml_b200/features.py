@@ -39,9 +39,20 @@ class Pedestrians(object):
     # ---- data.py:398-414 -------------------------------------------------------------------------------------
     @staticmethod
     def get_relative_quantity(A, B):
-        """relative_A[..., n, m, :] = B[..., m, :] - A[..., n, :].  Kept importable for the reference's polar /
-        symbolic-regression callers (out of the hot path); the fused kernels never materialise this tensor."""
-        return (B.unsqueeze(-3) - A.unsqueeze(-2)).contiguous()
+        """relative_A[..., n, m, :] = B[..., m, :] - A[..., n, :] as a dense (..., N, M, dim) tensor.  Kept for the
+        reference's polar / symbolic-regression callers (out of the hot path); the fused kernels never materialise it."""
+        _, origin, (A, B) = L.stage(A, B)
+        a, b = L.f32c(A), L.f32c(B)
+        if a.shape[:-2] != b.shape[:-2] or a.shape[-1] != b.shape[-1]:
+            raise ValueError("get_relative_quantity: A (..., N, dim) and B (..., M, dim) must share the leading dims")
+        lead, N, Mo, d = a.shape[:-2], a.shape[-2], b.shape[-2], a.shape[-1]
+        out = torch.empty(*lead, N, Mo, d, dtype=torch.float32, device=a.device)
+        frames = 1
+        for s_ in lead:
+            frames *= s_
+        L.check(L.load().piml_relative_quantity_f32(L.ptr(a), L.ptr(b), frames, N, Mo, d, L.ptr(out),
+                                                    L.stream_ptr(a.device)), "piml_relative_quantity_f32")
+        return out.to(origin)
 
     # ---- data.py:416-447 -------------------------------------------------------------------------------------
     def get_nearby_obj_in_sight(self, position, objects, heading_direction, k, angle_threshold):
@@ -74,9 +85,16 @@ class Pedestrians(object):
     def get_filtered_features(self, features, nearby_idx, nearby_dist, dist_threshold):
         """gather the k selected columns of (..., N, M, dim) and zero slots farther than dist_threshold.
         Only used by out-of-scope reference callers; the hot path uses the fused get_relative_features."""
-        dim = features.shape[-1]
-        gathered = torch.gather(features, -2, nearby_idx.unsqueeze(-1).expand(*nearby_idx.shape, dim))
-        return gathered * (~(nearby_dist > dist_threshold)).unsqueeze(-1)
+        _, origin, (features, nearby_idx, nearby_dist) = L.stage(features, nearby_idx, nearby_dist)
+        f, dist = L.f32c(features), L.f32c(nearby_dist)
+        idx = nearby_idx.to(torch.int64).contiguous()
+        Mo, d, k = f.shape[-2], f.shape[-1], idx.shape[-1]
+        rows = idx.numel() // max(k, 1)
+        out = torch.empty(*idx.shape, d, dtype=torch.float32, device=f.device)
+        L.check(L.load().piml_filtered_features_f32(L.ptr(f), L.ptr(idx), L.ptr(dist), rows, Mo, k, d,
+                                                    float(dist_threshold), L.ptr(out), L.stream_ptr(f.device)),
+                "piml_filtered_features_f32")
+        return out.to(origin)
 
     # ---- data.py:466-512 -------------------------------------------------------------------------------------
     def get_relative_features(self, position, velocity, acceleration, destination, obstacles, topk_ped,

@@ -8,6 +8,9 @@ from . import _lib as L
 from .features import Pedestrians
 
 
+MAX_AGENTS = 1024            # PIML_METRICS_MAX_AGENTS (include/piml_b200.h)
+
+
 def collision_count(position, threshold, real_position=None, reduction=None):
     """metrics.py:16-26."""
     collisions = Pedestrians.collision_detection(position, threshold, real_position)
@@ -34,6 +37,10 @@ def _frames(p, q, mask, want_ot, want_mmd, eps=0.1, max_iter=100, kernel_mul=2.0
     L.check(L.load().piml_metrics_frames_f32(L.ptr(p), L.ptr(q), L.ptr(m8), T, N, float(eps), int(max_iter),
                                              float(kernel_mul), int(kernel_num), L.ptr(mae), L.ptr(ot), L.ptr(mmd),
                                              L.ptr(cnt), L.stream_ptr(dev)), "piml_metrics_frames_f32")
+    if (want_ot or want_mmd) and T and int(cnt.max()) > MAX_AGENTS:
+        # the per-frame Sinkhorn / Gram kernel keeps a frame's points in shared memory; never return its NaN silently
+        raise NotImplementedError(f"ot / mmd with more than {MAX_AGENTS} masked agents in a frame "
+                                  f"(got {int(cnt.max())}); the reference has no such limit")
     return mae, ot, mmd, cnt
 
 

@@ -38,10 +38,13 @@ def model_tau(model, dataset_name):
 class NetSpec(object):
     """Static description of one PINNSF-family network (what piml_net_desc carries)."""
 
-    def __init__(self, enc_dims, proc_mode, dec_dims, coll_dims, kind, has_obs, tau, dropout=0.0):
+    def __init__(self, enc_dims, proc_mode, dec_dims, coll_dims, kind, has_obs, tau, dropout=0.0, n_blocks=None):
         self.enc_dims, self.proc_mode, self.dec_dims = list(enc_dims), int(proc_mode), list(dec_dims)
         self.coll_dims, self.kind, self.has_obs = list(coll_dims), int(kind), bool(has_obs)
         self.tau, self.dropout = float(tau), float(dropout)
+        # ResBlocks in the processor (= processor_hidden_layers): only matters for how many dropout masks the
+        # reference draws per forward in train() mode (model.py:115-119, one per block, the last one applied)
+        self.n_blocks = int(n_blocks) if n_blocks is not None else (1 if self.proc_mode == 1 else 16)
 
     @property
     def pw(self):
@@ -77,13 +80,18 @@ def spec_from_args(model, args):
     enc = [args.ped_feature_dim] + [args.encoder_hidden_size] * args.encoder_hidden_layers
     dec = [args.processor_hidden_size] + [args.decoder_hidden_size] * args.decoder_hidden_layers
     proc_mode = 0 if args.processor_hidden_layers > 1 else 1
+    if proc_mode == 1 and str(getattr(args, 'activation', 'relu')).lower() != 'relu':
+        # the single-block processor relu(Wx+b)+x is the only place args.activation reaches the forward
+        # (model.py:1164, :76); the kernels implement ReLU
+        raise NotImplementedError(f"processor activation {args.activation!r}: the CUDA path implements 'relu'")
     coll_dims = []
     if coll == 'dec':
         coll_dims = [dec[-1], dec[-1], 1]
     elif coll == 'proc':
         coll_dims = [args.processor_hidden_size, dec[-1], 1]
     return NetSpec(enc, proc_mode, dec, coll_dims, kind, args.obs_feature_dim > 0,
-                   model_tau(model, getattr(args, 'dataset_name', 'ucy')), getattr(args, 'dropout', 0.0))
+                   model_tau(model, getattr(args, 'dataset_name', 'ucy')), getattr(args, 'dropout', 0.0),
+                   n_blocks=args.processor_hidden_layers)
 
 
 def _linear_keys(spec, branch):
@@ -279,11 +287,16 @@ def _dropout_multipliers(spec, training, ped, obs):
     reference's order (ped first, then obs) and with the reference's shapes."""
     if not training or spec.dropout <= 0:
         return None, None
-    dp = torch.nn.functional.dropout(torch.ones(*ped.shape[:-1], spec.pw, device=ped.device), spec.dropout, True)
-    do = None
-    if spec.has_obs:
-        do = torch.nn.functional.dropout(torch.ones(*obs.shape[:-1], spec.pw, device=obs.device), spec.dropout, True)
-    return dp, do
+
+    def draw(x):
+        # ResDNN.forward (model.py:115-119) calls self.dropout once per block and keeps only the LAST result, so the
+        # reference consumes n_blocks masks per branch: draw and discard the first n_blocks - 1 to keep torch's RNG
+        # stream (the mask that is applied, and everything drawn afterwards) aligned with the reference under a seed
+        ones = torch.ones(*x.shape[:-1], spec.pw, device=x.device)
+        for _ in range(max(spec.n_blocks, 1) - 1):
+            torch.nn.functional.dropout(ones, spec.dropout, True)
+        return torch.nn.functional.dropout(ones, spec.dropout, True)
+    return draw(ped), (draw(obs) if spec.has_obs else None)
 
 
 # ---- containers with the reference's parameter names -------------------------------------------------------------
@@ -404,10 +417,15 @@ def spec_from_module(module):
             l += 1
         return dims
     enc, dec = widths("ped_encoder"), widths("ped_decoder")
-    proc_mode = 0 if len(module.ped_processor.resnet) > 1 else 1
+    n_blocks = len(module.ped_processor.resnet)
+    proc_mode = 0 if n_blocks > 1 else 1
+    if proc_mode == 1:
+        act = module.ped_processor.resnet[0].lin.mlp[1]
+        if not isinstance(act, nn.ReLU):        # an activation has no parameters: load_state_dict cannot catch this
+            raise NotImplementedError(f"processor activation {type(act).__name__}: the CUDA path implements ReLU")
     coll_dims = widths("ped_collision_predictor") if coll else []
     return NetSpec(enc, proc_mode, dec, coll_dims, kind, module.obs_feature_dim > 0, module.tau,
-                   module.ped_processor.dropout.p)
+                   module.ped_processor.dropout.p, n_blocks=n_blocks)
 
 
 _MODULE_CACHES = {}

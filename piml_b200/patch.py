@@ -19,6 +19,7 @@ switch off the reference is byte-for-byte itself.  Opt-in only: `install_from_en
     BaseSimulator.get_multiple_rollouts                            (src/models/simulators.py:556)
     BaseSimulator.test_multiple_rollouts_for_training              (src/models/simulators.py:659)
     Pedestrians.collision_detection                                (src/data/data.py:538)
+    TimeIndexedPedData.make_dataset                                (src/data/data.py:746; feature build of a whole clip)
     METRIC.collision_count / mae_with_time_mask / ot_with_time_mask / mmd_with_time_mask   (src/functions/metrics.py:16-91;
                                                                    pass METRIC=functions.metrics; (T,N,2) inputs)
 
@@ -27,6 +28,7 @@ Training: the patched model forwards record a CUDA backward (piml_b200.autograd)
 """
 import os
 
+from . import dataset as _dataset
 from . import features as _features
 from . import metrics as _metrics
 from . import mlapm as _mlapm
@@ -61,6 +63,9 @@ def install(DATA=None, MLAPM_MOD=None, MODEL=None, SIM=None, UTILS=None, METRIC=
         for m in PEDESTRIAN_METHODS:
             _swap(DATA.Pedestrians, m, _features.Pedestrians.__dict__[m])
             done.append(f"data.data.Pedestrians.{m}")
+        if hasattr(DATA, "TimeIndexedPedData"):
+            _swap(DATA.TimeIndexedPedData, "make_dataset", _dataset.make_dataset)
+            done.append("data.data.TimeIndexedPedData.make_dataset")
     if MODEL is not None:
         def forward(self, ped_features, obs_features, self_features):
             return _models.forward_from_module(self, ped_features, obs_features, self_features)

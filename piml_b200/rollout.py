@@ -73,7 +73,7 @@ class RolloutResult(object):
         self.num_steps, self.num_pedestrians = position.shape[-3], position.shape[-2]
 
 
-def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed_tc=None):
+def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed_tc=None, final_state=None):
     """Roll S independent scenes forward together (one launch per stage per step, no host sync).
 
     scene: dict of CUDA tensors
@@ -81,6 +81,7 @@ def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed
         dest_num (S,N) int64; obstacles (M,2) or (S,M,2); mask_p, mask_p_pred (S,T,N); desired_speed (S,N);
         ped_features0 (S,N,kp,6), obs_features0 (S,N,ko,6), self_features0 (S,N,7): features at t_start.
     Returns p_res, v_res, a_res (S,T,N,2) and mask_p_new (S,T,N) exactly as simulators.py:581-600 builds them.
+    final_state: optional dict that receives the loop's final `dest_idx` (S,N) and `hist_v` (S,N,2).
     """
     pos, vel, acc, dst = scene["position"], scene["velocity"], scene["acceleration"], scene["destination"]
     dev = L.require_cuda(pos, vel, acc, dst, packed)
@@ -142,6 +143,8 @@ def rollout_scenes(spec, packed, args, scene, t_start=0, num_frames=None, packed
         raise ValueError("the network has an obstacle branch but the scene has no obstacles")
     # the whole `for t in range(t_start, T)` loop of simulators.py:595-652: one C call, 3-4 launches per step
     L.check(L.load().piml_rollout_f32(L.C.byref(r), L.stream_ptr(dev)), "piml_rollout_f32")
+    if final_state is not None:
+        final_state["dest_idx"], final_state["hist_v"] = didx, hist
     return (p_res.transpose(0, 1), v_res.transpose(0, 1), a_res.transpose(0, 1), mask_new.transpose(0, 1))
 
 
@@ -187,14 +190,38 @@ def get_multiple_rollouts(simulator, data, t_start=0, load_model=True, result_cl
     if not hasattr(args, "time_unit"):
         args.time_unit = data.time_unit
     scene = scene_from_data(data, t_start, dev)
+    final = {}
     p_res, v_res, a_res, mask_new = rollout_scenes(spec, packed, _with_dt(args, data.time_unit), scene, t_start,
-                                                   data.num_frames, packed_tc=packed_tc)
+                                                   data.num_frames, packed_tc=packed_tc, final_state=final)
+    _write_back_side_effects(data, t_start, v_res[0], final)
     out_dev = data.position.device
     res = (p_res[0].to(out_dev), v_res[0].to(out_dev), a_res[0].to(out_dev))
     if result_cls is None:
         return RolloutResult(*res, data.destination, data.obstacles, mask_new[0].to(out_dev), data.meta_data)
     return result_cls(*res, data.destination, data.destination, data.obstacles, mask_new[0].to(out_dev),
                       meta_data=data.meta_data)
+
+
+def _write_back_side_effects(data, t_start, v_res, final):
+    """What a caller of the reference's loop can observe on `data` afterwards (simulators.py:571-578 hold VIEWS):
+    `dest_idx_cur` is data.dest_idx[t_start] and is advanced in place at every step (:609, :613, :638), so it ends as the
+    loop's final waypoint index; `hist_v` of the FIRST iteration is a view of data.self_features[t_start, :, 2:-3]
+    and receives that step's new velocities, entrants taking their recorded history (:624-639).  Later iterations
+    work on fresh tensors."""
+    T = min(int(data.num_frames), data.position.shape[-3])
+    if t_start >= T:
+        return
+    data.dest_idx[t_start].copy_(final["dest_idx"][0].to(data.dest_idx.device, data.dest_idx.dtype))
+    sf = data.self_features
+    if sf.shape[-1] != 7:                       # num_history_velocity == 1 is what the kernels implement
+        return
+    if t_start + 1 < T:
+        hist = v_res[t_start + 1].to(sf.device)
+        new = (data.mask_p[t_start + 1] - data.mask_p_pred[t_start + 1]).long().to(sf.device) == 1
+        hist = torch.where(new.unsqueeze(-1), sf[t_start + 1, :, 2:4], hist)
+    else:                                        # a single step at the last frame: v + a dt, never recorded
+        hist = data.velocity[t_start] + data.acceleration[t_start] * data.time_unit
+    sf[t_start, :, 2:4] = hist
 
 
 class _with_dt(object):

@@ -7,66 +7,17 @@ bookkeeping and a differentiable `get_relative_features`, all as eager ops recor
 those stages is a kernel of libpiml_b200.so wrapped in a `torch.autograd.Function` (piml_b200/autograd.py), so
 `loss.backward()` (:359) also runs in the library: network backward (dX chain, dW, db), feature scatter, Euler chain.
 The 'sum'-reduced position / collision / teacher losses (:795-824) are one fused kernel each way
-(`RolloutLossesFunction`); the torch restatements below remain for the other reductions
-('none', 'mean') and as the reference of the fused kernel's tests.
+(`RolloutLossesFunction`), the L1 regulariser (:735-737) and the collision-prediction BCE with its
+accuracy (:826-830) one small kernel each (`L1SumFunction`, `BceSumFunction`).  Plain-torch restatements of these
+losses live in tests/torch_ref.py as the reference of the kernels' tests -- nothing here computes a loss in eager torch.
 """
 import torch
-import torch.nn.functional as F
 
 from . import _lib as L
-from .autograd import IntegrateTrainFunction, RolloutLossesFunction
+from .autograd import BceSumFunction, IntegrateTrainFunction, L1SumFunction, RolloutLossesFunction
 from .features import Pedestrians
 
 _PEDS = Pedestrians()
-
-
-# ---- losses (simulators.py:153-249), restated -----------------------------------------------------------------------
-def reduction(values, mode):
-    if mode == 'sum':
-        return torch.sum(values)
-    if mode == 'mean':
-        return torch.mean(values)
-    if mode == 'none':
-        return values
-    raise NotImplementedError
-
-
-def l1_reg_loss(embeddings, weight=1e-3, mode='none'):
-    """simulators.py:169-170"""
-    return reduction(weight * torch.abs(embeddings), mode)
-
-
-def multiple_rollout_mse_loss(pred, labels, time_decay, mode='none', reverse=False):
-    """simulators.py:172-195: squared error with weight time_decay^(T-1-t) (or time_decay^t when reverse)."""
-    T = pred.shape[1]
-    loss = (pred - labels) * (pred - labels)
-    if not reverse:
-        decay = torch.tensor([time_decay ** (T - t - 1) for t in range(T)], device=pred.device)
-    else:
-        decay = torch.tensor([time_decay ** t for t in range(T)], device=pred.device)
-    return reduction(loss * decay.reshape(1, int(T), 1, 1), mode)
-
-
-def multiple_rollout_collision_avoidance_loss(pred, labels, time_decay, mode='none'):
-    """simulators.py:230-249: error of the component perpendicular to the label's overall displacement."""
-    ni = labels[:, -1:, :, :] - labels[:, 0:1, :, :]
-    ni = ni / (torch.norm(ni, p=2, dim=-1, keepdim=True) + 1e-6)
-    pred_ = pred - torch.sum(pred * ni, dim=-1, keepdim=True) * ni
-    labels_ = labels - torch.sum(labels * ni, dim=-1, keepdim=True) * ni
-    return reduction(multiple_rollout_mse_loss(pred_, labels_, time_decay, 'none'), mode)
-
-
-def multiple_rollout_collision_loss(pred, labels, time_decay, coll_focus_weight, collisions, mode='none',
-                                    abnormal_mask=None):
-    """simulators.py:197-228.  Mutates `collisions`' sum like the reference (binarised per pedestrian)."""
-    collisions = torch.sum(collisions, dim=1)
-    collisions[collisions > 0] = 1.
-    collision_w = collisions.unsqueeze(1).repeat(1, pred.shape[1], 1).unsqueeze(-1)
-    focus = multiple_rollout_collision_avoidance_loss(pred, labels, time_decay, 'none')
-    loss = collision_w * focus
-    if abnormal_mask is not None:
-        loss = loss * abnormal_mask.reshape(1, 1, -1, 1)
-    return reduction(loss, mode)
 
 
 # ---- the rollout ------------------------------------------------------------------------------------------------
@@ -131,7 +82,7 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
                 pred_collisions[:, t, ...] = predictions[-1]
                 true_collision[:, t, ...] = Pedestrians.calculate_collision_label(state_features[0])
             if args.reg_weight > 0:                                               # :735-737 (running sum, as is)
-                reg_loss += l1_reg_loss(p_msg, args.reg_weight, 'sum')
+                reg_loss = reg_loss + L1SumFunction.apply(p_msg, args.reg_weight)
                 loss = loss + reg_loss
         a_next = predictions[0]
         assert ~a_next.isnan().any(), print('find nan in epoch :', getattr(simulator, 'epoch', None),
@@ -186,8 +137,8 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
                                                  None)[0]
         loss = loss + a_mse_loss * args.teacher_weight
     if args.collision_pred_weight > 0:                                            # :826-830
-        collision_pred_loss = F.binary_cross_entropy(pred_collisions, true_collision,
-                                                     reduction='sum') * args.collision_pred_weight
-        collision_pred_acc = torch.sum(torch.round(pred_collisions) == true_collision) / true_collision.numel()
+        bce, hits = BceSumFunction.apply(pred_collisions, true_collision)
+        collision_pred_loss = bce * args.collision_pred_weight
+        collision_pred_acc = hits / true_collision.numel()
         loss = loss + collision_pred_loss
     return loss, mse_loss, collision_loss, hard_collision_loss, collision_pred_loss, collision_pred_acc, reg_loss

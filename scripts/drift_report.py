@@ -39,6 +39,59 @@ for name in ("rollout_gc_bm", "rollout_toy5_m", "rollout_ucy_bm"):
         lines.append(f"| {name} | {label} | {T - t0} | {mx(1):.2e} / {mx(10):.2e} / {mx(100):.2e} / {mx(300):.2e} / "
                      f"{np.nanmax(drift):.2e} | {end_mean:.2e} | {np.array_equal(mask, o['mask_p'])} | "
                      f"{np.array_equal(np.isnan(p_res), np.isnan(o['position']))} |")
+# ---- why the end-of-clip numbers differ between the two forward kernels: the chaos envelope of OUR OWN path --------------
+# The GC clip's end drift is 3e-2 m on the FP32-pipe forward and 4e-3 m on the tensor-core forward, although both are
+# 1e-5 m from the reference after 300 steps.  Re-run each kernel from a start frame perturbed by +-1 ulp per coordinate
+# (the SURVEY's probe on the reference itself) and compare with the SAME kernel's unperturbed run: if the kernel's own
+# perturbed runs spread as far as its distance to the reference, that distance is the clip's sensitivity to rounding
+# after step ~300, not an error of the kernel.
+lines += ["", "## Self-divergence under a 1-ulp perturbation of the start frame (same kernel, perturbed vs unperturbed)", "",
+          "| clip / model | forward kernel | max drift vs own unperturbed run at +100 / +300 / end, 4 seeds [m] | step / agent of the "
+          "largest distance to the reference | first step with > 1e-4 m to the reference |", "|---|---|---|---|---|"]
+for name in ("rollout_gc_bm",):
+    z, i, o, args, m = _rollout_inputs(name)
+    T, t0 = int(i["num_frames"]), int(i["t_start"])
+    base = {k: cu(i[k])[None] for k in ("position", "velocity", "acceleration", "destination", "waypoints",
+                                         "mask_p", "mask_p_pred", "desired_speed")}
+    base["dest_idx"] = cu(i["dest_idx"], torch.int64)[None]
+    base["dest_num"] = cu(i["dest_num"], torch.int64)[None]
+    base["obstacles"] = cu(i["obstacles"])
+    packed = M.pack_device(m.state_dict(), m.spec)
+    ptc = M.pack_device_tc(m.state_dict(), m.spec)
+    import piml_b200 as P2
+    from piml_b200.rollout import state_features
+
+    def run(scene, tc):
+        # features of the (possibly perturbed) start frame, rebuilt by the library like every later frame
+        p0, v0, a0 = scene["position"][:, t0].contiguous(), scene["velocity"][:, t0].contiguous(), \
+            scene["acceleration"][:, t0].contiguous()
+        hist = cu(i["self_features0"])[None][..., 2:4].contiguous()
+        pf, of, sf = state_features(p0, v0, a0, scene["destination"][:, t0].contiguous(), scene["obstacles"], hist,
+                                    scene["desired_speed"], args.topk_ped, args.sight_angle_ped, args.dist_threshold_ped,
+                                    args.topk_obs, args.sight_angle_obs, args.dist_threshold_obs)
+        sc = dict(scene, ped_features0=pf, obs_features0=of, self_features0=sf)
+        r = rollout_scenes(m.spec, packed, args, sc, t0, T, packed_tc=tc)
+        return npy(r[0][0])
+    for label, tc in (("FP32 pipe", None), ("tcgen05 3xTF32", ptc)):
+        ref_run = run(base, tc)
+        d_ref = np.linalg.norm(ref_run - o["position"], axis=-1)
+        worst = np.unravel_index(np.nanargmax(d_ref), d_ref.shape)
+        big = np.where(np.nanmax(np.nan_to_num(d_ref), axis=1) > 1e-4)[0]
+        spreads = []
+        for seed in range(4):
+            g = torch.Generator().manual_seed(seed)
+            pos = base["position"].clone()
+            sign = (torch.randint(0, 2, pos[:, t0].shape, generator=g) * 2 - 1).to(pos.device).float()
+            pos[:, t0] = torch.nextafter(pos[:, t0], pos[:, t0] + sign)
+            pr = run(dict(base, position=pos), tc)
+            d = np.linalg.norm(pr - ref_run, axis=-1)
+            mxk = lambda k: np.nanmax(d[:min(T - 1, t0 + k) + 1])
+            spreads.append((mxk(100), mxk(300), np.nanmax(d)))
+        sp = np.array(spreads)
+        lines.append(f"| {name} | {label} | {sp[:, 0].min():.1e}..{sp[:, 0].max():.1e} / {sp[:, 1].min():.1e}..{sp[:, 1].max():.1e} / "
+                     f"{sp[:, 2].min():.1e}..{sp[:, 2].max():.1e} | step +{worst[0] - t0}, agent {worst[1]} | "
+                     f"{('+' + str(big[0] - t0)) if len(big) else 'never'} |")
+
 # pure social-force rollout (BASELINE config 2): the composed reference module on the synthetic clip
 import piml_b200 as P                                         # noqa: E402
 from tests.golden_args import base_args                       # noqa: E402

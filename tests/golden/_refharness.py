@@ -1,7 +1,8 @@
-"""Harness that imports the UNMODIFIED reference from /root/reference (this container only).
+"""Harness that imports the UNMODIFIED reference from /root/reference (build container) or from its verbatim copy
+baseline/_ref/ (GPU box).
 
-Used only by tests/golden/make_golden.py to generate the committed golden vectors; nothing in
-tests/, bench.py or the product imports this at run time (the GPU box has no /root/reference).
+Used by tests/golden/make_golden.py to generate the committed golden vectors, by tests/test_gpu_dropin.py to run the
+real reference objects behind piml_b200.patch, and by bench.py's reference_pytorch timing; the product never imports it.
 Works around two reference defects without editing it: data files are
 loaded by absolute path, and `args` is built programmatically instead of through main.py.
 """
@@ -11,7 +12,10 @@ import io
 import os
 import sys
 
-REF_ROOT = os.environ.get("PIML_REFERENCE", "/root/reference")
+_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+# /root/reference in the build container; on the GPU box the unmodified copy __graft_entry__.build() staged in
+# git-ignored baseline/_ref/ (it travels with the gpurun snapshot)
+REF_ROOT = os.environ.get("PIML_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/src") else _COPY)
 REF_SRC = os.path.join(REF_ROOT, "src")
 REF_DATA = os.path.join(REF_ROOT, "data")
 
@@ -79,3 +83,7 @@ GC_CLIP = "GC_Dataset/GC_Dataset_ped1-12685_time1000-1060_interp9_xrange5-25_yra
 SYN_CLIP = "synthetic_data/GC_Dataset_ped1-12685_time1560-1620_interp9_xrange5-25_yrange15-35_simulation.npy"
 UCY_CLIP = "UCY_dataset/UCY_Dataset_time0-54_timeunit0.08.npy"
 TOY_CLIP = "GC_Dataset/GC_Dataset_toy5.npy"
+
+
+def available():
+    return os.path.isdir(REF_SRC) and os.path.isdir(REF_DATA)

@@ -978,3 +978,60 @@ def test_mlapm_symmetric_vs_ordered_at_bench_size():
     assert float((num / den).max()) < TOL
     assert np.abs(res[2][1] - res[1][1]).max() < 1e-4            # positions up to 450 m: a few fp32 ulps
     assert (res[2][2] != res[1][2]).sum() <= 2                    # arrival test at the radius boundary
+
+
+# ---- round 2: small kernels that replaced the last eager-torch helpers ---------------------------------------------------
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_ucy_bm", "rollout_toy5_m"])
+def test_desired_speed_kernel_matches_reference_and_oracle(name):
+    """piml_desired_speed_f32 (data.py:797-806) on the clips' velocities: the reference's own make_dataset values."""
+    from piml_b200.dataset import desired_speed
+    g = golden(name)
+    got = npy(desired_speed(cu(g["in/velocity"]), 25))
+    assert np.allclose(got, g["in/desired_speed"], rtol=1e-6, atol=0, equal_nan=True)
+    assert np.allclose(got, O.desired_speed(g["in/velocity"], 25), rtol=1e-6, atol=0, equal_nan=True)
+    v = g["in/velocity"].copy()
+    v[:, 3] = 0                                            # a pedestrian that never moves: frames [0, skip)
+    assert npy(desired_speed(cu(v), 25))[3] == 0.0
+    assert npy(desired_speed(cu(v[:5]), 25)).shape == (v.shape[1],)      # clip shorter than skip_frames
+
+
+def test_relative_quantity_and_filtered_features_helpers():
+    """get_relative_quantity (data.py:398-414) and get_filtered_features (:449-464) as dense kernels for the callers
+    outside the hot path: bit-exact against the reference's tensor expressions."""
+    import piml_b200 as P
+    rng = np.random.default_rng(11)
+    A = rng.normal(0, 3, (2, 3, 17, 6)).astype(np.float32)
+    B = rng.normal(0, 3, (2, 3, 9, 6)).astype(np.float32)
+    A[0, 1, 4] = np.nan
+    ped = P.Pedestrians()
+    rel = npy(ped.get_relative_quantity(cu(A), cu(B)))
+    want = B[:, :, None, :, :] - A[:, :, :, None, :]
+    assert rel.shape == (2, 3, 17, 9, 6) and np.array_equal(rel, want, equal_nan=True)
+    k = 4
+    idx = rng.integers(0, 9, (2, 3, 17, k)).astype(np.int64)
+    dist = rng.random((2, 3, 17, k)).astype(np.float32) * 8
+    dist[0, 0, 0, 0], dist[0, 0, 0, 1] = np.inf, np.nan
+    got = npy(ped.get_filtered_features(cu(want), cu(idx, torch.int64), cu(dist), 4))
+    ref = np.take_along_axis(want, idx[..., None].repeat(6, -1), axis=-2)
+    ref[dist > 4] = 0                                       # NaN > 4 is False: the slot is kept, as in the reference
+    assert np.array_equal(got, ref, equal_nan=True)
+
+
+def test_metrics_reject_frames_beyond_the_shared_memory_limit():
+    """more than 1024 masked agents in a frame used to give NaN OT / MMD and a truncated MAE silently."""
+    from piml_b200 import metrics as MT
+    rng = np.random.default_rng(5)
+    T, N = 2, 1500
+    p = rng.normal(0, 5, (T, N, 2)).astype(np.float32)
+    q = (p + rng.normal(0, 0.3, (T, N, 2))).astype(np.float32)
+    mask = np.ones((T, N), np.int64)
+    mask[1, 1000:] = 0
+    want = O.mae_with_time_mask(p, q, mask)
+    got = MT.mae_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum')
+    assert abs(got - want) <= 2e-5 * want                  # every masked agent counted, no 1024 cut-off
+    with pytest.raises(NotImplementedError):
+        MT.ot_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum')
+    with pytest.raises(NotImplementedError):
+        MT.mmd_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum')
+    mask[0, 1024:] = 0                                      # exactly at the limit: supported
+    assert np.isfinite(MT.mmd_with_time_mask(cu(p), cu(q), cu(mask, torch.int64), reduction='sum'))

@@ -247,9 +247,9 @@ def test_training_rollout_golden(case):
                                                                (1, 1, 5, False, True, False)])
 def test_fused_rollout_losses_match_the_torch_restatement(C, T, N, reverse, with_coll, with_mask):
     """piml_rollout_losses_f32 / _backward_f32 (simulators.py:172-249 with reduction 'sum', fused) against the plain
-    torch restatement of the same three losses (piml_b200.train_rollout.multiple_rollout_*), values and d/d pred, with
+    torch restatement of the same three losses (tests/torch_ref.py multiple_rollout_*), values and d/d pred, with
     labels read in place from a wider (.., 6 + k) tensor like data.labels[..., :2]."""
-    from piml_b200 import train_rollout as TR
+    from tests import torch_ref as TR
     from piml_b200.autograd import RolloutLossesFunction
     g = torch.Generator().manual_seed(C * 100 + T)
     pred = (torch.randn(C, T, N, 2, generator=g) * 3).cuda().requires_grad_(True)
@@ -302,3 +302,32 @@ def test_fused_rollout_losses_match_reference_methods(case):
     scale = float(np.abs(g["g_pred"]).max())
     assert float(np.abs(pred.grad.cpu().numpy() - g["g_pred"]).max()) <= 2e-5 * max(scale, 1.0)
     assert np.allclose(a_pred.grad.cpu().numpy(), g["g_a_pred"], rtol=2e-5, atol=2e-6)
+
+
+def test_l1_and_bce_sum_kernels_match_torch():
+    """L1SumFunction (simulators.py:169-170) and BceSumFunction (:826-830) against torch's own ops, values and
+    gradients, incl. saturated predictions (log clamp at -100) and exact zeros."""
+    from piml_b200.autograd import BceSumFunction, L1SumFunction
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 5, 144, 2, generator=g).cuda()
+    x[0, 0, :7] = 0
+    x.requires_grad_(True)
+    out = L1SumFunction.apply(x, 1e-3)
+    (out * 3).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    ref = TR.l1_reg_loss(xr, 1e-3, 'sum')
+    (ref * 3).backward()
+    assert abs(float(out) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert torch.equal(x.grad, xr.grad)
+    p = torch.rand(6, 5, 144, 6, generator=g).cuda()
+    p.view(-1)[:4] = torch.tensor([0.0, 1.0, 1e-30, 0.5]).cuda()
+    t = (torch.rand(6, 5, 144, 6, generator=g) < 0.2).float().cuda()
+    p.requires_grad_(True)
+    loss, hits = BceSumFunction.apply(p, t)
+    (loss * 10).backward()
+    pr = p.detach().clone().requires_grad_(True)
+    want = torch.nn.functional.binary_cross_entropy(pr, t, reduction='sum')
+    (want * 10).backward()
+    assert abs(float(loss) - float(want)) <= 2e-6 * abs(float(want))
+    assert float(hits) == float(torch.sum(torch.round(pr.detach()) == t))
+    assert torch.allclose(p.grad, pr.grad, rtol=1e-6, atol=0)

@@ -63,3 +63,55 @@ def test_spec_from_module_matches_spec_from_args():
         s1, s2 = M.spec_from_args(kind, args), M.spec_from_module(m)
         for f in ("enc_dims", "proc_mode", "dec_dims", "coll_dims", "kind", "has_obs", "tau"):
             assert getattr(s1, f) == getattr(s2, f), (kind, f)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src"), reason="reference tree not present")
+@pytest.mark.parametrize("layers", [16, 3, 1])
+def test_train_mode_dropout_masks_follow_the_reference_rng_stream(layers):
+    """ResDNN.forward draws one Dropout mask per block and applies only the last (model.py:115-119).  Under the same
+    seed the multipliers the CUDA path applies must be the reference's, and torch's RNG must end in the same state."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import _refharness as H
+    import torch
+    from piml_b200 import models as M
+    DATA, MODEL, *_ = H.import_reference()
+    args = H.default_args(model="pinnsf_bm", dataset_name="gc1560", processor_hidden_layers=layers)
+    torch.manual_seed(1)
+    net = MODEL.PINNSF_bottleneck_multitask(args).train()
+    spec = M.spec_from_module(net)
+    assert spec.n_blocks == layers and M.spec_from_args("pinnsf_bm", args).n_blocks == layers
+    ped, obs, slf = torch.randn(9, 6, 6), torch.randn(9, 10, 6), torch.randn(9, 7)
+    seen = []
+    hook = lambda mod, inp, out: seen.append((out / inp[0]).detach().clone())
+    handles = [net.ped_processor.dropout.register_forward_hook(hook), net.obs_processor.dropout.register_forward_hook(hook)]
+    torch.manual_seed(123)
+    net(ped, obs, slf)
+    after_ref = torch.rand(4)
+    for h in handles:
+        h.remove()
+    assert len(seen) == 2 * layers                        # one draw per block and branch
+    torch.manual_seed(123)
+    dp, do = M._dropout_multipliers(spec, True, ped, obs)
+    after = torch.rand(4)
+    want_p, want_o = torch.nan_to_num(seen[layers - 1], nan=0.0), torch.nan_to_num(seen[-1], nan=0.0)
+    ok_p, ok_o = seen[layers - 1].isfinite(), seen[-1].isfinite()          # 0/0 where the block output is exactly 0
+    assert torch.equal(dp[ok_p], want_p[ok_p]) and torch.equal(do[ok_o], want_o[ok_o])
+    assert ok_p.float().mean() > 0.9
+    assert torch.equal(after, after_ref)
+
+
+def test_non_relu_single_block_processor_is_rejected():
+    """args.activation only reaches the forward through the single-block processor; the kernels implement ReLU."""
+    import argparse
+    from piml_b200 import models as M
+    a = argparse.Namespace(model='pinnsf_bm', dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128,
+                           processor_hidden_size=128, decoder_hidden_size=64, encoder_hidden_layers=3,
+                           processor_hidden_layers=1, decoder_hidden_layers=2, ped_feature_dim=6, obs_feature_dim=6,
+                           self_feature_dim=7, activation='sigmoid')
+    with pytest.raises(NotImplementedError):
+        M.spec_from_args('pinnsf_bm', a)
+    a.activation = 'relu'
+    assert M.spec_from_args('pinnsf_bm', a).proc_mode == 1
+    a.processor_hidden_layers, a.activation = 16, 'leaky_relu'       # discarded Linear: activation never applied
+    assert M.spec_from_args('pinnsf_bm', a).proc_mode == 0

@@ -273,3 +273,14 @@ def test_metrics_match_reference(name):
     frames2, mm = O.mmd_with_time_mask(p, q, sub)
     assert np.array_equal(frames2, frames)
     assert np.allclose(mm, g["mmd"][idx], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["rollout_gc_bm", "rollout_ucy_bm", "rollout_toy5_m", "rollout_syn_sfm"])
+def test_desired_speed_matches_reference_make_dataset(name):
+    """data.py:797-806: the golden rollouts carry data.self_features[t, :, -1] of the reference's own make_dataset
+    (skip_frames = 25) next to the clip's velocities."""
+    g = golden(name)
+    got = O.desired_speed(g["in/velocity"], 25)
+    want = g["in/desired_speed"]
+    assert got.shape == want.shape
+    assert np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True)

@@ -30,6 +30,7 @@ def _fake_reference():
     class RawData(object):
         pass
     DATA.Pedestrians, DATA.RawData = Pedestrians, RawData
+    DATA.TimeIndexedPedData = type("TimeIndexedPedData", (Pedestrians,), {"make_dataset": lambda self, a, r: "ref"})
     MODEL = types.ModuleType("models.model")
     for c in ("PINNSF", "PINNSF_bottleneck", "PINNSF_bottleneck_multitask", "PINNSF_multitask"):
         setattr(MODEL, c, type(c, (), {"forward": lambda self, p, o, s: "ref"}))
@@ -55,7 +56,7 @@ def test_install_swaps_and_uninstall_restores(monkeypatch):
     assert UT.calc_acceleration() == "ref"
     monkeypatch.setenv("PIML_B200", "1")
     names = patch.install_from_env(DATA=DATA, MLAPM_MOD=ML, MODEL=MODEL, SIM=SIM, UTILS=UT)
-    assert len(names) == 6 + 4 + 1 + 1 + 2
+    assert len(names) == 6 + 1 + 4 + 1 + 1 + 2
     import piml_b200 as P
     assert UT.calc_acceleration is P.calc_acceleration
     assert DATA.Pedestrians.__dict__["get_relative_features"] is P.Pedestrians.__dict__["get_relative_features"]
@@ -69,6 +70,7 @@ def test_install_swaps_and_uninstall_restores(monkeypatch):
     assert ML.MLAPM().step() == "ref" and SIM.BaseSimulator().get_multiple_rollouts(None) == "ref"
     assert SIM.BaseSimulator().test_multiple_rollouts_for_training(None) == "ref"
     assert DATA.Pedestrians.collision_detection(0, 0) == "ref"
+    assert DATA.TimeIndexedPedData().make_dataset(None, None) == "ref"
     assert not hasattr(DATA.Pedestrians, "_relative_features_raw")       # helper added by install is removed again
 
 
@@ -85,7 +87,7 @@ def test_install_on_the_real_reference_modules():
     orig_ot = METRIC.ot_with_time_mask
     names = patch.install(DATA=DATA, MLAPM_MOD=MLAPM, MODEL=MODEL, SIM=SIM, UTILS=UTILS, METRIC=METRIC)
     try:
-        assert len(names) == 14 + 4
+        assert len(names) == 15 + 4
         assert SIM.BaseSimulator.get_relative_features is not orig
         import piml_b200.metrics as MT
         assert METRIC.ot_with_time_mask is MT.ot_with_time_mask and METRIC.collision_count is MT.collision_count

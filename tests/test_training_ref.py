@@ -82,9 +82,9 @@ def test_collision_detection_ref_shapes():
 
 @pytest.mark.parametrize("case", ["ucy", "gc", "tiny"])
 def test_loss_restatements_match_reference_methods(case):
-    """f-3: the torch restatements of the rollout losses (piml_b200.train_rollout.multiple_rollout_*) against the
+    """f-3: the torch restatements of the rollout losses (tests/torch_ref.py multiple_rollout_*) against the
     reference's own BaseSimulator methods (simulators.py:172-249) called on the same seeded tensors: values and d/d pred."""
-    from piml_b200 import train_rollout as TR
+    from tests import torch_ref as TR
     from tests.util import golden, group
     g = group(golden("losses"), case)
     wide = torch.from_numpy(g["wide"])

@@ -102,3 +102,44 @@ def collision_detection_ref(position, threshold, real_position=None):
     else:
         friends = (1 - (coll[:, :4].sum(1) > 0).float()).unsqueeze(1)
     return coll * friends
+
+
+# ---- rollout losses (reference src/models/simulators.py:169-249), plain torch ------------------------------------------
+def _reduce(x, mode):
+    return {"sum": torch.sum, "mean": torch.mean, "none": lambda t: t}[mode](x)
+
+
+def l1_reg_loss(embeddings, weight=1e-3, mode='none'):
+    """simulators.py:169-170."""
+    return _reduce(weight * embeddings.abs(), mode)
+
+
+def multiple_rollout_mse_loss(pred, labels, time_decay, mode='none', reverse=False):
+    """simulators.py:172-195: squared error of (C,T,N,2) tensors weighted by time_decay^(T-1-t) (time_decay^t if
+    `reverse`)."""
+    T = pred.shape[1]
+    powers = [t if reverse else T - 1 - t for t in range(T)]
+    w = torch.tensor([time_decay ** k for k in powers], device=pred.device).reshape(1, T, 1, 1)
+    return _reduce((pred - labels) ** 2 * w, mode)
+
+
+def _perpendicular(x, n):
+    return x - (x * n).sum(-1, keepdim=True) * n
+
+
+def multiple_rollout_collision_avoidance_loss(pred, labels, time_decay, mode='none'):
+    """simulators.py:230-249: the MSE of the components perpendicular to the label's first-to-last displacement."""
+    n = labels[:, -1:] - labels[:, :1]
+    n = n / (n.norm(p=2, dim=-1, keepdim=True) + 1e-6)
+    return _reduce(multiple_rollout_mse_loss(_perpendicular(pred, n), _perpendicular(labels, n), time_decay), mode)
+
+
+def multiple_rollout_collision_loss(pred, labels, time_decay, coll_focus_weight, collisions, mode='none',
+                                    abnormal_mask=None):
+    """simulators.py:197-228: the avoidance loss of every pedestrian that collided at any step of its channel
+    (`collisions` (C,T,N) summed over T and binarised), optionally masked per pedestrian."""
+    hit = (collisions.sum(dim=1) > 0).to(pred.dtype)                       # (C,N)
+    loss = hit[:, None, :, None] * multiple_rollout_collision_avoidance_loss(pred, labels, time_decay)
+    if abnormal_mask is not None:
+        loss = loss * abnormal_mask.reshape(1, 1, -1, 1)
+    return _reduce(loss, mode)
