@@ -6,4 +6,5 @@ timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_parity_s
 echo "suite rc=$?"; tail -3 gpurun_out/r02a_pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/r02a_bench.log 2>&1; tail -1 gpurun_out/r02a_bench.log | cut -c1-600
-bash scripts/gpu_sanitize.sh
+SAN_TOOLS="memcheck synccheck" SAN_TIMEOUT=420 bash scripts/gpu_sanitize.sh
+timeout 600 python scripts/drift_report.py > gpurun_out/r02a_drift.log 2>&1; tail -5 gpurun_out/r02a_drift.log | cut -c1-300
