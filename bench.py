@@ -249,6 +249,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.workload == "nn":
+        return run_reference_nn(a)
     from oracle import oracle as O
     import numpy as np
     N = a.agents
@@ -286,6 +288,59 @@ def run_reference(a):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_reference_nn(a):
+    """--impl reference --workload nn: the oracle's port of one NN rollout step on all host threads, sampled rows."""
+    N = a.agents
+    _, _, _, _, obs_h = synthetic_crowd(N)
+    budget = min(8.0, 90.0 / max(a.steps + a.warmup, 1))
+    cpu, R, _, dt = nn_cpu_baseline(N, obs_h, seconds=budget, steps=max(a.steps, 1))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "ms_per_full_step": N / cpu["value"] * 1e3,
+        "sample_rows_per_step": R, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": nn_config(N, int(obs_h.shape[0])), "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_nn(a):
+    """--workload nn: the NN-augmented rollout step as the main line (1 GPU: NNCrowd; torchrun: ShardedNNCrowd)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the piml_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N = a.agents
+    _, _, _, _, obs_h = synthetic_crowd(N)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    if world == 1:
+        blk = nn_workload(torch, dev, N, obs_h, a.steps, a.warmup, with_cpu=not a.no_cpu)
+        if sampler:
+            sampler.stop()
+        line = {"metric": METRIC, "value": blk["value"], "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": blk["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        line.update({k: v for k, v in blk.items() if k not in line})
+        line["clocks"] = sampler.summary() if sampler else None
+        print(json.dumps(line))
+        return
+    dist.init_process_group("nccl", device_id=dev)
+    blk = nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=a.steps)
+    if rank == 0:
+        sampler.stop()
+        ms = blk.get("ms_per_step")
+        print(json.dumps({"metric": METRIC, "value": (N / ms * 1e3) if ms else None, "unit": UNIT, "n_gpus": world,
+                          "steps": a.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": nn_config(N, int(obs_h.shape[0])), "detail": blk, "clocks": sampler.summary()}))
+    dist.destroy_process_group()
+
+
 def bench_config(N, world):
     """The workload both arms run (identical keys and values in `ours` and `--impl reference`)."""
     return {"workload": f"mlapm_gc_rollout_N{N}", "agents": N,
@@ -314,73 +369,223 @@ def probe_peaks(L, torch, dev):
     return res
 
 
-def nn_path_step(torch, dev, N, obs_h, iters=10):
-    """Secondary evidence (not the headline metric): one step of the NN-augmented rollout (simulators.py:602-652) on
-    the same crowd -- fused pinnsf_bm forward, fused integrate, cell-list feature rebuild -- device-resident."""
-    import argparse as ap
-    import piml_b200 as P
-    from piml_b200 import models as M
-    from piml_b200.rollout import integrate_step, state_features
-    args = ap.Namespace(model='pinnsf_bm', dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128,
-                        processor_hidden_size=128, decoder_hidden_size=64, encoder_hidden_layers=3,
-                        processor_hidden_layers=16, decoder_hidden_layers=2, ped_feature_dim=6, obs_feature_dim=6,
-                        self_feature_dim=7)
-    torch.manual_seed(666)
-    net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
-    packed = M.pack_device(net.state_dict(), net.spec, dev)
-    packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)          # tcgen05 (3xTF32) forward
-    p, v, ds, dest, _ = [x.to(dev) for x in synthetic_crowd(N)]
-    p, v, dest = p[None].contiguous(), v[None].contiguous(), dest[None].contiguous()
-    acc, hist = torch.zeros_like(v), v.clone()
-    dsp = ds.reshape(1, N).contiguous()
-    obs = obs_h.to(dev)
-    didx = torch.zeros(1, N, dtype=torch.int64, device=dev)
-    dnum = torch.ones(1, N, dtype=torch.int64, device=dev)
-    wp = dest[:, None].contiguous()
-    fargs = (6, 90, 4, 10, 90, 4)
-    bufs = None
+NN_ARGS = dict(model='pinnsf_bm', dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128,
+               processor_hidden_size=128, decoder_hidden_size=64, encoder_hidden_layers=3, processor_hidden_layers=16,
+               decoder_hidden_layers=2, ped_feature_dim=6, obs_feature_dim=6, self_feature_dim=7, topk_ped=6,
+               topk_obs=10, sight_angle_ped=90, sight_angle_obs=90, dist_threshold_ped=4, dist_threshold_obs=4,
+               time_unit=DT)
+NN_FEATURE_ARGS = (6, 90, 4, 10, 90, 4)
+NN_FLOP_PER_AGENT = 1.52e6            # pinnsf_bm forward, 6 ped + 10 obstacle slots
+# algorithmic HBM bytes per agent-step, stage by stage: features read 44 B of state and write
+# (6 + 10) slots x 24 B + 28 B self + 8 B dest; the forward reads those 420 B and writes 8 B; integrate reads 68 B and
+# writes 48 B.  A fully fused step would move 44 + 48 = 92 B (SURVEY.md 8d "68-92 B").
+NN_BYTES_PER_AGENT = 44 + 384 + 28 + 8 + 420 + 8 + 68 + 48
+NN_BYTES_PER_AGENT_FUSED = 92
 
-    def step():
-        nonlocal bufs
-        pf, of, sf = bufs[:3] if bufs else state_features(p, v, acc, dest, obs, hist, dsp, *fargs)
-        a_next = M.pinnsf_forward(net.spec, packed, pf.view(N, 6, 6), of.view(N, -1, 6), sf.view(N, 7),
-                                  need_msgs=False, packed_tc=packed_tc)[0].view(1, N, 2)
-        integrate_step(p, v, acc, a_next, dest, didx, dnum, wp, DT, False, hist_v=hist)
-        if bufs is None:
-            bufs = (pf, of, sf, torch.empty(1, N, 2, device=dev))
-        state_features(p, v, acc, dest, obs, hist, dsp, *fargs, out=bufs)
-    for _ in range(3):
-        step()
+
+def nn_config(N, M=2000):
+    return {"workload": f"pinnsf_bm_nn_rollout_N{N}", "agents": N, "obstacle_points": M,
+            "reference": "src/models/simulators.py:595-652 (model forward -> Euler / arrival -> get_relative_features), "
+                         "src/models/model.py:1185-1221, src/data/data.py:466-512",
+            "crowd": "SURVEY 8d config 4: seed 666, rho 0.5 ped/m^2, dt 0.08, k 6/10, 90 deg, 4 m; seed-666 weights",
+            "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region (GPU arm)"}
+
+
+class NNCrowd(object):
+    """One NN-augmented rollout step (simulators.py:602-652) on the synthetic crowd: pinnsf_bm forward (tcgen05),
+    integrate, cell-list feature rebuild.  Device-resident state; `step()` enqueues the stage kernels."""
+
+    def __init__(self, torch, dev, N, obs_h):
+        import argparse as ap
+        from piml_b200 import models as M
+        from piml_b200.rollout import integrate_step, state_features
+        self.torch, self.dev, self.N, self.models = torch, dev, N, M
+        self._integrate, self._features = integrate_step, state_features
+        torch.manual_seed(666)
+        self.net = M.PINNSF_bottleneck_multitask(ap.Namespace(**NN_ARGS)).to(dev).eval()
+        self.packed = M.pack_device(self.net.state_dict(), self.net.spec, dev)
+        self.packed_tc = M.pack_device_tc(self.net.state_dict(), self.net.spec, dev)
+        p, v, ds, dest, _ = synthetic_crowd(N)
+        self.host = {"p": p.pin_memory(), "v": v.pin_memory(), "a": torch.zeros_like(v).pin_memory(),
+                     "dest": dest.pin_memory(), "ds": ds.reshape(1, N).contiguous().pin_memory()}
+        self.p, self.v, self.dest = [x.to(dev)[None].contiguous() for x in (p, v, dest)]
+        self.acc, self.hist = torch.zeros_like(self.v), self.v.clone()
+        self.ds = ds.reshape(1, N).contiguous().to(dev)
+        self.obs = obs_h.to(dev)
+        self.didx = torch.zeros(1, N, dtype=torch.int64, device=dev)
+        self.dnum = torch.ones(1, N, dtype=torch.int64, device=dev)
+        self.wp = self.dest[:, None].contiguous()
+        self.bufs = tuple(self._features(self.p, self.v, self.acc, self.dest, self.obs, self.hist, self.ds,
+                                         *NN_FEATURE_ARGS)) + (torch.empty(1, N, 2, device=dev),)
+        self.a_next = None
+        self.out_h = [torch.empty(N, 2).pin_memory() for _ in range(3)]
+
+    def forward(self):
+        N, M = self.N, self.models
+        pf, of, sf = self.bufs[:3]
+        self.a_next = M.pinnsf_forward(self.net.spec, self.packed, pf.view(N, 6, 6), of.view(N, -1, 6), sf.view(N, 7),
+                                       need_msgs=False, packed_tc=self.packed_tc)[0].view(1, N, 2)
+
+    def integrate(self):
+        self._integrate(self.p, self.v, self.acc, self.a_next, self.dest, self.didx, self.dnum, self.wp, DT, False,
+                        hist_v=self.hist)
+
+    def features(self):
+        self._features(self.p, self.v, self.acc, self.dest, self.obs, self.hist, self.ds, *NN_FEATURE_ARGS,
+                       out=self.bufs)
+
+    def step(self):
+        self.forward(); self.integrate(); self.features()
+
+    def e2e_step(self):
+        """Host state in (pinned), one step, new p / v / a out: what a host-side simulation loop pays per step."""
+        h = self.host
+        self.p[0].copy_(h["p"], non_blocking=True); self.v[0].copy_(h["v"], non_blocking=True)
+        self.acc[0].copy_(h["a"], non_blocking=True); self.dest[0].copy_(h["dest"], non_blocking=True)
+        self.ds.copy_(h["ds"], non_blocking=True)
+        self.hist.copy_(self.v)
+        self.features(); self.forward(); self.integrate()
+        self.out_h[0].copy_(self.p[0]); self.out_h[1].copy_(self.v[0]); self.out_h[2].copy_(self.acc[0])
+
+    @property
+    def e2e_bytes(self):
+        return self.N * 4 * (2 + 2 + 2 + 2 + 1), self.N * 4 * 6
+
+
+def nn_cpu_baseline(N, obs_h, seconds=8.0, steps=1, rows0=0):
+    """Oracle C port of one NN rollout step on the host cores for rows [r0, r0+R) against all N agents / M obstacles:
+    get_relative_features (data.py:466-512) -> pinnsf_bm forward (model.py:1185-1221) -> Euler update
+    (simulators.py:603-604).  Returns (block, rows, (features, acceleration) of those rows for the parity check)."""
+    import argparse as ap
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    from piml_b200 import models as M
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    cores = O.num_threads()
+    torch.manual_seed(666)
+    net = M.PINNSF_bottleneck_multitask(ap.Namespace(**NN_ARGS)).eval()
+    desc = O.net_desc(net.spec.enc_dims, net.spec.proc_mode, net.spec.dec_dims, net.spec.coll_dims, net.spec.kind)
+    flat = M.pack_state_dict(net.state_dict(), net.spec).cpu().numpy()
+    p, v, ds, dest, _ = [x.numpy() for x in synthetic_crowd(N)]
+    a, obs = np.zeros_like(v), obs_h.numpy()
+
+    def rows_step(r0, r1):
+        w = O.relative_features_rows(p, v, a, dest, obs, (r0, r1), *NN_FEATURE_ARGS)
+        slf = np.concatenate([w[2], v[r0:r1], a[r0:r1], ds[r0:r1]], -1)
+        acc = O.pinnsf_forward(desc, flat, net.spec.tau, w[0], w[1], slf)[0]
+        R = r1 - r0
+        O.integrate_step(p[r0:r1], v[r0:r1], a[r0:r1], acc, dest[r0:r1], np.zeros(R, np.int64), np.ones(R, np.int64),
+                         dest[None, r0:r1], DT, remove_on_arrival=False)
+        return w, slf, acc
+    probe = max(64, cores * 8)
+    rows_step(0, probe)
+    t0 = time.perf_counter()
+    rows_step(0, probe)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    R = int(min(N, max(probe, rate * seconds)))
+    t0 = time.perf_counter()
+    for s_ in range(steps):
+        r0 = (rows0 + s_ * R) % max(N - R, 1)
+        w, slf, acc = rows_step(r0, r0 + R)
+    dt = (time.perf_counter() - t0) / steps
+    return ({"value": R / dt, "unit": UNIT, "cores": cores, "kind": "port",
+             "sample": f"oracle C port (OpenMP, {cores} threads) of one NN rollout step: rows [r0,r0+{R}) x all {N} "
+                       f"agents + {obs.shape[0]} obstacles (features), {R} x 16 slot rows through pinnsf_bm, Euler; "
+                       f"{dt:.1f} s per sampled step"}, R, (r0, w, slf, acc), dt)
+
+
+def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
+    """The NN-augmented rollout step as a full bench block (value / e2e / roofline / cpu_baseline / parity)."""
+    from piml_b200 import _lib as L
+    import numpy as np
+    crowd = NNCrowd(torch, dev, N, obs_h)
+    flush = torch.empty(FLUSH_MB << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(warmup, 3)):
+        flush.zero_(); crowd.step()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = [[ev() for _ in range(4)] for _ in range(steps)]
+    launches0 = L.launch_count()
+    e0, e1 = ev(), ev()
     e0.record()
-    for _ in range(iters):
-        step()
+    for s_ in range(steps):
+        flush.zero_()
+        marks[s_][0].record(); crowd.forward()
+        marks[s_][1].record(); crowd.integrate()
+        marks[s_][2].record(); crowd.features()
+        marks[s_][3].record()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    assert torch.isfinite(p).all()
-    # algorithmic HBM bytes per agent-step of the three stages (DESIGN.md 4.2-4.5): features read 44 B state and write
-    # (6 + 10) slots x 24 B + 28 B self + 8 B dest; the forward reads those 420 B and writes 8 B; integrate reads 68 B and
-    # writes 48 B
-    bytes_per_agent = 44 + 384 + 28 + 8 + 420 + 8 + 68 + 48
-    peak_gbs, peak_src = 6550.0, "fallback (B200_PROFILING.md)"
+    launches = L.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / steps
+    st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(3)]
+    assert torch.isfinite(crowd.p[0]).sum() > 0
+    # ---- end to end with host buffers
+    for _ in range(2):
+        crowd.e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    g0, g1 = ev(), ev()
+    g0.record()
+    for _ in range(steps):
+        crowd.e2e_step()
+    g1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3) / steps
+    h2d, d2h = crowd.e2e_bytes
+    peak_gbs, peak_src, bf16 = 6550.0, "fallback (B200_PROFILING.md)", 1650.0
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak_gbs, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            pk = json.load(f)
+            peak_gbs, bf16, peak_src = float(pk["hbm_gbs"]), float(pk["bf16_tflops"]), "MEASURED_PEAKS.json"
     except Exception:
         pass
-    gbs = bytes_per_agent * N / (ms * 1e-3) / 1e9
-    return {"workload": f"pinnsf_bm NN rollout step, N={N}, M={int(obs.shape[0])}, k=6/10 (forward + integrate + "
-                        "cell-list feature rebuild); forward on tcgen05 tensor cores (3xTF32), compact mode",
-            "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3,
-            "forward_flop_per_agent": 1.52e6, "tflops_algorithmic": 1.52e6 * N / ms * 1e3 / 1e12,
-            "hbm": {"bound": "hbm", "bytes_per_agent_step": bytes_per_agent, "achieved": gbs, "peak": peak_gbs,
-                    "unit": "GB/s", "frac": gbs / peak_gbs, "peak_source": peak_src,
-                    "note": "the gather / MLP / integrate stages are NOT HBM-bound at this size: the step is bound by "
-                            "the tensor-core forward (tensor pipe 29 % busy, MMA-issue and epilogue latency) and the "
-                            "latency-bound cell-list gather (profiles/r01c_ncu_pinnsf_tc_kernel.txt, "
-                            "r01c_ncu_features_cells_kernel.txt)"}}
+    gbs = NN_BYTES_PER_AGENT * N / (ms * 1e-3) / 1e9
+    fwd_tf = NN_FLOP_PER_AGENT * N / (st[0] * 1e-3) / 1e12
+    block = {
+        "metric": METRIC, "value": N / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "config": nn_config(N, int(obs_h.shape[0])), "dtype": "f32 (network contractions as 3-term split products on "
+                                                               "the tensor cores, fp32 accumulate)",
+        "stage_ms": {"forward": st[0], "integrate": st[1], "features": st[2]},
+        "roofline": {"bound": "tensor", "kernel": "pinnsf_tc_kernel (+ compaction, finish)",
+                     "achieved": fwd_tf, "peak": bf16 / 2.0, "unit": "TFLOP/s", "frac": fwd_tf / (bf16 / 2.0),
+                     "peak_source": peak_src + " bf16_tflops / 2 (dense tf32 rate)",
+                     "note": "achieved = 1.52 MFLOP per agent (SURVEY 8d, all 16 slots) / forward stage time; the "
+                             "kernel evaluates only non-empty slot rows (compact mode) but spends 3 MMAs per product "
+                             "(3-term split for fp32-grade results), so executed tensor FLOPs differ from algorithmic",
+                     "traffic": None,
+                     "hbm": {"bytes_per_agent_step": NN_BYTES_PER_AGENT, "bytes_per_agent_step_fused": NN_BYTES_PER_AGENT_FUSED,
+                             "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                             "note": "whole step against the HBM copy peak: the stages are tensor / latency bound, "
+                                     "not HBM bound, at this size"}},
+        "e2e": {"value": N / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "api": "pinned host p, v, a, dest, desired speed -> state_features, pinnsf_forward, integrate_step -> "
+                       "host p, v, a"},
+        "gpu_launches": launches,
+    }
+    if with_cpu:
+        cpu, R, (r0, w, slf, acc_ref), _ = nn_cpu_baseline(N, obs_h)
+        block["cpu_baseline"] = cpu
+        # parity of the timed path on the rows the CPU leg just computed (fresh crowd, first step)
+        chk = NNCrowd(torch, dev, N, obs_h)
+        pf, of, sf = [x[0, r0:r0 + R].cpu().numpy() for x in chk.bufs[:3]]
+        chk.forward()
+        acc = chk.a_next[0, r0:r0 + R].cpu().numpy().astype(np.float64)
+        n = np.linalg.norm(slf[:, :2], axis=-1, keepdims=True)
+        dterm = (slf[:, 6:7] * slf[:, :2] / np.where(n == 0, 0.1, n) - slf[:, 2:4]) / chk.net.spec.tau
+        err = np.linalg.norm(acc - acc_ref, axis=-1)
+        scale = np.maximum(np.maximum(np.linalg.norm(acc_ref, axis=-1), np.linalg.norm(dterm, axis=-1)), 1e-3)
+        block["parity"] = {"rows": R, "features_bit_exact": bool(np.array_equal(pf, w[0]) and np.array_equal(of, w[1])
+                                                                  and np.array_equal(sf, slf)),
+                           "max_rel_acceleration_operand_scaled": float((err / scale).max()),
+                           "max_rel_acceleration_strict": float((err / np.maximum(np.linalg.norm(acc_ref, axis=-1),
+                                                                                  1e-6)).max()),
+                           "gate": "features bit-exact; ||da|| <= 1e-5 max(||a||, ||dest term||) per agent"}
+        block["parity"]["pass"] = bool(block["parity"]["features_bit_exact"]
+                                       and block["parity"]["max_rel_acceleration_operand_scaled"] < 1e-5)
+    return block
 
 
 def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
@@ -629,7 +834,7 @@ def run_ours(a):
             "clocks": sampler.summary() if sampler else None,
         }
         if world == 1:
-            line["nn_path"] = nn_path_step(torch, dev, N, obs_h)
+            line["nn_path"] = nn_workload(torch, dev, N, obs_h, 10, 3, with_cpu=not a.no_cpu)
         else:
             line["nn_path"] = nn_sharded
         if world == 1 and not a.no_cpu:
@@ -648,12 +853,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=100000)
+    ap.add_argument("--workload", default="mlapm", choices=["mlapm", "nn"],
+                    help="mlapm: BASELINE configs[3] headline (MLAPM rollout); nn: the NN-augmented rollout step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="multi-GPU exchange: fused peer-memory push (default) or NCCL all-gather")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "nn":
+        run_nn(a)
     else:
         run_ours(a)
 

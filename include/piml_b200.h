@@ -284,6 +284,12 @@ PIML_API int piml_pinnsf_forward_f32(const piml_net_desc *desc, const float *par
  * with w (N,K) row-major; terms = 1: plain TF32, 3: 3xTF32 split (fp32-grade).  K % 8 == 0, N % 16 == 0, both <= 128. */
 PIML_API int piml_tc_selftest_f32(const float *x, const float *w, int K, int N, int terms, float *y, void *stream);
 
+/* The same product on the 16-bit path (tcgen05 kind::f16): x and w split into fp16 hi + lo, terms = 3:
+ * x_lo w_hi + x_hi w_lo + x_hi w_hi with fp32 accumulation in TMEM (fp32-grade, like 3xTF32, at twice the K per
+ * instruction and half the TMEM / shared-memory footprint).  K % 16 == 0, N % 16 == 0, both <= 128.  swap = 0. */
+PIML_API int piml_tc16_selftest_f32(const float *x, const float *w, int K, int N, int terms, int swap, float *y,
+                                    void *stream);
+
 /* Tensor-core forward (tcgen05 kind::tf32 with the 3xTF32 split, accumulators and activations in TMEM): the inference
  * path of the rollouts.  Same contract as piml_pinnsf_forward_f32 in eval mode without the collision head:
  * acc (R,2) and, for kind 0 models, optional 2-d messages ped_msgs (R,kp,2) / obs_msgs (R,ko,2) (NULL to skip).

@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "mlp_tc16.cuh"
 
 namespace piml {
 
@@ -130,9 +131,125 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float *__restric
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// Self test of the 16-bit path: the same product with x and W split into fp16 hi + lo (3 MMAs per K = 16 step,
+// kind::f16, two A elements per 32-bit TMEM column, eight W elements per 16-byte shared-memory cell).
+// swap != 0 puts the EVEN K index into the high half of a column / cell pair instead (bring-up knob).
+__global__ void __launch_bounds__(128, 1) tc16_probe_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                            int K, int N, int terms, int swap, float *__restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *w_hi = reinterpret_cast<uint16_t *>(smem_raw);                  // [K/8][N][8]
+    uint16_t *w_lo = w_hi + K * N;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int e = tid; e < N * K; e += 128) {
+        const int n = e / K, k = e % K;
+        uint16_t hi, lo;
+        tc::split_f16(w[e], hi, lo);
+        const int cell = ((k >> 3) * N + n) * 8 + (k & 7);
+        w_hi[cell] = hi; w_lo[cell] = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    const uint32_t lane_base = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t COL_D = 0, COL_AH = 128, COL_AL = 192;
+    for (int k0 = 0; k0 < K; k0 += 16) {                                      // A: thread = row, 8 columns per K = 16
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float a0 = x[tid * K + k0 + 2 * q], a1 = x[tid * K + k0 + 2 * q + 1];
+            if (swap > 0) tc::split_f16x2(a1, a0, hi[q], lo[q]); else tc::split_f16x2(a0, a1, hi[q], lo[q]);
+        }
+        tc::st8(lane_base + COL_AH + k0 / 2, hi);
+        tc::st8(lane_base + COL_AL + k0 / 2, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::idesc_f16(N);
+        const uint32_t lbo = N * 16, sbo = 128, kstep = 2 * N * 16;
+        bool acc = false;
+        for (int j = 0; j < K / 16; ++j) {
+            const uint64_t bh = tc::smem_desc(tc::smem_addr(w_hi) + j * kstep, lbo, sbo);
+            const uint64_t bl = tc::smem_desc(tc::smem_addr(w_lo) + j * kstep, lbo, sbo);
+            if (terms >= 3) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AL + j * 8, bh, idesc, acc); acc = true; }
+            if (terms >= 2) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bl, idesc, acc); acc = true; }
+            tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bh, idesc, acc);
+            acc = true;
+        }
+        tc::commit(&bar);
+    }
+    const bool done = mbar_wait_bounded(&bar, 0, 1u << 22);
+    tc::fence_after_sync();
+    if (swap < 0) {
+        // micro-benchmark (bring-up only): -swap repetitions of the whole chain; y[0] = issue cycles per MMA,
+        // y[1] = issue + drain cycles per MMA, y[2] = MMAs.  terms: 3 = the 3-term chain, 1 = hi*hi only
+        if (tid == 0 && done) {
+            const uint32_t idesc = tc::idesc_f16(N);
+            const uint32_t lbo = N * 16, sbo = 128, kstep = 2 * N * 16;
+            const long long t0 = clock64();
+            int cnt = 0;
+            for (int rep = 0; rep < -swap; ++rep)
+                for (int j = 0; j < K / 16; ++j) {
+                    const uint64_t bh = tc::smem_desc(tc::smem_addr(w_hi) + j * kstep, lbo, sbo);
+                    const uint64_t bl = tc::smem_desc(tc::smem_addr(w_lo) + j * kstep, lbo, sbo);
+                    if (terms >= 3) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AL + j * 8, bh, idesc, true); ++cnt; }
+                    if (terms >= 2) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bl, idesc, true); ++cnt; }
+                    tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bh, idesc, true); ++cnt;
+                }
+            tc::commit(&bar);
+            const long long t1 = clock64();
+            mbar_wait_bounded(&bar, 1, 1u << 26);
+            const long long t2 = clock64();
+            y[0] = static_cast<float>(t1 - t0) / cnt;
+            y[1] = static_cast<float>(t2 - t0) / cnt;
+            y[2] = static_cast<float>(cnt);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tbase, 512);
+        return;
+    }
+    if (!done) {
+        for (int n = 0; n < N; ++n) y[tid * N + n] = __int_as_float(0x7fc00000);
+    } else {
+        for (int n0 = 0; n0 < N; n0 += 32) {
+            uint32_t r[32];
+            tc::ld32(lane_base + COL_D + n0, r);
+            tc::wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (n0 + q < N) y[tid * N + n0 + q] = __uint_as_float(r[q]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace piml
 
 using namespace piml;
+
+extern "C" int piml_tc16_selftest_f32(const float *x, const float *w, int K, int N, int terms, int swap, float *y,
+                                      void *stream) {
+    PIML_REQUIRE(x && w && y, "piml_tc16_selftest_f32: null pointer");
+    PIML_REQUIRE(K >= 16 && K <= 128 && K % 16 == 0 && N >= 16 && N <= 128 && N % 16 == 0,
+                 "piml_tc16_selftest_f32: need K in [16,128] multiple of 16 and N in [16,128] multiple of 16");
+    PIML_REQUIRE(terms >= 1 && terms <= 3, "piml_tc16_selftest_f32: terms must be 1, 2 or 3");
+    const size_t smem = sizeof(uint16_t) * 2 * K * N;
+    PIML_CUDA(cudaFuncSetAttribute(tc16_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    tc16_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, w, K, N, terms, swap, y);
+    count_launch();
+    return check_launch("tc16_probe_kernel");
+}
 
 extern "C" int piml_tc_selftest_f32(const float *x, const float *w, int K, int N, int terms, float *y, void *stream) {
     int lbo_o = 0, sbo_o = 0;
@@ -831,7 +948,20 @@ extern "C" int64_t piml_pinnsf_packed_tc_floats(const piml_net_desc *desc) {
     TcPlan P;
     TcPackTab T;
     if (tc_build_plan(desc, &P, &T)) return -1;
+    Tc16Plan P16;                                                  // the 16-bit images follow the tf32 images
+    if (tc16_build_plan(desc, P.total, &P16) == 0) return P16.base + 2 * P16.branch_floats;
     return P.total;
+}
+
+static void tc16_sources(const TcPlan &P, const TcPackTab &T, Tc16Src *S) {
+    for (int br = 0; br < 2; ++br) {
+        for (int l = 0; l < P.nl; ++l) {
+            S->src_w[br * P.nl + l] = T.r[br * P.nl + l].src_w;
+            S->src_b[br * P.nl + l] = T.r[br * P.nl + l].src_b;
+        }
+        S->pred_src[br] = T.pred_src[br];
+    }
+    for (int l = 0; l < P.nl; ++l) S->scale[l] = T.r[l].scale;
 }
 
 extern "C" int piml_pinnsf_pack_tc_f32(const piml_net_desc *desc, const float *params_torch, float *packed_tc,
@@ -847,7 +977,15 @@ extern "C" int piml_pinnsf_pack_tc_f32(const piml_net_desc *desc, const float *p
                             static_cast<cudaStream_t>(stream)>>>(T, params_torch, packed_tc, P.nl, P.total / 2,
                                                                  P.b_off[0]);
     count_launch();
-    return check_launch("pinnsf_pack_tc_kernel");
+    rc = check_launch("pinnsf_pack_tc_kernel");
+    if (rc) return rc;
+    Tc16Plan P16;
+    if (tc16_build_plan(desc, P.total, &P16) == 0) {
+        Tc16Src S;
+        tc16_sources(P, T, &S);
+        rc = tc16_pack(P16, S, params_torch, packed_tc, static_cast<cudaStream_t>(stream));
+    }
+    return rc;
 }
 
 extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float *packed_tc, int has_obs, float tau,
@@ -956,11 +1094,39 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     }
     const int64_t tiles = compact ? (rows_ped + 128) / 128 + (has_obs ? (rows_obs + 128) / 128 : 0)
                                   : a.n_ped_tiles + a.n_obs_tiles + (compact2 ? 2 : 0);
+    // 16-bit path (two tiles in flight, resident weights): per-slot-decoder networks; PIML_TC_F16=0 keeps the tf32 kernel
+    Tc16Plan P16;
+    const char *e16 = getenv("PIML_TC_F16");
+    const bool use16 = !(e16 && atoi(e16) == 0) && !compact2 && tc16_build_plan(desc, P.total, &P16) == 0 &&
+                       (!has_obs || tiles >= 2);
+    if (use16) {
+        Tc16Args b;
+        b.params = packed_tc; b.ped = ped; b.obs = obs; b.R = R; b.kp = kp; b.ko = ko;
+        b.ag_ped = a.ag_ped; b.ag_obs = a.ag_obs; b.n_ped_tiles = a.n_ped_tiles; b.n_obs_tiles = a.n_obs_tiles;
+        b.sums = a.sums; b.ped_msgs = a.ped_msgs; b.obs_msgs = a.obs_msgs;
+        b.compact = compact ? 1 : 0; b.has_obs = a.has_obs;
+        b.list_ped = a.list_ped; b.list_obs = a.list_obs; b.counts = a.counts;
+        b.cmsg_ped = a.cmsg_ped; b.cmsg_obs = a.cmsg_obs; b.f0 = a.f0;
+        b.prof = a.prof; b.dbg = a.dbg;
+        rc = tc16_launch(P16, b, tiles, st);
+        if (rc) return rc;
+        if (a.prof) {
+            long long h[16];
+            PIML_CUDA(cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+            PIML_CUDA(cudaStreamSynchronize(st));
+            const long long t = h[15] > 0 ? h[15] : 1;
+            fprintf(stderr, "[tc16 prof, CTA 0, %lld tiles] cycles/tile: mma wait A %lld, wait W %lld, issue %lld | epilogue (slot 0, "
+                    "warp 2): wait D %lld, ld %lld, pass1 %lld, max exchange %lld, pass2 %lld, st+signal %lld\n", t, h[0] / t,
+                    h[1] / t, h[2] / t, h[3] * 2 / t, h[4] * 2 / t, h[5] * 2 / t, h[6] * 2 / t, h[7] * 2 / t, h[8] * 2 / t);
+            a.prof = nullptr;
+        }
+    } else {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     pinnsf_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, a);
     count_launch();
     rc = check_launch("pinnsf_tc_kernel");
     if (rc) return rc;
+    }
     if (a.prof) {
         long long h[16];
         PIML_CUDA(cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -47,6 +47,26 @@ __host__ __device__ __forceinline__ uint32_t idesc_tf32(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with fp16 A / B, fp32 accumulate, M = 128, both operands K-major.
+__host__ __device__ __forceinline__ uint32_t idesc_f16(int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 16 (fp16 operands, two per 32-bit TMEM column / eight per 16-byte
+// shared-memory cell).  Issued by ONE thread.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 8 (tf32).  Issued by ONE thread.
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             bool accumulate) {
@@ -123,6 +143,21 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     const float rest = x - __uint_as_float(hi);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+// x = hi + lo (+ O(2^-22 |x|)) with hi, lo fp16 (round to nearest): the 3xFP16 split.  Two values at a time:
+// returns the packed pairs {hi(x0), hi(x1)} and {lo(x0), lo(x1)} (x0 in the low half = the even K index).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));          // d.hi = cvt(a), d.lo = cvt(b)
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+        : "=f"(h0), "=f"(h1) : "r"(hi));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void split_f16(float x, uint16_t &hi, uint16_t &lo) {
+    uint32_t h, l;
+    split_f16x2(x, 0.f, h, l);
+    hi = static_cast<uint16_t>(h & 0xffffu); lo = static_cast<uint16_t>(l & 0xffffu);
 }
 
 }  // namespace tc
