@@ -196,13 +196,22 @@ __global__ void __launch_bounds__(128, 1) tc16_probe_kernel(const float *__restr
             const uint32_t lbo = N * 16, sbo = 128, kstep = 2 * N * 16;
             const long long t0 = clock64();
             int cnt = 0;
-            for (int rep = 0; rep < -swap; ++rep)
+            // variant (-swap / 1000): 0 one accumulator; 1 alternate D0 / D1 per chain; 2 = 1 + a commit per chain (on a
+            // dummy barrier); 3 alternate D0 / D1 per K step; 4 = 1 with acc = false on each chain's first MMA
+            const int variant = (-swap) / 1000, reps = (-swap) % 1000;
+            __shared__ __align__(8) uint64_t dummy;
+            if (variant == 2) { mbar_init(&dummy, 1); mbar_fence_init(); }
+            for (int rep = 0; rep < reps; ++rep)
                 for (int j = 0; j < K / 16; ++j) {
                     const uint64_t bh = tc::smem_desc(tc::smem_addr(w_hi) + j * kstep, lbo, sbo);
                     const uint64_t bl = tc::smem_desc(tc::smem_addr(w_lo) + j * kstep, lbo, sbo);
-                    if (terms >= 3) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AL + j * 8, bh, idesc, true); ++cnt; }
-                    if (terms >= 2) { tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bl, idesc, true); ++cnt; }
-                    tc::mma_f16_ts(tbase + COL_D, tbase + COL_AH + j * 8, bh, idesc, true); ++cnt;
+                    const int which = variant == 3 ? (j & 1) : ((variant == 1 || variant == 2 || variant == 4) ? (rep & 1) : 0);
+                    const uint32_t d = tbase + COL_D + which * 256, aoff = which * 256;
+                    const bool first = variant == 4 && j == 0;
+                    if (terms >= 3) { tc::mma_f16_ts(d, tbase + aoff + COL_AL + j * 8, bh, idesc, !first); ++cnt; }
+                    if (terms >= 2) { tc::mma_f16_ts(d, tbase + aoff + COL_AH + j * 8, bl, idesc, true); ++cnt; }
+                    tc::mma_f16_ts(d, tbase + aoff + COL_AH + j * 8, bh, idesc, true); ++cnt;
+                    if (variant == 2 && j == K / 16 - 1) tc::commit(&dummy);
                 }
             tc::commit(&bar);
             const long long t1 = clock64();
@@ -404,32 +413,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t pc = 0, aph = 0;                              // aph: phase bit per a_ready barrier
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int li = 0; li < P.nl; ++li) {
-                    const TcLayer &Ly = P.L[li];
-                    const uint32_t dcol = tbase + ((li & 1) ? TC_COL_D1 : TC_COL_D0);
-                    const uint32_t idesc = tc::idesc_tf32(Ly.N);
-                    const uint32_t lbo = Ly.N * 16, sbo = 128, kstep = 2 * lbo;
-                    bool acc = false;
-                    for (int c = 0; c < Ly.nchunks; ++c, ++pc) {
-                        const long long t0 = clock64();
-                        tc_wait(&a_ready[c], (aph >> c) & 1u);     // A columns of this K chunk are in TMEM
-                        aph ^= (1u << c);
-                        const long long t1 = clock64();
-                        const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
-                        tc_wait(&full[s], ph);
-                        tc::fence_after_sync();
-                        const long long t2 = clock64();
-                        if (a.prof && blockIdx.x == 0) { a.prof[1] += t1 - t0; a.prof[2] += t2 - t1; }
-                        const TcChunk &Ch = P.C[Ly.chunk0 + c];
-                        const uint32_t hi_addr = tc::smem_addr(ring + s * TC_STAGE_BYTES);
-                        uint64_t bh = tc::smem_desc(hi_addr, lbo, sbo);
-                        uint64_t bl = tc::smem_desc(hi_addr + Ch.cells * lbo, lbo, sbo);
-                        const uint64_t dstep = kstep >> 4;         // start-address field advances by one K = 8 step
-                        uint32_t ah = tbase + TC_COL_AH + c * 32, al = tbase + TC_COL_AL + c * 32;
-                        const int nks = Ch.cells / 2;
+        // The whole warp runs the loop on warp-uniform values and one elected lane issues (tc::elect_one): with the
+        // issuing code under `if (lane == 0)` ptxas wrapped every MMA in an R2UR waterfall loop (86 instead of 69 cycles
+        // per MMA in round 1's profile).
+        const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+        const uint32_t ring_addr = __shfl_sync(0xffffffffu, tc::smem_addr(ring), 0);
+        const long long nt = __shfl_sync(0xffffffffu, static_cast<long long>(ntiles), 0);
+        uint32_t pc = 0, aph = 0;                                  // aph: phase bit per a_ready barrier
+        for (long long tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+            for (int li = 0; li < P.nl; ++li) {
+                const TcLayer &Ly = P.L[li];
+                const uint32_t dcol = tb + ((li & 1) ? TC_COL_D1 : TC_COL_D0);
+                const uint32_t idesc = tc::idesc_tf32(Ly.N);
+                const uint32_t lbo = Ly.N * 16, sbo = 128, kstep = 2 * lbo;
+                bool acc = false;
+                for (int c = 0; c < Ly.nchunks; ++c, ++pc) {
+                    const long long t0 = clock64();
+                    tc_wait(&a_ready[c], (aph >> c) & 1u);         // A columns of this K chunk are in TMEM
+                    aph ^= (1u << c);
+                    const long long t1 = clock64();
+                    const uint32_t s = pc % TC_STAGES, ph = (pc / TC_STAGES) & 1u;
+                    tc_wait(&full[s], ph);
+                    tc::fence_after_sync();
+                    const long long t2 = clock64();
+                    const TcChunk &Ch = P.C[Ly.chunk0 + c];
+                    const uint32_t hi_addr = ring_addr + s * TC_STAGE_BYTES;
+                    uint64_t bh = tc::smem_desc(hi_addr, lbo, sbo);
+                    uint64_t bl = tc::smem_desc(hi_addr + Ch.cells * lbo, lbo, sbo);
+                    const uint64_t dstep = kstep >> 4;             // start-address field advances by one K = 8 step
+                    uint32_t ah = tb + TC_COL_AH + c * 32, al = tb + TC_COL_AL + c * 32;
+                    const int nks = Ch.cells / 2;
+                    if (tc::elect_one()) {
                         if (a.dbg & 2) {
                             for (int ks = 0; ks < nks; ++ks, bh += dstep, ah += 8) {
                                 tc::mma_tf32_ts(dcol, ah, bh, idesc, acc);
@@ -445,9 +459,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                             }
                         }
                         tc::commit(&empty[s]);                     // ring stage free once these MMAs have read it
-                        if (a.prof && blockIdx.x == 0) a.prof[3] += clock64() - t2;
+                        if (c == Ly.nchunks - 1) tc::commit(&d_ready[li & 1]);   // accumulator of this layer complete
                     }
-                    tc::commit(&d_ready[li & 1]);                  // accumulator of this layer complete
+                    acc = true;
+                    __syncwarp();
+                    if (a.prof && blockIdx.x == 0 && lane == 0) {
+                        a.prof[1] += t1 - t0; a.prof[2] += t2 - t1; a.prof[3] += clock64() - t2;
+                    }
                 }
             }
         }

@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     extern __shared__ __align__(128) unsigned char t16_smem[];
     unsigned char *wimg = t16_smem;                                               // the branch's weight images
     float *biasb = reinterpret_cast<float *>(wimg + P.w_bytes);                   // [bias_floats]
-    float *small = biasb + P.bias_floats;                                         // [2 slots][2 halves][128][2]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(small + 1024);
+    float *small = biasb + P.bias_floats;       // [2 slots][1024]: row maxima [2 parities][2 halves][128] | predictor scratch [512]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(small + 2048);
     uint64_t *w_ready = bars, *a_ready = bars + T16_MAXL, *d_ready = a_ready + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,34 +107,41 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         }
     } else if (warp == 1) {
         // ===== MMA issuer: round robin over the two slots =====
-        if (lane == 0) {
-            int64_t done[2] = {0, 0};                              // tiles finished per slot
-            int layer[2] = {0, 0};
-            uint32_t aph = 0, wseen = 0;
-            const int64_t n_slot[2] = {(my_tiles + 1) / 2, my_tiles / 2};
-            for (;;) {
-                bool any = false;
-                for (int s = 0; s < 2; ++s) {
-                    if (done[s] >= n_slot[s]) continue;
-                    any = true;
-                    const int li = layer[s];
-                    const Tc16Layer &Ly = P.L[li];
-                    const long long p0 = clock64();
-                    t16_wait(&a_ready[s], (aph >> s) & 1u);        // A of (this slot's tile, layer li) is in TMEM
-                    aph ^= (1u << s);
-                    const long long p1 = clock64();
-                    if (!((wseen >> li) & 1u)) { t16_wait(&w_ready[li], 0); wseen |= (1u << li); }
-                    tc::fence_after_sync();
-                    const long long p2 = clock64();
-                    const uint32_t dcol = tbase + s * T16_SLOT_COLS + T16_COL_D;
-                    uint32_t ah = tbase + s * T16_SLOT_COLS + T16_COL_AH, al = tbase + s * T16_SLOT_COLS + T16_COL_AL;
-                    const uint32_t idesc = tc::idesc_f16(Ly.N);
-                    const uint32_t lbo = Ly.N * 16, sbo = 128;
-                    const uint32_t hi_addr = tc::smem_addr(wimg + Ly.w_off);
-                    uint64_t bh = tc::smem_desc(hi_addr, lbo, sbo);
-                    uint64_t bl = tc::smem_desc(hi_addr + Ly.Kp * Ly.N * 2, lbo, sbo);
-                    const uint64_t dstep = (2 * lbo) >> 4;         // start-address field per K = 16 step
-                    const int nks = Ly.Kp / 16;
+        // The WHOLE warp runs this loop on warp-uniform values (broadcast through shfl so that ptxas knows it) and one
+        // elected lane issues: descriptors then live in uniform registers and an MMA costs one instruction, not a
+        // 10-instruction R2UR waterfall (see tc::elect_one).
+        const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+        const int mt = __shfl_sync(0xffffffffu, static_cast<int>(my_tiles), 0);
+        const uint32_t wbase = __shfl_sync(0xffffffffu, tc::smem_addr(wimg), 0);
+        int done[2] = {0, 0};                                      // tiles finished per slot
+        int layer[2] = {0, 0};
+        uint32_t aph = 0, wseen = 0;
+        const int n_slot[2] = {(mt + 1) / 2, mt / 2};
+        for (;;) {
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (done[s] >= n_slot[s]) continue;
+                any = true;
+                const int li = layer[s];
+                const Tc16Layer &Ly = P.L[li];
+                const long long p0 = clock64();
+                t16_wait(&a_ready[s], (aph >> s) & 1u);            // A of (this slot's tile, layer li) is in TMEM
+                aph ^= (1u << s);
+                const long long p1 = clock64();
+                if (!((wseen >> li) & 1u)) { t16_wait(&w_ready[li], 0); wseen |= (1u << li); }
+                tc::fence_after_sync();
+                const long long p2 = clock64();
+                const uint32_t dcol = tb + s * T16_SLOT_COLS + T16_COL_D;
+                uint32_t ah = tb + s * T16_SLOT_COLS + T16_COL_AH, al = tb + s * T16_SLOT_COLS + T16_COL_AL;
+                const uint32_t idesc = tc::idesc_f16(Ly.N);
+                const uint32_t lbo = Ly.N * 16, sbo = 128;
+                const uint32_t hi_addr = wbase + Ly.w_off;
+                uint64_t bh = tc::smem_desc(hi_addr, lbo, sbo);
+                uint64_t bl = tc::smem_desc(hi_addr + Ly.Kp * Ly.N * 2, lbo, sbo);
+                const uint64_t dstep = (2 * lbo) >> 4;             // start-address field per K = 16 step
+                const int nks = Ly.Kp / 16;
+                if (tc::elect_one()) {
                     bool acc = false;
 #pragma unroll 2
                     for (int ks = 0; ks < nks; ++ks, bh += dstep, bl += dstep, ah += 8, al += 8) {
@@ -144,14 +151,15 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                         acc = true;
                     }
                     tc::commit(&d_ready[s]);                       // accumulator of this (slot, layer) complete
-                    if (a.prof && blockIdx.x == 0) {
-                        a.prof[0] += p1 - p0; a.prof[1] += p2 - p1; a.prof[2] += clock64() - p2;
-                        if (li == 0) a.prof[15] += 1;
-                    }
-                    if (++layer[s] == P.nl) { layer[s] = 0; ++done[s]; }
                 }
-                if (!any) break;
+                __syncwarp();
+                if (a.prof && blockIdx.x == 0 && lane == 0) {
+                    a.prof[0] += p1 - p0; a.prof[1] += p2 - p1; a.prof[2] += clock64() - p2;
+                    if (li == 0) a.prof[15] += 1;
+                }
+                if (++layer[s] == P.nl) { layer[s] = 0; ++done[s]; }
             }
+            if (!any) break;
         }
     } else {
         // ===== epilogue warps: 8 per slot; thread = (tile row, column half) =====
@@ -165,7 +173,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
         const int *list = br == 0 ? a.list_ped : a.list_obs;
         const float *feat = br == 0 ? a.ped : a.obs;
-        float *sm2 = small + slot * 512;                           // [2 halves][128][2]: row maxima / predictor partials
+        float *smax = small + slot * 1024;                         // [2 parities][2 halves][128] row maxima
+        float *sm2 = smax + 512;                                   // [2 halves][128][2] predictor partials / slot sums
         uint32_t dph = 0;
         struct RowFeat { int64_t crow; float f[6]; bool live; };
         auto load_row = [&](int64_t j) {                           // j: index into this CTA's tile sequence
@@ -230,11 +239,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 const int hc = Ly.N >> 1;                          // columns of this thread: [half * hc, +hc), 16 at a time
                 const int nchunk = hc >> 4;
                 const long long q0 = clock64();
-                // ONE warp per slot polls the mbarrier, the others sleep in a hardware barrier: 16 warps spinning on
-                // shared-memory try_wait slow the tensor pipe's operand reads down (measured: 93 -> cycles per MMA)
-                if (((warp - 2) & 7) == 0) t16_wait(&d_ready[slot], dph);
+                t16_wait(&d_ready[slot], dph);
                 dph ^= 1u;
-                slot_barrier(slot);
                 tc::fence_after_sync();
                 const long long q1 = clock64();
                 const bool prof = a.prof && blockIdx.x == 0 && tid == 64;
@@ -260,20 +266,22 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 if (prof) a.prof[4] += q2 - q1;
                 float *v = reinterpret_cast<float *>(r);
                 float mx = 0.f;
+                const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (c < nchunk) {
 #pragma unroll
-                        for (int q4b = 0; q4b < 4; ++q4b) {
+                        for (int q4b = 0; q4b < 4; ++q4b) {        // packed FP32 (FFMA2): two columns per instruction
                             const float4 b4 = *reinterpret_cast<const float4 *>(bias + c * 16 + q4b * 4);
-                            float y0 = fmaf(v[c * 16 + q4b * 4 + 0], sc, b4.x);
-                            float y1 = fmaf(v[c * 16 + q4b * 4 + 1], sc, b4.y);
-                            float y2 = fmaf(v[c * 16 + q4b * 4 + 2], sc, b4.z);
-                            float y3 = fmaf(v[c * 16 + q4b * 4 + 3], sc, b4.w);
-                            if (Ly.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
-                            v[c * 16 + q4b * 4 + 0] = y0; v[c * 16 + q4b * 4 + 1] = y1;
-                            v[c * 16 + q4b * 4 + 2] = y2; v[c * 16 + q4b * 4 + 3] = y3;
-                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(y0), fabsf(y1))), fmaxf(fabsf(y2), fabsf(y3)));
+                            const int e = c * 16 + q4b * 4;
+                            float2 y01 = __ffma2_rn(make_float2(v[e], v[e + 1]), sc2, make_float2(b4.x, b4.y));
+                            float2 y23 = __ffma2_rn(make_float2(v[e + 2], v[e + 3]), sc2, make_float2(b4.z, b4.w));
+                            if (Ly.relu) {
+                                y01.x = fmaxf(y01.x, 0.f); y01.y = fmaxf(y01.y, 0.f);
+                                y23.x = fmaxf(y23.x, 0.f); y23.y = fmaxf(y23.y, 0.f);
+                            }
+                            v[e] = y01.x; v[e + 1] = y01.y; v[e + 2] = y23.x; v[e + 3] = y23.y;
+                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(y01.x), fabsf(y01.y))), fmaxf(fabsf(y23.x), fabsf(y23.y)));
                         }
                     }
                 }
@@ -292,20 +300,30 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 }
                 const long long q3 = clock64();
                 if (prof) a.prof[5] += q3 - q2;
-                sm2[(half * 128 + m) * 2] = mx;                    // row maximum over both column halves
+                float *mxb = smax + (li & 1) * 256;                // double buffered: one barrier per layer is enough
+                mxb[half * 128 + m] = mx;                          // row maximum over both column halves
                 slot_barrier(slot);
-                mx = fmaxf(mx, sm2[((half ^ 1) * 128 + m) * 2]);
+                mx = fmaxf(mx, mxb[(half ^ 1) * 128 + m]);
                 const long long q4c = clock64();
                 if (prof) a.prof[6] += q4c - q3;
                 float s;
                 row_scale(mx, s, inv_s);
+                // Split relative to the ROW: after scaling, |x| < 2^15; hi = x rounded to a multiple of 16 (the fp16
+                // spacing of [2^14, 2^15): exact in fp16, obtained with the add-magic-subtract trick on the packed FP32
+                // pipe), lo = x - hi in [-8, 8] rounded to fp16: |x - hi - lo| <= 2^-9 = 2^-23 of the row maximum.
+                const float2 s2 = make_float2(s, s), M2 = make_float2(201326592.f, 201326592.f), nM2 = make_float2(-201326592.f, -201326592.f);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (c < nchunk) {                              // scale, split, store as the next layer's A operand
                         uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            tc::split_f16x2(v[c * 16 + 2 * q] * s, v[c * 16 + 2 * q + 1] * s, hi[q], lo[q]);
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 x = __fmul2_rn(make_float2(v[c * 16 + 2 * q], v[c * 16 + 2 * q + 1]), s2);
+                            const float2 h = __fadd2_rn(__fadd2_rn(x, M2), nM2);
+                            const float2 l = __fadd2_rn(x, make_float2(-h.x, -h.y));
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi[q]) : "f"(h.y), "f"(h.x));
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[q]) : "f"(l.y), "f"(l.x));
+                        }
                         tc::st8(tl + T16_COL_AH + ((half * hc + c * 16) >> 1), hi);
                         tc::st8(tl + T16_COL_AL + ((half * hc + c * 16) >> 1), lo);
                     }
@@ -315,7 +333,6 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 tc::fence_before_sync();
                 tc::mbar_arrive(&a_ready[slot]);                   // the next layer of this slot may start
                 if (prof) { a.prof[7] += q5 - q4c; a.prof[8] += clock64() - q5; }
-                slot_barrier(slot);                                // sm2 maxima read before the next layer overwrites them
             }
             // combine the two column halves of the predictor
             sm2[(half * 128 + m) * 2] = m0;
@@ -380,13 +397,13 @@ int tc16_build_plan(const piml_net_desc *d, int64_t base_floats, Tc16Plan *P) {
     P->bias_floats = (boff + 3) & ~3;
     P->branch_floats = P->w_bytes / 4 + P->bias_floats;
     P->base = (base_floats + 31) & ~static_cast<int64_t>(31);      // 128-byte aligned behind the tf32 image
-    const size_t smem = static_cast<size_t>(P->w_bytes) + sizeof(float) * (P->bias_floats + 1024) + 8 * (T16_MAXL + 4) + 16;
+    const size_t smem = static_cast<size_t>(P->w_bytes) + sizeof(float) * (P->bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16;
     if (smem > 220 * 1024) return 1;                               // the branch must stay resident in shared memory
     return 0;
 }
 
 size_t tc16_smem_bytes(const Tc16Plan &P) {
-    return static_cast<size_t>(P.w_bytes) + sizeof(float) * (P.bias_floats + 1024) + 8 * (T16_MAXL + 4) + 16;
+    return static_cast<size_t>(P.w_bytes) + sizeof(float) * (P.bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16;
 }
 
 // ---- packing -----------------------------------------------------------------------------------------------------------

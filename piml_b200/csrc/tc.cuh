@@ -81,6 +81,22 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         : "memory");
 }
 
+// One lane of a converged warp (PTX elect.sync): a warp-UNIFORM predicate, so that code under it keeps its operands in
+// uniform registers.  tcgen05.mma takes its descriptors from uniform registers: when the issuing code is divergent
+// (`if (lane == 0)`) ptxas wraps EVERY MMA in an ELECT / 5 x R2UR.BROADCAST / branch "waterfall" loop, which costs
+// ~100 cycles per MMA in the issuing thread -- more than the MMA itself (65 cycles for M = 128, K = 16 fp16).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // All previously issued tcgen05.mma of this thread arrive (once) on `bar` when they complete.
 __device__ __forceinline__ void commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
