@@ -636,6 +636,140 @@ def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def crowd_1m_block(torch, dist, dev, world, rank, steps=3):
+    """BASELINE configs[4] (a): one MLAPM crowd of 1 000 000 agents, agent-sharded over the ranks (ShardedCrowd: block
+    ownership, shares and new state pushed over NVLink peer memory); one GPU: the unsharded symmetric kernel."""
+    import piml_b200 as P
+    N = 1000000
+    try:
+        p, v, ds, dest, _ = [x.to(dev) for x in synthetic_crowd(N)]
+        model = P.MLAPM(**MLAPM_KW)
+        crowd = None
+        if world > 1:
+            from piml_b200.sharded import ShardedCrowd
+            crowd = ShardedCrowd(N, device=dev)
+            crowd.load(p, v)
+        state = [p, v]
+
+        def one():
+            if crowd is not None:
+                crowd.step(model, ds, dest, DT, RADIUS)
+            else:
+                act, pn, _ = model.advance(state[0], state[1], ds, dest, DT, RADIUS)
+                state[0], state[1] = pn, act
+        one()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms)
+        fin = crowd.position if crowd is not None else state[0]
+        ok = bool(torch.isfinite(fin).all())
+        ws = (crowd._sym_ws.numel() if crowd is not None else model._ws.numel())
+        del crowd, model
+        torch.cuda.empty_cache()
+        return {"workload": f"mlapm_gc_rollout_N{N}, agent-sharded x{world}", "agents": N, "steps": steps,
+                "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3, "scaling": "strong",
+                "tflops_algorithmic": FLOP_PER_PAIR * N * N / (ms * 1e-3) / 1e12, "workspace_bytes_per_rank": int(ws),
+                "finite": ok}
+    except Exception as e:                                   # secondary block: never take the headline down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def scenes_block(torch, dist, dev, world, rank, S_total=4096, steps=100):
+    """BASELINE configs[4] (b): 4096 independent GC-shaped scenes (the GC clip's own state at t = 25, jittered per scene
+    by seeded N(0, 0.05 m)) rolled `steps` frames with pinnsf_bm; scene s runs on rank s mod G, no communication."""
+    import argparse as ap
+    import numpy as np
+    from piml_b200 import models as M
+    from piml_b200.rollout import rollout_scenes, state_features
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "rollout_gc_bm.npz"))
+        t0 = int(z["in/t_start"])
+        T = t0 + steps + 1
+        mine = list(range(rank, S_total, world))
+        S = len(mine)
+        g = torch.Generator().manual_seed(1234)
+        jitter = (0.05 * torch.randn(S_total, int(z["in/position"].shape[1]), 2, generator=g))[mine].to(dev)
+        cu = lambda k, dt=torch.float32: torch.as_tensor(z["in/" + k][:T] if z["in/" + k].ndim and z["in/" + k].shape[0] >= T
+                                                          and k not in ("waypoints", "obstacles", "dest_num", "desired_speed")
+                                                          else z["in/" + k]).to(dev, dt)
+        scene = {k: cu(k)[None].expand(S, *cu(k).shape).contiguous() for k in ("position", "velocity", "acceleration",
+                                                                              "destination", "mask_p", "mask_p_pred")}
+        scene["position"][:, t0] += jitter
+        scene["dest_idx"] = cu("dest_idx", torch.int64)[None].expand(S, -1, -1).contiguous()
+        scene["waypoints"] = cu("waypoints")[None].expand(S, -1, -1, -1).contiguous()
+        scene["dest_num"] = cu("dest_num", torch.int64)[None].expand(S, -1).contiguous()
+        scene["obstacles"] = cu("obstacles")
+        scene["desired_speed"] = cu("desired_speed")[None].expand(S, -1).contiguous()
+        args = ap.Namespace(**dict(NN_ARGS, time_unit=float(z["in/time_unit"])))
+        torch.manual_seed(666)
+        net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
+        net.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")})
+        packed = M.pack_device(net.state_dict(), net.spec, dev)
+        packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)
+        hist0 = cu("self_features0")[None, :, 2:4].expand(S, -1, -1).contiguous()
+        f0 = state_features(scene["position"][:, t0].contiguous(), scene["velocity"][:, t0].contiguous(),
+                            scene["acceleration"][:, t0].contiguous(), scene["destination"][:, t0].contiguous(),
+                            scene["obstacles"], hist0, scene["desired_speed"], *NN_FEATURE_ARGS)
+        scene["ped_features0"], scene["obs_features0"], scene["self_features0"] = f0
+        Ns = scene["position"].shape[2]
+        run = lambda: rollout_scenes(net.spec, packed, args, scene, t0, T, packed_tc=packed_tc)
+        run()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = run()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms)
+        nsteps = T - t0
+        active = float(res[3][:, t0:T].sum()) / max(S * nsteps, 1)
+        del scene, res
+        torch.cuda.empty_cache()
+        return {"workload": f"{S_total} GC-shaped scenes x {Ns} slots, pinnsf_bm rollout of {nsteps} frames from t = {t0}, "
+                            f"scene-parallel x{world} (no communication)", "scenes": S_total, "slots": int(Ns),
+                "frames": nsteps, "ms_total": ms, "ms_per_step": ms / nsteps, "scaling": "strong",
+                "agent_steps_per_sec": S_total * Ns * nsteps / ms * 1e3, "mean_active_agents_per_scene": active}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def sharded_timeline(torch, dist, dev, crowd, model, ds, dest, world, steps=5):
+    """Per-rank stage times of the agent-sharded MLAPM step (CUDA events at the stage boundaries inside
+    ShardedCrowd.step): pairs + share push | barrier 1 | finalize + state push | barrier 2, averaged over `steps`."""
+    names = ["pairs_and_share_push", "barrier_1", "finalize_and_state_push", "barrier_2"] if crowd.symmetric else \
+        ["rows_and_state_push", "barrier"]
+    acc = [0.0] * len(names)
+    for _ in range(steps):
+        tr = []
+        crowd.step(model, ds, dest, DT, RADIUS, trace=tr)
+        torch.cuda.synchronize()
+        for i in range(len(names)):
+            acc[i] += tr[i].elapsed_time(tr[i + 1]) / steps
+    mine = torch.tensor(acc, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    return {"stages": names, "ms_per_rank": [[round(float(x), 4) for x in r] for r in allr]}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -750,11 +884,24 @@ def run_ours(a):
         pnew_h = torch.empty(cr1 - cr0, 2).pin_memory()
         arr_h = torch.empty(cr1 - cr0, dtype=torch.bool).pin_memory()
 
+    e2e_scatter = crowd is not None
+    if crowd is not None:          # this rank's rows only: pinned host slices
+        own_h = [x[cr0:cr1].clone().pin_memory() for x in (p_h, v_h, ds_h, dest_h)]
+
     def e2e_step():
+        nonlocal e2e_scatter
         if crowd is not None:
-            crowd.position.copy_(p_h, non_blocking=True); crowd.velocity.copy_(v_h, non_blocking=True)
-            ds.copy_(ds_h, non_blocking=True); dest.copy_(dest_h, non_blocking=True)
-            arrived = crowd.step(model, ds, dest, DT, RADIUS)
+            if e2e_scatter:
+                try:               # 1/G of the state over PCIe, the rest over NVLink peer stores
+                    crowd.scatter_rows(own_h[0], own_h[1], own_h[3])
+                    ds[cr0:cr1].copy_(own_h[2], non_blocking=True)
+                    arrived = crowd.step(model, ds, crowd.dest_buf, DT, RADIUS)
+                except Exception:  # no get_buffer on this torch: whole state from the host
+                    e2e_scatter = False
+            if not e2e_scatter:
+                crowd.position.copy_(p_h, non_blocking=True); crowd.velocity.copy_(v_h, non_blocking=True)
+                ds.copy_(ds_h, non_blocking=True); dest.copy_(dest_h, non_blocking=True)
+                arrived = crowd.step(model, ds, dest, DT, RADIUS)
             act_h.copy_(crowd.velocity[cr0:cr1]); pnew_h.copy_(crowd.position[cr0:cr1]); arr_h.copy_(arrived)
             return
         act, pnew, arrived = model.advance(p_h, v_h, ds_h, dest_h, DT, RADIUS, rows=(r0, r1))   # host in, host out
@@ -777,10 +924,17 @@ def run_ours(a):
     if sampler:
         sampler.stop()
     h2d = (p_h.numel() + v_h.numel() + ds_h.numel() + dest_h.numel()) * 4
+    if crowd is not None and e2e_scatter:
+        h2d = sum(x.numel() for x in own_h) * 4 * world          # every rank uploads its own rows only
     d2h = (act_h.numel() + pnew_h.numel()) * 4 + arr_h.numel()
 
     sym_used = (world == 1 and N >= 16384) or (crowd is not None and crowd.symmetric)
     nn_sharded = nn_path_sharded(torch, dist, dev, N, obs_h, world) if world > 1 else None   # collective: all ranks
+    timeline = sharded_timeline(torch, dist, dev, crowd, model, ds, dest, world) if crowd is not None else None
+    extra = {}
+    if not a.no_config5:
+        extra["crowd_1m"] = crowd_1m_block(torch, dist, dev, world, rank)
+        extra["scenes_4096"] = scenes_block(torch, dist, dev, world, rank)
     if rank == 0:
         pairs = float(shard) * N                       # ordered pairs one launch of the pairs kernel evaluates
         achieved = FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12
@@ -829,7 +983,8 @@ def run_ours(a):
             "e2e": {"value": N * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
                     "api": ("piml_b200.MLAPM.advance(pinned host tensors) -> host tensors" if crowd is None else
-                            "piml_b200.sharded.ShardedCrowd: pinned host state in, step, this rank's rows out")},
+                            "piml_b200.sharded.ShardedCrowd: each rank uploads ITS rows (pinned host), scatter_rows over "
+                            "NVLink, step, this rank's rows out")},
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
         }
@@ -837,6 +992,8 @@ def run_ours(a):
             line["nn_path"] = nn_workload(torch, dev, N, obs_h, 10, 3, with_cpu=not a.no_cpu)
         else:
             line["nn_path"] = nn_sharded
+            line["timeline"] = timeline
+        line.update(extra)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"], rows = cpu_baseline(N)
             line["parity"] = parity_block(torch, dev, N, model, rows)
@@ -856,6 +1013,7 @@ def main():
     ap.add_argument("--workload", default="mlapm", choices=["mlapm", "nn"],
                     help="mlapm: BASELINE configs[3] headline (MLAPM rollout); nn: the NN-augmented rollout step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config5", action="store_true", help="skip the crowd_1m / scenes_4096 blocks")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="multi-GPU exchange: fused peer-memory push (default) or NCCL all-gather")
     a = ap.parse_args()

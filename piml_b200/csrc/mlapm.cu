@@ -448,9 +448,12 @@ struct MsSmem {
 // rec[j] = {px,py,vx,vy},{ex,ey,0,0}, e = F.normalize(destination - position) (mlapm.py:21); j >= N: padding agents
 // far away (their weight underflows to exactly 0 in both directions), so block tails need no masks.
 __global__ void mlapm_prep_sym_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
-                                      const float2 *__restrict__ dest, int N, int Npad, float4 *__restrict__ rec) {
+                                      const float2 *__restrict__ dest, int N, int Npad, float4 *__restrict__ rec,
+                                      ulonglong2 *__restrict__ colsum) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Npad) return;
+    colsum[2 * j] = make_ulonglong2(0ull, 0ull);                   // this step's column-direction accumulators
+    colsum[2 * j + 1] = make_ulonglong2(0ull, 0ull);
     if (j >= N) {
         rec[2 * j] = make_float4(MS_FAR, MS_FAR, 0.f, 0.f);
         rec[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -527,7 +530,8 @@ template <int VERSION, int CT, int BATCH, int RPS = 2>
 __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const float4 *__restrict__ rec, int T, int D,
                                                                          int I0, int per, int sub, M2Const k,
                                                                          float4 *__restrict__ partialR, int nrows_pad,
-                                                                         float4 *__restrict__ partialC) {
+                                                                         unsigned long long *__restrict__ colsum,
+                                                                         float colscale) {
     constexpr int THREADS = MS_BLOCK / (2 * RPS);
     static_assert(MS_BLOCK % CT == 0 && CT % BATCH == 0 && (BATCH == 8 || BATCH == 4), "bad stage shape");
     constexpr int SPB = MS_BLOCK / CT;                      // stages per block pair
@@ -636,7 +640,14 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
                 __syncwarp();
             }
             __syncthreads();
-            float4 *dst = partialC + (static_cast<int64_t>(blockIdx.x) * D + (d - 1)) * MS_BLOCK + (su * spc + s % spc) * CT;
+            // Column-direction sums of this stage's columns (block J), over the CTA's 512 rows: added into the crowd-wide
+            // FIXED-POINT accumulators colsum[agent][4] (int64, 2^-s resolution) with fire-and-forget 64-bit atomics.
+            // Integer addition is associative, so the total does not depend on the order in which the T/2 block pairs
+            // that share a column arrive: deterministic like the per-pair partial arrays this replaces, with O(N)
+            // instead of O(N^2 / 64) workspace and DRAM traffic.
+            int J = I + d;
+            J = J >= T ? J - T : J;
+            unsigned long long *dst = colsum + (static_cast<int64_t>(J) * MS_BLOCK + (su * spc + s % spc) * CT) * 4;
             for (int c = tid; c < CT; c += THREADS) {
                 float4 a = sm.colacc[0][c];
 #pragma unroll
@@ -644,7 +655,10 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
                     const float4 t = sm.colacc[wv][c];
                     a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                 }
-                dst[c] = a;
+                atomicAdd(dst + c * 4 + 0, static_cast<unsigned long long>(__float2ll_rn(a.x * colscale)));
+                atomicAdd(dst + c * 4 + 1, static_cast<unsigned long long>(__float2ll_rn(a.y * colscale)));
+                atomicAdd(dst + c * 4 + 2, static_cast<unsigned long long>(__float2ll_rn(a.z * colscale)));
+                atomicAdd(dst + c * 4 + 3, static_cast<unsigned long long>(__float2ll_rn(a.w * colscale)));
             }
         }
         __syncthreads();
@@ -661,31 +675,31 @@ __global__ void __launch_bounds__(MS_BLOCK / (2 * RPS)) mlapm_sym_kernel(const f
 // process over NVLink peer memory.  world == 0: no exchange.
 constexpr int ML_MAX_PEERS = 16;
 struct PeerPush { int world; float2 *pos[ML_MAX_PEERS]; float2 *vel[ML_MAX_PEERS]; };
-// Column-direction sums of the symmetric kernel (partialC == nullptr: ordered-pair kernel, row sums only).
+// Column-direction sums of the symmetric kernel (colsum == nullptr: ordered-pair kernel, row sums only): fixed-point
+// int64 accumulators per agent, value = colsum * inv_colscale.
 // inbox != nullptr (agent-sharded crowd): the column-direction sums were reduced per rank and delivered to the owner
 // of the rows (mlapm_sym_colpush_kernel); inbox[g * inbox_stride + local row] is rank g's share.
-struct SymPartials { const float4 *partialC; int T, D, I0, nrows_pad; const float4 *inbox; int world;
+struct SymPartials { const long long *colsum; float inv_colscale; int nrows_pad; const float4 *inbox; int world;
                      int64_t inbox_stride; };
 // Owners of the 512-agent blocks (rank g owns blocks [Ib[g], Ib[g+1])) and every rank's inbox as mapped here.
 struct PeerInbox { int world, rank; int Ib[ML_MAX_PEERS + 1]; float4 *inbox[ML_MAX_PEERS]; int64_t stride; };
 
 // Agent-sharded symmetric evaluation, first half of the exchange: this rank evaluated the block pairs (I, I + d) of
-// ITS row blocks I in [I0, I1); the column-direction sums of every agent m (its own or another rank's) are added over
-// those block pairs in a fixed order and stored into the inbox of the rank that owns m, over NVLink peer memory.
-__global__ void mlapm_sym_colpush_kernel(const float4 *__restrict__ partialC, int N, int T, int D, int I0, int I1,
+// ITS row blocks I in [I0, I1); the column-direction sum of every agent m (its own or another rank's) over those block
+// pairs sits in this rank's fixed-point accumulators and is stored, as fp32, into the inbox of the rank that owns m,
+// over NVLink peer memory.
+__global__ void mlapm_sym_colpush_kernel(const long long *__restrict__ colsum, float inv_colscale, int N,
                                          const __grid_constant__ PeerInbox peers) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= N) return;
-    const int J = m / MS_BLOCK, c = m % MS_BLOCK;
-    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int d = 1; d <= D; ++d) {
-        int I = J - d;
-        I = I < 0 ? I + T : I;
-        if (I < I0 || I >= I1) continue;
-        if (d == D && !(T & 1) && 2 * I >= T) continue;                  // even T: d = T/2 only for I < T/2
-        const float4 t = partialC[(static_cast<int64_t>(I - I0) * D + (d - 1)) * MS_BLOCK + c];
-        u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
-    }
+    const int J = m / MS_BLOCK;
+    const longlong2 c0 = reinterpret_cast<const longlong2 *>(colsum)[2 * m];
+    const longlong2 c1 = reinterpret_cast<const longlong2 *>(colsum)[2 * m + 1];
+    const double is = static_cast<double>(inv_colscale);
+    const float4 u = make_float4(static_cast<float>(static_cast<double>(c0.x) * is),
+                                 static_cast<float>(static_cast<double>(c0.y) * is),
+                                 static_cast<float>(static_cast<double>(c1.x) * is),
+                                 static_cast<float>(static_cast<double>(c1.y) * is));
     int h = 0;
     while (h + 1 < peers.world && J >= peers.Ib[h + 1]) ++h;
     peers.inbox[h][peers.rank * peers.stride + (m - peers.Ib[h] * MS_BLOCK)] = u;
@@ -714,7 +728,7 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
     float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t pstride = (sym.partialC || sym.inbox) ? sym.nrows_pad : nrows;
+    const int64_t pstride = (sym.colsum || sym.inbox) ? sym.nrows_pad : nrows;
     for (int q = 0; q < nsplit; ++q) {                            // fixed order: deterministic
         const float4 t = partial[static_cast<int64_t>(q) * pstride + rl];
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
@@ -727,19 +741,16 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
             u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
         }
         s.x -= u.x; s.y -= u.y; s.z -= u.z; s.w -= u.w;
-    } else if (sym.partialC) {
-        // symmetric evaluation: this agent was a COLUMN of the block pairs (I = J - d mod T, J), d = 1..D; their
-        // column-direction sums enter with the opposite sign (vr[m,n] = -vr[n,m]).  Fixed order again.
-        const int J = n / MS_BLOCK, c = n % MS_BLOCK;
-        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int d = 1; d <= sym.D; ++d) {
-            int I = J - d;
-            I = I < 0 ? I + sym.T : I;
-            if (d == sym.D && !(sym.T & 1) && 2 * I >= sym.T) continue;      // even T: d = T/2 only for I < T/2
-            const float4 t = sym.partialC[(static_cast<int64_t>(I - sym.I0) * sym.D + (d - 1)) * MS_BLOCK + c];
-            u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
-        }
-        s.x -= u.x; s.y -= u.y; s.z -= u.z; s.w -= u.w;
+    } else if (sym.colsum) {
+        // symmetric evaluation: this agent was a COLUMN of T/2 block pairs; their column-direction sums (exact integer
+        // total of the per-pair fp32 block sums) enter with the opposite sign (vr[m,n] = -vr[n,m]).
+        const longlong2 c0 = reinterpret_cast<const longlong2 *>(sym.colsum)[2 * n];
+        const longlong2 c1 = reinterpret_cast<const longlong2 *>(sym.colsum)[2 * n + 1];
+        const double is = static_cast<double>(sym.inv_colscale);
+        s.x -= static_cast<float>(static_cast<double>(c0.x) * is);
+        s.y -= static_cast<float>(static_cast<double>(c0.y) * is);
+        s.z -= static_cast<float>(static_cast<double>(c1.x) * is);
+        s.w -= static_cast<float>(static_cast<double>(c1.y) * is);
     }
     float sx, sy;
     if (version == 0) { sx = s.x; sy = s.y; }
@@ -879,11 +890,21 @@ static int sym_splits(int64_t nI, int64_t T, int *per, int *sub) {
     return static_cast<int>((T / 2 + 1 + *per - 1) / *per) * *sub;
 }
 
+// records (32 B per agent) + row-direction partials (16 B per agent and split) + column-direction fixed-point
+// accumulators (4 x int64 per agent): O(N) -- 0.15 GB at N = 10^6 (the per-pair column partials this replaces: 15.6 GB)
 static int64_t sym_workspace_bytes(int64_t N) {
-    const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
+    const int64_t T = sym_blocks(N), npad = T * MS_BLOCK;
     int per_, sub_;
     const int64_t S = sym_splits(T, T, &per_, &sub_);
-    return npad * MS_RECF * sizeof(float) + (S + D) * npad * 4 * sizeof(float) + 256;
+    return npad * MS_RECF * sizeof(float) + S * npad * 4 * sizeof(float) + npad * 4 * sizeof(long long) + 256;
+}
+
+// Fixed-point scale 2^s of the column accumulators: one pair contributes |w r| = exp(arg) <= exp(|C|) (B r + D r cos <= 0
+// is required by sym_params_ok), a column at most N of them; keep two bits of headroom below 2^63.
+static int sym_colscale_log2(int64_t N, const piml_mlapm_params *prm) {
+    const double c = prm->version == 0 ? 0.0 : fabs(static_cast<double>(prm->C));
+    const double bound = static_cast<double>(N) * exp(c);
+    return 61 - static_cast<int>(ceil(log2(bound > 1.0 ? bound : 1.0)));
 }
 
 extern "C" int piml_set_mlapm_algorithm(int algo) {
@@ -922,18 +943,19 @@ static MlConst mlapm_consts(const piml_mlapm_params *prm) {
 }
 
 // The padding agents of the symmetric kernel need a weight that underflows to 0 at large r.
-static bool sym_params_ok(const piml_mlapm_params *prm, const MlConst &k) {
-    return !prm->exact_math && (prm->version == 0 ? k.Bl < 0.f : k.Bl + fabsf(k.Dl) < 0.f);
+static bool sym_params_ok(const piml_mlapm_params *prm, const MlConst &k, int64_t N) {
+    return !prm->exact_math && (prm->version == 0 ? k.Bl < 0.f : k.Bl + fabsf(k.Dl) < 0.f) &&
+           sym_colscale_log2(N, prm) >= 30;                        // 2^-30 resolution at the very least (|C| < ~15)
 }
 
 // prep + symmetric pair kernel for the row blocks [I0, I0 + nI) of a crowd of T blocks.
 static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, const float2 *d2, int N, int64_t T,
                             int64_t I0, int64_t nI, int per, int sub, int S, const MlConst &k, float4 *rec, float4 *partialR,
-                            float4 *partialC, cudaStream_t st) {
+                            long long *colsum, float colscale, cudaStream_t st) {
     const int64_t D = T / 2, npad = T * MS_BLOCK;
     const int threads = 256;
     mlapm_prep_sym_kernel<<<static_cast<unsigned>((npad + threads - 1) / threads), threads, 0, st>>>(
-        p2, v2, d2, N, static_cast<int>(npad), rec);
+        p2, v2, d2, N, static_cast<int>(npad), rec, reinterpret_cast<ulonglong2 *>(colsum));
     count_launch();
     int rc = check_launch("mlapm_prep_sym_kernel");
     if (rc) return rc;
@@ -950,7 +972,7 @@ static int launch_sym_pairs(int version, const float2 *p2, const float2 *v2, con
                                            static_cast<int>(sizeof(Smem))));                                       \
         mlapm_sym_kernel<V, CT, BATCH, RPS><<<grid, MS_BLOCK / (2 * RPS), sizeof(Smem), st>>>(                     \
             rec, static_cast<int>(T), static_cast<int>(D), static_cast<int>(I0), per, sub, k2, partialR,           \
-            static_cast<int>(nI * MS_BLOCK), partialC);                                                            \
+            static_cast<int>(nI * MS_BLOCK), reinterpret_cast<unsigned long long *>(colsum), colscale);            \
     } while (0)
     // measured at N = 100k (ms per step): 8 rows per thread (64 threads) 6.81, 4 rows (128 threads) 6.99, 2 rows 7.16
     if (version == 0) PIML_LAUNCH_SYM(0, MS_CT, MS_BATCH, 2);
@@ -1012,19 +1034,22 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     }
     // production, whole crowd: symmetric evaluation (every unordered pair once) when the caller's workspace holds
     // the column-direction sums; row ranges (agent-sharded ranks) and small crowds use the ordered-pair kernel.
-    SymPartials symp{nullptr, 0, 0, 0, 0, nullptr, 0, 0};
-    const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) && sym_params_ok(prm, k);
+    SymPartials symp{nullptr, 0.f, 0, nullptr, 0, 0};
+    const bool sym_ok = row0 == 0 && row1 == N && workspace_bytes >= sym_workspace_bytes(N) && sym_params_ok(prm, k, N);
     if (sym_ok && (g_mlapm_algorithm == 2 || (g_mlapm_algorithm == 0 && N >= MS_AUTO_MIN_AGENTS))) {
         const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
         int per, sub;
         const int S = sym_splits(T, T, &per, &sub);
         float4 *rec = reinterpret_cast<float4 *>(workspace);
         float4 *partialR = rec + npad * 2;
-        float4 *partialC = partialR + static_cast<int64_t>(S) * npad;
-        rc = launch_sym_pairs(prm->version, p2, v2, d2, iN, T, 0, T, per, sub, S, k, rec, partialR, partialC, st);
+        long long *colsum = reinterpret_cast<long long *>(partialR + static_cast<int64_t>(S) * npad);
+        const int sl = sym_colscale_log2(N, prm);
+        rc = launch_sym_pairs(prm->version, p2, v2, d2, iN, T, 0, T, per, sub, S, k, rec, partialR, colsum,
+                              ldexpf(1.0f, sl), st);
         if (rc) return rc;
         const int threads = 256;
-        symp = SymPartials{partialC, static_cast<int>(T), static_cast<int>(D), 0, static_cast<int>(npad), nullptr, 0, 0};
+        (void)D;
+        symp = SymPartials{colsum, ldexpf(1.0f, -sl), static_cast<int>(npad), nullptr, 0, 0};
         mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
             p2, v2, desired_speed, ds_dim, d2, r0, r1, S, partialR, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
             dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
@@ -1173,14 +1198,14 @@ extern "C" int64_t piml_mlapm_sym_inbox_bytes(int64_t N, int world) {
 
 extern "C" int64_t piml_mlapm_sym_shard_workspace_bytes(int64_t N, int world) {
     if (N <= 0 || world < 1 || world > ML_MAX_PEERS) return 0;
-    const int64_t T = sym_blocks(N), D = T / 2, npad = T * MS_BLOCK;
+    const int64_t T = sym_blocks(N), npad = T * MS_BLOCK;
     const int64_t nI = (T + world - 1) / world;
     int per_, sub_;
     const int64_t S = sym_splits(nI, T, &per_, &sub_);
-    return npad * MS_RECF * sizeof(float) + (S + D) * nI * MS_BLOCK * 4 * sizeof(float) + 256;
+    return npad * MS_RECF * sizeof(float) + S * nI * MS_BLOCK * 4 * sizeof(float) + npad * 4 * sizeof(long long) + 256;
 }
 
-struct SymShardPlan { int64_t T, D, npad, I0, nI; int per, sub, S; float4 *rec, *partialR, *partialC; };
+struct SymShardPlan { int64_t T, D, npad, I0, nI; int per, sub, S; float4 *rec, *partialR; long long *colsum; };
 
 static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64_t workspace_bytes, SymShardPlan *pl) {
     PIML_REQUIRE(N > 0 && N < (1LL << 31) && world >= 1 && world <= ML_MAX_PEERS && rank >= 0 && rank < world,
@@ -1199,7 +1224,8 @@ static int sym_shard_plan(int64_t N, int world, int rank, void *workspace, int64
     pl->S = sym_splits((pl->T + world - 1) / world, pl->T, &pl->per, &pl->sub);
     pl->rec = reinterpret_cast<float4 *>(workspace);
     pl->partialR = pl->rec + pl->npad * 2;
-    pl->partialC = pl->partialR + static_cast<int64_t>(pl->S) * pl->nI * MS_BLOCK;
+    // the largest shard's row partials, so that every rank's layout is the same
+    pl->colsum = reinterpret_cast<long long *>(pl->partialR + static_cast<int64_t>(pl->S) * ((pl->T + world - 1) / world) * MS_BLOCK);
     return PIML_OK;
 }
 
@@ -1211,15 +1237,15 @@ extern "C" int piml_mlapm_sym_pairs_push_f32(const float *pos, const float *vel,
     PIML_REQUIRE(prm->version == 0 || prm->version == 1, "piml_mlapm_sym_pairs_push_f32: version %d unsupported",
                  prm->version);
     const MlConst k = mlapm_consts(prm);
-    PIML_REQUIRE(sym_params_ok(prm, k), "piml_mlapm_sym_pairs_push_f32: parameters outside the symmetric kernel's "
-                                         "domain (exact_math, or a weight that does not decay with distance)");
+    PIML_REQUIRE(sym_params_ok(prm, k, N), "piml_mlapm_sym_pairs_push_f32: parameters outside the symmetric kernel's "
+                                            "domain (exact_math, or a weight that does not decay with distance)");
     SymShardPlan pl;
     int rc = sym_shard_plan(N, world, rank, workspace, workspace_bytes, &pl);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     rc = launch_sym_pairs(prm->version, reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel),
                           reinterpret_cast<const float2 *>(dest), static_cast<int>(N), pl.T, pl.I0, pl.nI, pl.per, pl.sub, pl.S,
-                          k, pl.rec, pl.partialR, pl.partialC, st);
+                          k, pl.rec, pl.partialR, pl.colsum, ldexpf(1.0f, sym_colscale_log2(N, prm)), st);
     if (rc) return rc;
     PeerInbox peers;
     peers.world = world;
@@ -1234,8 +1260,7 @@ extern "C" int piml_mlapm_sym_pairs_push_f32(const float *pos, const float *vel,
     }
     const int threads = 256;
     mlapm_sym_colpush_kernel<<<static_cast<unsigned>((N + threads - 1) / threads), threads, 0, st>>>(
-        pl.partialC, static_cast<int>(N), static_cast<int>(pl.T), static_cast<int>(pl.D), static_cast<int>(pl.I0),
-        static_cast<int>(pl.I0 + pl.nI), peers);
+        pl.colsum, ldexpf(1.0f, -sym_colscale_log2(N, prm)), static_cast<int>(N), peers);
     count_launch();
     return check_launch("mlapm_sym_colpush_kernel");
 }
@@ -1265,9 +1290,8 @@ extern "C" int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *v
     row1 = row1 > N ? N : row1;
     const int64_t nrows = row1 - row0;
     if (nrows <= 0) return PIML_OK;
-    SymPartials symp{nullptr, static_cast<int>(pl.T), static_cast<int>(pl.D), static_cast<int>(pl.I0),
-                     static_cast<int>(pl.nI * MS_BLOCK), reinterpret_cast<const float4 *>(inbox_local), world,
-                     sym_inbox_stride(N, world)};
+    SymPartials symp{nullptr, 0.f, static_cast<int>(pl.nI * MS_BLOCK), reinterpret_cast<const float4 *>(inbox_local),
+                     world, sym_inbox_stride(N, world)};
     const int threads = 256;
     mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0,
                              static_cast<cudaStream_t>(stream)>>>(

@@ -460,7 +460,10 @@ __global__ void pinnsf_pack_tc16_kernel(const __grid_constant__ Tc16Plan P, cons
         reinterpret_cast<uint16_t *>(bdst)[off] = half == 0 ? hi : lo;
     } else {
         const int b = static_cast<int>(off - halfs);
-        if (b >= P.winv_off) return;                               // winv: written by tc16_wmax_kernel; padding stays
+        if (b >= P.winv_off) {                                     // winv: written by tc16_wmax_kernel; padding: zero
+            if (b >= P.winv_off + P.nl) bias_dst[b] = 0.f;
+            return;
+        }
         float v;
         if (b >= P.predb_off) v = src[S.pred_src[br] + 2LL * P.dw + (b - P.predb_off)];
         else if (b >= P.predw_off) v = src[S.pred_src[br] + (b - P.predw_off)];

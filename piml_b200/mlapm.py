@@ -1,6 +1,4 @@
 """Drop-in for the reference's `MLAPM` (src/models/mlapm.py:5-58) on the CUDA all-pairs kernel."""
-import os
-
 import torch
 
 from . import _lib as L
@@ -27,17 +25,13 @@ class MLAPM:
         return L.MlapmParams(_VERSIONS[ver], float(a['tau']), float(a['A']), float(a['B']), float(a.get('C', 0.0)),
                              float(a.get('D', 0.0)), float(a.get('theta', 0.0)), 1 if a.get('exact_math') else 0)
 
-    # the symmetric (unordered-pair) evaluation needs N^2/64 bytes for its column-direction sums; above this cap the
-    # ordered-pair kernel is used instead (PIML_MLAPM_SYM_MAX_BYTES overrides; 0 disables the symmetric path)
-    SYM_MAX_BYTES = int(os.environ.get("PIML_MLAPM_SYM_MAX_BYTES", 40 << 30))
-
     def _workspace(self, N, device, whole_crowd=False):
+        """Caller-owned scratch of the kernels: O(N) for both evaluations (symmetric: 32 B records + 16 B row partials
+        per split + 32 B fixed-point column accumulators per agent -- 0.15 GB at N = 10^6)."""
         lib = L.load()
         need = int(lib.piml_mlapm_workspace_bytes(N))
         if whole_crowd and not self.args.get('exact_math'):
-            sym = int(lib.piml_mlapm_workspace_bytes_sym(N))
-            if sym <= self.SYM_MAX_BYTES:
-                need = max(need, sym)
+            need = max(need, int(lib.piml_mlapm_workspace_bytes_sym(N)))
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws

@@ -86,6 +86,10 @@ class ShardedCrowd(object):
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         if len(self.ptrs) != self.world:
             raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peer buffers")
+        # destinations of ALL agents (the column side of the symmetric gates needs them): symmetric too, so that a rank
+        # can upload only its own rows and hand them to its peers (scatter_rows)
+        self.dest_buf = symm.empty((N, 2), dtype=torch.float32, device=self.device)
+        self.dest_hdl = symm.rendezvous(self.dest_buf, self.group)
         self.parity = 0
         self.arrived = torch.empty(self.shard, dtype=torch.uint8, device=self.device)
         plane = N * 2 * 4                                        # bytes of one (N,2) fp32 array
@@ -102,6 +106,25 @@ class ShardedCrowd(object):
         torch.cuda.current_stream(self.device).synchronize()
         dist.barrier(self.group)
 
+    def scatter_rows(self, position_rows, velocity_rows, destination_rows=None):
+        """The host-buffer entry of a sharded step: every rank passes ONLY ITS rows [rows[0], rows[1]) (pinned host or
+        device tensors): one H2D of 1/G of the state, then the rows are stored into every rank's current-state arrays
+        over NVLink peer memory and a barrier makes the crowd complete everywhere.  destination_rows likewise into
+        .dest_buf."""
+        r0, r1 = self.rows
+        dev = self.device
+        stage = [x.to(dev, non_blocking=True) if not x.is_cuda else x for x in (position_rows, velocity_rows)]
+        dst = destination_rows
+        if dst is not None and not dst.is_cuda:
+            dst = dst.to(dev, non_blocking=True)
+        for g in range(self.world):
+            peer = self.hdl.get_buffer(g, (2, 2, self.N, 2), torch.float32)
+            peer[self.parity, 0, r0:r1].copy_(stage[0], non_blocking=True)
+            peer[self.parity, 1, r0:r1].copy_(stage[1], non_blocking=True)
+            if dst is not None:
+                self.dest_hdl.get_buffer(g, (self.N, 2), torch.float32)[r0:r1].copy_(dst, non_blocking=True)
+        self.hdl.barrier(channel=0)
+
     @property
     def position(self):
         return self.buf[self.parity, 0]
@@ -110,33 +133,48 @@ class ShardedCrowd(object):
     def velocity(self):
         return self.buf[self.parity, 1]
 
-    def step(self, model, desired_speed, destination, dt, radius=0.3):
+    def step(self, model, desired_speed, destination, dt, radius=0.3, trace=None):
         """One iteration of src/main_mlapm.py:18-36 for this rank's rows, exchange included.  Returns arrived[bool]
-        for the local rows; afterwards .position / .velocity hold the new state of ALL agents."""
+        for the local rows; afterwards .position / .velocity hold the new state of ALL agents.
+        trace: optional list that receives CUDA events at the stage boundaries of this step (pairs + share push |
+        barrier | finalize + state push | barrier), for per-rank timelines."""
         nxt = 1 - self.parity
         pos_tab, vel_tab = self._tables[nxt]
         ds = desired_speed if desired_speed.dim() == 2 else desired_speed.unsqueeze(-1)
         r0, r1 = self.rows
+
+        def mark():
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                trace.append(e)
+        mark()
         if self.symmetric:
             lib, prm, st = L.load(), model._params(), L.stream_ptr(self.device)
             L.check(lib.piml_mlapm_sym_pairs_push_f32(
                 L.ptr(self.position), L.ptr(self.velocity), L.ptr(destination), self.N, self.world, self.rank,
                 C.byref(prm), self._inbox_tab, L.ptr(self._sym_ws), self._sym_ws.numel(), st),
                 "piml_mlapm_sym_pairs_push_f32")
+            mark()
             self.hdl.barrier(channel=0)    # every rank's column-direction shares have landed in the owners' inboxes
+            mark()
             L.check(lib.piml_mlapm_sym_finalize_push_f32(
                 L.ptr(self.position), L.ptr(self.velocity), L.ptr(ds), ds.shape[1], L.ptr(destination), self.N,
                 self.world, self.rank, C.byref(prm), float(dt), float(radius), L.ptr(self.inbox), pos_tab, vel_tab,
                 L.ptr(self.arrived), L.ptr(self._sym_ws), self._sym_ws.numel(), st),
                 "piml_mlapm_sym_finalize_push_f32")
+            mark()
             self.hdl.barrier(channel=0)    # ... and every rank's new rows in every rank's next-state arrays
+            mark()
             self.parity = nxt
             return self.arrived.bool()
         L.check(L.load().piml_mlapm_advance_push_f32(
             L.ptr(self.position), L.ptr(self.velocity), L.ptr(ds), ds.shape[1], L.ptr(destination), self.N, r0, r1,
             C.byref(model._params()), float(dt), float(radius), self.world, pos_tab, vel_tab, L.ptr(self.arrived),
             L.ptr(model._workspace(self.N, self.device)), L.stream_ptr(self.device)), "piml_mlapm_advance_push_f32")
+        mark()
         self.hdl.barrier(channel=0)        # every rank's rows have landed in every rank's next-state arrays
+        mark()
         self.parity = nxt
         return self.arrived.bool()
 

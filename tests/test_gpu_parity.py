@@ -951,7 +951,9 @@ def test_edge_sizes_do_not_break_the_adapters():
 
 def test_mlapm_symmetric_vs_ordered_at_bench_size():
     """BASELINE config 4 size (N = 100 000, T = 196 blocks): the symmetric kernel the bench times against the ordered-pair
-    kernel (itself checked against the oracle up to N = 8192), two consecutive steps on one workspace."""
+    kernel, two consecutive steps on one workspace.  Both kernels get the SAME inputs at each step (the second step starts
+    from the symmetric kernel's state: a free-running comparison would measure how fp32 rounding of step 1 flips
+    borderline gates in step 2, not the kernels).  The oracle check at this size is tests/test_gpu_parity_sizes.py."""
     import sys
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -960,24 +962,24 @@ def test_mlapm_symmetric_vs_ordered_at_bench_size():
     N = 100000
     p, v, ds, dest, _ = [x.cuda() for x in bench.synthetic_crowd(N)]
     model = P.MLAPM(**bench.MLAPM_KW)
-    res = {}
-    for algo in (2, 1):
-        _mlapm_algorithm(algo)
-        try:
-            pp, vv = p.clone(), v.clone()
-            for _ in range(2):
+    pp, vv = p.clone(), v.clone()
+    for step in range(2):
+        res = {}
+        for algo in (2, 1):
+            _mlapm_algorithm(algo)
+            try:
                 act, pn, arr = model.advance(pp, vv, ds, dest, bench.DT, bench.RADIUS)
-                pp, vv = pn, act
-            res[algo] = (npy(vv), npy(pp), npy(arr))
-        finally:
-            _mlapm_algorithm(0)
-    vs, vo = res[2][0], res[1][0]
-    assert np.isfinite(vs).all()
-    num = np.linalg.norm(vs.astype(np.float64) - vo, axis=-1)
-    den = np.maximum(np.maximum(np.linalg.norm(vo, axis=-1), np.linalg.norm(npy(v), axis=-1)), 1e-6)
-    assert float((num / den).max()) < TOL
-    assert np.abs(res[2][1] - res[1][1]).max() < 1e-4            # positions up to 450 m: a few fp32 ulps
-    assert (res[2][2] != res[1][2]).sum() <= 2                    # arrival test at the radius boundary
+                res[algo] = (act, pn, arr)
+            finally:
+                _mlapm_algorithm(0)
+        vs, vo = npy(res[2][0]), npy(res[1][0])
+        assert np.isfinite(vs).all()
+        num = np.linalg.norm(vs.astype(np.float64) - vo, axis=-1)
+        den = np.maximum(np.maximum(np.linalg.norm(vo, axis=-1), np.linalg.norm(npy(vv), axis=-1)), 1e-6)
+        assert float((num / den).max()) < TOL, (step, float((num / den).max()))
+        assert np.abs(npy(res[2][1]) - npy(res[1][1])).max() < 1e-4        # positions up to 450 m: a few fp32 ulps
+        assert (npy(res[2][2]) != npy(res[1][2])).sum() <= 2                # arrival test at the radius boundary
+        pp, vv = res[2][1], res[2][0]
 
 
 # ---- round 2: small kernels that replaced the last eager-torch helpers ---------------------------------------------------
