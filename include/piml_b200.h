@@ -203,6 +203,14 @@ PIML_API int piml_mlapm_advance_push_f32(const float *pos, const float *vel, con
                                 const uint64_t *peer_pos_next_host, const uint64_t *peer_vel_next_host,
                                 uint8_t *arrived, void *workspace, void *stream);
 
+/* Host-buffer entry of an agent-sharded step (piml_b200.sharded.ShardedCrowd.scatter_rows): this rank's rows
+ * [row0, row0 + nrows) of position / velocity (and destination, may be NULL) -- device copies of what the rank uploaded
+ * from the host -- are stored into EVERY rank's state arrays over NVLink peer memory by one kernel.  peer_*_host: host
+ * arrays of `world` device pointers to each rank's (N,2) arrays.  The caller follows with a cross-rank barrier. */
+PIML_API int piml_scatter_rows_push_f32(const float *pos_rows, const float *vel_rows, const float *dest_rows, int64_t row0,
+                                        int64_t nrows, int world, const uint64_t *peer_pos_host,
+                                        const uint64_t *peer_vel_host, const uint64_t *peer_dest_host, void *stream);
+
 /* Agent-sharded crowd on the symmetric (unordered-pair) evaluation.  Rank g owns the 512-agent blocks
  * [g T / G, (g+1) T / G), T = ceil(N / 512) (piml_mlapm_sym_shard_rows), and evaluates the block pairs of its own row
  * blocks; the exchange is fused into two kernels over NVLink / NVSwitch peer memory:

@@ -15,7 +15,7 @@ struct IntArgs {
     float2 *hist_v; float2 *rec_p, *rec_v, *rec_a; float *rec_mask;
 };
 
-__global__ void integrate_kernel(IntArgs g) {
+__device__ __forceinline__ void integrate_body(const IntArgs &g) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<int64_t>(g.S) * g.N) return;
     const int s = static_cast<int>(i / g.N), n = static_cast<int>(i % g.N);
@@ -36,6 +36,48 @@ __global__ void integrate_kernel(IntArgs g) {
     }
     g.p[i] = pn; g.v[i] = vn; g.a[i] = an; g.dest[i] = d; g.dest_idx[i] = di;
     if (g.hist_v) g.hist_v[i] = hv;
+}
+
+__global__ void integrate_kernel(IntArgs g) { integrate_body(g); }
+
+// The same step with the frame index read from device memory: `g` carries the BASE pointers of the time-major
+// ground-truth / record arrays, frame t = *t_dev selects the slices (record into frame t, entries from frame t + 1).
+// Every launch of a rollout step then has constant arguments, so one captured CUDA graph replays the whole loop
+// (rollout.cu); a one-thread kernel advances the counter at the end of the step.
+__global__ void integrate_indirect_kernel(IntArgs g, const int *__restrict__ t_dev) {
+    const int t = *t_dev;
+    const int64_t SN = static_cast<int64_t>(g.S) * g.N;
+    g.entry += (t + 1) * SN; g.dest_idx_gt += (t + 1) * SN;
+    g.p_gt += (t + 1) * SN; g.v_gt += (t + 1) * SN; g.a_gt += (t + 1) * SN; g.dest_gt += (t + 1) * SN;
+    g.rec_p += t * SN; g.rec_v += t * SN; g.rec_a += t * SN; g.rec_mask += t * SN;
+    integrate_body(g);
+}
+
+__global__ void advance_counter_kernel(int *t_dev) { *t_dev += 1; }
+
+// rollout.cu: one step of the captured loop (frames t_start + 1 .. T - 2 all have a successor frame to enter from)
+int integrate_step_indirect(const piml_rollout_args *r, const int *t_dev, cudaStream_t st) {
+    IntArgs g;
+    g.p = reinterpret_cast<float2 *>(r->p); g.v = reinterpret_cast<float2 *>(r->v); g.a = reinterpret_cast<float2 *>(r->a);
+    g.a_next = reinterpret_cast<const float2 *>(r->a_next); g.dest = reinterpret_cast<float2 *>(r->dest);
+    g.dest_idx = r->dest_idx; g.dest_num = r->dest_num; g.waypoints = reinterpret_cast<const float2 *>(r->waypoints);
+    g.S = r->S; g.D = r->D; g.N = r->N; g.dt = r->dt; g.remove_on_arrival = 1; g.entry = r->entry_tm;
+    g.p_gt = reinterpret_cast<const float2 *>(r->pos_tm); g.v_gt = reinterpret_cast<const float2 *>(r->vel_tm);
+    g.a_gt = reinterpret_cast<const float2 *>(r->acc_tm); g.dest_gt = reinterpret_cast<const float2 *>(r->dest_tm);
+    g.dest_idx_gt = r->dest_idx_tm; g.hist_v = reinterpret_cast<float2 *>(r->hist_v);
+    g.rec_p = reinterpret_cast<float2 *>(r->rec_p); g.rec_v = reinterpret_cast<float2 *>(r->rec_v);
+    g.rec_a = reinterpret_cast<float2 *>(r->rec_a); g.rec_mask = r->rec_mask;
+    const int64_t tot = static_cast<int64_t>(r->S) * r->N;
+    const int threads = 128;
+    integrate_indirect_kernel<<<static_cast<unsigned>((tot + threads - 1) / threads), threads, 0, st>>>(g, t_dev);
+    count_launch();
+    return check_launch("integrate_indirect_kernel");
+}
+
+int advance_counter(int *t_dev, cudaStream_t st) {
+    advance_counter_kernel<<<1, 1, 0, st>>>(t_dev);
+    count_launch();
+    return check_launch("advance_counter_kernel");
 }
 
 // backward of v' = v + a dt, p' = p + v dt, a' = a_next with teacher-forced entry (simulators.py:741-769)

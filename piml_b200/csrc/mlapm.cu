@@ -691,20 +691,24 @@ struct PeerInbox { int world, rank; int Ib[ML_MAX_PEERS + 1]; float4 *inbox[ML_M
 __global__ void mlapm_sym_colpush_kernel(const long long *__restrict__ colsum, float inv_colscale, int N,
                                          const __grid_constant__ PeerInbox peers) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= N) return;
-    const int J = m / MS_BLOCK;
-    const longlong2 c0 = reinterpret_cast<const longlong2 *>(colsum)[2 * m];
-    const longlong2 c1 = reinterpret_cast<const longlong2 *>(colsum)[2 * m + 1];
-    const double is = static_cast<double>(inv_colscale);
-    const float4 u = make_float4(static_cast<float>(static_cast<double>(c0.x) * is),
-                                 static_cast<float>(static_cast<double>(c0.y) * is),
-                                 static_cast<float>(static_cast<double>(c1.x) * is),
-                                 static_cast<float>(static_cast<double>(c1.y) * is));
-    int h = 0;
-    while (h + 1 < peers.world && J >= peers.Ib[h + 1]) ++h;
-    peers.inbox[h][peers.rank * peers.stride + (m - peers.Ib[h] * MS_BLOCK)] = u;
-    __threadfence_system();                                               // visible to the owner before the barrier
+    if (m < N) {
+        const int J = m / MS_BLOCK;
+        const longlong2 c0 = reinterpret_cast<const longlong2 *>(colsum)[2 * m];
+        const longlong2 c1 = reinterpret_cast<const longlong2 *>(colsum)[2 * m + 1];
+        const double is = static_cast<double>(inv_colscale);
+        const float4 u = make_float4(static_cast<float>(static_cast<double>(c0.x) * is),
+                                     static_cast<float>(static_cast<double>(c0.y) * is),
+                                     static_cast<float>(static_cast<double>(c1.x) * is),
+                                     static_cast<float>(static_cast<double>(c1.y) * is));
+        int h = 0;
+        while (h + 1 < peers.world && J >= peers.Ib[h + 1]) ++h;
+        peers.inbox[h][peers.rank * peers.stride + (m - peers.Ib[h] * MS_BLOCK)] = u;
+    }
+    __syncthreads();                                                      // one cumulative system fence per CTA:
+    if (threadIdx.x == 0) __threadfence_system();                         // visible to the owner before the barrier
 }
+
+constexpr int FZ_LPR = 8;                        // lanes per row in the finalize kernel
 
 // force = (v0*ed - v)/tau - A*R(sum partial) ; action = v + force*dt ; optional p' = p + action*dt and arrival.
 __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const float2 *__restrict__ vel,
@@ -714,10 +718,30 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
                                        float2 *__restrict__ action, float2 *__restrict__ pos_new,
                                        uint8_t *__restrict__ arrived, const __grid_constant__ PeerPush push,
                                        const __grid_constant__ SymPartials sym) {
-    const int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    // FZ_LPR lanes share a row: lane j adds the split partials j, j + FZ_LPR, ... and the lanes' sums are combined in
+    // lane order -- a fixed order (deterministic), but FZ_LPR loads in flight per row instead of one dependent chain of
+    // up to 396 (an 8-way shard of 100k agents): the kernel was latency bound at 70 us of a 1.05 ms step.
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rl_raw = gt / FZ_LPR, sub = gt % FZ_LPR;
     const int nrows = row1 - row0;
-    if (rl >= nrows) return;
+    const bool live = rl_raw < nrows;
+    const int rl = live ? rl_raw : nrows - 1;                     // idle lanes shadow the last row (shuffles stay converged)
+    const int64_t pstride = (sym.colsum || sym.inbox) ? sym.nrows_pad : nrows;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = sub; q < nsplit; q += FZ_LPR) {
+        const float4 t = partial[static_cast<int64_t>(q) * pstride + rl];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+#pragma unroll
+    for (int o = 1; o < FZ_LPR; o <<= 1) {                        // tree in a fixed shape: deterministic
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+        s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+    }
     const int n = row0 + rl;
+    float qx = 0.f, qy = 0.f, ax = 0.f, ay = 0.f;
+    if (live && sub == 0) {
     const float2 p = pos[n], v = vel[n], d = dest[n];
     const float dx = __fsub_rn(d.x, p.x), dy = __fsub_rn(d.y, p.y);
     const float dn = fmaxf(norm2_rn(dx, dy), 1e-12f);
@@ -727,12 +751,6 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     // force += (desired_speed * ed - velocity) / tau      (mlapm.py:22)
     float fx = __fdiv_rn(__fsub_rn(__fmul_rn(dsx, ex), v.x), tau);
     float fy = __fdiv_rn(__fsub_rn(__fmul_rn(dsy, ey), v.y), tau);
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t pstride = (sym.colsum || sym.inbox) ? sym.nrows_pad : nrows;
-    for (int q = 0; q < nsplit; ++q) {                            // fixed order: deterministic
-        const float4 t = partial[static_cast<int64_t>(q) * pstride + rl];
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-    }
     if (sym.inbox) {
         // agent-sharded symmetric evaluation: one pre-reduced share per rank, added in rank order
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -760,23 +778,32 @@ __global__ void mlapm_finalize2_kernel(const float2 *__restrict__ pos, const flo
     }
     fx = __fsub_rn(fx, __fmul_rn(A, sx));                         // force -= (...).sum(dim=1)   (mlapm.py:29/39)
     fy = __fsub_rn(fy, __fmul_rn(A, sy));
-    const float ax = __fadd_rn(v.x, __fmul_rn(fx, dt));           // action = velocity + force*dt (mlapm.py:57)
-    const float ay = __fadd_rn(v.y, __fmul_rn(fy, dt));
+    ax = __fadd_rn(v.x, __fmul_rn(fx, dt));                       // action = velocity + force*dt (mlapm.py:57)
+    ay = __fadd_rn(v.y, __fmul_rn(fy, dt));
     if (action) action[rl] = make_float2(ax, ay);
     if (pos_new || arrived || push.world > 0) {
-        const float qx = __fadd_rn(p.x, __fmul_rn(ax, dt));       // p = position + v*dt          (main_mlapm.py:26)
-        const float qy = __fadd_rn(p.y, __fmul_rn(ay, dt));
+        qx = __fadd_rn(p.x, __fmul_rn(ax, dt));                   // p = position + v*dt          (main_mlapm.py:26)
+        qy = __fadd_rn(p.y, __fmul_rn(ay, dt));
         if (pos_new) pos_new[rl] = make_float2(qx, qy);
         if (arrived)                                              // ||p - destination|| < radius (main_mlapm.py:34)
             arrived[rl] = norm2_rn(__fsub_rn(qx, d.x), __fsub_rn(qy, d.y)) < radius ? 1 : 0;
-        if (push.world > 0) {
-            // the path's one exchange, fused: store this row's new state into every rank's next-state arrays
-            for (int g = 0; g < push.world; ++g) {
+    }
+    }
+    if (push.world > 0) {
+        // the path's one exchange, fused: the row's new state goes into EVERY rank's next-state arrays; the row's
+        // FZ_LPR lanes take one peer each, so the remote stores of a row are issued in parallel
+        const int lead = (threadIdx.x & 31) & ~(FZ_LPR - 1);
+        qx = __shfl_sync(0xffffffffu, qx, lead); qy = __shfl_sync(0xffffffffu, qy, lead);
+        ax = __shfl_sync(0xffffffffu, ax, lead); ay = __shfl_sync(0xffffffffu, ay, lead);
+        if (live)
+            for (int g = sub; g < push.world; g += FZ_LPR) {
                 push.pos[g][n] = make_float2(qx, qy);
                 push.vel[g][n] = make_float2(ax, ay);
             }
-            __threadfence_system();                               // visible to the peers before the step barrier
-        }
+        // one system-scope fence per CTA (fences are cumulative over the CTA barrier): the stores are visible to the
+        // peers before the step barrier that follows the kernel
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
     }
 }
 
@@ -1050,7 +1077,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
         const int threads = 256;
         (void)D;
         symp = SymPartials{colsum, ldexpf(1.0f, -sl), static_cast<int>(npad), nullptr, 0, 0};
-        mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+        mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows * FZ_LPR + threads - 1) / threads), threads, 0, st>>>(
             p2, v2, desired_speed, ds_dim, d2, r0, r1, S, partialR, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
             dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
         count_launch();
@@ -1098,7 +1125,7 @@ static int mlapm_advance_impl(const float *pos, const float *vel, const float *d
     rc = check_launch("mlapm_pairs2_kernel");
     if (rc) return rc;
     const int threads = 256;
-    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0, st>>>(
+    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows * FZ_LPR + threads - 1) / threads), threads, 0, st>>>(
         p2, v2, desired_speed, ds_dim, d2, r0, r1, nsplit, partial4, prm->A, k.cos_t, k.sin_t, prm->version, prm->tau,
         dt, radius, reinterpret_cast<float2 *>(action), reinterpret_cast<float2 *>(pos_new), arrived, push, symp);
     count_launch();
@@ -1293,7 +1320,7 @@ extern "C" int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *v
     SymPartials symp{nullptr, 0.f, static_cast<int>(pl.nI * MS_BLOCK), reinterpret_cast<const float4 *>(inbox_local),
                      world, sym_inbox_stride(N, world)};
     const int threads = 256;
-    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0,
+    mlapm_finalize2_kernel<<<static_cast<unsigned>((nrows * FZ_LPR + threads - 1) / threads), threads, 0,
                              static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2 *>(pos), reinterpret_cast<const float2 *>(vel), desired_speed, ds_dim,
         reinterpret_cast<const float2 *>(dest), static_cast<int>(row0), static_cast<int>(row1), pl.S, pl.partialR,
@@ -1301,3 +1328,54 @@ extern "C" int piml_mlapm_sym_finalize_push_f32(const float *pos, const float *v
     count_launch();
     return check_launch("mlapm_finalize2_kernel");
 }
+
+// ---- host-buffer entry of an agent-sharded step ------------------------------------------------------------------------
+// Every rank uploads ONLY its own rows (1/G of the state over PCIe); this kernel stores them into every rank's
+// current-state arrays over NVLink peer memory in ONE launch (the caller follows with a cross-rank barrier).
+namespace piml {
+struct ScatterPeers { int world; float2 *pos[ML_MAX_PEERS]; float2 *vel[ML_MAX_PEERS]; float2 *dest[ML_MAX_PEERS]; };
+
+__global__ void scatter_rows_push_kernel(const float2 *__restrict__ pos_rows, const float2 *__restrict__ vel_rows,
+                                         const float2 *__restrict__ dest_rows, int64_t row0, int64_t nrows,
+                                         const __grid_constant__ ScatterPeers peers) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nrows) {
+        const float2 p = pos_rows[i], v = vel_rows[i];
+        const float2 d = dest_rows ? dest_rows[i] : make_float2(0.f, 0.f);
+        for (int g = 0; g < peers.world; ++g) {
+            peers.pos[g][row0 + i] = p;
+            peers.vel[g][row0 + i] = v;
+            if (dest_rows) peers.dest[g][row0 + i] = d;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+}
+}  // namespace piml
+
+extern "C" int piml_scatter_rows_push_f32(const float *pos_rows, const float *vel_rows, const float *dest_rows,
+                                          int64_t row0, int64_t nrows, int world, const uint64_t *peer_pos_host,
+                                          const uint64_t *peer_vel_host, const uint64_t *peer_dest_host, void *stream) {
+    PIML_REQUIRE(world >= 1 && world <= ML_MAX_PEERS && row0 >= 0 && nrows >= 0, "piml_scatter_rows_push_f32: bad shard");
+    if (nrows == 0) return PIML_OK;
+    PIML_REQUIRE(pos_rows && vel_rows && peer_pos_host && peer_vel_host && (!dest_rows || peer_dest_host),
+                 "piml_scatter_rows_push_f32: null pointer");
+    ScatterPeers peers;
+    peers.world = world;
+    for (int g = 0; g < ML_MAX_PEERS; ++g) {
+        peers.pos[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_pos_host[g])) : nullptr;
+        peers.vel[g] = g < world ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_vel_host[g])) : nullptr;
+        peers.dest[g] = (g < world && dest_rows) ? reinterpret_cast<float2 *>(static_cast<uintptr_t>(peer_dest_host[g]))
+                                                 : nullptr;
+        PIML_REQUIRE(g >= world || (peers.pos[g] && peers.vel[g] && (!dest_rows || peers.dest[g])),
+                     "piml_scatter_rows_push_f32: bad peer pointer for rank %d", g);
+    }
+    const int threads = 256;
+    scatter_rows_push_kernel<<<static_cast<unsigned>((nrows + threads - 1) / threads), threads, 0,
+                               static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(pos_rows), reinterpret_cast<const float2 *>(vel_rows),
+        reinterpret_cast<const float2 *>(dest_rows), row0, nrows, peers);
+    count_launch();
+    return check_launch("scatter_rows_push_kernel");
+}
+

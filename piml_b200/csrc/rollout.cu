@@ -5,12 +5,73 @@
 // step t+1 are queued while step t runs.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace piml {
 bool sfm_rollout_fits(const piml_rollout_args *r);                 // rollout_sfm.cu
 int sfm_rollout_launch(const piml_rollout_args *r, cudaStream_t st);
+int integrate_step_indirect(const piml_rollout_args *r, const int *t_dev, cudaStream_t st);   // integrate.cu
+int advance_counter(int *t_dev, cudaStream_t st);
+
+// frame counter of the captured loop + a capture-capable stream (the legacy default stream cannot be captured): one
+// per calling thread and device
+static int frame_counter(int **out, cudaStream_t *side, cudaEvent_t *ev) {
+    struct Slot { int dev; int *p; cudaStream_t st; cudaEvent_t ev; };
+    static thread_local Slot slots[16] = {};
+    static thread_local int used = 0;
+    int dev = 0;
+    PIML_CUDA(cudaGetDevice(&dev));
+    for (int i = 0; i < used; ++i)
+        if (slots[i].dev == dev) { *out = slots[i].p; *side = slots[i].st; *ev = slots[i].ev; return PIML_OK; }
+    PIML_REQUIRE(used < 16, "piml_rollout_f32: too many devices in one thread");
+    Slot s{dev, nullptr, nullptr, nullptr};
+    PIML_CUDA(cudaMalloc(&s.p, sizeof(int)));
+    PIML_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    PIML_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    slots[used++] = s;
+    *out = s.p; *side = s.st; *ev = s.ev;
+    return PIML_OK;
+}
 }  // namespace piml
 
 using namespace piml;
+
+// One step of the loop: a_next = model(features); record / Euler / arrival / entry; features of the new state.
+// t_dev != nullptr: the frame index comes from device memory (constant launch arguments: graph capture).
+static int rollout_step(const piml_rollout_args *r, int t, const int *t_dev, int64_t SN, int kp, int ko, int has_obs,
+                        void *stream) {
+    int rc;
+    // a_next = model(*state_features)[0]                                               (simulators.py:602)
+    if (r->sfm)                                // pure social-force mode (BASELINE config 2)
+        rc = piml_sfm_forward_f32(r->sfm, r->ped_f, has_obs ? r->obs_f : nullptr, r->self_f, SN, kp, has_obs ? ko : 0,
+                                  r->a_next, nullptr, nullptr, stream);
+    else if (r->packed_tc)
+        rc = piml_pinnsf_forward_tc_f32(r->desc, r->packed_tc, has_obs, r->tau, r->ped_f, r->obs_f, r->self_f, SN, kp,
+                                        ko, 0, r->a_next, nullptr, nullptr, stream);
+    else
+        rc = piml_pinnsf_forward_f32(r->desc, r->packed, has_obs, r->tau, r->ped_f, r->obs_f, r->self_f, SN, kp, ko, 0,
+                                     nullptr, nullptr, r->a_next, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    // record, Euler, arrival / waypoint switch, entry from the data at t+1, hist_v           (:596-639)
+    if (t_dev) {
+        rc = integrate_step_indirect(r, t_dev, static_cast<cudaStream_t>(stream));
+    } else {
+        const bool last = t >= r->T - 1;
+        const int64_t o2 = static_cast<int64_t>(t + 1) * SN * 2, o1 = static_cast<int64_t>(t + 1) * SN;
+        const int64_t q2 = static_cast<int64_t>(t) * SN * 2, q1 = static_cast<int64_t>(t) * SN;
+        rc = piml_integrate_step_f32(r->p, r->v, r->a, r->a_next, r->dest, r->dest_idx, r->dest_num, r->waypoints,
+                                     r->S, r->D, r->N, r->dt, 1, last ? nullptr : r->entry_tm + o1,
+                                     last ? nullptr : r->pos_tm + o2, last ? nullptr : r->vel_tm + o2,
+                                     last ? nullptr : r->acc_tm + o2, last ? nullptr : r->dest_tm + o2,
+                                     last ? nullptr : r->dest_idx_tm + o1, r->hist_v, r->rec_p + q2, r->rec_v + q2,
+                                     r->rec_a + q2, r->rec_mask + q1, stream);
+    }
+    if (rc) return rc;
+    // features of the new state + self_features = cat(dest_f, hist_v, a, desired_speed)      (:642-652)
+    return piml_state_features_f32(r->p, r->v, r->a, r->dest, r->obstacles, r->obs_per_scene, r->S, r->N, r->M, r->kp,
+                                   r->cos_p, r->thr_p, r->ko, r->cos_o, r->thr_o, r->hist_v, r->desired_speed,
+                                   r->ped_f, r->obs_f, r->self_f, r->dest_f, stream);
+}
 
 extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
     PIML_REQUIRE(r && (r->sfm || (r->desc && (r->packed || r->packed_tc))),
@@ -31,35 +92,67 @@ extern "C" int piml_rollout_f32(const piml_rollout_args *r, void *stream) {
     const int has_obs = (r->has_obs && ko > 0) ? 1 : 0;
     // pure social-force model on GC-shaped scenes: the whole loop in one persistent kernel (rollout_sfm.cu)
     if (r->sfm && sfm_rollout_fits(r)) return sfm_rollout_launch(r, static_cast<cudaStream_t>(stream));
-    for (int t = r->t_start; t < r->T; ++t) {
-        int rc;
-        // a_next = model(*state_features)[0]                                               (simulators.py:602)
-        if (r->sfm)                            // pure social-force mode (BASELINE config 2)
-            rc = piml_sfm_forward_f32(r->sfm, r->ped_f, has_obs ? r->obs_f : nullptr, r->self_f, SN, kp,
-                                      has_obs ? ko : 0, r->a_next, nullptr, nullptr, stream);
-        else if (r->packed_tc)
-            rc = piml_pinnsf_forward_tc_f32(r->desc, r->packed_tc, has_obs, r->tau, r->ped_f, r->obs_f, r->self_f, SN,
-                                            kp, ko, 0, r->a_next, nullptr, nullptr, stream);
-        else
-            rc = piml_pinnsf_forward_f32(r->desc, r->packed, has_obs, r->tau, r->ped_f, r->obs_f, r->self_f, SN, kp,
-                                         ko, 0, nullptr, nullptr, r->a_next, nullptr, nullptr, nullptr, stream);
+    // Frames t_start + 1 .. T - 2 are identical launches once the frame index lives in device memory: capture ONE step
+    // into a CUDA graph and replay it (a GC-sized scene is launch-latency bound: ~15 launches per step).  The first
+    // step runs eagerly (it sizes the library's scratch buffers, which must not happen during capture), the last
+    // one too (no successor frame to take entries from).  PIML_ROLLOUT_GRAPH=0 keeps the eager loop.
+    cudaStream_t user = static_cast<cudaStream_t>(stream), st = user;
+    const char *ge = getenv("PIML_ROLLOUT_GRAPH");
+    const int replays = r->T - 2 - r->t_start;                     // frames t_start + 1 .. T - 2
+    const bool use_graph = !(ge && atoi(ge) == 0) && replays >= 8;
+    int *t_dev = nullptr;
+    cudaEvent_t ev = nullptr;
+    if (use_graph) {
+        cudaStream_t side = nullptr;
+        int rc0 = frame_counter(&t_dev, &side, &ev);
+        if (rc0) return rc0;
+        if (user == nullptr || user == cudaStreamLegacy) {         // the legacy default stream cannot be captured:
+            PIML_CUDA(cudaEventRecord(ev, user));                  // run the loop on a side stream ordered after it
+            PIML_CUDA(cudaStreamWaitEvent(side, ev, 0));
+            st = side;
+        }
+    }
+    stream = st;
+    int t = r->t_start;
+    int rc = rollout_step(r, t, nullptr, SN, kp, ko, has_obs, stream);
+    if (rc) return rc;
+    ++t;
+    if (use_graph) {
+        PIML_CUDA(cudaMemcpyAsync(t_dev, &t, sizeof(int), cudaMemcpyHostToDevice, st));
+        PIML_CUDA(cudaStreamSynchronize(st));                      // `t` is a stack variable
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int64_t c0 = piml_launch_count();
+        PIML_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = rollout_step(r, -1, t_dev, SN, kp, ko, has_obs, stream);
+        if (!rc) rc = advance_counter(t_dev, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        const int64_t per_step = piml_launch_count() - c0;         // kernels of one captured step
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc) return rc;
+            return piml::fail(PIML_ERR_CUDA, "piml_rollout_f32: stream capture failed: %s", cudaGetErrorString(ce));
+        }
+        PIML_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        for (int i = 0; i < replays; ++i) {
+            const cudaError_t le = cudaGraphLaunch(exec, st);
+            if (le != cudaSuccess) {
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+                return piml::fail(PIML_ERR_CUDA, "piml_rollout_f32: graph launch failed: %s", cudaGetErrorString(le));
+            }
+        }
+        count_launch(static_cast<int>((replays - 1) * per_step)); // the capture counted one step's kernels
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        t += replays;
+    }
+    for (; t < r->T; ++t) {
+        rc = rollout_step(r, t, nullptr, SN, kp, ko, has_obs, stream);
         if (rc) return rc;
-        // record, Euler, arrival / waypoint switch, entry from the data at t+1, hist_v           (:596-639)
-        const bool last = t >= r->T - 1;
-        const int64_t o2 = static_cast<int64_t>(t + 1) * SN * 2, o1 = static_cast<int64_t>(t + 1) * SN;
-        const int64_t q2 = static_cast<int64_t>(t) * SN * 2, q1 = static_cast<int64_t>(t) * SN;
-        rc = piml_integrate_step_f32(r->p, r->v, r->a, r->a_next, r->dest, r->dest_idx, r->dest_num, r->waypoints,
-                                     r->S, r->D, r->N, r->dt, 1, last ? nullptr : r->entry_tm + o1,
-                                     last ? nullptr : r->pos_tm + o2, last ? nullptr : r->vel_tm + o2,
-                                     last ? nullptr : r->acc_tm + o2, last ? nullptr : r->dest_tm + o2,
-                                     last ? nullptr : r->dest_idx_tm + o1, r->hist_v, r->rec_p + q2, r->rec_v + q2,
-                                     r->rec_a + q2, r->rec_mask + q1, stream);
-        if (rc) return rc;
-        // features of the new state + self_features = cat(dest_f, hist_v, a, desired_speed)      (:642-652)
-        rc = piml_state_features_f32(r->p, r->v, r->a, r->dest, r->obstacles, r->obs_per_scene, r->S, r->N, r->M,
-                                     r->kp, r->cos_p, r->thr_p, r->ko, r->cos_o, r->thr_o, r->hist_v,
-                                     r->desired_speed, r->ped_f, r->obs_f, r->self_f, r->dest_f, stream);
-        if (rc) return rc;
+    }
+    if (st != user) {                                              // the caller's stream continues after the loop
+        PIML_CUDA(cudaEventRecord(ev, st));
+        PIML_CUDA(cudaStreamWaitEvent(user, ev, 0));
     }
     return PIML_OK;
 }

@@ -90,6 +90,7 @@ class ShardedCrowd(object):
         # can upload only its own rows and hand them to its peers (scatter_rows)
         self.dest_buf = symm.empty((N, 2), dtype=torch.float32, device=self.device)
         self.dest_hdl = symm.rendezvous(self.dest_buf, self.group)
+        self._dest_tab = (C.c_uint64 * self.world)(*[int(p) for p in self.dest_hdl.buffer_ptrs])
         self.parity = 0
         self.arrived = torch.empty(self.shard, dtype=torch.uint8, device=self.device)
         plane = N * 2 * 4                                        # bytes of one (N,2) fp32 array
@@ -113,16 +114,14 @@ class ShardedCrowd(object):
         .dest_buf."""
         r0, r1 = self.rows
         dev = self.device
-        stage = [x.to(dev, non_blocking=True) if not x.is_cuda else x for x in (position_rows, velocity_rows)]
+        stage = [L.f32c(x.to(dev, non_blocking=True) if not x.is_cuda else x) for x in (position_rows, velocity_rows)]
         dst = destination_rows
-        if dst is not None and not dst.is_cuda:
-            dst = dst.to(dev, non_blocking=True)
-        for g in range(self.world):
-            peer = self.hdl.get_buffer(g, (2, 2, self.N, 2), torch.float32)
-            peer[self.parity, 0, r0:r1].copy_(stage[0], non_blocking=True)
-            peer[self.parity, 1, r0:r1].copy_(stage[1], non_blocking=True)
-            if dst is not None:
-                self.dest_hdl.get_buffer(g, (self.N, 2), torch.float32)[r0:r1].copy_(dst, non_blocking=True)
+        if dst is not None:
+            dst = L.f32c(dst.to(dev, non_blocking=True) if not dst.is_cuda else dst)
+        pos_tab, vel_tab = self._tables[self.parity]
+        L.check(L.load().piml_scatter_rows_push_f32(
+            L.ptr(stage[0]), L.ptr(stage[1]), L.ptr(dst), r0, r1 - r0, self.world, pos_tab, vel_tab,
+            self._dest_tab if dst is not None else None, L.stream_ptr(dev)), "piml_scatter_rows_push_f32")
         self.hdl.barrier(channel=0)
 
     @property

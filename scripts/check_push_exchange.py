@@ -69,5 +69,36 @@ dist.all_reduce(t2, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"symmetric sharded: identical on all ranks {same}; max |dp| vs unsharded symmetric {e_sym:.2e} m, vs "
           f"ordered {e_ord:.2e} m, max rel dv {e_v:.2e} after {steps} steps (rows of rank 0: {sym.rows}): {bool(int(t2))}")
+# ---- the benchmarked configuration against the ORACLE, sharded: N = 100 000, one step, force level (dt = 2^20) ----------
+import numpy as np
+from oracle import oracle as O
+N2 = 100000
+p2, v2, ds2, dest2, _ = bench.synthetic_crowd(N2)
+big = ShardedCrowd(N2, device=dev)                      # symmetric (>= 16 384 agents)
+big.load(p2.to(dev), v2.to(dev))
+r0, r1 = big.rows
+# host-buffer entry: every rank hands over only its rows; afterwards all ranks must hold the full state
+big.scatter_rows(p2[r0:r1].pin_memory(), v2[r0:r1].pin_memory(), dest2[r0:r1].pin_memory())
+torch.cuda.synchronize()
+ok_sc = bool(torch.equal(big.position.cpu(), p2) and torch.equal(big.velocity.cpu(), v2) and torch.equal(big.dest_buf.cpu(), dest2))
+BIG_DT = float(2 ** 20)
+big.step(model, ds2.to(dev), big.dest_buf, BIG_DT, bench.RADIUS)
+torch.cuda.synchronize()
+act_big = big.velocity.cpu().numpy().astype(np.float64)
+rows = [(r0, min(r0 + 300, r1)), (max(r1 - 300, r0), r1), ((r0 + r1) // 2 + 37, min((r0 + r1) // 2 + 337, r1))]
+worst, worst_k, nrows_chk, okf = 0.0, 0.0, 0, True
+for (a_, b_) in rows:
+    _, force, opsum = O.mlapm_step_diag(p2.numpy(), v2.numpy(), ds2.numpy(), dest2.numpy(), bench.DT, "GC", rows=(a_, b_))
+    F = (act_big[a_:b_] - v2.numpy()[a_:b_].astype(np.float64)) / BIG_DT
+    e = np.linalg.norm(F - force, axis=-1); nF = np.linalg.norm(force, axis=-1)
+    okf = okf and bool((e <= 1e-5 * np.maximum(nF, opsum / 16.0)).all())
+    i = int(np.argmax(e / nF))
+    if (e / nF)[i] > worst:
+        worst, worst_k = float((e / nF)[i]), float(opsum[i] / nF[i])
+    nrows_chk += b_ - a_
+t3 = torch.tensor([1 if (okf and ok_sc) else 0], device=dev)
+dist.all_reduce(t3, op=dist.ReduceOp.MIN)
+print(f"rank {rank}: N={N2} sharded symmetric step vs oracle on {nrows_chk} of its rows [{r0},{r1}): strict force error max "
+      f"{worst:.2e} (kappa {worst_k:.0f}), gate ok {okf}; scatter_rows rebuilt the full state: {ok_sc}", flush=True)
 dist.destroy_process_group()
-sys.exit(0 if int(t) and int(t2) else 1)
+sys.exit(0 if int(t) and int(t2) and int(t3) else 1)
