@@ -42,7 +42,7 @@ MLAPM_KW = dict(version='GC', tau=0.5, A=7.55, B=-3.00, C=0.2, D=-0.3, theta=56)
 DT, RADIUS = 0.08, 0.3
 FLUSH_MB = 160                 # L2 is 126 MB
 MLAPM_DRAM_BYTES_PER_LAUNCH = 5629952 + 1383680     # ordered-pair kernel: ncu --set full, N = 100k (profiles/r01b_...)
-MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 4000512 + 181217792  # symmetric kernel (profiles/r01d_ncu_mlapm_sym_kernel.txt)
+MLAPM_SYM_DRAM_BYTES_PER_LAUNCH = 6473472 + 27649792   # symmetric kernel (profiles/r02i_ncu_mlapm_sym_kernel.txt)
 
 
 def synthetic_crowd(N, M=2000, seed=666, rho=0.5):
@@ -770,6 +770,99 @@ def sharded_timeline(torch, dist, dev, crowd, model, ds, dest, world, steps=5):
     return {"stages": names, "ms_per_rank": [[round(float(x), 4) for x in r] for r in allr]}
 
 
+def training_block(torch, dev, with_reference=True):
+    """BASELINE configs[2]: one rollout-training step (UCY clip, pinnsf_bm, channelled windows of 5 steps, 144 slots):
+    test_multiple_rollouts_for_training + loss.backward() + Adam, every kernel from libpiml_b200.so, on the reference's own
+    batch (tests/golden/training_rollout.npz, 6 channels) tiled to the config's batch of C = 32 channels; next to it the
+    UNMODIFIED reference (baseline/_ref, PyTorch CPU, all host threads) on the 6-channel batch it was generated from."""
+    import argparse as ap
+    try:
+        import piml_b200 as P
+        from piml_b200 import train_rollout as TRO
+        from tests.golden_args import base_args
+        from tests.test_gpu_training import _batch_from_golden, mirror
+        from tests.util import golden, group
+        g = group(golden("training_rollout"), "ucy_bm")
+        kind, dsn = str(g["in/model"]), str(g["in/dataset_name"])
+        x = g["in/args"]
+        args = base_args(model=kind, dataset_name=dsn, reg_weight=float(x[0]), collision_threshold=float(x[1]),
+                         collision_loss_weight=float(x[2]), hard_collision_penalty=float(x[3]),
+                         teacher_weight=float(x[4]), collision_pred_weight=float(x[5]),
+                         collision_focus_weight=float(x[6]), new_collision_loss_flag=int(x[7]), time_decay=float(x[8]),
+                         collision_loss_version=str(g["in/collision_loss_version"]))
+        net = mirror(kind, dsn, None, True)
+        opt = torch.optim.Adam(net.parameters(), lr=4e-6)
+        sim = ap.Namespace(args=args, model=net, collision_count=0, hard_collision_count=0, epoch=0, batch_idx=0)
+        base = _batch_from_golden(g)
+        C0 = base.position.shape[0]
+        rep = (32 + C0 - 1) // C0
+
+        def make_batch():
+            b = type(base)()
+            for k, v in base.__dict__.items():
+                if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == C0 and k not in ("obstacles", "dest_num"):
+                    v = v.repeat(rep, *([1] * (v.dim() - 1)))[:32].clone()
+                elif torch.is_tensor(v):
+                    v = v.clone()
+                setattr(b, k, v)
+            return b
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            res = TRO.test_multiple_rollouts_for_training(sim, make_batch())
+            res[0].backward()
+            opt.step()
+            return res
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        l0, t0, n = P._lib.launch_count(), time.perf_counter(), 10
+        for _ in range(n):
+            res = step()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / n * 1e3
+        b = make_batch()
+        C, T, N = [int(v) for v in b.position.shape[:3]]
+        blk = {"workload": f"rollout-training step {kind}/{dsn}: C={C} channels x T={T} steps x N={N} slots, forward rollout + "
+                           "losses + backward + Adam", "ms_per_step": ms, "agent_steps_per_sec": C * T * N / ms * 1e3,
+               "library_launches_per_step": (P._lib.launch_count() - l0) / n, "loss": float(res[0])}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    if with_reference and _import_reference():
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import _refharness as H
+            DATA, MODEL, MLAPM_MOD, SIM, UTILS = H.import_reference()
+            keep = torch.get_num_threads()
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            rargs = H.default_args(model=kind, dataset_name=dsn, valid_steps=T)
+            data = H.make_time_indexed(rargs, H.load_raw(H.UCY_CLIP))
+            ch = DATA.ChanneledTimeIndexedPedData()
+            with H.quiet():
+                ch.load_from_time_indexed_peddata(data, stride=T, mode='slice')
+            batch = DATA.ChanneledTimeIndexedPedData.slice(ch, slice(200, 200 + C0))
+            torch.manual_seed(666)
+            with H.quiet():
+                rsim = SIM.BaseSimulator(rargs)
+            rsim.collision_count, rsim.hard_collision_count, rsim.epoch, rsim.batch_idx = 0, 0, 0, 0
+            t0 = time.perf_counter()
+            with H.quiet():
+                out = rsim.test_multiple_rollouts_for_training(batch)
+            t1 = time.perf_counter()
+            out[0].backward()
+            t2 = time.perf_counter()
+            torch.set_num_threads(keep)
+            blk["reference_pytorch"] = {"channels": C0, "steps": T, "slots": N, "threads": len(os.sched_getaffinity(0)),
+                                        "forward_s": t1 - t0, "backward_s": t2 - t1,
+                                        "agent_steps_per_sec": C0 * T * N / (t2 - t0),
+                                        "note": "the unmodified reference on the host cores, ONE run of the 6-channel batch "
+                                                "(its C = 32, T = 10 batch takes 19.2 s + 0.48 s in the build container, "
+                                                "SURVEY 8a row a12)"}
+        except Exception as e:
+            blk["reference_pytorch"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return blk
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -963,18 +1056,18 @@ def run_ours(a):
                          "traffic": (None if N != 100000 else MLAPM_SYM_DRAM_BYTES_PER_LAUNCH / world if sym_used
                                      else MLAPM_DRAM_BYTES_PER_LAUNCH * (shard / N)),
                          "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read+write, profiles/"
-                                         "r01d_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
+                                         "r02i_ncu_mlapm_sym_kernel.txt / r01b_ncu_mlapm_pairs2_kernel.txt); "
                                          "algorithmic work is FLOPs",
                          "note": "achieved = 51 algorithmic FLOP per ORDERED pair (SURVEY 8d) x N^2 / kernel time.  "
                                  "The symmetric kernel evaluates the n<->m-symmetric part of the formula once per "
                                  "unordered pair, so it executes fewer FLOP than the algorithmic count and the "
-                                 "fraction can exceed 1; ncu: FMA pipe 67.0 % busy, MUFU 49 %, ALU 33 % "
-                                 "(profiles/r01d_ncu_mlapm_sym_kernel.txt)",
+                                 "fraction can exceed 1; ncu: FMA pipe 66.6 % busy, MUFU 49 %, ALU 32 % "
+                                 "(profiles/r02i_ncu_mlapm_sym_kernel.txt)",
                          "peak_source": "live FFMA-chain probe (piml_pipe_probe), best of 6; FP32 is not in "
                                         "MEASURED_PEAKS.json",
                          "executed": ({"fp32_lane_instructions_per_ordered_pair": 16.3,
                                        "fma_pipe_busy_ncu": 0.670, "mufu_pipe_busy_ncu": 0.488,
-                                       "source": "profiles/r01d_ncu_mlapm_sym_kernel.txt (32 packed FP32 instructions "
+                                       "source": "profiles/r02i_ncu_mlapm_sym_kernel.txt (32 packed FP32 instructions "
                                                  "per 128 ordered pairs + 9 FADD per 256 and warp)"} if sym_used else
                                       {"fp32_lane_instructions_per_ordered_pair": 24.0, "fma_pipe_busy_ncu": 0.718,
                                        "source": "profiles/r01b_ncu_mlapm_pairs2_kernel.txt"}),
@@ -994,6 +1087,8 @@ def run_ours(a):
             line["nn_path"] = nn_sharded
             line["timeline"] = timeline
         line.update(extra)
+        if world == 1:
+            line["training"] = training_block(torch, dev, with_reference=not a.no_cpu)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"], rows = cpu_baseline(N)
             line["parity"] = parity_block(torch, dev, N, model, rows)
