@@ -418,6 +418,7 @@ class NNCrowd(object):
         self.bufs = tuple(self._features(self.p, self.v, self.acc, self.dest, self.obs, self.hist, self.ds,
                                          *NN_FEATURE_ARGS)) + (torch.empty(1, N, 2, device=dev),)
         self.a_next = None
+        self._fused = None
         self.out_h = [torch.empty(N, 2).pin_memory() for _ in range(3)]
 
     def forward(self):
@@ -436,6 +437,15 @@ class NNCrowd(object):
 
     def step(self):
         self.forward(); self.integrate(); self.features()
+
+    def step_fused(self):
+        """The same step as ONE library call (piml_nn_step_f32): features -> forward -> integrate on the state."""
+        if self._fused is None:
+            from piml_b200.rollout import NNStep
+            self._fused = NNStep(self.net.spec, self.packed_tc, self.p, self.v, self.acc, self.dest, self.didx,
+                                 self.hist, self.dnum, self.wp, self.ds, self.obs, DT, *NN_FEATURE_ARGS,
+                                 remove_on_arrival=False)
+        self._fused.step()
 
     def e2e_step(self):
         """Host state in (pinned), one step, new p / v / a out: what a host-side simulation loop pays per step."""

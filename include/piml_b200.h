@@ -430,6 +430,37 @@ typedef struct {
 /* Enqueues the whole loop (3-4 launches per step, no host synchronisation) on `stream`. */
 PIML_API int piml_rollout_f32(const piml_rollout_args *args, void *stream);
 
+/* ---- one NN-augmented rollout step, fused: src/models/simulators.py:595-652 ----------------------------------------- */
+
+/* The loop body of get_multiple_rollouts re-ordered around the state: features of the current state
+ * (get_relative_features without a heading argument, data.py:466-512, incl. the in-place NaN -> 0 of v and a) ->
+ * a_next = model(features) (model.py:1185-1221) -> record / Euler / arrival / entry (simulators.py:596-639), as ONE call:
+ * cell-list features in compact form -> tensor cores -> slot sums + destination term + state update (nn_step.cu).
+ * Bit-identical to piml_state_features_f32 -> piml_pinnsf_forward_tc_f32 -> piml_integrate_step_f32 on the same state.
+ * For the networks piml_nn_step_supported() accepts (per-slot decoders with hidden widths 32 / 64 / 128: pinnsf_bm,
+ * pinnsf_bottleneck) and finite distance thresholds; otherwise PIML_ERR_UNSUPPORTED / PIML_ERR_INVALID and the caller
+ * uses the three calls. */
+typedef struct {
+    const piml_net_desc *desc;      /* network */
+    const float *packed_tc;         /* piml_pinnsf_pack_tc_f32 vector */
+    int has_obs; float tau;
+    int S, N, M, D; float dt; int remove_on_arrival;
+    int kp; float cos_p, thr_p; int ko; float cos_o, thr_o;            /* topk / cos(sight angle) / distance threshold */
+    const float *obstacles; int obs_per_scene;                          /* (M,2) or (S,M,2) */
+    const int64_t *dest_num;                                            /* (S,N) */
+    const float *waypoints;                                             /* (S,D,N,2) */
+    const float *desired_speed;                                         /* (S,N) */
+    float *p, *v, *a, *dest; int64_t *dest_idx; float *hist_v;          /* (S,N,..) state, updated in place */
+    const int64_t *entry;                                               /* (S,N) or NULL: teacher-forced entry ... */
+    const float *p_gt, *v_gt, *a_gt, *dest_gt; const int64_t *dest_idx_gt;   /* ... from the data at t+1, (S,N,..) */
+    float *rec_p, *rec_v, *rec_a, *rec_mask;                            /* (S,N,2) x3, (S,N): the state at t, or NULL */
+    float *a_next;                                                      /* (S,N,2) out: the model output, or NULL */
+    float *ped_f, *obs_f, *self_f, *dest_f;   /* optional dense features of the state at t (all or none): (S,N,kp,6), ... */
+} piml_nn_step_args;
+
+PIML_API int piml_nn_step_supported(const piml_net_desc *desc);         /* 1 if piml_nn_step_f32 can run this network */
+PIML_API int piml_nn_step_f32(const piml_nn_step_args *args, void *stream);
+
 /* Backward of the differentiable rollout's state update (simulators.py:741-769: v' = v + a dt, p' = p + v dt,
  * a' = model output; agents overwritten by teacher-forced entry get no gradient).  n = S*N agents.
  * entry (n) int64 or NULL; g_p2,g_v2,g_a2 (n,2) = gradients of the updated state -> g_p,g_v,g_a,g_a_next (n,2). */

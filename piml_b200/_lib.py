@@ -41,6 +41,18 @@ class RolloutArgs(C.Structure):
                 ("rec_p", vp), ("rec_v", vp), ("rec_a", vp), ("rec_mask", vp), ("sfm", vp)]
 
 
+class NnStepArgs(C.Structure):
+    """piml_nn_step_args"""
+    _fields_ = [("desc", C.POINTER(NetDesc)), ("packed_tc", vp), ("has_obs", i32), ("tau", f32),
+                ("S", i32), ("N", i32), ("M", i32), ("D", i32), ("dt", f32), ("remove_on_arrival", i32),
+                ("kp", i32), ("cos_p", f32), ("thr_p", f32), ("ko", i32), ("cos_o", f32), ("thr_o", f32),
+                ("obstacles", vp), ("obs_per_scene", i32), ("dest_num", vp), ("waypoints", vp), ("desired_speed", vp),
+                ("p", vp), ("v", vp), ("a", vp), ("dest", vp), ("dest_idx", vp), ("hist_v", vp),
+                ("entry", vp), ("p_gt", vp), ("v_gt", vp), ("a_gt", vp), ("dest_gt", vp), ("dest_idx_gt", vp),
+                ("rec_p", vp), ("rec_v", vp), ("rec_a", vp), ("rec_mask", vp), ("a_next", vp),
+                ("ped_f", vp), ("obs_f", vp), ("self_f", vp), ("dest_f", vp)]
+
+
 class SfmParams(C.Structure):
     """piml_sfm_params"""
     _fields_ = [("A_ped", f32), ("B_ped", f32), ("A_obs", f32), ("B_obs", f32), ("eps", f32), ("tau", f32)]
@@ -115,6 +127,8 @@ SIGNATURES = {
     "piml_relative_features_backward_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_collision_detection_f32": (i32, [vp, vp, i32, i32, i32, f32, i32, vp, vp, vp]),
     "piml_rollout_f32": (i32, [C.POINTER(RolloutArgs), vp]),
+    "piml_nn_step_supported": (i32, [C.POINTER(NetDesc)]),
+    "piml_nn_step_f32": (i32, [C.POINTER(NnStepArgs), vp]),
     "piml_integrate_step_backward_f32": (i32, [vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_integrate_step_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp,
                                       vp, vp, vp, vp, vp, vp, vp]),

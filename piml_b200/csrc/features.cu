@@ -660,10 +660,11 @@ extern "C" int piml_set_feature_algorithm(int algo) {
     return PIML_OK;
 }
 
-namespace piml { void tc_scratch_free(); }                        // mlp_tc.cu
+namespace piml { void tc_scratch_free(); void nn_scratch_free(); }   // mlp_tc.cu, nn_step.cu
 
 extern "C" int piml_free_workspace(void) {
     cell_scratch_free();
     piml::tc_scratch_free();
+    piml::nn_scratch_free();
     return PIML_OK;
 }

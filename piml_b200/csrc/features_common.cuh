@@ -89,8 +89,17 @@ static inline float prefilter_sq(float thr) {
     return static_cast<float>(t * t * (1.0 + 1e-6)) + 1e-30f;
 }
 
+// Compact slot rows of the fused NN step (nn_step.cu): only the non-empty slots of each branch, 6 floats per row in
+// arrival order (a row's message does not depend on its place), and for every (agent, slot) the row it went to
+// (-1: an empty, zero-padded slot, whose message is the network's f(0)).  counts[2] must be zero on entry.
+struct CompactOut {
+    float *rows_ped, *rows_obs;    // [counts[0]][6], [counts[1]][6]
+    int *map_ped, *map_obs;        // (B*N, kp), (B*N, ko)
+    int *counts;                   // nullptr: no compact output
+};
+
 // features_cells.cu
-int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st);
+int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, const CompactOut *co = nullptr);
 void cell_scratch_free();
 
 }  // namespace piml

@@ -28,4 +28,34 @@ __device__ __forceinline__ void integrate_update(AgentState &s, float2 a_next, f
     s.hv = vn;                                                                 // :624-626
 }
 
+// One thread's whole step of integrate_kernel (integrate.cu) / nn_finish_integrate_kernel (nn_step.cu): record the
+// state at t, update, teacher-forced entry from the data at t + 1, history velocity.  simulators.py:596-639.
+struct IntArgs {
+    float2 *p, *v, *a; const float2 *a_next; float2 *dest; int64_t *dest_idx; const int64_t *dest_num;
+    const float2 *waypoints; int S, D, N; float dt; int remove_on_arrival;
+    const int64_t *entry; const float2 *p_gt, *v_gt, *a_gt, *dest_gt; const int64_t *dest_idx_gt;
+    float2 *hist_v; float2 *rec_p, *rec_v, *rec_a; float *rec_mask;
+};
+
+__device__ __forceinline__ void integrate_agent(const IntArgs &g, int64_t i, float2 a_next) {
+    const int s = static_cast<int>(i / g.N), n = static_cast<int>(i % g.N);
+    const float2 p = g.p[i], v = g.v[i], a = g.a[i];
+    // p_res[t] = p_cur ... mask_p_new[t][~isnan(p.x)] = 1          (simulators.py:596-600)
+    if (g.rec_p) g.rec_p[i] = p;
+    if (g.rec_v) g.rec_v[i] = v;
+    if (g.rec_a) g.rec_a[i] = a;
+    if (g.rec_mask && !(p.x != p.x)) g.rec_mask[i] = 1.0f;
+    AgentState st{p, v, a, g.dest[i], g.dest_idx[i], make_float2(0.f, 0.f)};
+    integrate_update(st, a_next, g.dt, g.remove_on_arrival, g.dest_num[i],
+                     g.waypoints + static_cast<int64_t>(s) * g.D * g.N + n, g.N);
+    float2 pn = st.p, vn = st.v, an = st.a, d = st.dest, hv = st.hv;
+    int64_t di = st.di;
+    if (g.entry && g.entry[i] == 1) {                                          // :629-639
+        pn = g.p_gt[i]; vn = g.v_gt[i]; an = g.a_gt[i]; d = g.dest_gt[i]; di = g.dest_idx_gt[i];
+        hv = vn;
+    }
+    g.p[i] = pn; g.v[i] = vn; g.a[i] = an; g.dest[i] = d; g.dest_idx[i] = di;
+    if (g.hist_v) g.hist_v[i] = hv;
+}
+
 }  // namespace piml

@@ -971,6 +971,15 @@ extern "C" int64_t piml_pinnsf_packed_tc_floats(const piml_net_desc *desc) {
     return P.total;
 }
 
+namespace piml {
+int tc16_plan_for(const piml_net_desc *d, Tc16Plan *P16) {
+    TcPlan P;
+    TcPackTab T;
+    if (d->kind != 0 || d->proc_mode != 0 || tc_build_plan(d, &P, &T)) return 1;
+    return tc16_build_plan(d, P.total, P16);
+}
+}  // namespace piml
+
 static void tc16_sources(const TcPlan &P, const TcPackTab &T, Tc16Src *S) {
     for (int br = 0; br < 2; ++br) {
         for (int l = 0; l < P.nl; ++l) {
@@ -1081,8 +1090,8 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
     if (const char *e = getenv("PIML_TC_DEBUG")) a.dbg = atoi(e);
     if (getenv("PIML_TC_PROF")) {
         static long long *prof_buf = nullptr;
-        if (!prof_buf) { PIML_CUDA(cudaMalloc(&prof_buf, 16 * sizeof(long long))); }
-        PIML_CUDA(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), st));
+        if (!prof_buf) { PIML_CUDA(cudaMalloc(&prof_buf, 512 * sizeof(long long))); }
+        PIML_CUDA(cudaMemsetAsync(prof_buf, 0, 512 * sizeof(long long), st));
         a.prof = prof_buf;
     }
     const size_t smem = static_cast<size_t>(TC_STAGES) * TC_STAGE_BYTES +
@@ -1129,13 +1138,28 @@ extern "C" int piml_pinnsf_forward_tc_f32(const piml_net_desc *desc, const float
         rc = tc16_launch(P16, b, tiles, st);
         if (rc) return rc;
         if (a.prof) {
-            long long h[16];
+            long long h[512];
             PIML_CUDA(cudaMemcpyAsync(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
             PIML_CUDA(cudaStreamSynchronize(st));
+            {
+                long long kmin = 1LL << 62, kmax = 0, lmax = 0; int imax = 0;
+                for (int c = 0; c < 148; ++c) {
+                    const long long k = h[16 + 3 * c];
+                    if (k == 0) continue;
+                    if (k < kmin) kmin = k;
+                    if (k > kmax) { kmax = k; imax = c; }
+                    if (h[17 + 3 * c] > lmax) lmax = h[17 + 3 * c];
+                }
+                fprintf(stderr, "[tc16 prof] kernel cycles per CTA: min %lld max %lld (CTA %d, %lld tiles); CTA 0: %lld, slot-0 loop %lld, "
+                        "%lld tiles; CTA 147: %lld, %lld tiles; longest slot-0 loop %lld\n", kmin, kmax, imax, h[18 + 3 * imax],
+                        h[16], h[17], h[18], h[16 + 3 * 147], h[18 + 3 * 147], lmax);
+            }
             const long long t = h[15] > 0 ? h[15] : 1;
             fprintf(stderr, "[tc16 prof, CTA 0, %lld tiles] cycles/tile: mma wait A %lld, wait W %lld, issue %lld | epilogue (slot 0, "
-                    "warp 2): wait D %lld, ld %lld, pass1 %lld, max exchange %lld, pass2 %lld, st+signal %lld\n", t, h[0] / t,
-                    h[1] / t, h[2] / t, h[3] * 2 / t, h[4] * 2 / t, h[5] * 2 / t, h[6] * 2 / t, h[7] * 2 / t, h[8] * 2 / t);
+                    "warp 2): wait D %lld, ld %lld, pass1 %lld, max exchange %lld, pass2 %lld, st+signal %lld, tile start %lld, "
+                    "predictor + tile end %lld, whole tile %lld\n", t, h[0] / t,
+                    h[1] / t, h[2] / t, h[3] * 2 / t, h[4] * 2 / t, h[5] * 2 / t, h[6] * 2 / t, h[7] * 2 / t, h[8] * 2 / t,
+                    h[10] * 2 / t, h[9] * 2 / t, h[11] * 2 / t);
             a.prof = nullptr;
         }
     } else {

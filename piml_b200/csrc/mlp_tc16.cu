@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     uint64_t *bars = reinterpret_cast<uint64_t *>(small + 2048);
     uint64_t *w_ready = bars, *a_ready = bars + T16_MAXL, *d_ready = a_ready + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 2);
+    long long *sprof = reinterpret_cast<long long *>(d_ready + 4);     // [16] cycle counters (PIML_TC_PROF), flushed at the end
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 16) sprof[tid] = 0;
+    const long long k_start = clock64();
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
@@ -73,12 +76,18 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     const int64_t nP = a.compact ? (cnt_ped + 127) / 128 : a.n_ped_tiles;
     const int64_t nO = a.compact ? (cnt_obs + 127) / 128 : a.n_obs_tiles;
     const int G = gridDim.x;
+    // CTAs per branch (one branch per CTA: its weights stay resident).  The kernel ends with its slowest CTA, so the
+    // split minimises the larger per-CTA tile count: start from the proportional share and give the obstacle branch
+    // CTAs until it is no longer the straggler (rounding to nearest left 43 obstacle tiles on ONE CTA next to 32 per
+    // pedestrian CTA at N = 100k: the kernel took 539k cycles where the pedestrian CTAs needed 390k).
     int gO = 0;
     if (nO > 0) {
-        gO = static_cast<int>((static_cast<int64_t>(G) * nO + (nP + nO) / 2) / (nP + nO));
-        gO = gO < 1 ? 1 : gO;
-        if (nP > 0 && gO > G - 1) gO = G - 1;
         if (nP == 0) gO = G;
+        else {
+            gO = static_cast<int>((static_cast<int64_t>(G) * nO) / (nP + nO));
+            gO = gO < 1 ? 1 : (gO > G - 1 ? G - 1 : gO);
+            while (gO < G - 1 && (nO + gO - 1) / gO > (nP + (G - gO) - 1) / (G - gO)) ++gO;
+        }
     }
     const int gP = G - gO;
     const int br = static_cast<int>(blockIdx.x) < gP ? 0 : 1;
@@ -153,9 +162,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     tc::commit(&d_ready[s]);                       // accumulator of this (slot, layer) complete
                 }
                 __syncwarp();
-                if (a.prof && blockIdx.x == 0 && lane == 0) {
-                    a.prof[0] += p1 - p0; a.prof[1] += p2 - p1; a.prof[2] += clock64() - p2;
-                    if (li == 0) a.prof[15] += 1;
+                if (a.prof && lane == 0) {
+                    sprof[0] += p1 - p0; sprof[1] += p2 - p1; sprof[2] += clock64() - p2;
+                    if (li == 0) sprof[15] += 1;
                 }
                 if (++layer[s] == P.nl) { layer[s] = 0; ++done[s]; }
             }
@@ -187,7 +196,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             int64_t src;
             if (a.compact) {
                 const int nrows = static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128));
-                if (m < nrows && tloc * 128 + m < cnt - 1) rf.crow = list[tloc * 128 + m];
+                if (m < nrows && tloc * 128 + m < cnt - 1)                // no list (fused NN step): rows are stored compactly
+                    rf.crow = list ? list[tloc * 128 + m] : static_cast<int>(tloc * 128 + m);
                 rf.live = rf.crow >= 0;
                 src = rf.crow;
             } else {
@@ -212,6 +222,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             const int64_t row0 = agent0 * k;
             const int64_t crow = nxt.crow;
             float inv_s;
+            const long long t0 = clock64();
+            long long tl2 = t0;
             {   // the 6-d features of this row as the first A operand: K padded to 16 with zeros, row-scaled
                 float mx = 0.f;
 #pragma unroll
@@ -232,6 +244,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 tc::mbar_arrive(&a_ready[slot]);
             }
             nxt = load_row(j + 2);                                 // in flight while this tile runs
+            if (a.prof && tid == 64) sprof[10] += clock64() - t0;
             float m0 = 0.f, m1 = 0.f;
             for (int li = 0; li < P.nl; ++li) {
                 const Tc16Layer &Ly = P.L[li];
@@ -243,8 +256,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 dph ^= 1u;
                 tc::fence_after_sync();
                 const long long q1 = clock64();
-                const bool prof = a.prof && blockIdx.x == 0 && tid == 64;
-                if (prof) a.prof[3] += q1 - q0;
+                const bool prof = a.prof && tid == 64;
+                if (prof) sprof[3] += q1 - q0;
                 if (a.dbg & 1) {                                   // timing experiment: no epilogue work at all
                     if (!last) { tc::fence_before_sync(); tc::mbar_arrive(&a_ready[slot]); }
                     continue;
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     tc::wait_ld();
                 }
                 const long long q2 = clock64();
-                if (prof) a.prof[4] += q2 - q1;
+                if (prof) sprof[4] += q2 - q1;
                 float *v = reinterpret_cast<float *>(r);
                 float mx = 0.f;
                 const float2 sc2 = make_float2(sc, sc);
@@ -286,6 +299,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     }
                 }
                 if (last) {                                        // predictor Linear(dw, 2) on the CUDA cores
+                    tl2 = q2;
                     const float *w0 = biasb + P.predw_off + half * hc, *w1 = w0 + P.dw;
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -299,13 +313,13 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     break;
                 }
                 const long long q3 = clock64();
-                if (prof) a.prof[5] += q3 - q2;
+                if (prof) sprof[5] += q3 - q2;
                 float *mxb = smax + (li & 1) * 256;                // double buffered: one barrier per layer is enough
                 mxb[half * 128 + m] = mx;                          // row maximum over both column halves
                 slot_barrier(slot);
                 mx = fmaxf(mx, mxb[(half ^ 1) * 128 + m]);
                 const long long q4c = clock64();
-                if (prof) a.prof[6] += q4c - q3;
+                if (prof) sprof[6] += q4c - q3;
                 float s;
                 row_scale(mx, s, inv_s);
                 // Split relative to the ROW: after scaling, |x| < 2^15; hi = x rounded to a multiple of 16 (the fp16
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 tc::wait_st();
                 tc::fence_before_sync();
                 tc::mbar_arrive(&a_ready[slot]);                   // the next layer of this slot may start
-                if (prof) { a.prof[7] += q5 - q4c; a.prof[8] += clock64() - q5; }
+                if (prof) { sprof[7] += q5 - q4c; sprof[8] += clock64() - q5; }
             }
             // combine the two column halves of the predictor
             sm2[(half * 128 + m) * 2] = m0;
@@ -362,11 +376,18 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 }
                 slot_barrier(slot);                                // sm2 is free for this slot's next tile
             }
+            if (a.prof && tid == 64) { const long long te = clock64(); sprof[9] += te - tl2; sprof[11] += te - t0; }
         }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
+    if (a.prof && blockIdx.x == 0 && tid < 16) a.prof[tid] = sprof[tid];
+    if (a.prof && tid == 64 && blockIdx.x < 160) {                 // per CTA: whole kernel, slot-0 tile loop, tiles
+        a.prof[16 + 3 * blockIdx.x] = clock64() - k_start;
+        a.prof[17 + 3 * blockIdx.x] = sprof[11];
+        a.prof[18 + 3 * blockIdx.x] = my_tiles;
+    }
 }
 
 // ---- plan ------------------------------------------------------------------------------------------------------------
@@ -397,13 +418,13 @@ int tc16_build_plan(const piml_net_desc *d, int64_t base_floats, Tc16Plan *P) {
     P->bias_floats = (boff + 3) & ~3;
     P->branch_floats = P->w_bytes / 4 + P->bias_floats;
     P->base = (base_floats + 31) & ~static_cast<int64_t>(31);      // 128-byte aligned behind the tf32 image
-    const size_t smem = static_cast<size_t>(P->w_bytes) + sizeof(float) * (P->bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16;
+    const size_t smem = static_cast<size_t>(P->w_bytes) + sizeof(float) * (P->bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16 + 128;
     if (smem > 220 * 1024) return 1;                               // the branch must stay resident in shared memory
     return 0;
 }
 
 size_t tc16_smem_bytes(const Tc16Plan &P) {
-    return static_cast<size_t>(P.w_bytes) + sizeof(float) * (P.bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16;
+    return static_cast<size_t>(P.w_bytes) + sizeof(float) * (P.bias_floats + 2048) + 8 * (T16_MAXL + 4) + 16 + 128;
 }
 
 // ---- packing -----------------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ struct Tc16Args {
     int64_t R; int kp, ko, ag_ped, ag_obs; int64_t n_ped_tiles, n_obs_tiles;
     float *sums; float *ped_msgs; float *obs_msgs;
     int compact, has_obs;
-    const int *list_ped, *list_obs; const int *counts;
+    const int *list_ped, *list_obs; const int *counts;   // lists NULL: ped / obs hold the compact rows themselves (nn_step.cu)
     float *cmsg_ped, *cmsg_obs; float *f0;
     long long *prof;                           // optional cycle counters of CTA 0 (PIML_TC_PROF, bring-up only)
     int dbg;                                   // timing experiments only (PIML_TC_DEBUG): 1 = no epilogue work, 4 = no TMEM ld/st
@@ -40,5 +40,6 @@ int tc16_build_plan(const piml_net_desc *d, int64_t base_floats, Tc16Plan *P);  
 size_t tc16_smem_bytes(const Tc16Plan &P);
 int tc16_pack(const Tc16Plan &P, const Tc16Src &S, const float *params_torch, float *packed, cudaStream_t st);
 int tc16_launch(const Tc16Plan &P, const Tc16Args &a, int64_t tiles_bound, cudaStream_t st);
+int tc16_plan_for(const piml_net_desc *d, Tc16Plan *P);    // mlp_tc.cu: plan inside a piml_pinnsf_pack_tc_f32 vector; 0 = ok
 
 }  // namespace piml

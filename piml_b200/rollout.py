@@ -60,6 +60,63 @@ def state_features(p, v, a, dest, obstacles, hist_v, desired_speed, topk_ped, si
     return ped_f, obs_f, self_f
 
 
+class NNStep(object):
+    """One NN-augmented rollout step as ONE library call (piml_nn_step_f32, csrc/nn_step.cu): features of the current
+    state -> a_next = model(features) -> Euler / arrival / waypoints / entry, i.e. simulators.py:642-652, :602, :596-639
+    in the order a loop over the STATE runs them.  Bit-identical to `state_features` -> `models.pinnsf_forward` ->
+    `integrate_step`, in 7 launches instead of 12 and without the dense feature tensors.
+
+    The state tensors p, v, a, dest, hist_v (S,N,2) and dest_idx (S,N) are bound once and updated in place by every
+    `step()`; the other arguments are fixed for the object's lifetime.  Raises if the network is not one
+    `piml_nn_step_supported` accepts (use the three calls then)."""
+
+    def __init__(self, spec, packed_tc, p, v, a, dest, dest_idx, hist_v, dest_num, waypoints, desired_speed, obstacles,
+                 dt, topk_ped, sight_angle_ped, dist_threshold_ped, topk_obs, sight_angle_obs, dist_threshold_obs,
+                 remove_on_arrival=True, a_next=None, dense=None):
+        dev = L.require_cuda(p, v, a, dest, dest_idx, hist_v, dest_num, waypoints, desired_speed, obstacles, packed_tc)
+        for t in (p, v, a, dest, dest_idx, hist_v):
+            if not t.is_contiguous() or t.dim() != (2 if t is dest_idx else 3):
+                raise ValueError("NNStep updates its state tensors in place; they must be contiguous (S,N,..) tensors")
+        S, N = p.shape[0], p.shape[1]
+        Mo = obstacles.shape[-2] if obstacles.numel() else 0
+        self._desc = spec.desc()
+        if not L.load().piml_nn_step_supported(L.C.byref(self._desc)):
+            raise NotImplementedError("piml_nn_step_f32 runs per-slot-decoder networks with hidden widths 32/64/128")
+        if spec.has_obs and not Mo:
+            raise ValueError("the network has an obstacle branch but the scene has no obstacles")
+        dn = dest_num if dest_num.numel() == S * N else dest_num.expand(S, N)
+        # everything the argument block points at stays referenced by the object
+        self._keep = [packed_tc, p, v, a, dest, dest_idx, hist_v, dn.contiguous(), L.f32c(waypoints),
+                      L.f32c(desired_speed), L.f32c(obstacles), a_next, dense]
+        self.device = dev
+        r = L.NnStepArgs()
+        r.desc, r.packed_tc = L.C.pointer(self._desc), L.ptr(packed_tc)
+        r.has_obs, r.tau = (1 if (spec.has_obs and Mo) else 0), spec.tau
+        r.S, r.N, r.M, r.D, r.dt = S, N, Mo, self._keep[8].shape[-3], float(dt)
+        r.remove_on_arrival = 1 if remove_on_arrival else 0
+        r.kp, r.cos_p, r.thr_p = topk_ped, cos_threshold(sight_angle_ped), float(dist_threshold_ped)
+        r.ko, r.cos_o, r.thr_o = topk_obs, cos_threshold(sight_angle_obs), float(dist_threshold_obs)
+        r.obstacles = L.ptr(self._keep[10]) if Mo else None
+        r.obs_per_scene = 1 if (obstacles.dim() == 3 and Mo) else 0
+        r.dest_num, r.waypoints, r.desired_speed = L.ptr(self._keep[7]), L.ptr(self._keep[8]), L.ptr(self._keep[9])
+        r.p, r.v, r.a, r.dest, r.dest_idx, r.hist_v = [L.ptr(x) for x in (p, v, a, dest, dest_idx, hist_v)]
+        r.a_next = L.ptr(a_next)
+        if dense is not None:                  # (ped_f, obs_f, self_f, dest_f) of the state the step starts from
+            r.ped_f, r.obs_f, r.self_f, r.dest_f = [L.ptr(x) for x in dense]
+        self._args = r
+        self._fn = L.load().piml_nn_step_f32
+
+    def step(self, entry=None, gt=None, rec=None):
+        """gt = (p, v, a, dest, dest_idx) of the data at t+1 when `entry` (S,N) int64 is given; rec = (p, v, a, mask)
+        buffers that receive the state at t."""
+        r = self._args
+        r.entry = L.ptr(entry)
+        if entry is not None:
+            r.p_gt, r.v_gt, r.a_gt, r.dest_gt, r.dest_idx_gt = [L.ptr(x) for x in gt]
+        r.rec_p, r.rec_v, r.rec_a, r.rec_mask = [L.ptr(x) for x in rec] if rec is not None else [None] * 4
+        L.check(self._fn(L.C.byref(r), L.stream_ptr(self.device)), "piml_nn_step_f32")
+
+
 class RolloutResult(object):
     """What the reference returns as `RawData(p_res, v_res, a_res, destination, destination, obstacles, mask_p_new)`
     (simulators.py:655-656)."""

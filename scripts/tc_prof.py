@@ -25,3 +25,13 @@ for _ in range(3):
 torch.cuda.synchronize()
 nz_p = int((feats[0][0].abs().sum(-1) > 0).sum()); nz_o = int((feats[1][0].abs().sum(-1) > 0).sum())
 print(f"non-zero slot rows: ped {nz_p} of {N * 6}, obs {nz_o} of {N * 10}")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+os.environ.pop("PIML_TC_PROF", None)
+for _ in range(2):
+    M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False, packed_tc=ptc)
+e0.record()
+for _ in range(10):
+    M.pinnsf_forward(net.spec, packed, feats[0][0], feats[1][0], slf, need_msgs=False, packed_tc=ptc)
+e1.record()
+torch.cuda.synchronize()
+print(f"forward (compact + tc16 + finish), no profiling: {e0.elapsed_time(e1) / 10:.4f} ms")
