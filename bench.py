@@ -454,7 +454,7 @@ class NNCrowd(object):
         self.acc[0].copy_(h["a"], non_blocking=True); self.dest[0].copy_(h["dest"], non_blocking=True)
         self.ds.copy_(h["ds"], non_blocking=True)
         self.hist.copy_(self.v)
-        self.features(); self.forward(); self.integrate()
+        self.step_fused()
         self.out_h[0].copy_(self.p[0]); self.out_h[1].copy_(self.v[0]); self.out_h[2].copy_(self.acc[0])
 
     @property
@@ -511,25 +511,39 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
     import numpy as np
     crowd = NNCrowd(torch, dev, N, obs_h)
     flush = torch.empty(FLUSH_MB << 20, dtype=torch.uint8, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # ---- the three-call route (state_features / pinnsf_forward / integrate_step): per-stage times, and the forward
+    # stage's time for the tensor roofline (the fused step launches the same forward kernel inside one C call)
     for _ in range(max(warmup, 3)):
         flush.zero_(); crowd.step()
     torch.cuda.synchronize()
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = [[ev() for _ in range(4)] for _ in range(steps)]
-    launches0 = L.launch_count()
-    e0, e1 = ev(), ev()
-    e0.record()
+    u0, u1 = ev(), ev()
+    u0.record()
     for s_ in range(steps):
         flush.zero_()
         marks[s_][0].record(); crowd.forward()
         marks[s_][1].record(); crowd.integrate()
         marks[s_][2].record(); crowd.features()
         marks[s_][3].record()
+    u1.record()
+    torch.cuda.synchronize()
+    ms3 = u0.elapsed_time(u1) / steps
+    st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(3)]
+    # ---- the timed path: the fused step, ONE library call per step (piml_nn_step_f32)
+    for _ in range(max(warmup, 3)):
+        flush.zero_(); crowd.step_fused()
+    torch.cuda.synchronize()
+    launches0 = L.launch_count()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for s_ in range(steps):
+        flush.zero_()
+        crowd.step_fused()
     e1.record()
     torch.cuda.synchronize()
     launches = L.launch_count() - launches0
     ms = e0.elapsed_time(e1) / steps
-    st = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / steps for i in range(3)]
     assert torch.isfinite(crowd.p[0]).sum() > 0
     # ---- end to end with host buffers
     for _ in range(2):
@@ -551,14 +565,19 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
             peak_gbs, bf16, peak_src = float(pk["hbm_gbs"]), float(pk["bf16_tflops"]), "MEASURED_PEAKS.json"
     except Exception:
         pass
-    gbs = NN_BYTES_PER_AGENT * N / (ms * 1e-3) / 1e9
+    gbs = NN_BYTES_PER_AGENT_FUSED * N / (ms * 1e-3) / 1e9
     fwd_tf = NN_FLOP_PER_AGENT * N / (st[0] * 1e-3) / 1e12
     block = {
         "metric": METRIC, "value": N / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "config": nn_config(N, int(obs_h.shape[0])), "dtype": "f32 (network contractions as 3-term split products on "
                                                                "the tensor cores, fp32 accumulate)",
-        "stage_ms": {"forward": st[0], "integrate": st[1], "features": st[2]},
-        "roofline": {"bound": "tensor", "kernel": "pinnsf_tc_kernel (+ compaction, finish)",
+        "api": "piml_b200.rollout.NNStep.step -> piml_nn_step_f32: cell-list features (compact slot rows) -> tcgen05 "
+               "forward -> slot sums + destination term + Euler, 7 launches",
+        "three_call_route": {"ms_per_step": ms3, "stage_ms": {"forward": st[0], "integrate": st[1], "features": st[2]},
+                             "note": "state_features -> pinnsf_forward -> integrate_step (12 stream operations); the "
+                                     "fused step is bit-identical to it (parity.fused_step_bit_identical)"},
+        "roofline": {"bound": "tensor", "kernel": "pinnsf_tc16_kernel (+ compaction, finish: the forward stage of the "
+                                                  "three-call route, same kernel on the same rows)",
                      "achieved": fwd_tf, "peak": bf16 / 2.0, "unit": "TFLOP/s", "frac": fwd_tf / (bf16 / 2.0),
                      "peak_source": peak_src + " bf16_tflops / 2 (dense tf32 rate)",
                      "note": "achieved = 1.52 MFLOP per agent (SURVEY 8d, all 16 slots) / forward stage time; the "
@@ -567,12 +586,12 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
                      "traffic": None,
                      "hbm": {"bytes_per_agent_step": NN_BYTES_PER_AGENT, "bytes_per_agent_step_fused": NN_BYTES_PER_AGENT_FUSED,
                              "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
-                             "note": "whole step against the HBM copy peak: the stages are tensor / latency bound, "
-                                     "not HBM bound, at this size"}},
+                             "note": "whole fused step, its algorithmic bytes (state in / out, bytes_per_agent_step_fused) "
+                                     "against the HBM copy peak: the step is tensor / instruction bound, not HBM bound, "
+                                     "at this size; bytes_per_agent_step is what the unfused stages move"}},
         "e2e": {"value": N / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
-                "api": "pinned host p, v, a, dest, desired speed -> state_features, pinnsf_forward, integrate_step -> "
-                       "host p, v, a"},
+                "api": "pinned host p, v, a, dest, desired speed -> NNStep.step (piml_nn_step_f32) -> host p, v, a"},
         "gpu_launches": launches,
     }
     if with_cpu:
@@ -593,7 +612,15 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
                            "max_rel_acceleration_strict": float((err / np.maximum(np.linalg.norm(acc_ref, axis=-1),
                                                                                   1e-6)).max()),
                            "gate": "features bit-exact; ||da|| <= 1e-5 max(||a||, ||dest term||) per agent"}
-        block["parity"]["pass"] = bool(block["parity"]["features_bit_exact"]
+        # the fused step against the three calls on fresh crowds: every state tensor bit for bit after 2 steps
+        c3, cf = NNCrowd(torch, dev, N, obs_h), NNCrowd(torch, dev, N, obs_h)
+        for _ in range(2):
+            c3.features(); c3.forward(); c3.integrate()
+            cf.step_fused()
+        same = all(np.array_equal(x.cpu().numpy(), y.cpu().numpy(), equal_nan=True)
+                   for x, y in ((c3.p, cf.p), (c3.v, cf.v), (c3.acc, cf.acc), (c3.dest, cf.dest), (c3.hist, cf.hist)))
+        block["parity"]["fused_step_bit_identical"] = bool(same)
+        block["parity"]["pass"] = bool(block["parity"]["features_bit_exact"] and same
                                        and block["parity"]["max_rel_acceleration_operand_scaled"] < 1e-5)
     return block
 

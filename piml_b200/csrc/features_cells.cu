@@ -352,7 +352,6 @@ constexpr int SORT_G = 4;
 // and parks the survivors (relative position, index) in a per-lane shared-memory list; one within GATE_MARGIN = 1e-4 of
 // the threshold (or with a NaN / degenerate c') is flagged.  Pass 2 drains the list densely: exact distance (the sort
 // key) for all, the exact gate only for the flagged ones.  The decisions are those of gated_distance, bit for bit.
-constexpr int PEND_CAP = 8;
 constexpr float GATE_MARGIN = 1e-4f;
 constexpr int BND_WORDS = 27;                  // per group: first record, end, packed cell of the 9 buckets
 
@@ -362,77 +361,94 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
-// pending survivors of pass 1, per lane, in shared memory: [field][entry][thread] (conflict-free)
+// pending survivors of pass 1, pooled per GROUP in shared memory so that pass 2 is balanced over the group's lanes:
+// [field][group][entry], group stride POOL_STRIDE words (bank = 4 * group + lane for the pass-2 reads: conflict-free)
+constexpr int POOL_CAP = 32, POOL_STRIDE = POOL_CAP + 4, POOL_GROUPS = CELL_THREADS / SORT_G;
 struct Pending {
     float *rx, *ry; uint32_t *id;              // id: candidate index | (gate undecided << 31)
     __device__ __forceinline__ Pending(float *base) {
-        rx = base + threadIdx.x; ry = rx + PEND_CAP * CELL_THREADS;
-        id = reinterpret_cast<uint32_t *>(ry + PEND_CAP * CELL_THREADS);
+        rx = base + (threadIdx.x / SORT_G) * POOL_STRIDE; ry = rx + POOL_GROUPS * POOL_STRIDE;
+        id = reinterpret_cast<uint32_t *>(ry + POOL_GROUPS * POOL_STRIDE);
     }
 };
 
 // One flattened loop over the lane's share (every G-th record) of the 9 buckets, so that the lanes of a warp stay
 // converged across bucket boundaries and the code stays small (an unrolled bucket loop with the insertion inlined nine
 // times was 150 KB of SASS: the warps starved on instruction fetch).  The group's lanes share the 18 bucket-bound
-// lookups through shared memory (`bnd`), the next record is loaded while the current one is tested, and ONE drain site
-// runs pass 2 whenever a lane's pending list is full or its records are exhausted.
+// lookups through shared memory (`bnd`), and ONE drain site runs pass 2 -- for the whole warp at once, with the
+// group's survivors dealt evenly to its lanes -- when a group's pool is nearly full or no lane has a record left.
 template <int KMAX, int G>
 __device__ __forceinline__ void scan_cells_split(TopK<KMAX> &best, const HashGrid &g, int64_t gframe, bool present,
                                                  int cx, int cy, int lane, float px, float py, float hx, float hy,
                                                  float cos_thr, float thr, float pre2, int idx_base, const Pending &pd,
                                                  int *bnd) {
+    // bnd[c]: first record of bucket c MINUS the flat position where the bucket starts, bnd[9 + c]: flat end of bucket c,
+    // bnd[18 + c]: its packed cell.  Flat position t = lane, lane + G, ... runs over the concatenation of the 9 ranges.
     const int *st = g.start + gframe * g.H;
     for (int c = lane; c < 9; c += G) {
         const int ccx = cx + (c % 3) - 1, ccy = cy + (c / 3) - 1;
         const uint32_t b = bucket_of(ccx, ccy, g.H);
-        bnd[c] = present ? st[b] : 0;
-        bnd[9 + c] = present ? st[b + 1] : 0;
+        const int2 se = present ? make_int2(st[b], st[b + 1]) : make_int2(0, 0);
+        bnd[c] = se.x;
+        bnd[9 + c] = se.y - se.x;
         bnd[18 + c] = static_cast<int>(pack_cell(ccx, ccy));
     }
     __syncwarp();
+    if (lane == 0) {                                               // lengths -> flat ends, starts -> offsets
+        int run = 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const int len = bnd[9 + c];
+            bnd[c] -= run;
+            run += len;
+            bnd[9 + c] = run;
+        }
+    }
+    __syncwarp();
     const float c_lo = cos_thr - GATE_MARGIN, c_hi = cos_thr + GATE_MARGIN;
-    int c = 0, e = bnd[0] + lane, e_end = bnd[9];
+    const int T = bnd[17];
+    int c = 0, off = bnd[0], t_end = bnd[9];
     uint32_t want = static_cast<uint32_t>(bnd[18]);
-    int cnt = 0;
-    float4 r_n = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t want_n = 0;
-    bool have_n;
-    auto fetch = [&]() {                                           // the lane's next record, if any
-        while (e >= e_end && c < 9) {
-            ++c;
-            if (c < 9) { e = bnd[c] + lane; e_end = bnd[9 + c]; want = static_cast<uint32_t>(bnd[18 + c]); }
-        }
-        have_n = c < 9;
-        if (have_n) { r_n = g.rec[e]; want_n = want; e += G; }
-    };
-    fetch();
-    for (;;) {
-        const bool have = have_n;
-        const float4 r = r_n;
-        const uint32_t wnt = want_n;
-        if (have) {
-            fetch();                                               // in flight while this record is tested
-            if (__float_as_uint(r.w) == wnt) {                     // else: hash collision or a wrapped neighbour cell
-                const float rx = __fsub_rn(r.x, px), ry = __fsub_rn(r.y, py);
-                const float d2 = __fmaf_rn(ry, ry, __fmul_rn(rx, rx));
-                const float ca = fmaf(rx, hx, ry * hy) * rsqrt_approx(d2);
-                if (d2 <= pre2 && !(ca < c_lo)) {                  // not certainly outside the radius / field of view
-                    const uint32_t unsure = (ca > c_hi && d2 >= 1e-12f) ? 0u : 0x80000000u;   // NaN compares false
-                    pd.rx[cnt * CELL_THREADS] = rx; pd.ry[cnt * CELL_THREADS] = ry;
-                    pd.id[cnt * CELL_THREADS] = static_cast<uint32_t>(__float_as_int(r.z) - idx_base) | unsure;
-                    ++cnt;
-                }
+    // The warp stays converged: every lane runs until no lane has a record left, and all lanes drain together.
+    const int wl = threadIdx.x & 31;
+    const unsigned gbits = ((1u << G) - 1u) << (wl & ~(G - 1)), below = (1u << wl) - 1u;
+    int gcnt = 0;                                                  // the group's pending entries (same on its lanes)
+    for (int t = lane;; t += G) {
+        bool push = false;
+        float rx = 0.f, ry = 0.f;
+        uint32_t id = 0;
+        if (t < T) {
+            while (t >= t_end) {                                   // next non-empty bucket (c < 9 because t < T)
+                ++c;
+                off = bnd[c]; t_end = bnd[9 + c]; want = static_cast<uint32_t>(bnd[18 + c]);
             }
+            const float4 r = g.rec[t + off];
+            rx = __fsub_rn(r.x, px); ry = __fsub_rn(r.y, py);
+            const float d2 = __fmaf_rn(ry, ry, __fmul_rn(rx, rx));
+            const float ca = fmaf(rx, hx, ry * hy) * rsqrt_approx(d2);
+            // same cell (else: hash collision or a wrapped neighbour cell), not certainly outside radius / field of view
+            push = __float_as_uint(r.w) == want && d2 <= pre2 && !(ca < c_lo);
+            id = static_cast<uint32_t>(__float_as_int(r.z) - idx_base) |
+                 ((ca > c_hi && d2 >= 1e-12f) ? 0u : 0x80000000u);  // NaN compares false: undecided
         }
-        if (cnt == PEND_CAP || !have) {                            // pass 2: exact distance (and gate where undecided)
-            for (int q = 0; q < cnt; ++q) {
-                const float rx = pd.rx[q * CELL_THREADS], ry = pd.ry[q * CELL_THREADS];
-                const uint32_t w = pd.id[q * CELL_THREADS];
-                const float d = (w >> 31) ? gated_distance(rx, ry, hx, hy, cos_thr) : norm2_rn(rx, ry);
+        const unsigned mine = __ballot_sync(0xffffffffu, push) & gbits;
+        if (push) {
+            const int pos = gcnt + __popc(mine & below);
+            pd.rx[pos] = rx; pd.ry[pos] = ry; pd.id[pos] = id;
+        }
+        gcnt += __popc(mine);
+        const bool more = __any_sync(0xffffffffu, t + G < T);
+        if (!more || __any_sync(0xffffffffu, gcnt > POOL_CAP - G)) {
+            __syncwarp();                                          // pass 2: exact distance (and gate where undecided)
+            for (int q = lane; q < gcnt; q += G) {
+                const float qx = pd.rx[q], qy = pd.ry[q];
+                const uint32_t w = pd.id[q];
+                const float d = (w >> 31) ? gated_distance(qx, qy, hx, hy, cos_thr) : norm2_rn(qx, qy);
                 if (d <= thr) best.insert(make_key(d, static_cast<int>(w & 0x7fffffffu)));
             }
-            cnt = 0;
-            if (!have) break;
+            __syncwarp();
+            gcnt = 0;
+            if (!more) break;
         }
     }
     __syncwarp();                                                  // `bnd` is reused by the next branch
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
                                                                        double inv_cs, const int *__restrict__ absent,
                                                                        CompactOut co) {
     constexpr int G = SORT_G;
-    __shared__ float pend_all[3 * PEND_CAP * CELL_THREADS];
+    __shared__ float pend_all[3 * POOL_GROUPS * POOL_STRIDE];
     __shared__ int bnd_all[BND_WORDS * (CELL_THREADS / SORT_G)];
     const Pending pend(pend_all);
     int *bnd = bnd_all + BND_WORDS * (threadIdx.x / SORT_G);
@@ -735,7 +751,8 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     CompactOut c{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (co) c = *co;
     const unsigned blocks = static_cast<unsigned>((totalP * SORT_G + CELL_THREADS - 1) / CELL_THREADS);
-    if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
+    if (a.kp <= 6 && a.ko <= 10) features_sorted_kernel<6, 10><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);   // the reference's topk
+    else if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
     else if (a.kp <= 16 && a.ko <= 16) features_sorted_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
     else features_sorted_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
     count_launch();
