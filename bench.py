@@ -626,8 +626,8 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
 
 
 def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
-    """Secondary evidence under torchrun: the same NN rollout step agent-sharded (piml_b200.sharded.ShardedNNCrowd:
-    own-row features + forward, NCCL all-gather of the accelerations, replicated state update)."""
+    """Under torchrun: the same NN rollout step agent-sharded (piml_b200.sharded.ShardedNNCrowd: the fused step on the
+    rank's own rows, new state pushed to the peers from the last kernel's epilogue)."""
     import argparse as ap
     from piml_b200 import models as M
     from piml_b200.sharded import ShardedNNCrowd
@@ -666,8 +666,12 @@ def nn_path_sharded(torch, dist, dev, N, obs_h, world, iters=10):
         ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms = float(ms)
-        return {"workload": f"pinnsf_bm NN rollout step, N={N}, agent-sharded x{world}: own-row cell-list features + "
-                            "tcgen05 forward, NCCL all-gather of the accelerations (8 B/agent), replicated integrate",
+        how = ("fused step per rank (piml_nn_step_shard_f32): cell list over all agents, own rows in sorted order -> "
+               "tcgen05 forward -> Euler; new p, v, a pushed into every rank's next state over NVLink peer memory "
+               "(24 B/agent/peer), one barrier") if getattr(crowd, "fused", False) else \
+              ("own-row cell-list features + tcgen05 forward, NCCL all-gather of the accelerations (8 B/agent), "
+               "replicated integrate")
+        return {"workload": f"pinnsf_bm NN rollout step, N={N}, agent-sharded x{world}: {how}",
                 "ms_per_step": ms, "agent_steps_per_sec": N / ms * 1e3}
     except Exception as e:                               # secondary evidence must never take the headline down
         return {"error": f"{type(e).__name__}: {e}"[:300]}

@@ -461,6 +461,16 @@ typedef struct {
 PIML_API int piml_nn_step_supported(const piml_net_desc *desc);         /* 1 if piml_nn_step_f32 can run this network */
 PIML_API int piml_nn_step_f32(const piml_nn_step_args *args, void *stream);
 
+/* The same step for ONE RANK of an agent-sharded crowd (one scene): the rank holds the whole current state (args->p, v,
+ * a: every agent's, read only), evaluates rows [row0, row1) -- features against all agents, network, state update --
+ * and stores the new p, v, a of its rows into EVERY rank's next-state arrays p_next[g], v_next[g], a_next[g] (device
+ * pointers of `world` <= 8 peers, this rank's own arrays included; NVLink peer memory) from the epilogue of its last
+ * kernel.  dest / dest_idx / hist_v are updated in place for the own rows only (nobody else reads them).  The caller
+ * separates steps with a cross-rank barrier and swaps current / next.  No dense feature outputs. */
+PIML_API int piml_nn_step_shard_f32(const piml_nn_step_args *args, int64_t row0, int64_t row1, int world,
+                                    const uint64_t *p_next, const uint64_t *v_next, const uint64_t *a_next,
+                                    void *stream);
+
 /* Backward of the differentiable rollout's state update (simulators.py:741-769: v' = v + a dt, p' = p + v dt,
  * a' = model output; agents overwritten by teacher-forced entry get no gradient).  n = S*N agents.
  * entry (n) int64 or NULL; g_p2,g_v2,g_a2 (n,2) = gradients of the updated state -> g_p,g_v,g_a,g_a_next (n,2). */

@@ -129,6 +129,7 @@ SIGNATURES = {
     "piml_rollout_f32": (i32, [C.POINTER(RolloutArgs), vp]),
     "piml_nn_step_supported": (i32, [C.POINTER(NetDesc)]),
     "piml_nn_step_f32": (i32, [C.POINTER(NnStepArgs), vp]),
+    "piml_nn_step_shard_f32": (i32, [C.POINTER(NnStepArgs), i64, i64, i32, vp, vp, vp, vp]),
     "piml_integrate_step_backward_f32": (i32, [vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "piml_integrate_step_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp,
                                       vp, vp, vp, vp, vp, vp, vp]),

@@ -153,12 +153,13 @@ __global__ void __launch_bounds__(256) scan_apply_fused_kernel(int *__restrict__
         if (base + q < n) out[base + q] = run;
         run += v[q];
     }
-    if (base <= n - 1 && n - 1 < base + 8) { out[n] = run; in[n] = 0; }   // the thread owning the last element
+    if (base <= n - 1 && n - 1 < base + 8) { out[n] = run; in[n] = 0; in[n + 1] = 0; }   // the thread owning the last element
 }
 
 // The agents without a position (NaN: absent from the frame) are in no bucket; the count kernel lists them so that the
 // sorted-order feature kernel can still write their (all-zero) rows: absent[0 .. total0 - present).  The list's
-// counter lives right behind the bucket counters (counts[cells]) and is zeroed with them.
+// counter lives right behind the bucket counters (counts[cells]; counts[cells + 1] counts a rank's own-agent list)
+// and is zeroed with them.
 // Both point sets of a feature call (agents and obstacles) in ONE counting-sort chain: the cell arrays are
 // concatenated (agents' buckets first), so one count / scan / scatter sequence builds both grids -- 6 stream
 // operations per call instead of 12.  set 0: points [0, total0), n0 per frame, H0 buckets per frame, cells from 0;
@@ -485,13 +486,16 @@ __device__ __forceinline__ int compact_append(bool live, int *counter) {
 template <int KP, int KO>
 __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs a, HashGrid gp, HashGrid go,
                                                                        double inv_cs, const int *__restrict__ absent,
-                                                                       CompactOut co) {
+                                                                       CompactOut co, const int *__restrict__ order,
+                                                                       int n_order) {
     constexpr int G = SORT_G;
     __shared__ float pend_all[3 * POOL_GROUPS * POOL_STRIDE];
     __shared__ int bnd_all[BND_WORDS * (CELL_THREADS / SORT_G)];
     const Pending pend(pend_all);
     int *bnd = bnd_all + BND_WORDS * (threadIdx.x / SORT_G);
-    const int64_t all_rows = static_cast<int64_t>(a.B) * a.N;
+    // groups take the agents in sorted order: all of them, or (agent-sharded ranks) the `order` list of this rank's
+    // own agents -- sorted positions, or -(row + 1) for an absent agent (own_list_kernel)
+    const int64_t all_rows = order ? n_order : static_cast<int64_t>(a.B) * a.N;
     const int64_t grp = (static_cast<int64_t>(blockIdx.x) * CELL_THREADS + threadIdx.x) / G;
     const int l = threadIdx.x % G;
     const bool valid = grp < all_rows;                             // no early exit: the group shuffles need every lane
@@ -499,12 +503,13 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
     int64_t row = 0;
     float2 p = make_float2(CUDART_NAN_F, CUDART_NAN_F);
     if (valid) {
-        if (grp < n_present) {
-            const float4 r = gp.rec[grp];
+        const int64_t s = order ? order[grp] : (grp < n_present ? grp : -static_cast<int64_t>(absent[grp - n_present]) - 1);
+        if (s >= 0) {
+            const float4 r = gp.rec[s];
             row = __float_as_int(r.z);
             p = make_float2(r.x, r.y);
         } else {
-            row = absent[grp - n_present];
+            row = -(s + 1);
             p = reinterpret_cast<const float2 *>(a.pos)[row];
         }
     }
@@ -631,6 +636,24 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
     }
 }
 
+// Agent-sharded ranks: the sorted positions of the agents in rows [row0, row1) (warp-aggregated append: the entries a
+// warp appends are neighbours in space, which is all the feature kernel's coherence needs), absent agents as -(row+1).
+__global__ void own_list_kernel(const float4 *__restrict__ rec, const int *__restrict__ start_end,
+                                const int *__restrict__ absent, int64_t total, int64_t row0, int64_t row1,
+                                int *__restrict__ order, int *__restrict__ counter) {
+    const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t n_present = *start_end;
+    int entry = 0;
+    bool own = false;
+    if (s < total) {
+        const int64_t row = s < n_present ? __float_as_int(rec[s].z) : absent[s - n_present];
+        own = row >= row0 && row < row1;
+        entry = s < n_present ? static_cast<int>(s) : -static_cast<int>(row) - 1;
+    }
+    const int pos = compact_append(own, counter);
+    if (own) order[pos] = entry;
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 struct ByteScratch { cudaStream_t st; int dev; char *buf; size_t cap; int64_t zeroed; };
 static ByteScratch g_cell_scratch[8] = {};
@@ -695,33 +718,34 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     const double inv_cs = 1.0 / (static_cast<double>(thr) * (1.0 + 1e-5));
     PIML_REQUIRE(static_cast<int64_t>(a.B) * a.N < (1LL << 31) && static_cast<int64_t>(obs_frames) * a.M < (1LL << 31),
                  "cell-list features: too many points");
-    PIML_REQUIRE(!co || a.row1 == 0, "cell-list features: compact rows are emitted by whole-row calls only");
+    PIML_REQUIRE(!(co && a.row1 > 0) || a.B == 1, "cell-list features: a row range with compact rows needs one frame");
     // one counting-sort chain for both point sets (see TwoSets)
     const int HP = pow2_at_least(2LL * a.N), HO = a.M > 0 ? pow2_at_least(2LL * a.M) : 0;
     const int64_t cellsP = static_cast<int64_t>(a.B) * HP, cellsO = a.M > 0 ? static_cast<int64_t>(obs_frames) * HO : 0;
     const int64_t cells = cellsP + cellsO;
     const int64_t totalP = static_cast<int64_t>(a.B) * a.N, totalO = a.M > 0 ? static_cast<int64_t>(obs_frames) * a.M : 0;
     const int nblocks = static_cast<int>((cells + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
-    const size_t bytes = align256(sizeof(int) * (cells + 1)) + align256(sizeof(int) * (cells + 1)) +
+    const size_t bytes = align256(sizeof(int) * (cells + 2)) + align256(sizeof(int) * (cells + 1)) +
                          align256(sizeof(int) * (totalP + totalO)) + align256(sizeof(int) * (nblocks + 1)) +
-                         align256(sizeof(int) * totalP) + align256(sizeof(float4) * (totalP + totalO));
+                         2 * align256(sizeof(int) * totalP) + align256(sizeof(float4) * (totalP + totalO));
     char *base = nullptr;
     ByteScratch *slot = nullptr;
     int rc = cell_scratch_get(st, bytes, &base, &slot);
     if (rc) return rc;
-    int *counts = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 1));   // + absent counter
+    int *counts = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 2));   // + absent, own-list counters
     int *start = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 1));
     int *rank = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (totalP + totalO));
     int *bsums = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (nblocks + 1));
     int *absent = reinterpret_cast<int *>(base); base += align256(sizeof(int) * totalP);
+    int *order = reinterpret_cast<int *>(base); base += align256(sizeof(int) * totalP);
     float4 *rec = reinterpret_cast<float4 *>(base);
     TwoSets ts{reinterpret_cast<const float2 *>(a.pos), reinterpret_cast<const float2 *>(a.obs), totalP, totalO, a.N,
                a.M > 0 ? a.M : 1, HP, HO > 0 ? HO : 1, cellsP};
     // the fused scan leaves the counters zeroed for the next call with the same layout
     const bool fused = nblocks <= SCAN_FUSED_BLOCKS;
-    if (slot->zeroed != cells + 1) {
-        PIML_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (cells + 1), st));
-        slot->zeroed = fused ? cells + 1 : 0;
+    if (slot->zeroed != cells + 2) {
+        PIML_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (cells + 2), st));
+        slot->zeroed = fused ? cells + 2 : 0;
     }
     const unsigned pblocks = static_cast<unsigned>((totalP + totalO + CELL_THREADS - 1) / CELL_THREADS);
     cell_count2_kernel<<<pblocks, CELL_THREADS, 0, st>>>(ts, inv_cs, counts, rank, absent, counts + cells);
@@ -739,7 +763,7 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     if (rc) return rc;
     HashGrid hp{HP, a.B, a.N, start, rec}, ho{0, 0, 0, nullptr, nullptr};
     if (a.M > 0) ho = HashGrid{HO, obs_frames, a.M, start + cellsP, rec};
-    if (a.row1 > 0) {                                              // row range: one thread per agent, index order
+    if (a.row1 > 0 && !co) {                                       // row range: one thread per agent, index order
         const int64_t rows = a.row1 - a.row0;
         const unsigned blocks = static_cast<unsigned>((rows + CELL_THREADS - 1) / CELL_THREADS);
         if (a.kp <= 8 && a.ko <= 16) features_cells_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs);
@@ -750,11 +774,21 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     }
     CompactOut c{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (co) c = *co;
-    const unsigned blocks = static_cast<unsigned>((totalP * SORT_G + CELL_THREADS - 1) / CELL_THREADS);
-    if (a.kp <= 6 && a.ko <= 10) features_sorted_kernel<6, 10><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);   // the reference's topk
-    else if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
-    else if (a.kp <= 16 && a.ko <= 16) features_sorted_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
-    else features_sorted_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c);
+    const int *ord = nullptr;
+    int64_t groups = totalP;
+    if (a.row1 > 0) {                                              // agent-sharded rank: its own agents, in sorted order
+        own_list_kernel<<<static_cast<unsigned>((totalP + 255) / 256), 256, 0, st>>>(rec, start + cellsP, absent, totalP,
+                                                                                     a.row0, a.row1, order, counts + cells + 1);
+        count_launch();
+        ord = order;
+        groups = a.row1 - a.row0;
+    }
+    const int n_ord = static_cast<int>(groups);
+    const unsigned blocks = static_cast<unsigned>((groups * SORT_G + CELL_THREADS - 1) / CELL_THREADS);
+    if (a.kp <= 6 && a.ko <= 10) features_sorted_kernel<6, 10><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);   // the reference's topk
+    else if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
+    else if (a.kp <= 16 && a.ko <= 16) features_sorted_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
+    else features_sorted_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
     count_launch();
     return check_launch("features_sorted_kernel");
 }

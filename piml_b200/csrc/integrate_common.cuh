@@ -37,7 +37,10 @@ struct IntArgs {
     float2 *hist_v; float2 *rec_p, *rec_v, *rec_a; float *rec_mask;
 };
 
-__device__ __forceinline__ void integrate_agent(const IntArgs &g, int64_t i, float2 a_next) {
+struct AgentNext { float2 p, v, a, dest, hv; int64_t di; };
+
+// reads agent i's state, records it, returns the updated state (nothing of the state is written)
+__device__ __forceinline__ AgentNext integrate_agent_compute(const IntArgs &g, int64_t i, float2 a_next) {
     const int s = static_cast<int>(i / g.N), n = static_cast<int>(i % g.N);
     const float2 p = g.p[i], v = g.v[i], a = g.a[i];
     // p_res[t] = p_cur ... mask_p_new[t][~isnan(p.x)] = 1          (simulators.py:596-600)
@@ -48,14 +51,18 @@ __device__ __forceinline__ void integrate_agent(const IntArgs &g, int64_t i, flo
     AgentState st{p, v, a, g.dest[i], g.dest_idx[i], make_float2(0.f, 0.f)};
     integrate_update(st, a_next, g.dt, g.remove_on_arrival, g.dest_num[i],
                      g.waypoints + static_cast<int64_t>(s) * g.D * g.N + n, g.N);
-    float2 pn = st.p, vn = st.v, an = st.a, d = st.dest, hv = st.hv;
-    int64_t di = st.di;
+    AgentNext o{st.p, st.v, st.a, st.dest, st.hv, st.di};
     if (g.entry && g.entry[i] == 1) {                                          // :629-639
-        pn = g.p_gt[i]; vn = g.v_gt[i]; an = g.a_gt[i]; d = g.dest_gt[i]; di = g.dest_idx_gt[i];
-        hv = vn;
+        o.p = g.p_gt[i]; o.v = g.v_gt[i]; o.a = g.a_gt[i]; o.dest = g.dest_gt[i]; o.di = g.dest_idx_gt[i];
+        o.hv = o.v;
     }
-    g.p[i] = pn; g.v[i] = vn; g.a[i] = an; g.dest[i] = d; g.dest_idx[i] = di;
-    if (g.hist_v) g.hist_v[i] = hv;
+    return o;
+}
+
+__device__ __forceinline__ void integrate_agent(const IntArgs &g, int64_t i, float2 a_next) {
+    const AgentNext o = integrate_agent_compute(g, i, a_next);
+    g.p[i] = o.p; g.v[i] = o.v; g.a[i] = o.a; g.dest[i] = o.dest; g.dest_idx[i] = o.di;
+    if (g.hist_v) g.hist_v[i] = o.hv;
 }
 
 }  // namespace piml

@@ -213,38 +213,44 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             }
             return rf;
         };
+        // the 6-d features of a row as the first A operand of its tile: K padded to 16 with zeros, row-scaled
+        auto write_features = [&](const RowFeat &rf, float &inv_s_out) {
+            float mx = 0.f;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) mx = fmaxf(mx, fabsf(rf.f[q]));
+            float s;
+            row_scale(mx, s, inv_s_out);
+            if (half == 0) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) tc::split_f16x2(rf.f[2 * q] * s, rf.f[2 * q + 1] * s, hi[q], lo[q]);
+#pragma unroll
+                for (int q = 3; q < 8; ++q) { hi[q] = 0u; lo[q] = 0u; }
+                tc::st8(tl + T16_COL_AH, hi);
+                tc::st8(tl + T16_COL_AL, lo);
+                tc::wait_st();
+                tc::fence_before_sync();
+            }
+            tc::mbar_arrive(&a_ready[slot]);
+        };
+        // Software pipeline across tiles: the operand of tile j + 2 (this slot's next tile) is written as soon as the
+        // LAST accumulator of tile j has been read out, so its first layer runs on the tensor pipe while tile j's
+        // predictor, exchange and stores are still in progress; the rows of tile j + 4 are then prefetched.
         RowFeat nxt = load_row(slot);
+        float inv_s = 1.f;
+        int64_t crow = nxt.crow;
+        if (slot < my_tiles) write_features(nxt, inv_s);
+        nxt = load_row(slot + 2);
         for (int64_t j = slot; j < my_tiles; j += 2) {
             const int64_t tloc = first + j * stride;
             const int64_t agent0 = tloc * AG;
             const int na = a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
             const int nrows = a.compact ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
             const int64_t row0 = agent0 * k;
-            const int64_t crow = nxt.crow;
-            float inv_s;
+            float inv_s_next = 1.f;
+            int64_t crow_next = -1;
             const long long t0 = clock64();
             long long tl2 = t0;
-            {   // the 6-d features of this row as the first A operand: K padded to 16 with zeros, row-scaled
-                float mx = 0.f;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) mx = fmaxf(mx, fabsf(nxt.f[q]));
-                float s;
-                row_scale(mx, s, inv_s);
-                if (half == 0) {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) tc::split_f16x2(nxt.f[2 * q] * s, nxt.f[2 * q + 1] * s, hi[q], lo[q]);
-#pragma unroll
-                    for (int q = 3; q < 8; ++q) { hi[q] = 0u; lo[q] = 0u; }
-                    tc::st8(tl + T16_COL_AH, hi);
-                    tc::st8(tl + T16_COL_AL, lo);
-                    tc::wait_st();
-                    tc::fence_before_sync();
-                }
-                tc::mbar_arrive(&a_ready[slot]);
-            }
-            nxt = load_row(j + 2);                                 // in flight while this tile runs
-            if (a.prof && tid == 64) sprof[10] += clock64() - t0;
             float m0 = 0.f, m1 = 0.f;
             for (int li = 0; li < P.nl; ++li) {
                 const Tc16Layer &Ly = P.L[li];
@@ -260,6 +266,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 if (prof) sprof[3] += q1 - q0;
                 if (a.dbg & 1) {                                   // timing experiment: no epilogue work at all
                     if (!last) { tc::fence_before_sync(); tc::mbar_arrive(&a_ready[slot]); }
+                    else {
+                        crow_next = nxt.crow;
+                        if (j + 2 < my_tiles) write_features(nxt, inv_s_next);
+                        nxt = load_row(j + 4);
+                    }
                     continue;
                 }
                 const float *bias = biasb + Ly.bias_off + half * hc;
@@ -274,6 +285,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     else if (nchunk == 2) tc::ld32(tl + T16_COL_D + half * hc, r0);
                     else tc::ld16(tl + T16_COL_D + half * hc, h0);
                     tc::wait_ld();
+                }
+                if (last) {                                        // D and A of this slot are free: next tile's operand
+                    crow_next = nxt.crow;
+                    if (j + 2 < my_tiles) write_features(nxt, inv_s_next);
+                    nxt = load_row(j + 4);
                 }
                 const long long q2 = clock64();
                 if (prof) sprof[4] += q2 - q1;
@@ -348,20 +364,21 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 tc::mbar_arrive(&a_ready[slot]);                   // the next layer of this slot may start
                 if (prof) { sprof[7] += q5 - q4c; sprof[8] += clock64() - q5; }
             }
-            // combine the two column halves of the predictor
-            sm2[(half * 128 + m) * 2] = m0;
-            sm2[(half * 128 + m) * 2 + 1] = m1;
-            slot_barrier(slot);
-            if (half == 0) {
-                m0 = m0 + sm2[(128 + m) * 2] + biasb[P.predb_off];
-                m1 = m1 + sm2[(128 + m) * 2 + 1] + biasb[P.predb_off + 1];
+            // combine the two column halves of the predictor: half 1 hands its partial sums over and moves on
+            // (bar.arrive), only half 0 waits (the next write of sm2 is several slot barriers away)
+            if (half == 1) {
+                sm2[m * 2] = m0; sm2[m * 2 + 1] = m1;
+                asm volatile("bar.arrive %0, 256;" ::"r"(3 + slot) : "memory");
+            } else {
+                asm volatile("bar.sync %0, 256;" ::"r"(3 + slot) : "memory");
+                m0 = m0 + sm2[m * 2] + biasb[P.predb_off];
+                m1 = m1 + sm2[m * 2 + 1] + biasb[P.predb_off + 1];
             }
             if (a.compact) {
                 if (half == 0 && m < nrows) {                      // slot sums are formed by the finish kernel
                     float *dst = crow >= 0 ? (br == 0 ? a.cmsg_ped : a.cmsg_obs) + crow * 2 : a.f0 + br * 2;
                     dst[0] = m0; dst[1] = m1;
                 }
-                slot_barrier(slot);                                // sm2 is free for this slot's next tile
             } else {
                 float *msgs_out = br == 0 ? a.ped_msgs : a.obs_msgs;
                 if (half == 0 && msgs_out && m < nrows) { msgs_out[(row0 + m) * 2] = m0; msgs_out[(row0 + m) * 2 + 1] = m1; }
@@ -376,6 +393,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 }
                 slot_barrier(slot);                                // sm2 is free for this slot's next tile
             }
+            inv_s = inv_s_next; crow = crow_next;
             if (a.prof && tid == 64) { const long long te = clock64(); sprof[9] += te - tl2; sprof[11] += te - t0; }
         }
     }

@@ -32,18 +32,8 @@ struct FinishArgs {
 };
 
 // acc = sum over the k slots (slot order, f(0) for the empty ones) of both branches + destination term: the arithmetic
-// of pinnsf_tc_finish_compact_kernel (mlp_tc.cu) for both components, followed by integrate_agent.
-__global__ void __launch_bounds__(128) nn_finish_integrate_kernel(IntArgs g, FinishArgs f, const int *__restrict__ t_dev) {
-    const int64_t SN = static_cast<int64_t>(g.S) * g.N;
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i == 0) { f.counts[0] = 0; f.counts[1] = 0; }
-    if (i >= SN) return;
-    if (t_dev) {                                                   // captured loop: frame index from device memory
-        const int t = *t_dev;
-        g.entry += (t + 1) * SN; g.dest_idx_gt += (t + 1) * SN;
-        g.p_gt += (t + 1) * SN; g.v_gt += (t + 1) * SN; g.a_gt += (t + 1) * SN; g.dest_gt += (t + 1) * SN;
-        g.rec_p += t * SN; g.rec_v += t * SN; g.rec_a += t * SN; g.rec_mask += t * SN;
-    }
+// of pinnsf_tc_finish_compact_kernel (mlp_tc.cu) for both components.
+__device__ __forceinline__ float2 nn_agent_output(const IntArgs &g, const FinishArgs &f, int64_t i) {
     const float2 p = g.p[i], d = g.dest[i], hv = g.hist_v[i];
     const float ds = f.desired_speed[i];
     // self features: dest_f = nan_to_zero(dest - p) (data.py:502-503), hist_v, desired speed (simulators.py:651)
@@ -70,9 +60,44 @@ __global__ void __launch_bounds__(128) nn_finish_integrate_kernel(IntArgs g, Fin
         }
         acc[c] = __fadd_rn(mm, dterm);
     }
-    const float2 a_next = make_float2(acc[0], acc[1]);
+    return make_float2(acc[0], acc[1]);
+}
+
+// slot sums + destination term (model.py:1205-1210) followed by integrate_agent, one thread per agent
+__global__ void __launch_bounds__(128) nn_finish_integrate_kernel(IntArgs g, FinishArgs f, const int *__restrict__ t_dev) {
+    const int64_t SN = static_cast<int64_t>(g.S) * g.N;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i == 0) { f.counts[0] = 0; f.counts[1] = 0; }
+    if (i >= SN) return;
+    if (t_dev) {                                                   // captured loop: frame index from device memory
+        const int t = *t_dev;
+        g.entry += (t + 1) * SN; g.dest_idx_gt += (t + 1) * SN;
+        g.p_gt += (t + 1) * SN; g.v_gt += (t + 1) * SN; g.a_gt += (t + 1) * SN; g.dest_gt += (t + 1) * SN;
+        g.rec_p += t * SN; g.rec_v += t * SN; g.rec_a += t * SN; g.rec_mask += t * SN;
+    }
+    const float2 a_next = nn_agent_output(g, f, i);
     if (f.a_out) f.a_out[i] = a_next;
     integrate_agent(g, i, a_next);
+}
+
+// Agent-sharded ranks: the same for the rank's own rows [row0, row0 + rows); the new p, v, a of a row are stored into
+// EVERY rank's next-state arrays over NVLink peer memory (the step's only exchange, riding on this kernel's epilogue:
+// 24 B per agent and peer); dest, dest_idx and hist_v of a row are only ever read by its owner and stay local.
+struct PushTabs { float2 *p[8], *v[8], *a[8]; int world; };
+
+__global__ void __launch_bounds__(128) nn_finish_integrate_push_kernel(IntArgs g, FinishArgs f, PushTabs t, int64_t row0,
+                                                                       int64_t rows) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k == 0) { f.counts[0] = 0; f.counts[1] = 0; }
+    if (k >= rows) return;
+    const int64_t i = row0 + k;
+    const float2 a_next = nn_agent_output(g, f, i);
+    if (f.a_out) f.a_out[i] = a_next;
+    const AgentNext o = integrate_agent_compute(g, i, a_next);
+    g.dest[i] = o.dest; g.dest_idx[i] = o.di;
+    if (g.hist_v) g.hist_v[i] = o.hv;
+    for (int r = 0; r < t.world; ++r) { t.p[r][i] = o.p; t.v[r][i] = o.v; t.a[r][i] = o.a; }
+    __threadfence_system();                                        // visible to the peers before the step's barrier
 }
 
 // scratch of the fused step, cached per calling thread, device and stream; released by piml_free_workspace()
@@ -120,8 +145,11 @@ static int nn_scratch_get(cudaStream_t st, size_t bytes, char **out, bool *fresh
 
 static size_t al256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
+struct ShardInfo { int64_t row0, row1; PushTabs tabs; };
+
 // t_dev != nullptr: entry_* / rec_* are the BASE pointers of time-major arrays and the frame comes from device memory
-int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st) {
+// sh != nullptr: this rank evaluates rows [row0, row1) only and pushes their new state to every rank
+int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st, const ShardInfo *sh = nullptr) {
     Tc16Plan P16;
     if (tc16_plan_for(r->desc, &P16))
         return fail(PIML_ERR_UNSUPPORTED, "piml_nn_step_f32: the network does not fit the 16-bit tensor-core kernel "
@@ -163,7 +191,7 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     a.ped_f = r->ped_f; a.obs_f = r->M > 0 ? r->obs_f : nullptr; a.dest_f = r->dest_f;
     a.ped_idx = nullptr; a.ped_dist = nullptr; a.obs_idx = nullptr; a.obs_dist = nullptr;
     a.hist_v = r->hist_v; a.desired_speed = r->desired_speed; a.self_f = r->dest_f ? r->self_f : nullptr;
-    a.row0 = 0; a.row1 = 0;
+    a.row0 = sh ? sh->row0 : 0; a.row1 = sh ? sh->row1 : 0;
     CompactOut co{rows_p, rows_o, map_p, map_o, counts};
     rc = relative_features_cells(a, r->obs_per_scene ? r->S : 1, st, &co);
     if (rc) return rc;
@@ -195,6 +223,13 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     FinishArgs f{msg_p, msg_o, map_p, map_o, f0, r->desired_speed, kp, ko, has_obs, r->tau,
                  reinterpret_cast<float2 *>(r->a_next), counts};
     const int threads = 128;
+    if (sh) {
+        const int64_t rows = sh->row1 - sh->row0;
+        nn_finish_integrate_push_kernel<<<static_cast<unsigned>((rows + threads - 1) / threads), threads, 0, st>>>(
+            g, f, sh->tabs, sh->row0, rows);
+        count_launch();
+        return check_launch("nn_finish_integrate_push_kernel");
+    }
     nn_finish_integrate_kernel<<<static_cast<unsigned>((SN + threads - 1) / threads), threads, 0, st>>>(g, f, t_dev);
     count_launch();
     return check_launch("nn_finish_integrate_kernel");
@@ -222,4 +257,28 @@ extern "C" int piml_nn_step_f32(const piml_nn_step_args *r, void *stream) {
                  "piml_nn_step_f32: dense feature outputs must be given together");
     PIML_REQUIRE(aligned16(r->packed_tc), "piml_nn_step_f32: packed_tc must be 16-byte aligned");
     return nn_step_launch(r, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int piml_nn_step_shard_f32(const piml_nn_step_args *r, int64_t row0, int64_t row1, int world,
+                                      const uint64_t *p_next, const uint64_t *v_next, const uint64_t *a_next,
+                                      void *stream) {
+    PIML_REQUIRE(r && r->desc && r->packed_tc, "piml_nn_step_shard_f32: null descriptor / parameters");
+    PIML_REQUIRE(r->S == 1 && r->N >= 1 && r->D >= 1 && r->M >= 0, "piml_nn_step_shard_f32: one scene per sharded crowd");
+    PIML_REQUIRE(r->p && r->v && r->a && r->dest && r->dest_idx && r->hist_v && r->dest_num && r->waypoints &&
+                     r->desired_speed && (r->M == 0 || r->obstacles),
+                 "piml_nn_step_shard_f32: null state / static input");
+    PIML_REQUIRE(!r->entry || (r->p_gt && r->v_gt && r->a_gt && r->dest_gt && r->dest_idx_gt),
+                 "piml_nn_step_shard_f32: entry mask given without ground-truth arrays");
+    PIML_REQUIRE(!r->dest_f && !r->ped_f && !r->obs_f && !r->self_f, "piml_nn_step_shard_f32: no dense feature outputs");
+    PIML_REQUIRE(0 <= row0 && row0 < row1 && row1 <= r->N, "piml_nn_step_shard_f32: bad row range");
+    PIML_REQUIRE(world >= 1 && world <= 8 && p_next && v_next && a_next, "piml_nn_step_shard_f32: bad peer tables");
+    PIML_REQUIRE(aligned16(r->packed_tc), "piml_nn_step_shard_f32: packed_tc must be 16-byte aligned");
+    ShardInfo sh;
+    sh.row0 = row0; sh.row1 = row1; sh.tabs.world = world;
+    for (int g = 0; g < world; ++g) {
+        sh.tabs.p[g] = reinterpret_cast<float2 *>(p_next[g]);
+        sh.tabs.v[g] = reinterpret_cast<float2 *>(v_next[g]);
+        sh.tabs.a[g] = reinterpret_cast<float2 *>(a_next[g]);
+    }
+    return nn_step_launch(r, nullptr, static_cast<cudaStream_t>(stream), &sh);
 }

@@ -182,14 +182,19 @@ class ShardedNNCrowd(object):
     """Agent-sharded NN-augmented (or pure social-force) rollout of ONE large scene: the loop body of
     `get_multiple_rollouts` (simulators.py:602-652) with rank g computing rows [g N/G, (g+1) N/G).
 
-    Every rank keeps the whole state.  Per step: feature rebuild of the OWN rows against all agents
-    (`piml_state_features_rows_f32`, cell list) -> network forward of the own rows -> the path's one exchange, an
-    all-gather of the new accelerations (8 B per agent -- the only quantity a rank cannot compute for rows it does not
-    own) -> the cheap elementwise state update (Euler / arrival / waypoints, `piml_integrate_step_f32`) replicated on
-    every rank, which keeps the replicas bit-identical without exchanging positions and velocities.
-    Works on NCCL; results are bit-identical to the unsharded step sequence (`scripts/check_nn_sharded.py`)."""
+    *Fused path* (per-slot-decoder networks the tensor-core step runs, `piml_nn_step_shard_f32`): every rank holds every
+    agent's p, v, a, double-buffered in symmetric memory.  Per step a rank builds the cell list over all agents, evaluates
+    features -> network -> Euler / arrival for its OWN rows in sorted (spatial) order, and the last kernel stores the new
+    p, v, a of those rows into every rank's next-state arrays over NVLink peer memory; one cross-rank barrier ends the
+    step.  No collective, no replicated state update; dest / dest_idx / hist_v of a row live on its owner only
+    (`gather_state()` assembles them everywhere on request).
 
-    def __init__(self, model, args, N, obstacles, group=None, device=None):
+    *Three-call path* (social-force model, other networks): own-row features (`piml_state_features_rows_f32`) -> forward
+    -> NCCL all-gather of the new accelerations (8 B per agent) -> the elementwise state update replicated on every rank.
+
+    Both are bit-identical to the unsharded step sequence (`scripts/check_nn_sharded.py`)."""
+
+    def __init__(self, model, args, N, obstacles, group=None, device=None, fused=None):
         from . import models as M
         from .sfm import SocialForce
         self.group = group if group is not None else dist.group.WORLD
@@ -204,24 +209,96 @@ class ShardedNNCrowd(object):
             self.packed_tc = M.pack_device_tc(model.state_dict(), self.spec, self.device)
         self.obstacles = L.f32c(obstacles.to(self.device))
         self.Mo = self.obstacles.shape[-2] if self.obstacles.numel() else 0
-        n = self.rows[1] - self.rows[0]
-        kp, ko = min(args.topk_ped, N), (min(args.topk_obs, self.Mo) if self.Mo else 0)
+        can_fuse = False
+        if not self.sfm and self.packed_tc is not None and M.tc_enabled():
+            self._desc = self.spec.desc()
+            can_fuse = bool(L.load().piml_nn_step_supported(C.byref(self._desc))) and self.world <= 8
+        self.fused = can_fuse if fused is None else (bool(fused) and can_fuse)
         dev = self.device
-        self.ped_f, self.obs_f = torch.empty(n, kp, 6, device=dev), torch.empty(n, ko, 6, device=dev)
-        self.self_f, self.dest_f = torch.empty(n, 7, device=dev), torch.empty(n, 2, device=dev)
-        self.a_next = torch.empty(1, N, 2, device=dev)
+        if self.fused:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty((2, 3, N, 2), dtype=torch.float32, device=dev)     # [parity][p | v | a]
+            self.hdl = symm.rendezvous(self.buf, self.group)
+            ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+            plane = N * 2 * 4
+            self._tabs = [[(C.c_uint64 * self.world)(*[q + (par * 3 + k) * plane for q in ptrs]) for k in range(3)]
+                          for par in (0, 1)]
+            self.parity = 0
+        else:
+            n = self.rows[1] - self.rows[0]
+            kp, ko = min(args.topk_ped, N), (min(args.topk_obs, self.Mo) if self.Mo else 0)
+            self.ped_f, self.obs_f = torch.empty(n, kp, 6, device=dev), torch.empty(n, ko, 6, device=dev)
+            self.self_f, self.dest_f = torch.empty(n, 7, device=dev), torch.empty(n, 2, device=dev)
+            self.a_next = torch.empty(1, N, 2, device=dev)
 
     def load(self, position, velocity, acceleration, destination, dest_idx, dest_num, waypoints, desired_speed,
              hist_v=None):
         """Every rank passes the whole initial state: (N,2) x4, dest_idx / dest_num (N) int64, waypoints (D,N,2),
         desired_speed (N)."""
         dv = lambda x, dt=torch.float32: x.to(self.device, dt).contiguous()
-        self.p, self.v, self.a, self.dest = [dv(x)[None].clone() for x in (position, velocity, acceleration,
-                                                                           destination)]
+        if self.fused:
+            for k, x in enumerate((position, velocity, acceleration)):
+                self.buf[self.parity, k].copy_(dv(x))
+            self.dest = dv(destination)[None].clone()
+        else:
+            self.p, self.v, self.a, self.dest = [dv(x)[None].clone() for x in (position, velocity, acceleration,
+                                                                               destination)]
         self.didx, self.dnum = dv(dest_idx, torch.int64)[None].clone(), dv(dest_num, torch.int64)[None].clone()
         self.wp, self.ds = dv(waypoints)[None].clone(), dv(desired_speed).reshape(1, self.N).clone()
-        self.hist = (dv(hist_v)[None] if hist_v is not None else self.v).clone()
-        self._features()
+        self.hist = (dv(hist_v)[None] if hist_v is not None else dv(velocity)[None]).clone()
+        if self.fused:
+            self._bind()
+            torch.cuda.current_stream(self.device).synchronize()
+            dist.barrier(self.group)
+        else:
+            self._features()
+
+    # ---- fused path
+    def _bind(self):
+        from .features import cos_threshold
+        a, r = self.args, L.NnStepArgs()
+        r.desc, r.packed_tc = C.pointer(self._desc), L.ptr(self.packed_tc)
+        r.has_obs, r.tau = (1 if (self.spec.has_obs and self.Mo) else 0), self.spec.tau
+        r.S, r.N, r.M, r.D = 1, self.N, self.Mo, self.wp.shape[-3]
+        r.kp, r.cos_p, r.thr_p = a.topk_ped, cos_threshold(a.sight_angle_ped), float(a.dist_threshold_ped)
+        r.ko, r.cos_o, r.thr_o = a.topk_obs, cos_threshold(a.sight_angle_obs), float(a.dist_threshold_obs)
+        r.obstacles, r.obs_per_scene = (L.ptr(self.obstacles) if self.Mo else None), 0
+        r.dest_num, r.waypoints, r.desired_speed = L.ptr(self.dnum), L.ptr(self.wp), L.ptr(self.ds)
+        r.dest, r.dest_idx, r.hist_v = L.ptr(self.dest), L.ptr(self.didx), L.ptr(self.hist)
+        self._args = r
+        self._fn = L.load().piml_nn_step_shard_f32
+
+    @property
+    def p(self):
+        return self.buf[self.parity, 0][None] if self.fused else self._p
+
+    @p.setter
+    def p(self, x):
+        self._p = x
+
+    @property
+    def v(self):
+        return self.buf[self.parity, 1][None] if self.fused else self._v
+
+    @v.setter
+    def v(self, x):
+        self._v = x
+
+    @property
+    def a(self):
+        return self.buf[self.parity, 2][None] if self.fused else self._a
+
+    @a.setter
+    def a(self, x):
+        self._a = x
+
+    def gather_state(self):
+        """Fused path: dest, dest_idx and hist_v of a row are kept by its owner; this assembles them on every rank."""
+        if self.fused and self.world > 1:
+            r0, r1 = self.rows
+            for full in (self.dest, self.hist, self.didx):
+                allgather_rows(full[0], full[0, r0:r1].clone(), self.group)
+        return self.dest, self.didx, self.hist
 
     def _features(self):
         from .features import cos_threshold
@@ -238,6 +315,16 @@ class ShardedNNCrowd(object):
         from . import models as M
         from .rollout import integrate_step
         dt = float(self.args.time_unit if dt is None else dt)
+        if self.fused:
+            r, cur, nxt = self._args, self.buf[self.parity], 1 - self.parity
+            r.p, r.v, r.a = L.ptr(cur[0]), L.ptr(cur[1]), L.ptr(cur[2])
+            r.dt, r.remove_on_arrival = dt, (1 if remove_on_arrival else 0)
+            tp, tv, ta = self._tabs[nxt]
+            L.check(self._fn(C.byref(r), self.rows[0], self.rows[1], self.world, tp, tv, ta,
+                             L.stream_ptr(self.device)), "piml_nn_step_shard_f32")
+            self.hdl.barrier(channel=0)        # every rank's new rows are in every rank's next-state arrays
+            self.parity = nxt
+            return
         if self.sfm:
             a_own = self.model(self.ped_f, self.obs_f, self.self_f)[0]
         else:

@@ -1,6 +1,7 @@
-"""torchrun --nproc-per-node G scripts/check_nn_sharded.py : the agent-sharded NN rollout step (ShardedNNCrowd: own-row
-features + forward, all-gather of the accelerations, replicated state update) must be bit-identical to the unsharded
-step sequence on every rank; also times both."""
+"""torchrun --nproc-per-node G scripts/check_nn_sharded.py : the agent-sharded NN rollout step (ShardedNNCrowd; pinnsf_bm:
+the fused step with the peer-memory state push, social force: own-row features + forward, all-gather of the
+accelerations, replicated state update) must be bit-identical to the unsharded step sequence on every rank; also times
+both."""
 import os, sys
 import torch
 import torch.distributed as dist
@@ -60,6 +61,7 @@ for label, net in (("pinnsf_bm", None), ("social force", P.SocialForce("gc1560")
         t1.record(); torch.cuda.synchronize()
         ms_s = t0.elapsed_time(t1) / steps
     P._lib.check(P._lib.load().piml_set_feature_algorithm(0), "algo")
+    crowd.gather_state()
     eq = lambda x, y: bool(((x == y) | (x.isnan() & y.isnan())).all())       # arrived agents are NaN in both
     same = eq(crowd.p, pu) and eq(crowd.v, vu) and eq(crowd.a, au) and eq(crowd.dest, du)
     arrived = int(pu.isnan().any(-1).sum())
