@@ -388,7 +388,7 @@ def nn_config(N, M=2000):
             "reference": "src/models/simulators.py:595-652 (model forward -> Euler / arrival -> get_relative_features), "
                          "src/models/model.py:1185-1221, src/data/data.py:466-512",
             "crowd": "SURVEY 8d config 4: seed 666, rho 0.5 ped/m^2, dt 0.08, k 6/10, 90 deg, 4 m; seed-666 weights",
-            "l2": f"{FLUSH_MB} MB memset between steps, inside the timed region (GPU arm)"}
+            "l2": f"{FLUSH_MB} MB memset before every step; each step has its own CUDA-event pair (GPU arm)"}
 
 
 class NNCrowd(object):
@@ -535,15 +535,13 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
         flush.zero_(); crowd.step_fused()
     torch.cuda.synchronize()
     launches0 = L.launch_count()
-    e0, e1 = ev(), ev()
-    e0.record()
+    pairs = [(ev(), ev()) for _ in range(steps)]
     for s_ in range(steps):
-        flush.zero_()
-        crowd.step_fused()
-    e1.record()
+        flush.zero_()                                       # L2 flushed before every step, outside its event pair
+        pairs[s_][0].record(); crowd.step_fused(); pairs[s_][1].record()
     torch.cuda.synchronize()
     launches = L.launch_count() - launches0
-    ms = e0.elapsed_time(e1) / steps
+    ms = sum(a_.elapsed_time(b_) for a_, b_ in pairs) / steps
     assert torch.isfinite(crowd.p[0]).sum() > 0
     # ---- end to end with host buffers
     for _ in range(2):
