@@ -172,15 +172,23 @@ struct TwoSets {
 __global__ void cell_count2_kernel(const TwoSets t, double inv_cs, int *__restrict__ counts, int *__restrict__ rank,
                                    int *__restrict__ absent, int *__restrict__ n_absent) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= t.total0 + t.total1) return;
+    const bool in = i < t.total0 + t.total1;
     const bool second = i >= t.total0;
     const int64_t j = second ? i - t.total0 : i;
-    const float2 p = (second ? t.pts1 : t.pts0)[j];
-    if (p.x != p.x || p.y != p.y) {
-        rank[i] = -1;
-        if (!second) absent[atomicAdd(n_absent, 1)] = static_cast<int>(j);
-        return;
+    float2 p = make_float2(0.f, 0.f);
+    if (in) p = (second ? t.pts1 : t.pts0)[j];
+    const bool nan = in && (p.x != p.x || p.y != p.y);
+    // absent agents: one atomic per warp (4096 mostly empty scenes list 400k of them per step)
+    const unsigned m = __ballot_sync(0xffffffffu, nan && !second);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(n_absent, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (nan && !second) absent[base + __popc(m & ((1u << lane) - 1))] = static_cast<int>(j);
     }
+    if (!in) return;
+    if (nan) { rank[i] = -1; return; }
     const int n = second ? t.n1 : t.n0, H = second ? t.H1 : t.H0;
     const int64_t frame = j / n;
     const uint32_t b = bucket_of(cell_coord(p.x, inv_cs), cell_coord(p.y, inv_cs), H);
@@ -457,8 +465,10 @@ __device__ __forceinline__ void scan_cells_split(TopK<KMAX> &best, const HashGri
 
 // The group's k smallest keys in ascending order, dealt to the lanes round robin: slot j ends up in
 // mine[j / G] of lane j % G.  Keys are unique (one candidate is seen by exactly one lane), EMPTY_KEY pads.
+// Returns the number of non-empty keys among the k (the agent's live slots: a prefix of its slots).
 template <int KMAX, int G>
-__device__ __forceinline__ void merge_deal(TopK<KMAX> &best, int k, int lane, uint64_t (&mine)[(KMAX + G - 1) / G]) {
+__device__ __forceinline__ int merge_deal(TopK<KMAX> &best, int k, int lane, uint64_t (&mine)[(KMAX + G - 1) / G]) {
+    int nlive = 0;
 #pragma unroll
     for (int q = 0; q < (KMAX + G - 1) / G; ++q) mine[q] = EMPTY_KEY;
 #pragma unroll
@@ -469,7 +479,9 @@ __device__ __forceinline__ void merge_deal(TopK<KMAX> &best, int k, int lane, ui
         if (__all_sync(0xffffffffu, w == EMPTY_KEY)) break;       // nothing left in any group of the warp (uniform)
         if (h == w && w != EMPTY_KEY) best.pop_front();
         if ((j % G) == lane) mine[j / G] = w;
+        nlive += (w != EMPTY_KEY) ? 1 : 0;
     }
+    return nlive;
 }
 
 // Append the warp's live rows to a branch's compact row list; returns this lane's row (-1: not live).
@@ -542,13 +554,50 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
     const bool present = valid && !(p.x != p.x || p.y != p.y);
     const int cx = present ? cell_coord(p.x, inv_cs) : 0, cy = present ? cell_coord(p.y, inv_cs) : 0;
 
+    int live_ped = 0, live_obs = 0;
+    // A warp none of whose agents has a position (the tail of the order: a batch of mostly empty scenes lists 400k
+    // absent slots per step) has nothing to search: all slots empty.
+    if (!__any_sync(0xffffffffu, present)) {
+        if (valid) {
+            const float2 z = make_float2(0.f, 0.f);
+            if (a.ped_f)
+                for (int j = l; j < a.kp; j += G) {
+                    float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + j) * 3;
+                    out[0] = z; out[1] = z; out[2] = z;
+                    if (a.ped_idx) a.ped_idx[row * a.kp + j] = -1;
+                    if (a.ped_dist) a.ped_dist[row * a.kp + j] = CUDART_INF_F;
+                }
+            if (a.obs_f && a.M > 0)
+                for (int j = l; j < a.ko; j += G) {
+                    float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + j) * 3;
+                    out[0] = z; out[1] = z; out[2] = z;
+                    if (a.obs_idx) a.obs_idx[row * a.ko + j] = -1;
+                    if (a.obs_dist) a.obs_dist[row * a.ko + j] = CUDART_INF_F;
+                }
+            if (l == 0) {
+                if (a.dest_f) {
+                    const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
+                    const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+                    reinterpret_cast<float2 *>(a.dest_f)[row] = df;
+                    if (a.self_f) {
+                        const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
+                        float *sf = a.self_f + row * 7;
+                        sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
+                        sf[6] = a.desired_speed[row];
+                    }
+                }
+                if (co.counts) co.live[row] = 0;
+            }
+        }
+        return;
+    }
     // ---- pedestrian - pedestrian ----
     {
         TopK<KP> best;
         best.init();
         scan_cells_split<KP, G>(best, gp, b, present, cx, cy, l, p.x, p.y, h.x, h.y, a.cos_p, a.thr_p, a.pre2_p, b * a.N, pend, bnd);
         uint64_t mine[(KP + G - 1) / G];
-        merge_deal<KP, G>(best, a.kp, l, mine);
+        live_ped = merge_deal<KP, G>(best, a.kp, l, mine);
         const float2 *fp = reinterpret_cast<const float2 *>(a.pos) + static_cast<int64_t>(b) * a.N;
         const float2 *fv = reinterpret_cast<const float2 *>(a.vel) + static_cast<int64_t>(b) * a.N;
         const float2 *fa = reinterpret_cast<const float2 *>(a.acc) + static_cast<int64_t>(b) * a.N;
@@ -579,7 +628,7 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
                     float2 *out = reinterpret_cast<float2 *>(co.rows_ped) + static_cast<int64_t>(crow) * 3;
                     out[0] = f0; out[1] = f1; out[2] = f2;
                 }
-                if (in) co.map_ped[row * a.kp + j] = crow;
+                if (live) co.map_ped[row * a.kp + j] = crow;
             }
         }
     }
@@ -602,7 +651,7 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
         const int oframe = a.obs_frame_stride == 0 ? 0 : (a.obs_channel_T > 0 ? b / a.obs_channel_T : b);
         scan_cells_split<KO, G>(best, go, oframe, present, cx, cy, l, p.x, p.y, h.x, h.y, a.cos_o, a.thr_o, a.pre2_o, 0, pend, bnd);
         uint64_t mine[(KO + G - 1) / G];
-        merge_deal<KO, G>(best, a.ko, l, mine);
+        live_obs = merge_deal<KO, G>(best, a.ko, l, mine);
         const float2 *cand = reinterpret_cast<const float2 *>(a.obs + static_cast<int64_t>(oframe) * a.obs_frame_stride);
 #pragma unroll
         for (int jj = 0; jj < (KO + G - 1) / G; ++jj) {
@@ -630,10 +679,11 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
                     float2 *out = reinterpret_cast<float2 *>(co.rows_obs) + static_cast<int64_t>(crow) * 3;
                     out[0] = f0; out[1] = f1; out[2] = f2;
                 }
-                if (in) co.map_obs[row * a.ko + j] = crow;
+                if (live) co.map_obs[row * a.ko + j] = crow;
             }
         }
     }
+    if (co.counts && valid && l == 0) co.live[row] = static_cast<uint16_t>(live_ped | (live_obs << 8));
 }
 
 // Agent-sharded ranks: the sorted positions of the agents in rows [row0, row1) (warp-aggregated append: the entries a
@@ -772,7 +822,7 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
         count_launch();
         return check_launch("features_cells_kernel");
     }
-    CompactOut c{nullptr, nullptr, nullptr, nullptr, nullptr};
+    CompactOut c{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (co) c = *co;
     const int *ord = nullptr;
     int64_t groups = totalP;

@@ -91,10 +91,12 @@ static inline float prefilter_sq(float thr) {
 
 // Compact slot rows of the fused NN step (nn_step.cu): only the non-empty slots of each branch, 6 floats per row in
 // arrival order (a row's message does not depend on its place), and for every (agent, slot) the row it went to
-// (-1: an empty, zero-padded slot, whose message is the network's f(0)).  counts[2] must be zero on entry.
+// (empty, zero-padded slots yield the network's f(0)).  counts[2] must be zero on entry.
 struct CompactOut {
     float *rows_ped, *rows_obs;    // [counts[0]][6], [counts[1]][6]
-    int *map_ped, *map_obs;        // (B*N, kp), (B*N, ko)
+    int *map_ped, *map_obs;        // (B*N, kp), (B*N, ko): written for the LIVE slots only, which are a prefix of an
+                                   // agent's slots (ascending keys, empty slots last)
+    uint16_t *live;                // (B*N): live pedestrian slots | live obstacle slots << 8
     int *counts;                   // nullptr: no compact output
 };
 

@@ -51,6 +51,10 @@ __device__ __forceinline__ void row_scale(float mx, float &s, float &inv_s) {
     inv_s = __uint_as_float(static_cast<uint32_t>(E - 14) << 23);
 }
 
+// PROF: in-kernel cycle counters (PIML_TC_PROF); compiled out of the production instantiation (the clock reads and
+// their branches were 4 % of the epilogue's instructions).
+#define T16_CLOCK() (PROF ? clock64() : 0LL)
+template <bool PROF>
 __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __grid_constant__ Tc16Plan P,
                                                                      const __grid_constant__ Tc16Args a) {
     extern __shared__ __align__(128) unsigned char t16_smem[];
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     long long *sprof = reinterpret_cast<long long *>(d_ready + 4);     // [16] cycle counters (PIML_TC_PROF), flushed at the end
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 16) sprof[tid] = 0;
-    const long long k_start = clock64();
+    const long long k_start = T16_CLOCK();
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 32) {
@@ -134,13 +138,13 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 any = true;
                 const int li = layer[s];
                 const Tc16Layer &Ly = P.L[li];
-                const long long p0 = clock64();
+                const long long p0 = T16_CLOCK();
                 t16_wait(&a_ready[s], (aph >> s) & 1u);            // A of (this slot's tile, layer li) is in TMEM
                 aph ^= (1u << s);
-                const long long p1 = clock64();
+                const long long p1 = T16_CLOCK();
                 if (!((wseen >> li) & 1u)) { t16_wait(&w_ready[li], 0); wseen |= (1u << li); }
                 tc::fence_after_sync();
-                const long long p2 = clock64();
+                const long long p2 = T16_CLOCK();
                 const uint32_t dcol = tb + s * T16_SLOT_COLS + T16_COL_D;
                 uint32_t ah = tb + s * T16_SLOT_COLS + T16_COL_AH, al = tb + s * T16_SLOT_COLS + T16_COL_AL;
                 const uint32_t idesc = tc::idesc_f16(Ly.N);
@@ -162,8 +166,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     tc::commit(&d_ready[s]);                       // accumulator of this (slot, layer) complete
                 }
                 __syncwarp();
-                if (a.prof && lane == 0) {
-                    sprof[0] += p1 - p0; sprof[1] += p2 - p1; sprof[2] += clock64() - p2;
+                if (PROF && a.prof && lane == 0) {
+                    sprof[0] += p1 - p0; sprof[1] += p2 - p1; sprof[2] += T16_CLOCK() - p2;
                     if (li == 0) sprof[15] += 1;
                 }
                 if (++layer[s] == P.nl) { layer[s] = 0; ++done[s]; }
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             const int64_t row0 = agent0 * k;
             float inv_s_next = 1.f;
             int64_t crow_next = -1;
-            const long long t0 = clock64();
+            const long long t0 = T16_CLOCK();
             long long tl2 = t0;
             float m0 = 0.f, m1 = 0.f;
             for (int li = 0; li < P.nl; ++li) {
@@ -257,12 +261,12 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 const bool last = li == P.nl - 1;
                 const int hc = Ly.N >> 1;                          // columns of this thread: [half * hc, +hc), 16 at a time
                 const int nchunk = hc >> 4;
-                const long long q0 = clock64();
+                const long long q0 = T16_CLOCK();
                 t16_wait(&d_ready[slot], dph);
                 dph ^= 1u;
                 tc::fence_after_sync();
-                const long long q1 = clock64();
-                const bool prof = a.prof && tid == 64;
+                const long long q1 = T16_CLOCK();
+                const bool prof = PROF && a.prof && tid == 64;
                 if (prof) sprof[3] += q1 - q0;
                 if (a.dbg & 1) {                                   // timing experiment: no epilogue work at all
                     if (!last) { tc::fence_before_sync(); tc::mbar_arrive(&a_ready[slot]); }
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     if (j + 2 < my_tiles) write_features(nxt, inv_s_next);
                     nxt = load_row(j + 4);
                 }
-                const long long q2 = clock64();
+                const long long q2 = T16_CLOCK();
                 if (prof) sprof[4] += q2 - q1;
                 float *v = reinterpret_cast<float *>(r);
                 float mx = 0.f;
@@ -328,13 +332,13 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                         }
                     break;
                 }
-                const long long q3 = clock64();
+                const long long q3 = T16_CLOCK();
                 if (prof) sprof[5] += q3 - q2;
                 float *mxb = smax + (li & 1) * 256;                // double buffered: one barrier per layer is enough
                 mxb[half * 128 + m] = mx;                          // row maximum over both column halves
                 slot_barrier(slot);
                 mx = fmaxf(mx, mxb[(half ^ 1) * 128 + m]);
-                const long long q4c = clock64();
+                const long long q4c = T16_CLOCK();
                 if (prof) sprof[6] += q4c - q3;
                 float s;
                 row_scale(mx, s, inv_s);
@@ -358,11 +362,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                         tc::st8(tl + T16_COL_AL + ((half * hc + c * 16) >> 1), lo);
                     }
                 }
-                const long long q5 = clock64();
+                const long long q5 = T16_CLOCK();
                 tc::wait_st();
                 tc::fence_before_sync();
                 tc::mbar_arrive(&a_ready[slot]);                   // the next layer of this slot may start
-                if (prof) { sprof[7] += q5 - q4c; sprof[8] += clock64() - q5; }
+                if (prof) { sprof[7] += q5 - q4c; sprof[8] += T16_CLOCK() - q5; }
             }
             // combine the two column halves of the predictor: half 1 hands its partial sums over and moves on
             // (bar.arrive), only half 0 waits (the next write of sm2 is several slot barriers away)
@@ -394,15 +398,15 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 slot_barrier(slot);                                // sm2 is free for this slot's next tile
             }
             inv_s = inv_s_next; crow = crow_next;
-            if (a.prof && tid == 64) { const long long te = clock64(); sprof[9] += te - tl2; sprof[11] += te - t0; }
+            if (PROF && a.prof && tid == 64) { const long long te = T16_CLOCK(); sprof[9] += te - tl2; sprof[11] += te - t0; }
         }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, 512);
-    if (a.prof && blockIdx.x == 0 && tid < 16) a.prof[tid] = sprof[tid];
-    if (a.prof && tid == 64 && blockIdx.x < 160) {                 // per CTA: whole kernel, slot-0 tile loop, tiles
-        a.prof[16 + 3 * blockIdx.x] = clock64() - k_start;
+    if (PROF && a.prof && blockIdx.x == 0 && tid < 16) a.prof[tid] = sprof[tid];
+    if (PROF && a.prof && tid == 64 && blockIdx.x < 160) {                 // per CTA: whole kernel, slot-0 tile loop, tiles
+        a.prof[16 + 3 * blockIdx.x] = T16_CLOCK() - k_start;
         a.prof[17 + 3 * blockIdx.x] = sprof[11];
         a.prof[18 + 3 * blockIdx.x] = my_tiles;
     }
@@ -528,9 +532,14 @@ int tc16_pack(const Tc16Plan &P, const Tc16Src &S, const float *params_torch, fl
 
 int tc16_launch(const Tc16Plan &P, const Tc16Args &a, int64_t tiles_bound, cudaStream_t st) {
     const size_t smem = tc16_smem_bytes(P);
-    PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int grid = static_cast<int>(tiles_bound < sm_count() ? tiles_bound : sm_count());
-    pinnsf_tc16_kernel<<<grid, T16_THREADS, smem, st>>>(P, a);
+    if (a.prof) {
+        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        pinnsf_tc16_kernel<true><<<grid, T16_THREADS, smem, st>>>(P, a);
+    } else {
+        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        pinnsf_tc16_kernel<false><<<grid, T16_THREADS, smem, st>>>(P, a);
+    }
     count_launch();
     return check_launch("pinnsf_tc16_kernel");
 }

@@ -23,7 +23,8 @@ namespace piml {
 
 struct FinishArgs {
     const float *cmsg_ped, *cmsg_obs;          // per compact row (2)
-    const int *map_ped, *map_obs;              // (S*N, kp), (S*N, ko): compact row or -1
+    const int *map_ped, *map_obs;              // (S*N, kp), (S*N, ko): compact row of each LIVE slot
+    const uint16_t *live;                      // (S*N): live pedestrian | obstacle << 8 slots (a prefix of the slots)
     const float *f0;                           // [2][2] message of a zero row per branch
     const float *desired_speed;
     int kp, ko, has_obs; float tau;
@@ -40,25 +41,28 @@ __device__ __forceinline__ float2 nn_agent_output(const IntArgs &g, const Finish
     const float sf0 = nan_to_zero(__fsub_rn(d.x, p.x)), sf1 = nan_to_zero(__fsub_rn(d.y, p.y));
     float nrm = norm2_rn(sf0, sf1);
     if (nrm == 0.f) nrm = __fadd_rn(nrm, 0.1f);
+    const int lv = f.live[i], np = lv & 0xff, no = lv >> 8;
+    float2 mm = make_float2(0.f, 0.f);
+    for (int j = 0; j < f.kp; ++j) {                               // slot order; empty slots (the tail) yield f(0)
+        float2 x = make_float2(f.f0[0], f.f0[1]);
+        if (j < np) x = reinterpret_cast<const float2 *>(f.cmsg_ped)[f.map_ped[i * f.kp + j]];
+        mm.x += x.x; mm.y += x.y;
+    }
+    if (f.has_obs) {
+        float2 mo = make_float2(0.f, 0.f);
+        for (int j = 0; j < f.ko; ++j) {
+            float2 x = make_float2(f.f0[2], f.f0[3]);
+            if (j < no) x = reinterpret_cast<const float2 *>(f.cmsg_obs)[f.map_obs[i * f.ko + j]];
+            mo.x += x.x; mo.y += x.y;
+        }
+        mm = make_float2(__fadd_rn(mm.x, mo.x), __fadd_rn(mm.y, mo.y));
+    }
     float acc[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const float dir = __fdiv_rn(c == 0 ? sf0 : sf1, nrm);
         const float dterm = __fdiv_rn(__fsub_rn(__fmul_rn(ds, dir), c == 0 ? hv.x : hv.y), f.tau);
-        float mm = 0.f;
-        for (int j = 0; j < f.kp; ++j) {
-            const int r = f.map_ped[i * f.kp + j];
-            mm += r < 0 ? f.f0[c] : f.cmsg_ped[static_cast<int64_t>(r) * 2 + c];
-        }
-        if (f.has_obs) {
-            float mo = 0.f;
-            for (int j = 0; j < f.ko; ++j) {
-                const int r = f.map_obs[i * f.ko + j];
-                mo += r < 0 ? f.f0[2 + c] : f.cmsg_obs[static_cast<int64_t>(r) * 2 + c];
-            }
-            mm = __fadd_rn(mm, mo);
-        }
-        acc[c] = __fadd_rn(mm, dterm);
+        acc[c] = __fadd_rn(c == 0 ? mm.x : mm.y, dterm);
     }
     return make_float2(acc[0], acc[1]);
 }
@@ -164,10 +168,11 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     // scratch: f0 [4] + counts [2] (+ pad) | compact rows (+ 1 row of slack) | messages | maps
     const size_t b_head = 256, b_rp = al256(sizeof(float) * 6 * (rows_ped + 1)), b_ro = al256(sizeof(float) * 6 * (rows_obs + 1)),
                  b_mp = al256(sizeof(float) * 2 * (rows_ped + 1)), b_mo = al256(sizeof(float) * 2 * (rows_obs + 1)),
-                 b_ip = al256(sizeof(int) * (rows_ped + 1)), b_io = al256(sizeof(int) * (rows_obs + 1));
+                 b_ip = al256(sizeof(int) * (rows_ped + 1)), b_io = al256(sizeof(int) * (rows_obs + 1)),
+                 b_lv = al256(sizeof(uint16_t) * (SN + 1));
     char *base = nullptr;
     bool fresh = false;
-    int rc = nn_scratch_get(st, b_head + b_rp + b_ro + b_mp + b_mo + b_ip + b_io, &base, &fresh);
+    int rc = nn_scratch_get(st, b_head + b_rp + b_ro + b_mp + b_mo + b_ip + b_io + b_lv, &base, &fresh);
     if (rc) return rc;
     float *f0 = reinterpret_cast<float *>(base);
     int *counts = reinterpret_cast<int *>(base + 16);
@@ -177,7 +182,8 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     float *msg_p = reinterpret_cast<float *>(base); base += b_mp;
     float *msg_o = reinterpret_cast<float *>(base); base += b_mo;
     int *map_p = reinterpret_cast<int *>(base); base += b_ip;
-    int *map_o = reinterpret_cast<int *>(base);
+    int *map_o = reinterpret_cast<int *>(base); base += b_io;
+    uint16_t *live = reinterpret_cast<uint16_t *>(base);
     if (fresh) PIML_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));       // afterwards the finish kernel zeroes them
 
     // ---- features of the current state, compact rows only (dense copies on request)
@@ -192,7 +198,7 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     a.ped_idx = nullptr; a.ped_dist = nullptr; a.obs_idx = nullptr; a.obs_dist = nullptr;
     a.hist_v = r->hist_v; a.desired_speed = r->desired_speed; a.self_f = r->dest_f ? r->self_f : nullptr;
     a.row0 = sh ? sh->row0 : 0; a.row1 = sh ? sh->row1 : 0;
-    CompactOut co{rows_p, rows_o, map_p, map_o, counts};
+    CompactOut co{rows_p, rows_o, map_p, map_o, live, counts};
     rc = relative_features_cells(a, r->obs_per_scene ? r->S : 1, st, &co);
     if (rc) return rc;
 
@@ -220,7 +226,7 @@ int nn_step_launch(const piml_nn_step_args *r, const int *t_dev, cudaStream_t st
     g.dest_idx_gt = r->dest_idx_gt; g.hist_v = reinterpret_cast<float2 *>(r->hist_v);
     g.rec_p = reinterpret_cast<float2 *>(r->rec_p); g.rec_v = reinterpret_cast<float2 *>(r->rec_v);
     g.rec_a = reinterpret_cast<float2 *>(r->rec_a); g.rec_mask = r->rec_mask;
-    FinishArgs f{msg_p, msg_o, map_p, map_o, f0, r->desired_speed, kp, ko, has_obs, r->tau,
+    FinishArgs f{msg_p, msg_o, map_p, map_o, live, f0, r->desired_speed, kp, ko, has_obs, r->tau,
                  reinterpret_cast<float2 *>(r->a_next), counts};
     const int threads = 128;
     if (sh) {
