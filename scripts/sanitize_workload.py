@@ -132,7 +132,45 @@ def part_misc():
     torch.cuda.synchronize()
 
 
-PARTS = {"smoke": part_smoke, "rollout": part_rollout, "train": part_train, "misc": part_misc}
+def part_nnstep():
+    """The fused NN step (cell-list build, sorted-order feature kernel with its shared-memory pools, tensor-core forward
+    on compact rows, finish + integrate), the cell-list feature call (dense outputs) and the fused loop inside
+    piml_rollout_f32, on small crowds with absent / stationary agents and several scenes."""
+    from piml_b200.rollout import NNStep, rollout_scenes, state_features
+    args = bm_args()
+    torch.manual_seed(666)
+    net = M.PINNSF_bottleneck_multitask(args).cuda().eval()
+    packed_tc = M.pack_device_tc(net.state_dict(), net.spec)
+    g = torch.Generator().manual_seed(3)
+    P._lib.check(P._lib.load().piml_set_feature_algorithm(2), "algo")
+    for S, N, Mo in ((1, 1500, 200), (3, 200, 60)):
+        side = (N / 0.5) ** 0.5
+        p = (torch.rand(S, N, 2, generator=g) * side).cuda()
+        v = (torch.randn(S, N, 2, generator=g)).cuda()
+        a = (0.3 * torch.randn(S, N, 2, generator=g)).cuda()
+        p[:, ::7] = float('nan'); v[:, 5::11] = 0.0
+        dest = (torch.rand(S, N, 2, generator=g) * side).cuda()
+        obs = (torch.rand(S, Mo, 2, generator=g) * side).cuda() if S > 1 else (torch.rand(Mo, 2, generator=g) * side).cuda()
+        ds = torch.full((S, N), 1.3).cuda()
+        hist = torch.where(torch.isnan(v), torch.zeros_like(v), v).contiguous()
+        didx = torch.zeros(S, N, dtype=torch.int64).cuda()
+        dnum = torch.ones(S, N, dtype=torch.int64).cuda()
+        wp = dest[:, None].contiguous()
+        state_features(p, v.clone(), a.clone(), dest, obs, hist, ds, 6, 90, 4, 10, 90, 4)
+        step = NNStep(net.spec, packed_tc, p, v, a, dest, didx, hist, dnum, wp, ds, obs, 0.08, 6, 90, 4, 10, 90, 4)
+        for _ in range(3):
+            step.step()
+        torch.cuda.synchronize()
+        assert torch.isfinite(p).any()
+    P._lib.check(P._lib.load().piml_set_feature_algorithm(0), "algo")
+    os.environ["PIML_ROLLOUT_FUSED"] = "1"
+    try:
+        part_rollout()
+    finally:
+        os.environ.pop("PIML_ROLLOUT_FUSED", None)
+
+
+PARTS = {"smoke": part_smoke, "rollout": part_rollout, "train": part_train, "misc": part_misc, "nnstep": part_nnstep}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
