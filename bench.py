@@ -830,7 +830,7 @@ def training_block(torch, dev, with_reference=True):
                          collision_focus_weight=float(x[6]), new_collision_loss_flag=int(x[7]), time_decay=float(x[8]),
                          collision_loss_version=str(g["in/collision_loss_version"]))
         net = mirror(kind, dsn, None, True)
-        opt = torch.optim.Adam(net.parameters(), lr=4e-6)
+        opt = torch.optim.Adam(net.parameters(), lr=4e-6, capturable=True)
         sim = ap.Namespace(args=args, model=net, collision_count=0, hard_collision_count=0, epoch=0, batch_idx=0)
         base = _batch_from_golden(g)
         C0 = base.position.shape[0]
@@ -859,12 +859,31 @@ def training_block(torch, dev, with_reference=True):
         for _ in range(n):
             res = step()
         torch.cuda.synchronize()
+        ms_eager = (time.perf_counter() - t0) / n * 1e3
+        launches = (P._lib.launch_count() - l0) / n
+        # the same step captured once into a CUDA graph (piml_b200.train_graph) and replayed per batch
+        from piml_b200.train_graph import GraphedRolloutTraining
+        import gc
+        res = None                      # the eager steps' autograd graph (AccumulateGrad nodes bound to this stream)
+        opt.zero_grad(set_to_none=True)
+        gc.collect()
+        graphed = GraphedRolloutTraining(sim, opt, make_batch())
+        batches = [make_batch() for _ in range(n)]
+        for b in batches[:2]:
+            graphed.step(b)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in batches:
+            res = graphed.step(b)
+        torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / n * 1e3
         b = make_batch()
         C, T, N = [int(v) for v in b.position.shape[:3]]
         blk = {"workload": f"rollout-training step {kind}/{dsn}: C={C} channels x T={T} steps x N={N} slots, forward rollout + "
-                           "losses + backward + Adam", "ms_per_step": ms, "agent_steps_per_sec": C * T * N / ms * 1e3,
-               "library_launches_per_step": (P._lib.launch_count() - l0) / n, "loss": float(res[0])}
+                           "losses + backward + Adam, the whole step replayed as ONE captured CUDA graph "
+                           "(piml_b200.train_graph; batch copied into static buffers, one read-back per step)",
+               "ms_per_step": ms, "agent_steps_per_sec": C * T * N / ms * 1e3, "ms_per_step_eager": ms_eager,
+               "library_launches_per_step": launches, "loss": float(res[0])}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"[:300]}
     if with_reference and _import_reference():

@@ -21,8 +21,13 @@ _PEDS = Pedestrians()
 
 
 # ---- the rollout ------------------------------------------------------------------------------------------------
-def test_multiple_rollouts_for_training(simulator, data, t_start=0):
+def test_multiple_rollouts_for_training(simulator, data, t_start=0, _sync_free=False):
     """Drop-in body for `BaseSimulator.test_multiple_rollouts_for_training(self, data, t_start=0)`.
+
+    `_sync_free` (used by piml_b200.train_graph, which captures the whole training step in a CUDA graph): no device ->
+    host reads inside the call -- the per-frame `torch.sum(mask) > 0` test of :705 is taken as true (the caller checks
+    it for the whole batch before replaying), the NaN assert of :745 and the two collision counters become device
+    tensors in `simulator._deferred = (nan_flag, collision_sum, hard_collision_sum)` for the caller to read afterwards.
 
     `simulator` provides .args, .model (a reference PINNSF module patched by piml_b200.patch, or a piml_b200.models
     mirror) and the counters .collision_count / .hard_collision_count.  `data` is a channelled clip
@@ -53,7 +58,7 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
     dest_num = data.dest_num
     new_peds_flag = (data.mask_p - data.mask_p_pred).long()                      # c, t, n  (:688)
 
-    loss = torch.tensor(0., requires_grad=True, device=dev)
+    loss = torch.zeros((), device=dev, requires_grad=True)      # (no host scalar: the step may be captured in a graph)
     p_res = torch.zeros(data.position.shape, device=dev)
     collisions = torch.zeros(mask_p_.shape, device=dev)
     hard_collisions = torch.zeros(mask_p_.shape, device=dev)
@@ -62,14 +67,15 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
     a_res = torch.zeros(data.acceleration.shape, device=dev)
     pred_collisions = torch.zeros(data.ped_features[..., 0].shape, device=dev)
     true_collision = torch.zeros(data.ped_features[..., 0].shape, device=dev)
-    reg_loss = torch.tensor(0., device=dev)
+    reg_loss = torch.zeros((), device=dev)
     thr = args.collision_threshold
     T = data.num_frames
+    nan_flag = torch.zeros((), dtype=torch.bool, device=dev)
     for t in range(t_start, T):
         predictions = model(*state_features)                                      # :701  CUDA fwd (+ stash)
         p_msg = predictions[1]
         mask = mask_p_[:, t, :]
-        if torch.sum(mask) > 0:                                                   # :705
+        if _sync_free or torch.sum(mask) > 0:                                     # :705
             p_det = p_cur.clone().detach()
             lab = data.labels[:, t, :, :2]
             collisions[:, t, :] = _PEDS.collision_detection(p_det, thr, rowsum_only=True)            # :707-709
@@ -85,8 +91,11 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
                 reg_loss = reg_loss + L1SumFunction.apply(p_msg, args.reg_weight)
                 loss = loss + reg_loss
         a_next = predictions[0]
-        assert ~a_next.isnan().any(), print('find nan in epoch :', getattr(simulator, 'epoch', None),
-                                            getattr(simulator, 'batch_idx', None))              # :745
+        if _sync_free:
+            nan_flag = nan_flag | a_next.isnan().any()
+        else:
+            assert ~a_next.isnan().any(), print('find nan in epoch :', getattr(simulator, 'epoch', None),
+                                                getattr(simulator, 'batch_idx', None))          # :745
         # Euler with the old a and v, waypoint switch without removal, teacher-forced entry   (:741-769)
         last = t >= T - 1
         entry = None if last else new_peds_flag[..., t + 1, :]
@@ -108,17 +117,21 @@ def test_multiple_rollouts_for_training(simulator, data, t_start=0):
         label_collisions = torch.sum(label_collisions, dim=-2, keepdim=True).repeat(1, collisions.shape[1], 1)
         label_hard_collisions = torch.sum(label_hard_collisions, dim=-2, keepdim=True).repeat(
             1, hard_collisions.shape[1], 1)
-        collisions[label_collisions > 0] = 0
-        hard_collisions[label_hard_collisions > 0] = 0
-    simulator.collision_count = getattr(simulator, 'collision_count', 0) + torch.sum(collisions).item()
-    simulator.hard_collision_count = getattr(simulator, 'hard_collision_count', 0) + torch.sum(hard_collisions).item()
+        collisions = collisions.masked_fill(label_collisions > 0, 0.)
+        hard_collisions = hard_collisions.masked_fill(label_hard_collisions > 0, 0.)
+    if _sync_free:
+        simulator._deferred = (nan_flag, torch.sum(collisions), torch.sum(hard_collisions))
+    else:
+        simulator.collision_count = getattr(simulator, 'collision_count', 0) + torch.sum(collisions).item()
+        simulator.hard_collision_count = getattr(simulator, 'hard_collision_count', 0) + \
+            torch.sum(hard_collisions).item()
 
-    p_res[mask_p_ == 0] = 0.                                                      # :792-793
-    data.labels[mask_p_ == 0] = 0.
+    p_res.masked_fill_((mask_p_ == 0).unsqueeze(-1), 0.)                          # :792-793
+    data.labels.masked_fill_((mask_p_ == 0).unsqueeze(-1), 0.)
     labels_p = data.labels[:, :, :, :2]
     # the three 'sum'-reduced position losses of :795-813 in ONE fused pass (piml_rollout_losses_f32); the collision
     # weights are only needed when their loss is switched on
-    zero = torch.tensor(0., device=dev)
+    zero = torch.zeros((), device=dev)
     collision_loss, hard_collision_loss, collision_pred_loss, collision_pred_acc = zero, zero, zero, zero
     want_coll = args.collision_loss_weight > 0 and args.collision_loss_version in ('v0', 'v2')
     am = data.abnormal_mask if (want_coll and args.collision_loss_version == 'v2') else None

@@ -331,3 +331,50 @@ def test_l1_and_bce_sum_kernels_match_torch():
     assert abs(float(loss) - float(want)) <= 2e-6 * abs(float(want))
     assert float(hits) == float(torch.sum(torch.round(pr.detach()) == t))
     assert torch.allclose(p.grad, pr.grad, rtol=1e-6, atol=0)
+
+
+def test_graphed_training_step_equals_the_eager_step():
+    """piml_b200.train_graph: rollout + backward + Adam captured in ONE CUDA graph must do what the eager step does: same
+    losses, same collision counters, same parameters after several steps (eval-mode network: no dropout RNG)."""
+    from piml_b200 import train_rollout as TRO
+    from piml_b200.train_graph import GraphedRolloutTraining
+    g = group(golden("training_rollout"), "ucy_bm")
+    kind, dsn = str(g["in/model"]), str(g["in/dataset_name"])
+    a = g["in/args"]
+    args = base_args(model=kind, dataset_name=dsn, reg_weight=float(a[0]), collision_threshold=float(a[1]),
+                     collision_loss_weight=float(a[2]), hard_collision_penalty=float(a[3]), teacher_weight=float(a[4]),
+                     collision_pred_weight=float(a[5]), collision_focus_weight=float(a[6]),
+                     new_collision_loss_flag=int(a[7]), time_decay=float(a[8]),
+                     collision_loss_version=str(g["in/collision_loss_version"]))
+
+    def make():
+        net = mirror(kind, dsn, None, False)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True)
+        sim = argparse.Namespace(args=args, model=net, collision_count=0, hard_collision_count=0, epoch=0, batch_idx=0)
+        return net, opt, sim
+    fresh = lambda: _batch_from_golden(g)
+    net_e, opt_e, sim_e = make()
+    net_g, opt_g, sim_g = make()
+    WARM = 3
+    graphed = GraphedRolloutTraining(sim_g, opt_g, fresh(), warmup=WARM)
+    sim_g.collision_count = sim_g.hard_collision_count = 0
+    for _ in range(WARM):                                         # the eager twin takes the same number of steps
+        opt_e.zero_grad(set_to_none=True)
+        TRO.test_multiple_rollouts_for_training(sim_e, fresh())[0].backward()
+        opt_e.step()
+    sim_e.collision_count = sim_e.hard_collision_count = 0
+    for it in range(3):
+        opt_e.zero_grad(set_to_none=True)
+        b = fresh()
+        res_e = TRO.test_multiple_rollouts_for_training(sim_e, b)
+        res_e[0].backward()
+        opt_e.step()
+        bg = fresh()
+        res_g = graphed.step(bg)
+        for i, (x, y) in enumerate(zip(res_e, res_g)):
+            x, y = float(x.detach()), float(y.detach())
+            assert abs(x - y) <= 1e-5 * max(abs(x), 1e-3), (it, i, x, y)
+    assert sim_e.collision_count == sim_g.collision_count
+    assert sim_e.hard_collision_count == sim_g.hard_collision_count
+    for (k, p), (_, q) in zip(net_e.named_parameters(), net_g.named_parameters()):
+        assert max_rel(q.detach().cpu().numpy(), p.detach().cpu().numpy()) < 1e-5, k
