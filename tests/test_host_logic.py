@@ -115,3 +115,34 @@ def test_non_relu_single_block_processor_is_rejected():
     assert M.spec_from_args('pinnsf_bm', a).proc_mode == 1
     a.processor_hidden_layers, a.activation = 16, 'leaky_relu'       # discarded Linear: activation never applied
     assert M.spec_from_args('pinnsf_bm', a).proc_mode == 0
+
+
+def test_fused_step_host_side():
+    """piml_nn_step_supported (pure host logic of the library, no GPU needed): per-slot-decoder networks with widths the
+    16-bit tensor-core kernel runs are accepted, the summed-embedding kind and odd widths are not; NNStep has no CPU
+    fallback; the graphed training step insists on a capturable optimizer before it touches the device."""
+    import argparse
+    from piml_b200 import _lib as L, models as M
+    from piml_b200.rollout import NNStep
+    from piml_b200.train_graph import GraphedRolloutTraining
+    base = dict(dataset_name='gc1560', dropout=0.5, encoder_hidden_size=128, processor_hidden_size=128,
+                decoder_hidden_size=64, encoder_hidden_layers=3, processor_hidden_layers=16, decoder_hidden_layers=2,
+                ped_feature_dim=6, obs_feature_dim=6, self_feature_dim=7)
+    lib = L.load()
+    ok = lambda model, **kw: bool(lib.piml_nn_step_supported(
+        L.C.byref(M.spec_from_args(model, argparse.Namespace(model=model, **dict(base, **kw))).desc())))
+    assert ok('pinnsf_bm') and ok('pinnsf_bottleneck')
+    assert ok('pinnsf_bm', encoder_hidden_size=64, processor_hidden_size=64, decoder_hidden_size=32)
+    assert not ok('pinnsf_m')                                             # summed embeddings: not a per-slot decoder
+    assert not ok('pinnsf_bm', decoder_hidden_size=48)                    # width the kernel has no tile shape for
+    assert not ok('pinnsf_bm', processor_hidden_layers=1)                 # single-block processor: FP32-pipe path only
+    if not torch.cuda.is_available():
+        spec = M.spec_from_args('pinnsf_bm', argparse.Namespace(model='pinnsf_bm', **base))
+        z = torch.zeros(1, 8, 2)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            NNStep(spec, torch.zeros(4), z, z.clone(), z.clone(), z.clone(), torch.zeros(1, 8, dtype=torch.int64),
+                   z.clone(), torch.ones(1, 8, dtype=torch.int64), z[:, None].clone(), torch.ones(1, 8), torch.zeros(3, 2),
+                   0.08, 6, 90, 4, 10, 90, 4)
+    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(2))], lr=1e-3)
+    with pytest.raises(ValueError, match="capturable"):
+        GraphedRolloutTraining(argparse.Namespace(), opt, argparse.Namespace())
