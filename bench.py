@@ -565,6 +565,9 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
         pass
     gbs = NN_BYTES_PER_AGENT_FUSED * N / (ms * 1e-3) / 1e9
     fwd_tf = NN_FLOP_PER_AGENT * N / (st[0] * 1e-3) / 1e12
+    # what the tensor cores actually execute: the non-empty slot rows only, 3 fp16 MMA terms per product
+    live_rows = int((crowd.bufs[0].abs().sum(-1) > 0).sum()) + int((crowd.bufs[1].abs().sum(-1) > 0).sum())
+    exec_tf = 3.0 * live_rows * (NN_FLOP_PER_AGENT / 16.0) / (st[0] * 1e-3) / 1e12
     block = {
         "metric": METRIC, "value": N / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": steps,
         "config": nn_config(N, int(obs_h.shape[0])), "dtype": "f32 (network contractions as 3-term split products on "
@@ -582,6 +585,11 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
                              "kernel evaluates only non-empty slot rows (compact mode) but spends 3 MMAs per product "
                              "(3-term split for fp32-grade results), so executed tensor FLOPs differ from algorithmic",
                      "traffic": None,
+                     "executed": {"slot_rows_evaluated": live_rows, "slot_rows_dense": 16 * N,
+                                  "fp16_tensor_tflops_executed": exec_tf, "fp16_peak_tflops": bf16,
+                                  "frac_of_fp16_peak": exec_tf / bf16, "tensor_pipe_busy_ncu": 0.363,
+                                  "source": "profiles/r02l_ncu_pinnsf_tc16_kernel.txt; 36 of a tile's 87 MMAs are N = 64 "
+                                            "(half a pipe pass each), so pipe-busy sits below the FLOP fraction"},
                      "hbm": {"bytes_per_agent_step": NN_BYTES_PER_AGENT, "bytes_per_agent_step_fused": NN_BYTES_PER_AGENT_FUSED,
                              "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
                              "note": "whole fused step, its algorithmic bytes (state in / out, bytes_per_agent_step_fused) "

@@ -624,8 +624,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinnsf_tc_kernel(const __grid_c
                     half_barrier(0);                               // every partial read before the totals overwrite
                     small[m * 2] = m0; small[m * 2 + 1] = m1;
                     half_barrier(0);
-                    if (m < 2 * na) {                              // torch.sum(dim=-2) over the k slots (model.py:1194)
-                        const int ag = m >> 1, c = m & 1;
+                    for (int e = m; e < 2 * na; e += 128) {        // torch.sum(dim=-2) over the k slots (model.py:1194);
+                        const int ag = e >> 1, c = e & 1;          // k = 1: 128 agents per tile, two sums per thread
                         float s = 0.f;
                         for (int j = 0; j < k; ++j) s += small[(ag * k + j) * 2 + c];
                         a.sums[(agent0 + ag) * 4 + br * 2 + c] = s;

@@ -389,12 +389,13 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 slot_barrier(slot);                                // every partial read before the totals overwrite
                 if (half == 0) { sm2[m * 2] = m0; sm2[m * 2 + 1] = m1; }
                 slot_barrier(slot);
-                if (half == 0 && m < 2 * na) {                     // torch.sum(dim=-2) over the k slots (model.py:1194)
-                    const int ag = m >> 1, c = m & 1;
-                    float sum = 0.f;
-                    for (int jj = 0; jj < k; ++jj) sum += sm2[(ag * k + jj) * 2 + c];
-                    a.sums[(agent0 + ag) * 4 + br * 2 + c] = sum;
-                }
+                if (half == 0)
+                    for (int e = m; e < 2 * na; e += 128) {        // torch.sum(dim=-2) over the k slots (model.py:1194);
+                        const int ag = e >> 1, c = e & 1;          // k = 1: 128 agents per tile, two sums per thread
+                        float sum = 0.f;
+                        for (int jj = 0; jj < k; ++jj) sum += sm2[(ag * k + jj) * 2 + c];
+                        a.sums[(agent0 + ag) * 4 + br * 2 + c] = sum;
+                    }
                 slot_barrier(slot);                                // sm2 is free for this slot's next tile
             }
             inv_s = inv_s_next; crow = crow_next;

@@ -3,6 +3,8 @@
    2. cell-list vs all-pairs neighbour features, random N, M, k, angles, thresholds: bit-identical
    3. tensor-core forward compact vs dense (pinnsf_bm row level, pinnsf_m agent level): bit-identical
    4. persistent social-force rollout kernel vs the per-step route: bit-identical
+   5. fused NN step (piml_nn_step_f32) vs state_features -> pinnsf_forward -> integrate_step, and the rollout loop with the
+      fused step forced vs the per-stage loop: random scenes / sizes / k / angles / thresholds, absent agents: bit-identical
 Prints one line per family; exits non-zero on the first disagreement."""
 import argparse, os, sys, time
 import numpy as np
@@ -17,7 +19,7 @@ a = ap.parse_args()
 rng = np.random.default_rng(a.seed)
 dev = torch.device("cuda")
 cu = lambda x, dt=torch.float32: torch.as_tensor(np.asarray(x), dtype=dt).to(dev)
-budget = a.seconds / 4
+budget = a.seconds / 5
 
 
 def crowd(N, rho):
@@ -138,5 +140,74 @@ def fuzz_sfm_rollout():
     print(f"persistent social-force rollout vs per-step route: {n} scene batches, bit-identical")
 
 
-fuzz_mlapm(); fuzz_features(); fuzz_tc(); fuzz_sfm_rollout()
+def fuzz_nn_step():
+    from piml_b200.rollout import NNStep, integrate_step, rollout_scenes, state_features
+    import argparse as ap2
+    t0, n, nr = time.time(), 0, 0
+    torch.manual_seed(1)
+    net = M.CLASSES["pinnsf_bm"](base_args(model="pinnsf_bm", dataset_name="gc1560")).to(dev).eval()
+    packed, ptc = M.pack_device(net.state_dict(), net.spec, dev), M.pack_device_tc(net.state_dict(), net.spec, dev)
+    while time.time() - t0 < budget:
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        if n % 4 == 3:                         # whole rollouts: fused loop forced vs per-stage loop
+            S, T, Ns, Mo = int(rng.integers(1, 6)), int(rng.integers(5, 40)), int(rng.integers(12, 200)), int(rng.integers(10, 200))
+            side = float(np.sqrt(Ns / 0.3)) + 2
+            ob = (torch.rand(Mo, 2, generator=g) * side).to(dev)
+            P0 = (torch.rand(S, T, Ns, 2, generator=g) * side).to(dev)
+            P0[(torch.rand(S, 1, Ns, generator=g) < 0.3).expand(S, T, Ns).to(dev)] = float('nan')
+            entry = (torch.rand(S, T, Ns, generator=g) < 0.02).float().to(dev)
+            scene = {"position": P0, "velocity": (torch.randn(S, T, Ns, 2, generator=g) * 0.8).to(dev),
+                     "acceleration": (torch.randn(S, T, Ns, 2, generator=g) * 0.2).to(dev),
+                     "destination": (torch.rand(S, T, Ns, 2, generator=g) * side).to(dev),
+                     "dest_idx": torch.zeros(S, T, Ns, dtype=torch.int64, device=dev),
+                     "waypoints": (torch.rand(S, 2, Ns, 2, generator=g) * side).to(dev),
+                     "dest_num": torch.full((S, Ns), 2, dtype=torch.int64, device=dev), "obstacles": ob,
+                     "mask_p": torch.ones(S, T, Ns, device=dev), "mask_p_pred": 1 - entry,
+                     "desired_speed": (1.0 + torch.rand(S, Ns, generator=g)).to(dev)}
+            v0 = scene["velocity"][:, 0].contiguous()
+            f0 = state_features(P0[:, 0].contiguous(), v0, scene["acceleration"][:, 0].contiguous(),
+                                scene["destination"][:, 0].contiguous(), ob, v0.clone(), scene["desired_speed"], 6, 90, 4, 10, 90, 4)
+            scene["ped_features0"], scene["obs_features0"], scene["self_features0"] = f0
+            rargs = ap2.Namespace(time_unit=0.08, topk_ped=6, sight_angle_ped=90, dist_threshold_ped=4, topk_obs=10,
+                                  sight_angle_obs=90, dist_threshold_obs=4)
+            outs = {}
+            for mode in ("1", "0"):
+                os.environ["PIML_ROLLOUT_FUSED"] = mode
+                outs[mode] = [x.clone() for x in rollout_scenes(net.spec, packed, rargs, scene, 0, T, packed_tc=ptc)]
+            os.environ.pop("PIML_ROLLOUT_FUSED", None)
+            for x, y in zip(outs["1"], outs["0"]):
+                assert torch.equal(x.view(torch.int32), y.view(torch.int32)), ("fused rollout", S, T, Ns, Mo)
+            nr += 1
+        else:
+            S = int(rng.choice([1, 1, 2, 5])); N = int(rng.integers(7, 20000 // S)); Mo = int(rng.integers(11, 1500))
+            kp, ko = int(rng.integers(1, 7)), int(rng.integers(1, 11))
+            ang = int(rng.choice([60, 90, 90, 120, 170])); thr = float(rng.choice([1.5, 4.0, 6.0]))
+            side = float(np.sqrt(N / float(rng.choice([0.2, 0.5, 2.0]))))
+            p = torch.rand(S, N, 2, generator=g) * side
+            p[torch.rand(S, N, generator=g) < 0.1] = float('nan')
+            v = torch.randn(S, N, 2, generator=g); v[torch.rand(S, N, generator=g) < 0.05] = 0
+            acc = torch.randn(S, N, 2, generator=g) * 0.3
+            dest = torch.rand(S, N, 2, generator=g) * side
+            ob = torch.rand(*((S, Mo, 2) if rng.random() < 0.3 else (Mo, 2)), generator=g) * side
+            ds = 1.0 + torch.rand(S, N, generator=g)
+            st = lambda: [x.clone().to(dev) for x in (p, v, acc, dest)] + [torch.zeros(S, N, dtype=torch.int64, device=dev),
+                                                                          torch.nan_to_num(v).to(dev)]
+            A, B = st(), st()
+            dn, wp, dsd, obd = torch.ones(S, N, dtype=torch.int64, device=dev), dest[:, None].to(dev).contiguous(), ds.to(dev), ob.to(dev)
+            fa = (kp, ang, thr, ko, ang, thr)
+            step = NNStep(net.spec, ptc, *B, dn, wp, dsd, obd, 0.08, *fa)
+            for _ in range(2):
+                pf, of, sf = state_features(A[0], A[1], A[2], A[3], obd, A[5], dsd, *fa)
+                an = M.pinnsf_forward(net.spec, packed, pf.view(S * N, -1, 6), of.view(S * N, -1, 6), sf.view(S * N, 7),
+                                      need_msgs=False, packed_tc=ptc)[0].view(S, N, 2)
+                integrate_step(A[0], A[1], A[2], an, A[3], A[4], dn, wp, 0.08, True, hist_v=A[5])
+                step.step()
+            for x, y in zip(A, B):
+                assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                   y.view(torch.int32) if y.dtype == torch.float32 else y), ("fused step", S, N, Mo, kp, ko, ang, thr)
+        n += 1
+    print(f"fused NN step vs three calls: {n - nr} crowds; fused rollout loop vs per-stage loop: {nr} scene batches; bit-identical")
+
+
+fuzz_mlapm(); fuzz_features(); fuzz_tc(); fuzz_sfm_rollout(); fuzz_nn_step()
 print("fuzz ok")

@@ -446,6 +446,29 @@ def test_pinnsf_forward_tensor_cores_vs_fp32_kernel(kind, R, kp, ko, chan, has_o
             assert float((got[2] - ref[2]).abs().max()) < TOL * float(ref[2].abs().max())
 
 
+@pytest.mark.parametrize("f16", ["1", "0"])
+@pytest.mark.parametrize("R,kp,ko", [(700, 1, 1), (401, 1, 7), (333, 2, 1), (130, 3, 1)])
+def test_tensor_core_forward_with_one_slot_per_agent(R, kp, ko, f16, monkeypatch):
+    """topk = 1 packs 128 agents into a dense tile: 256 slot sums for 128 threads (the dense mode of both tensor-core
+    kernels wrote only the first 64 agents' sums until round 2; found by scripts/fuzz_parity.py's fused-step family)."""
+    from piml_b200 import models as M
+    from .golden_args import base_args
+    monkeypatch.setenv("PIML_TC_F16", f16)
+    net = M.CLASSES["pinnsf_bm"](base_args(model="pinnsf_bm", dataset_name="gc1560")).cuda().eval()
+    g = torch.Generator().manual_seed(R)
+    ped = torch.randn(R, kp, 6, generator=g).cuda()
+    obs = torch.randn(R, ko, 6, generator=g).cuda()
+    obs[::3] = 0
+    slf = torch.randn(R, 7, generator=g).cuda()
+    packed = M.pack_device(net.state_dict(), net.spec)
+    ptc = M.pack_device_tc(net.state_dict(), net.spec)
+    ref = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True)
+    for need in (False, True):
+        got = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=need, packed_tc=ptc)
+        err = accel_err(npy(got[0]), npy(ref[0]), npy(slf), net.spec.tau)
+        assert err < TOL, (need, err)
+
+
 @pytest.mark.parametrize("R,kp,ko,pz,chan", [(3001, 6, 10, 0.6, 0), (700, 6, 10, 1.0, 0), (129, 6, 10, 0.0, 0),
                                              (5000, 6, 0, 0.3, 0), (1280, 4, 7, 0.8, 5)])
 def test_tensor_core_compact_mode_is_bit_identical(R, kp, ko, pz, chan):
