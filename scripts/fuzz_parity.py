@@ -5,6 +5,7 @@
    4. persistent social-force rollout kernel vs the per-step route: bit-identical
    5. fused NN step (piml_nn_step_f32) vs state_features -> pinnsf_forward -> integrate_step, and the rollout loop with the
       fused step forced vs the per-stage loop: random scenes / sizes / k / angles / thresholds, absent agents: bit-identical
+   6. tensor-core forwards vs the FP32-pipe forward: random rows / topk / zero patterns: 1e-5 of the summed operands
 Prints one line per family; exits non-zero on the first disagreement."""
 import argparse, os, sys, time
 import numpy as np
@@ -19,7 +20,7 @@ a = ap.parse_args()
 rng = np.random.default_rng(a.seed)
 dev = torch.device("cuda")
 cu = lambda x, dt=torch.float32: torch.as_tensor(np.asarray(x), dtype=dt).to(dev)
-budget = a.seconds / 5
+budget = a.seconds / 6
 
 
 def crowd(N, rho):
@@ -209,5 +210,37 @@ def fuzz_nn_step():
     print(f"fused NN step vs three calls: {n - nr} crowds; fused rollout loop vs per-stage loop: {nr} scene batches; bit-identical")
 
 
-fuzz_mlapm(); fuzz_features(); fuzz_tc(); fuzz_sfm_rollout(); fuzz_nn_step()
+def fuzz_tc_vs_fp32():
+    """6. both tensor-core forwards (fp16 split / 3xTF32, dense and compact as the size decides) vs the FP32-pipe kernel:
+    random row counts, topk, zero-slot patterns, with and without the per-slot messages; 1e-5 of the summed operands."""
+    from tests.util import accel_err
+    t0, n, worst = time.time(), 0, 0.0
+    nets = {}
+    for kind in ("pinnsf_bm", "pinnsf_m"):
+        torch.manual_seed(2)
+        net = M.CLASSES[kind](base_args(model=kind, dataset_name="gc1560")).to(dev).eval()
+        nets[kind] = (net, M.pack_device(net.state_dict(), net.spec, dev), M.pack_device_tc(net.state_dict(), net.spec, dev))
+    while time.time() - t0 < budget:
+        kind = "pinnsf_bm" if rng.random() < 0.6 else "pinnsf_m"
+        net, packed, ptc = nets[kind]
+        R = int(rng.integers(1, 9000)); kp = int(rng.integers(1, 9)); ko = int(rng.integers(1, 13)); pz = float(rng.random())
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        ped = torch.randn(R, kp, 6, generator=g); obs = torch.randn(R, ko, 6, generator=g)
+        ped[torch.rand(R, kp, generator=g) < pz] = 0; obs[torch.rand(R, ko, generator=g) < pz] = 0
+        slf = torch.randn(R, 7, generator=g)
+        ped, obs, slf = ped.to(dev), obs.to(dev), slf.to(dev)
+        ref = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=True)[0]
+        for f16 in ("1", "0"):
+            os.environ["PIML_TC_F16"] = f16
+            for need in ((False, True) if kind == "pinnsf_bm" else (False,)):
+                got = M.pinnsf_forward(net.spec, packed, ped, obs, slf, need_msgs=need, packed_tc=ptc)[0]
+                err = accel_err(got.cpu().numpy(), ref.cpu().numpy(), slf.cpu().numpy(), net.spec.tau)
+                worst = max(worst, err)
+                assert err < 1e-5, ("tc vs fp32", kind, R, kp, ko, pz, f16, need, err)
+        os.environ.pop("PIML_TC_F16", None)
+        n += 1
+    print(f"tensor-core forwards vs FP32-pipe forward: {n} batches, worst operand-scaled error {worst:.2e}")
+
+
+fuzz_mlapm(); fuzz_features(); fuzz_tc(); fuzz_sfm_rollout(); fuzz_nn_step(); fuzz_tc_vs_fp32()
 print("fuzz ok")
