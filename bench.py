@@ -406,11 +406,14 @@ class NNCrowd(object):
         self.packed = M.pack_device(self.net.state_dict(), self.net.spec, dev)
         self.packed_tc = M.pack_device_tc(self.net.state_dict(), self.net.spec, dev)
         p, v, ds, dest, _ = synthetic_crowd(N)
-        self.host = {"p": p.pin_memory(), "v": v.pin_memory(), "a": torch.zeros_like(v).pin_memory(),
-                     "dest": dest.pin_memory(), "ds": ds.reshape(1, N).contiguous().pin_memory()}
-        self.p, self.v, self.dest = [x.to(dev)[None].contiguous() for x in (p, v, dest)]
-        self.acc, self.hist = torch.zeros_like(self.v), self.v.clone()
-        self.ds = ds.reshape(1, N).contiguous().to(dev)
+        # the crowd's state in ONE device buffer [p | v | a | dest | desired speed] (9 N floats) with a pinned host twin:
+        # a host-side loop then pays one H2D and one D2H per step instead of five + three
+        self.h_state = torch.cat([p.reshape(-1), v.reshape(-1), torch.zeros(2 * N), dest.reshape(-1),
+                                  ds.reshape(-1)]).pin_memory()
+        self.d_state = self.h_state.to(dev)
+        self.p, self.v, self.acc, self.dest = [self.d_state[2 * N * k:2 * N * (k + 1)].view(1, N, 2) for k in range(4)]
+        self.ds = self.d_state[8 * N:].view(1, N)
+        self.hist = self.v.clone()
         self.obs = obs_h.to(dev)
         self.didx = torch.zeros(1, N, dtype=torch.int64, device=dev)
         self.dnum = torch.ones(1, N, dtype=torch.int64, device=dev)
@@ -419,7 +422,7 @@ class NNCrowd(object):
                                          *NN_FEATURE_ARGS)) + (torch.empty(1, N, 2, device=dev),)
         self.a_next = None
         self._fused = None
-        self.out_h = [torch.empty(N, 2).pin_memory() for _ in range(3)]
+        self.h_out = torch.empty(6 * N).pin_memory()           # new p | v | a
 
     def forward(self):
         N, M = self.N, self.models
@@ -449,13 +452,10 @@ class NNCrowd(object):
 
     def e2e_step(self):
         """Host state in (pinned), one step, new p / v / a out: what a host-side simulation loop pays per step."""
-        h = self.host
-        self.p[0].copy_(h["p"], non_blocking=True); self.v[0].copy_(h["v"], non_blocking=True)
-        self.acc[0].copy_(h["a"], non_blocking=True); self.dest[0].copy_(h["dest"], non_blocking=True)
-        self.ds.copy_(h["ds"], non_blocking=True)
+        self.d_state.copy_(self.h_state, non_blocking=True)
         self.hist.copy_(self.v)
         self.step_fused()
-        self.out_h[0].copy_(self.p[0]); self.out_h[1].copy_(self.v[0]); self.out_h[2].copy_(self.acc[0])
+        self.h_out.copy_(self.d_state[:6 * self.N])
 
     @property
     def e2e_bytes(self):
@@ -597,7 +597,8 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
                                      "at this size; bytes_per_agent_step is what the unfused stages move"}},
         "e2e": {"value": N / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
-                "api": "pinned host p, v, a, dest, desired speed -> NNStep.step (piml_nn_step_f32) -> host p, v, a"},
+                "api": "pinned host state [p | v | a | dest | desired speed] (one buffer, one H2D) -> NNStep.step "
+                       "(piml_nn_step_f32) -> host [p | v | a] (one D2H)"},
         "gpu_launches": launches,
     }
     if with_cpu:
