@@ -8,15 +8,19 @@
 // evaluate the same exact-arithmetic predicate (gated_distance) and keep the k smallest (distance, index) keys.
 //
 // Pipeline per call (no host synchronisation, all on the caller's stream):
-//   1. cell_count_kernel   : cell of every point -> spatial-hash bucket; atomic count per bucket, rank of the point
-//   2. scan (3 tiny kernels): exclusive prefix sum of the bucket counts
-//   3. cell_scatter_kernel : records {x, y, index, packed cell} sorted by bucket (counting sort)
+//   1. cell_count2_kernel  : cell of every point -> spatial-hash bucket; atomic count per bucket, rank of the point;
+//                            agents without a position go to the `absent` list (one atomic per warp)
+//   2. scan (2 kernels)    : exclusive prefix sum of the bucket counts; the second kernel zeroes the counters it has
+//                            read, so the next call needs no memset (3 kernels + memset beyond 4096 scan blocks)
+//   3. cell_scatter2_kernel: records {x, y, flat row | obstacle index, packed cell} sorted by bucket (counting sort)
 //   4. features_sorted_kernel: G = 4 lanes per agent, agents taken in SORTED (bucket) order, so the lanes of a warp walk
 //      the same 9 buckets (coherent trip counts, broadcast loads); each lane keeps the k best of every 4th candidate,
 //      the lists are merged with shuffles and the lanes share the slot outputs.  Hash collisions and repeated buckets
 //      are filtered by comparing the record's packed cell with the cell being visited.  Optionally it also emits the
 //      COMPACT slot rows (non-empty slots only, + a slot -> row map) the fused NN step feeds to the tensor cores
-//      (nn_step.cu).  Row-range calls (agent-sharded ranks) keep the one-thread-per-agent features_cells_kernel.
+//      (nn_step.cu); agent-sharded ranks of the fused step pass the list of their own agents (own_list_kernel).
+//      Row-range calls with DENSE outputs (the three-call sharded route) keep the one-thread-per-agent
+//      features_cells_kernel.
 // Buckets are a hash of the integer cell coordinates (no bounding box needed => no device->host read of extents);
 // cell coordinates are computed in fp64 so that rounding can never move a candidate two cells away.
 #include <mutex>

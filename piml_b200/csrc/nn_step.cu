@@ -14,7 +14,12 @@
 //     same order as the dense evaluation), adds the destination term (model.py:1205-1210) and applies the state update
 //     of integrate_kernel in the same thread: the model output never round-trips through HBM between two launches;
 //   * the cell-list build needs no memset and 4 launches (fused scan, counters zeroed by their reader).
-// Results are bit-identical to the three-call route (tests/test_gpu_nn_step.py).
+//   * empty slots are not represented at all: a per-agent live-slot count (the live slots are a prefix of an agent's
+//     slots) replaces map entries, and warps none of whose agents has a position skip the search (batches of mostly
+//     empty scenes).
+// Results are bit-identical to the three-call route (tests/test_gpu_nn_step.py; scripts/fuzz_parity.py family 5).
+// piml_nn_step_shard_f32 is the same chain for one rank of an agent-sharded crowd: own agents only, new p, v, a stored
+// into every rank's next-state arrays over NVLink peer memory by the finish kernel.
 #include "features_common.cuh"
 #include "integrate_common.cuh"
 #include "mlp_tc16.cuh"
