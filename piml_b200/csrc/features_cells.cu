@@ -9,7 +9,7 @@
 //
 // Pipeline per call (no host synchronisation, all on the caller's stream):
 //   1. cell_count2_kernel  : cell of every point -> spatial-hash bucket; atomic count per bucket, rank of the point;
-//                            agents without a position go to the `absent` list (one atomic per warp)
+//                            agents without a position get their (all-empty) outputs right here
 //   2. scan (2 kernels)    : exclusive prefix sum of the bucket counts; the second kernel zeroes the counters it has
 //                            read, so the next call needs no memset (3 kernels + memset beyond 4096 scan blocks)
 //   3. cell_scatter2_kernel: records {x, y, flat row | obstacle index, packed cell} sorted by bucket (counting sort)
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int *__restrict__
 
 // phases 2 + 3 in one launch for up to SCAN_FUSED_BLOCKS blocks: every block adds up the totals of the blocks before
 // it by itself (a few hundred ints from L2) instead of waiting for a one-block offsets kernel.  It also ZEROES the
-// counters it has read (and the absent-agent counter behind them), so the next call's count kernel needs no memset:
+// counters it has read (and the own-list counter behind them), so the next call's count kernel needs no memset:
 // the grid build is 4 launches (count, block sums, this, scatter).
 constexpr int SCAN_FUSED_BLOCKS = 4096;
 __global__ void __launch_bounds__(256) scan_apply_fused_kernel(int *__restrict__ in, int64_t n,
@@ -160,39 +160,74 @@ __global__ void __launch_bounds__(256) scan_apply_fused_kernel(int *__restrict__
     if (base <= n - 1 && n - 1 < base + 8) { out[n] = run; in[n] = 0; in[n + 1] = 0; }   // the thread owning the last element
 }
 
-// The agents without a position (NaN: absent from the frame) are in no bucket; the count kernel lists them so that the
-// sorted-order feature kernel can still write their (all-zero) rows: absent[0 .. total0 - present).  The list's
-// counter lives right behind the bucket counters (counts[cells]; counts[cells + 1] counts a rank's own-agent list)
-// and is zeroed with them.
 // Both point sets of a feature call (agents and obstacles) in ONE counting-sort chain: the cell arrays are
-// concatenated (agents' buckets first), so one count / scan / scatter sequence builds both grids -- 6 stream
-// operations per call instead of 12.  set 0: points [0, total0), n0 per frame, H0 buckets per frame, cells from 0;
+// concatenated (agents' buckets first), so one count / scan / scatter sequence builds both grids.
+// set 0: points [0, total0), n0 per frame, H0 buckets per frame, cells from 0;
 // set 1: the following total1 points, cells from cells0 on.  The exclusive scan runs over the concatenation, so the
 // obstacle grid's start values already include the number of agent records and both grids index the SAME record array.
 struct TwoSets {
     const float2 *pts0, *pts1; int64_t total0, total1; int n0, n1, H0, H1; int64_t cells0;
 };
 
+// The agents without a position (NaN: absent from the frame) are in no bucket and need no search: everything the
+// feature call owes them -- all-zero slots (a live-slot count of 0 in the compact form), dest_f / self_f, the in-place
+// NaN -> 0 of their velocity and acceleration (data.py:483-484) -- is written right here by the count kernel, which
+// sees every agent anyway; the sorted-order feature kernel then takes the present agents only.  (A list of the absent
+// agents for that kernel's tail was tried first: 4096 mostly empty scenes append 400k entries per step through ONE
+// counter, 25 us of same-address atomics even when aggregated per warp.)
+struct AbsentOut {
+    bool enabled;                  // false: the one-thread-per-agent kernel handles absent rows itself (row-range calls)
+    FeatArgs a;                    // output pointers, dims, row range (row1 > 0: only rows [row0, row1) are written)
+    uint16_t *live;                // compact form: live-slot counts, or nullptr
+};
+
 __global__ void cell_count2_kernel(const TwoSets t, double inv_cs, int *__restrict__ counts, int *__restrict__ rank,
-                                   int *__restrict__ absent, int *__restrict__ n_absent) {
+                                   const AbsentOut ab) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool in = i < t.total0 + t.total1;
+    if (i >= t.total0 + t.total1) return;
     const bool second = i >= t.total0;
     const int64_t j = second ? i - t.total0 : i;
-    float2 p = make_float2(0.f, 0.f);
-    if (in) p = (second ? t.pts1 : t.pts0)[j];
-    const bool nan = in && (p.x != p.x || p.y != p.y);
-    // absent agents: one atomic per warp (4096 mostly empty scenes list 400k of them per step)
-    const unsigned m = __ballot_sync(0xffffffffu, nan && !second);
-    if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(n_absent, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (nan && !second) absent[base + __popc(m & ((1u << lane) - 1))] = static_cast<int>(j);
+    const float2 p = (second ? t.pts1 : t.pts0)[j];
+    if (p.x != p.x || p.y != p.y) {
+        rank[i] = -1;
+        const FeatArgs &a = ab.a;
+        if (second || !ab.enabled || (a.row1 > 0 && (j < a.row0 || j >= a.row1))) return;
+        const int64_t row = j;
+        float2 v = reinterpret_cast<const float2 *>(a.vel)[row], ac = reinterpret_cast<const float2 *>(a.acc)[row];
+        if (v.x != v.x || v.y != v.y)
+            reinterpret_cast<float2 *>(a.vel)[row] = make_float2(nan_to_zero(v.x), nan_to_zero(v.y));
+        if (ac.x != ac.x || ac.y != ac.y)
+            reinterpret_cast<float2 *>(a.acc)[row] = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+        ac = make_float2(nan_to_zero(ac.x), nan_to_zero(ac.y));
+        const float2 z = make_float2(0.f, 0.f);
+        if (a.ped_f)
+            for (int q = 0; q < a.kp; ++q) {
+                float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + q) * 3;
+                out[0] = z; out[1] = z; out[2] = z;
+                if (a.ped_idx) a.ped_idx[row * a.kp + q] = -1;
+                if (a.ped_dist) a.ped_dist[row * a.kp + q] = CUDART_INF_F;
+            }
+        if (a.obs_f && a.M > 0)
+            for (int q = 0; q < a.ko; ++q) {
+                float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + q) * 3;
+                out[0] = z; out[1] = z; out[2] = z;
+                if (a.obs_idx) a.obs_idx[row * a.ko + q] = -1;
+                if (a.obs_dist) a.obs_dist[row * a.ko + q] = CUDART_INF_F;
+            }
+        if (a.dest_f) {
+            const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
+            const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
+            reinterpret_cast<float2 *>(a.dest_f)[row] = df;
+            if (a.self_f) {
+                const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
+                float *sf = a.self_f + row * 7;
+                sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
+                sf[6] = a.desired_speed[row];
+            }
+        }
+        if (ab.live) ab.live[row] = 0;
+        return;
     }
-    if (!in) return;
-    if (nan) { rank[i] = -1; return; }
     const int n = second ? t.n1 : t.n0, H = second ? t.H1 : t.H0;
     const int64_t frame = j / n;
     const uint32_t b = bucket_of(cell_coord(p.x, inv_cs), cell_coord(p.y, inv_cs), H);
@@ -501,33 +536,28 @@ __device__ __forceinline__ int compact_append(bool live, int *counter) {
 
 template <int KP, int KO>
 __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs a, HashGrid gp, HashGrid go,
-                                                                       double inv_cs, const int *__restrict__ absent,
-                                                                       CompactOut co, const int *__restrict__ order,
-                                                                       int n_order) {
+                                                                       double inv_cs, CompactOut co,
+                                                                       const int *__restrict__ order,
+                                                                       const int *__restrict__ n_order) {
     constexpr int G = SORT_G;
     __shared__ float pend_all[3 * POOL_GROUPS * POOL_STRIDE];
     __shared__ int bnd_all[BND_WORDS * (CELL_THREADS / SORT_G)];
     const Pending pend(pend_all);
     int *bnd = bnd_all + BND_WORDS * (threadIdx.x / SORT_G);
-    // groups take the agents in sorted order: all of them, or (agent-sharded ranks) the `order` list of this rank's
-    // own agents -- sorted positions, or -(row + 1) for an absent agent (own_list_kernel)
-    const int64_t all_rows = order ? n_order : static_cast<int64_t>(a.B) * a.N;
+    // groups take the PRESENT agents in sorted order: all of them, or (agent-sharded ranks) the `order` list of this
+    // rank's own agents (sorted positions, own_list_kernel); absent agents were served by the count kernel
+    const int64_t n_present = gp.start[static_cast<int64_t>(a.B) * gp.H];
+    const int64_t all_rows = order ? *n_order : n_present;
     const int64_t grp = (static_cast<int64_t>(blockIdx.x) * CELL_THREADS + threadIdx.x) / G;
+    if (static_cast<int64_t>(blockIdx.x) * CELL_THREADS / G >= all_rows) return;   // whole CTA beyond the list (uniform)
     const int l = threadIdx.x % G;
     const bool valid = grp < all_rows;                             // no early exit: the group shuffles need every lane
-    const int64_t n_present = gp.start[static_cast<int64_t>(a.B) * gp.H];
     int64_t row = 0;
     float2 p = make_float2(CUDART_NAN_F, CUDART_NAN_F);
     if (valid) {
-        const int64_t s = order ? order[grp] : (grp < n_present ? grp : -static_cast<int64_t>(absent[grp - n_present]) - 1);
-        if (s >= 0) {
-            const float4 r = gp.rec[s];
-            row = __float_as_int(r.z);
-            p = make_float2(r.x, r.y);
-        } else {
-            row = -(s + 1);
-            p = reinterpret_cast<const float2 *>(a.pos)[row];
-        }
+        const float4 r = gp.rec[order ? order[grp] : grp];
+        row = __float_as_int(r.z);
+        p = make_float2(r.x, r.y);
     }
     const int b = static_cast<int>(row / a.N);
     float2 v = make_float2(0.f, 0.f), ac = v;
@@ -559,42 +589,6 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
     const int cx = present ? cell_coord(p.x, inv_cs) : 0, cy = present ? cell_coord(p.y, inv_cs) : 0;
 
     int live_ped = 0, live_obs = 0;
-    // A warp none of whose agents has a position (the tail of the order: a batch of mostly empty scenes lists 400k
-    // absent slots per step) has nothing to search: all slots empty.
-    if (!__any_sync(0xffffffffu, present)) {
-        if (valid) {
-            const float2 z = make_float2(0.f, 0.f);
-            if (a.ped_f)
-                for (int j = l; j < a.kp; j += G) {
-                    float2 *out = reinterpret_cast<float2 *>(a.ped_f) + (row * a.kp + j) * 3;
-                    out[0] = z; out[1] = z; out[2] = z;
-                    if (a.ped_idx) a.ped_idx[row * a.kp + j] = -1;
-                    if (a.ped_dist) a.ped_dist[row * a.kp + j] = CUDART_INF_F;
-                }
-            if (a.obs_f && a.M > 0)
-                for (int j = l; j < a.ko; j += G) {
-                    float2 *out = reinterpret_cast<float2 *>(a.obs_f) + (row * a.ko + j) * 3;
-                    out[0] = z; out[1] = z; out[2] = z;
-                    if (a.obs_idx) a.obs_idx[row * a.ko + j] = -1;
-                    if (a.obs_dist) a.obs_dist[row * a.ko + j] = CUDART_INF_F;
-                }
-            if (l == 0) {
-                if (a.dest_f) {
-                    const float2 d = reinterpret_cast<const float2 *>(a.dest)[row];
-                    const float2 df = make_float2(nan_to_zero(__fsub_rn(d.x, p.x)), nan_to_zero(__fsub_rn(d.y, p.y)));
-                    reinterpret_cast<float2 *>(a.dest_f)[row] = df;
-                    if (a.self_f) {
-                        const float2 hv = reinterpret_cast<const float2 *>(a.hist_v)[row];
-                        float *sf = a.self_f + row * 7;
-                        sf[0] = df.x; sf[1] = df.y; sf[2] = hv.x; sf[3] = hv.y; sf[4] = ac.x; sf[5] = ac.y;
-                        sf[6] = a.desired_speed[row];
-                    }
-                }
-                if (co.counts) co.live[row] = 0;
-            }
-        }
-        return;
-    }
     // ---- pedestrian - pedestrian ----
     {
         TopK<KP> best;
@@ -690,22 +684,18 @@ __global__ void __launch_bounds__(CELL_THREADS) features_sorted_kernel(FeatArgs 
     if (co.counts && valid && l == 0) co.live[row] = static_cast<uint16_t>(live_ped | (live_obs << 8));
 }
 
-// Agent-sharded ranks: the sorted positions of the agents in rows [row0, row1) (warp-aggregated append: the entries a
-// warp appends are neighbours in space, which is all the feature kernel's coherence needs), absent agents as -(row+1).
-__global__ void own_list_kernel(const float4 *__restrict__ rec, const int *__restrict__ start_end,
-                                const int *__restrict__ absent, int64_t total, int64_t row0, int64_t row1,
-                                int *__restrict__ order, int *__restrict__ counter) {
+// Agent-sharded ranks: the sorted positions of the PRESENT agents in rows [row0, row1) (warp-aggregated append: the
+// entries a warp appends are neighbours in space, which is all the feature kernel's coherence needs).
+__global__ void own_list_kernel(const float4 *__restrict__ rec, const int *__restrict__ start_end, int64_t row0,
+                                int64_t row1, int *__restrict__ order, int *__restrict__ counter) {
     const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t n_present = *start_end;
-    int entry = 0;
     bool own = false;
-    if (s < total) {
-        const int64_t row = s < n_present ? __float_as_int(rec[s].z) : absent[s - n_present];
+    if (s < *start_end) {
+        const int64_t row = __float_as_int(rec[s].z);
         own = row >= row0 && row < row1;
-        entry = s < n_present ? static_cast<int>(s) : -static_cast<int>(row) - 1;
     }
     const int pos = compact_append(own, counter);
-    if (own) order[pos] = entry;
+    if (own) order[pos] = static_cast<int>(s);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -781,16 +771,15 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     const int nblocks = static_cast<int>((cells + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);
     const size_t bytes = align256(sizeof(int) * (cells + 2)) + align256(sizeof(int) * (cells + 1)) +
                          align256(sizeof(int) * (totalP + totalO)) + align256(sizeof(int) * (nblocks + 1)) +
-                         2 * align256(sizeof(int) * totalP) + align256(sizeof(float4) * (totalP + totalO));
+                         align256(sizeof(int) * totalP) + align256(sizeof(float4) * (totalP + totalO));
     char *base = nullptr;
     ByteScratch *slot = nullptr;
     int rc = cell_scratch_get(st, bytes, &base, &slot);
     if (rc) return rc;
-    int *counts = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 2));   // + absent, own-list counters
+    int *counts = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 2));   // + own-list counter (+ 1 spare)
     int *start = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (cells + 1));
     int *rank = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (totalP + totalO));
     int *bsums = reinterpret_cast<int *>(base); base += align256(sizeof(int) * (nblocks + 1));
-    int *absent = reinterpret_cast<int *>(base); base += align256(sizeof(int) * totalP);
     int *order = reinterpret_cast<int *>(base); base += align256(sizeof(int) * totalP);
     float4 *rec = reinterpret_cast<float4 *>(base);
     TwoSets ts{reinterpret_cast<const float2 *>(a.pos), reinterpret_cast<const float2 *>(a.obs), totalP, totalO, a.N,
@@ -802,7 +791,11 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
         slot->zeroed = fused ? cells + 2 : 0;
     }
     const unsigned pblocks = static_cast<unsigned>((totalP + totalO + CELL_THREADS - 1) / CELL_THREADS);
-    cell_count2_kernel<<<pblocks, CELL_THREADS, 0, st>>>(ts, inv_cs, counts, rank, absent, counts + cells);
+    AbsentOut ab;
+    ab.enabled = !(a.row1 > 0 && !co);                             // the row-range dense kernel serves its absent rows itself
+    ab.a = a;
+    ab.live = co ? co->live : nullptr;
+    cell_count2_kernel<<<pblocks, CELL_THREADS, 0, st>>>(ts, inv_cs, counts, rank, ab);
     scan_block_sums_kernel<<<nblocks, 256, 0, st>>>(counts, cells, bsums);
     if (fused) {
         scan_apply_fused_kernel<<<nblocks, 256, 0, st>>>(counts, cells, bsums, start);
@@ -831,18 +824,18 @@ int relative_features_cells(const FeatArgs &a, int obs_frames, cudaStream_t st, 
     const int *ord = nullptr;
     int64_t groups = totalP;
     if (a.row1 > 0) {                                              // agent-sharded rank: its own agents, in sorted order
-        own_list_kernel<<<static_cast<unsigned>((totalP + 255) / 256), 256, 0, st>>>(rec, start + cellsP, absent, totalP,
-                                                                                     a.row0, a.row1, order, counts + cells + 1);
+        own_list_kernel<<<static_cast<unsigned>((totalP + 255) / 256), 256, 0, st>>>(rec, start + cellsP, a.row0, a.row1,
+                                                                                     order, counts + cells + 1);
         count_launch();
         ord = order;
         groups = a.row1 - a.row0;
     }
-    const int n_ord = static_cast<int>(groups);
+    const int *n_ord = counts + cells + 1;                         // own-list length (device)
     const unsigned blocks = static_cast<unsigned>((groups * SORT_G + CELL_THREADS - 1) / CELL_THREADS);
-    if (a.kp <= 6 && a.ko <= 10) features_sorted_kernel<6, 10><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);   // the reference's topk
-    else if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
-    else if (a.kp <= 16 && a.ko <= 16) features_sorted_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
-    else features_sorted_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, absent, c, ord, n_ord);
+    if (a.kp <= 6 && a.ko <= 10) features_sorted_kernel<6, 10><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, c, ord, n_ord);   // the reference's topk
+    else if (a.kp <= 8 && a.ko <= 16) features_sorted_kernel<8, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, c, ord, n_ord);
+    else if (a.kp <= 16 && a.ko <= 16) features_sorted_kernel<16, 16><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, c, ord, n_ord);
+    else features_sorted_kernel<32, 32><<<blocks, CELL_THREADS, 0, st>>>(a, hp, ho, inv_cs, c, ord, n_ord);
     count_launch();
     return check_launch("features_sorted_kernel");
 }
