@@ -766,6 +766,53 @@ def nn_crowd_1m_block(torch, dist, dev, world, rank, steps=5):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def clip_rollouts_block(torch, dev):
+    """BASELINE configs[0] / [1] as the reference runs them: ONE clip rolled from t = 25 to its last frame through
+    `piml_rollout_f32` -- the GC clip (N = 122 slots, 750 frames, pinnsf_bm with the golden run's weights) and the
+    synthetic social-force clip (N = 110, 750 frames, the pure social-force model in the persistent kernel).  A single
+    scene is launch-latency bound; the reference takes 13-20 ms per step on CPU."""
+    import argparse as ap
+    import numpy as np
+    import piml_b200 as P
+    from piml_b200 import models as M
+    from piml_b200.rollout import rollout_scenes
+    out = {}
+    for name, key in (("rollout_gc_bm", "gc_clip_pinnsf_bm"), ("rollout_syn_sfm", "synthetic_clip_social_force")):
+        try:
+            z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+            t0, T = int(z["in/t_start"]), int(z["in/position"].shape[0])
+            cu = lambda k, dt=torch.float32: torch.as_tensor(z["in/" + k]).to(dev, dt)
+            scene = {k: cu(k)[None].contiguous() for k in ("position", "velocity", "acceleration", "destination",
+                                                           "mask_p", "mask_p_pred", "waypoints", "desired_speed")}
+            scene["dest_idx"], scene["dest_num"] = cu("dest_idx", torch.int64)[None], cu("dest_num", torch.int64)[None]
+            scene["obstacles"] = cu("obstacles")
+            for k in ("ped_features0", "obs_features0", "self_features0"):
+                scene[k] = cu(k)[None]
+            args = ap.Namespace(**dict(NN_ARGS, time_unit=float(z["in/time_unit"])))
+            if str(z["in/model"]) == "sfm":
+                spec, packed, packed_tc = P.SocialForce(str(z["in/dataset_name"])).spec, None, None
+            else:
+                torch.manual_seed(666)
+                net = M.PINNSF_bottleneck_multitask(args).to(dev).eval()
+                net.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")})
+                spec, packed = net.spec, M.pack_device(net.state_dict(), net.spec, dev)
+                packed_tc = M.pack_device_tc(net.state_dict(), net.spec, dev)
+            run = lambda: rollout_scenes(spec, packed, args, scene, t0, T, packed_tc=packed_tc)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms, N, steps = e0.elapsed_time(e1), int(scene["position"].shape[2]), T - t0
+            out[key] = {"slots": N, "frames": steps, "ms_total": ms, "ms_per_step": ms / steps,
+                        "agent_steps_per_sec": N * steps / ms * 1e3, "finite_positions": int(torch.isfinite(res[0]).sum())}
+        except Exception as e:                               # secondary block: never take the headline down
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
+
+
 def scenes_block(torch, dist, dev, world, rank, S_total=4096, steps=100):
     """BASELINE configs[4] (b): 4096 independent GC-shaped scenes (the GC clip's own state at t = 25, jittered per scene
     by seeded N(0, 0.05 m)) rolled `steps` frames with pinnsf_bm; scene s runs on rank s mod G, no communication."""
@@ -1183,6 +1230,7 @@ def run_ours(a):
         }
         if world == 1:
             line["nn_path"] = nn_workload(torch, dev, N, obs_h, 10, 3, with_cpu=not a.no_cpu)
+            line["clip_rollouts"] = clip_rollouts_block(torch, dev)
         else:
             line["nn_path"] = nn_sharded
             line["timeline"] = timeline
