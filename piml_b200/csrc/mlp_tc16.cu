@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 const long long q2 = T16_CLOCK();
                 if (prof) sprof[4] += q2 - q1;
                 float *v = reinterpret_cast<float *>(r);
-                float mx = 0.f;
+                float mx = 0.f, mxb4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent maximum chains (ILP), merged below
                 const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -314,10 +314,11 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                                 y23.x = fmaxf(y23.x, 0.f); y23.y = fmaxf(y23.y, 0.f);
                             }
                             v[e] = y01.x; v[e + 1] = y01.y; v[e + 2] = y23.x; v[e + 3] = y23.y;
-                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(y01.x), fabsf(y01.y))), fmaxf(fabsf(y23.x), fabsf(y23.y)));
+                            mxb4[q4b] = fmaxf(fmaxf(mxb4[q4b], fmaxf(fabsf(y01.x), fabsf(y01.y))), fmaxf(fabsf(y23.x), fabsf(y23.y)));
                         }
                     }
                 }
+                mx = fmaxf(fmaxf(mxb4[0], mxb4[1]), fmaxf(mxb4[2], mxb4[3]));
                 if (last) {                                        // predictor Linear(dw, 2) on the CUDA cores
                     tl2 = q2;
                     const float *w0 = biasb + P.predw_off + half * hc, *w1 = w0 + P.dw;
