@@ -76,9 +76,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         mbar_fence_init();
     }
     // tiles of both branches (compact mode: the listed non-zero rows + ONE zero row per branch), CTAs split in proportion
-    const int64_t cnt_ped = a.compact ? a.counts[0] + 1 : 0, cnt_obs = (a.compact && a.has_obs) ? a.counts[1] + 1 : 0;
-    const int64_t nP = a.compact ? (cnt_ped + 127) / 128 : a.n_ped_tiles;
-    const int64_t nO = a.compact ? (cnt_obs + 127) / 128 : a.n_obs_tiles;
+    // 32-bit bookkeeping throughout (row counts are < 2^31 by the callers' checks): the epilogue lives at a 96-register ceiling
+    const int cnt_ped = a.compact ? a.counts[0] + 1 : 0, cnt_obs = (a.compact && a.has_obs) ? a.counts[1] + 1 : 0;
+    const int nP = a.compact ? (cnt_ped + 127) / 128 : static_cast<int>(a.n_ped_tiles);
+    const int nO = a.compact ? (cnt_obs + 127) / 128 : static_cast<int>(a.n_obs_tiles);
     const int G = gridDim.x;
     // CTAs per branch (one branch per CTA: its weights stay resident).  The kernel ends with its slowest CTA, so the
     // split minimises the larger per-CTA tile count: start from the proportional share and give the obstacle branch
@@ -95,10 +96,10 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     }
     const int gP = G - gO;
     const int br = static_cast<int>(blockIdx.x) < gP ? 0 : 1;
-    const int64_t first = br == 0 ? blockIdx.x : blockIdx.x - gP;
-    const int64_t stride = br == 0 ? gP : gO;
-    const int64_t ntiles_br = br == 0 ? nP : nO;
-    const int64_t my_tiles = first < ntiles_br ? (ntiles_br - first + stride - 1) / stride : 0;
+    const int first = br == 0 ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) - gP;
+    const int stride = br == 0 ? gP : gO;
+    const int ntiles_br = br == 0 ? nP : nO;
+    const int my_tiles = first < ntiles_br ? (ntiles_br - first + stride - 1) / stride : 0;
 
     const float *branch = a.params + P.base + static_cast<int64_t>(br) * P.branch_floats;
     for (int e = tid; e < P.bias_floats; e += T16_THREADS) biasb[e] = branch[P.w_bytes / 4 + e];
@@ -183,29 +184,29 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         const uint32_t tl = tbase + (static_cast<uint32_t>(q4 * 32) << 16) + slot * T16_SLOT_COLS;
         const int k = br == 0 ? a.kp : a.ko;
         const int AG = br == 0 ? a.ag_ped : a.ag_obs;
-        const int64_t cnt = br == 0 ? cnt_ped : cnt_obs;
+        const int cnt = br == 0 ? cnt_ped : cnt_obs;
         const int *list = br == 0 ? a.list_ped : a.list_obs;
         const float *feat = br == 0 ? a.ped : a.obs;
         float *smax = small + slot * 1024;                         // [2 parities][2 halves][128] row maxima
         float *sm2 = smax + 512;                                   // [2 halves][128][2] predictor partials / slot sums
         uint32_t dph = 0;
-        struct RowFeat { int64_t crow; float f[6]; bool live; };
-        auto load_row = [&](int64_t j) {                           // j: index into this CTA's tile sequence
+        struct RowFeat { int crow; float f[6]; bool live; };
+        auto load_row = [&](int j) {                           // j: index into this CTA's tile sequence
             RowFeat rf;
             rf.crow = -1; rf.live = false;
 #pragma unroll
             for (int q = 0; q < 6; ++q) rf.f[q] = 0.f;
             if (j >= my_tiles) return rf;
-            const int64_t tloc = first + j * stride;
+            const int tloc = first + j * stride;
             int64_t src;
             if (a.compact) {
-                const int nrows = static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128));
+                const int nrows = min(128, cnt - tloc * 128);
                 if (m < nrows && tloc * 128 + m < cnt - 1)                // no list (fused NN step): rows are stored compactly
                     rf.crow = list ? list[tloc * 128 + m] : static_cast<int>(tloc * 128 + m);
                 rf.live = rf.crow >= 0;
                 src = rf.crow;
             } else {
-                const int64_t agent0 = tloc * AG;
+                const int64_t agent0 = static_cast<int64_t>(tloc) * AG;
                 const int na = static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
                 rf.live = m < na * k;
                 src = agent0 * k + m;
@@ -242,17 +243,17 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         // predictor, exchange and stores are still in progress; the rows of tile j + 4 are then prefetched.
         RowFeat nxt = load_row(slot);
         float inv_s = 1.f;
-        int64_t crow = nxt.crow;
+        int crow = nxt.crow;
         if (slot < my_tiles) write_features(nxt, inv_s);
         nxt = load_row(slot + 2);
-        for (int64_t j = slot; j < my_tiles; j += 2) {
-            const int64_t tloc = first + j * stride;
-            const int64_t agent0 = tloc * AG;
+        for (int j = slot; j < my_tiles; j += 2) {
+            const int tloc = first + j * stride;
+            const int64_t agent0 = static_cast<int64_t>(tloc) * AG;
             const int na = a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
-            const int nrows = a.compact ? static_cast<int>(min(static_cast<int64_t>(128), cnt - tloc * 128)) : na * k;
+            const int nrows = a.compact ? min(128, cnt - tloc * 128) : na * k;
             const int64_t row0 = agent0 * k;
             float inv_s_next = 1.f;
-            int64_t crow_next = -1;
+            int crow_next = -1;
             const long long t0 = T16_CLOCK();
             long long tl2 = t0;
             float m0 = 0.f, m1 = 0.f;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             }
             if (a.compact) {
                 if (half == 0 && m < nrows) {                      // slot sums are formed by the finish kernel
-                    float *dst = crow >= 0 ? (br == 0 ? a.cmsg_ped : a.cmsg_obs) + crow * 2 : a.f0 + br * 2;
+                    float *dst = crow >= 0 ? (br == 0 ? a.cmsg_ped : a.cmsg_obs) + static_cast<int64_t>(crow) * 2 : a.f0 + br * 2;
                     dst[0] = m0; dst[1] = m1;
                 }
             } else {
