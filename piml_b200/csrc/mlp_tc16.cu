@@ -240,12 +240,15 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         };
         // Software pipeline across tiles: the operand of tile j + 2 (this slot's next tile) is written as soon as the
         // LAST accumulator of tile j has been read out, so its first layer runs on the tensor pipe while tile j's
-        // predictor, exchange and stores are still in progress; the rows of tile j + 4 are then prefetched.
-        RowFeat nxt = load_row(slot);
+        // predictor, exchange and stores are still in progress.  (Its rows are loaded right there: holding them in
+        // registers across the tile cost 8 of the 96 registers the epilogue has, i.e. spills.)
         float inv_s = 1.f;
-        int crow = nxt.crow;
-        if (slot < my_tiles) write_features(nxt, inv_s);
-        nxt = load_row(slot + 2);
+        int crow = -1;
+        {
+            const RowFeat first_rows = load_row(slot);
+            crow = first_rows.crow;
+            if (slot < my_tiles) write_features(first_rows, inv_s);
+        }
         for (int j = slot; j < my_tiles; j += 2) {
             const int tloc = first + j * stride;
             const int64_t agent0 = static_cast<int64_t>(tloc) * AG;
@@ -272,9 +275,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 if (a.dbg & 1) {                                   // timing experiment: no epilogue work at all
                     if (!last) { tc::fence_before_sync(); tc::mbar_arrive(&a_ready[slot]); }
                     else {
+                        const RowFeat nxt = load_row(j + 2);
                         crow_next = nxt.crow;
                         if (j + 2 < my_tiles) write_features(nxt, inv_s_next);
-                        nxt = load_row(j + 4);
                     }
                     continue;
                 }
@@ -292,9 +295,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                     tc::wait_ld();
                 }
                 if (last) {                                        // D and A of this slot are free: next tile's operand
+                    const RowFeat nxt = load_row(j + 2);           // (loaded here: 8 registers less across the tile)
                     crow_next = nxt.crow;
                     if (j + 2 < my_tiles) write_features(nxt, inv_s_next);
-                    nxt = load_row(j + 4);
                 }
                 const long long q2 = T16_CLOCK();
                 if (prof) sprof[4] += q2 - q1;
