@@ -54,7 +54,7 @@ __device__ __forceinline__ void row_scale(float mx, float &s, float &inv_s) {
 // PROF: in-kernel cycle counters (PIML_TC_PROF); compiled out of the production instantiation (the clock reads and
 // their branches were 4 % of the epilogue's instructions).
 #define T16_CLOCK() (PROF ? clock64() : 0LL)
-template <bool PROF>
+template <bool PROF, bool COMPACT>
 __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __grid_constant__ Tc16Plan P,
                                                                      const __grid_constant__ Tc16Args a) {
     extern __shared__ __align__(128) unsigned char t16_smem[];
@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
     }
     // tiles of both branches (compact mode: the listed non-zero rows + ONE zero row per branch), CTAs split in proportion
     // 32-bit bookkeeping throughout (row counts are < 2^31 by the callers' checks): the epilogue lives at a 96-register ceiling
-    const int cnt_ped = a.compact ? a.counts[0] + 1 : 0, cnt_obs = (a.compact && a.has_obs) ? a.counts[1] + 1 : 0;
-    const int nP = a.compact ? (cnt_ped + 127) / 128 : static_cast<int>(a.n_ped_tiles);
-    const int nO = a.compact ? (cnt_obs + 127) / 128 : static_cast<int>(a.n_obs_tiles);
+    const int cnt_ped = COMPACT ? a.counts[0] + 1 : 0, cnt_obs = (COMPACT && a.has_obs) ? a.counts[1] + 1 : 0;
+    const int nP = COMPACT ? (cnt_ped + 127) / 128 : static_cast<int>(a.n_ped_tiles);
+    const int nO = COMPACT ? (cnt_obs + 127) / 128 : static_cast<int>(a.n_obs_tiles);
     const int G = gridDim.x;
     // CTAs per branch (one branch per CTA: its weights stay resident).  The kernel ends with its slowest CTA, so the
     // split minimises the larger per-CTA tile count: start from the proportional share and give the obstacle branch
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
             if (j >= my_tiles) return rf;
             const int tloc = first + j * stride;
             int64_t src;
-            if (a.compact) {
+            if (COMPACT) {
                 const int nrows = min(128, cnt - tloc * 128);
                 if (m < nrows && tloc * 128 + m < cnt - 1)                // no list (fused NN step): rows are stored compactly
                     rf.crow = list ? list[tloc * 128 + m] : static_cast<int>(tloc * 128 + m);
@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
         for (int j = slot; j < my_tiles; j += 2) {
             const int tloc = first + j * stride;
             const int64_t agent0 = static_cast<int64_t>(tloc) * AG;
-            const int na = a.compact ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
-            const int nrows = a.compact ? min(128, cnt - tloc * 128) : na * k;
+            const int na = COMPACT ? 0 : static_cast<int>(min(static_cast<int64_t>(AG), a.R - agent0));
+            const int nrows = COMPACT ? min(128, cnt - tloc * 128) : na * k;
             const int64_t row0 = agent0 * k;
             float inv_s_next = 1.f;
             int crow_next = -1;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) pinnsf_tc16_kernel(const __gri
                 m0 = m0 + sm2[m * 2] + biasb[P.predb_off];
                 m1 = m1 + sm2[m * 2 + 1] + biasb[P.predb_off + 1];
             }
-            if (a.compact) {
+            if (COMPACT) {
                 if (half == 0 && m < nrows) {                      // slot sums are formed by the finish kernel
                     float *dst = crow >= 0 ? (br == 0 ? a.cmsg_ped : a.cmsg_obs) + static_cast<int64_t>(crow) * 2 : a.f0 + br * 2;
                     dst[0] = m0; dst[1] = m1;
@@ -539,13 +539,17 @@ int tc16_pack(const Tc16Plan &P, const Tc16Src &S, const float *params_torch, fl
 int tc16_launch(const Tc16Plan &P, const Tc16Args &a, int64_t tiles_bound, cudaStream_t st) {
     const size_t smem = tc16_smem_bytes(P);
     const int grid = static_cast<int>(tiles_bound < sm_count() ? tiles_bound : sm_count());
-    if (a.prof) {
-        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        pinnsf_tc16_kernel<true><<<grid, T16_THREADS, smem, st>>>(P, a);
-    } else {
-        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        pinnsf_tc16_kernel<false><<<grid, T16_THREADS, smem, st>>>(P, a);
-    }
+    // (the compact / dense and the profiling variants are separate instantiations: at the epilogue's 96-register ceiling
+    // every dead path costs spills)
+#define T16_LAUNCH(PROF_, COMPACT_)                                                                                        \
+    do {                                                                                                                   \
+        PIML_CUDA(cudaFuncSetAttribute(pinnsf_tc16_kernel<PROF_, COMPACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       static_cast<int>(smem)));                                                           \
+        pinnsf_tc16_kernel<PROF_, COMPACT_><<<grid, T16_THREADS, smem, st>>>(P, a);                                        \
+    } while (0)
+    if (a.prof) { if (a.compact) T16_LAUNCH(true, true); else T16_LAUNCH(true, false); }
+    else { if (a.compact) T16_LAUNCH(false, true); else T16_LAUNCH(false, false); }
+#undef T16_LAUNCH
     count_launch();
     return check_launch("pinnsf_tc16_kernel");
 }
