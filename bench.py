@@ -587,8 +587,8 @@ def nn_workload(torch, dev, N, obs_h, steps, warmup, with_cpu=True):
                      "traffic": None,
                      "executed": {"slot_rows_evaluated": live_rows, "slot_rows_dense": 16 * N,
                                   "fp16_tensor_tflops_executed": exec_tf, "fp16_peak_tflops": bf16,
-                                  "frac_of_fp16_peak": exec_tf / bf16, "tensor_pipe_busy_ncu": 0.363,
-                                  "source": "profiles/r02l_ncu_pinnsf_tc16_kernel.txt; 36 of a tile's 87 MMAs are N = 64 "
+                                  "frac_of_fp16_peak": exec_tf / bf16, "tensor_pipe_busy_ncu": 0.429,
+                                  "source": "profiles/r02m_ncu_pinnsf_tc16_kernel.txt; 36 of a tile's 87 MMAs are N = 64 "
                                             "(half a pipe pass each), so pipe-busy sits below the FLOP fraction"},
                      "hbm": {"bytes_per_agent_step": NN_BYTES_PER_AGENT, "bytes_per_agent_step_fused": NN_BYTES_PER_AGENT_FUSED,
                              "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
